@@ -1,0 +1,200 @@
+"""FITS header -> gnomonic (TAN) WCS constants, and a small host-side pixel<->world evaluator.
+
+Stands in for `astropy.wcs.WCS(hdr)` on the pointing-search path. Reference call sites:
+`hdrshift/alignment.py:1041-1065` (`WCS(hdr)`, `world_to_pixel`), `utils/Util.py:283-290`
+(`WCS(hdr)`, `pixel_to_world`), `synras/map_builder.py:119-127`.
+
+Only what that path needs is modelled: two celestial axes with a `-TAN` projection,
+CUNIT in {deg, arcsec, arcmin, rad}, PCi_j (or CROTA/CROTA2 in the AIPS convention, or CDi_j),
+LONPOLE. wcslib rescales CRVAL/CDELT to degrees when the WCS is set up; so does `TanWcs`.
+
+The *per-pixel* work is done on the device (csrc/coreg_kernels.cu, `coreg_tan_pix2world`,
+`coreg_tan_world2pix`). The numpy evaluator at the bottom of this file is for a handful of points
+(synras bookkeeping, FOV limits) and is written in closed form; the wcslib-structured restatement
+used as the checker lives in `oracle/`, not here.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, replace
+
+import numpy as np
+
+from . import units
+
+R2D = 180.0 / math.pi
+D2R = math.pi / 180.0
+
+
+def _axis_unit(hdr, i):
+    unit = hdr.get("CUNIT%d" % i, "deg") if hasattr(hdr, "get") else hdr["CUNIT%d" % i]
+    if unit is None or str(unit).strip() == "":
+        unit = "deg"
+    return units.canon(unit)
+
+
+def celestial_axes(hdr, lon_prefixes=("HPLN", "RA--", "CRLN", "GLON", "ELON", "SOLX"),
+                   naxis=None):
+    """Return the 1-based indices (ilon, ilat) of the celestial pair in `hdr`."""
+    n = int(naxis if naxis is not None else hdr.get("WCSAXES", hdr.get("NAXIS", 2)))
+    ilon = ilat = None
+    for i in range(1, max(n, 2) + 1):
+        key = "CTYPE%d" % i
+        if key not in hdr:
+            continue
+        ct = str(hdr[key]).upper()
+        if ct[:4] in lon_prefixes or ct[1:4] == "LON":
+            ilon = i
+        elif ct[:4] in ("HPLT", "DEC-", "CRLT", "GLAT", "ELAT", "SOLY") or ct[1:4] == "LAT":
+            ilat = i
+    if ilon is None or ilat is None:
+        raise ValueError("no celestial axis pair found in header")
+    return ilon, ilat
+
+
+@dataclass(frozen=True)
+class TanWcs:
+    """Constants of a 2-D TAN WCS, all angles in degrees (as wcslib holds them after wcsset)."""
+    crpix1: float
+    crpix2: float
+    cdelt1: float
+    cdelt2: float
+    pc11: float
+    pc12: float
+    pc21: float
+    pc22: float
+    crval1: float
+    crval2: float
+    lonpole: float
+    naxis1: int
+    naxis2: int
+    unit_scale1: float = 1.0  # CUNIT1 -> deg factor that was applied
+    unit_scale2: float = 1.0
+
+    # -- construction ----------------------------------------------------
+    @classmethod
+    def from_header(cls, hdr, ilon: int | None = None, ilat: int | None = None):
+        if ilon is None or ilat is None:
+            ilon, ilat = celestial_axes(hdr)
+        for i in (ilon, ilat):
+            ct = str(hdr["CTYPE%d" % i]).upper()
+            if not ct.endswith("TAN"):
+                raise NotImplementedError(
+                    f"CTYPE{i}={ct!r}: only the gnomonic -TAN projection is on the device path")
+        s1 = units.factor(_axis_unit(hdr, ilon), "deg")
+        s2 = units.factor(_axis_unit(hdr, ilat), "deg")
+        cdelt1 = float(hdr.get("CDELT%d" % ilon, 1.0))
+        cdelt2 = float(hdr.get("CDELT%d" % ilat, 1.0))
+        k = lambda a, b: "PC%d_%d" % (a, b)  # noqa: E731
+        c = lambda a, b: "CD%d_%d" % (a, b)  # noqa: E731
+        if any(k(a, b) in hdr for a in (ilon, ilat) for b in (ilon, ilat)):
+            pc11 = float(hdr.get(k(ilon, ilon), 1.0))
+            pc12 = float(hdr.get(k(ilon, ilat), 0.0))
+            pc21 = float(hdr.get(k(ilat, ilon), 0.0))
+            pc22 = float(hdr.get(k(ilat, ilat), 1.0))
+        elif any(c(a, b) in hdr for a in (ilon, ilat) for b in (ilon, ilat)):
+            # CDi_j form: wcslib sets PC=CD and CDELT=1
+            pc11 = float(hdr.get(c(ilon, ilon), 0.0))
+            pc12 = float(hdr.get(c(ilon, ilat), 0.0))
+            pc21 = float(hdr.get(c(ilat, ilon), 0.0))
+            pc22 = float(hdr.get(c(ilat, ilat), 0.0))
+            cdelt1 = cdelt2 = 1.0
+        else:
+            rot = None
+            for key in ("CROTA%d" % ilat, "CROTA"):
+                if key in hdr:
+                    rot = float(hdr[key])
+                    break
+            if rot is None or rot == 0.0:
+                pc11, pc12, pc21, pc22 = 1.0, 0.0, 0.0, 1.0
+            else:
+                # AIPS convention as translated by wcslib
+                cr, sr = math.cos(rot * D2R), math.sin(rot * D2R)
+                pc11, pc22 = cr, cr
+                pc12 = -sr * cdelt2 / cdelt1
+                pc21 = sr * cdelt1 / cdelt2
+        crval1 = float(hdr.get("CRVAL%d" % ilon, 0.0)) * s1
+        crval2 = float(hdr.get("CRVAL%d" % ilat, 0.0)) * s2
+        if "LONPOLE" in hdr:
+            lonpole = float(hdr["LONPOLE"])
+        else:
+            lonpole = 0.0 if crval2 >= 90.0 else 180.0
+        nax1 = hdr.get("ZNAXIS%d" % ilon, hdr.get("NAXIS%d" % ilon, 0))
+        nax2 = hdr.get("ZNAXIS%d" % ilat, hdr.get("NAXIS%d" % ilat, 0))
+        return cls(crpix1=float(hdr.get("CRPIX%d" % ilon, 0.0)), crpix2=float(hdr.get("CRPIX%d" % ilat, 0.0)),
+                   cdelt1=cdelt1 * s1, cdelt2=cdelt2 * s2,
+                   pc11=pc11, pc12=pc12, pc21=pc21, pc22=pc22,
+                   crval1=crval1, crval2=crval2, lonpole=lonpole,
+                   naxis1=int(nax1), naxis2=int(nax2), unit_scale1=s1, unit_scale2=s2)
+
+    def replace(self, **kw):
+        return replace(self, **kw)
+
+    # -- derived constants --------------------------------------------------
+    def forward_matrix(self):
+        """2x2 matrix taking pixel offsets (p - CRPIX) to projection-plane degrees."""
+        return np.array([[self.cdelt1 * self.pc11, self.cdelt1 * self.pc12],
+                         [self.cdelt2 * self.pc21, self.cdelt2 * self.pc22]], dtype=np.float64)
+
+    def inverse_matrix(self):
+        """2x2 matrix taking projection-plane degrees to pixel offsets."""
+        m = self.forward_matrix()
+        det = m[0, 0] * m[1, 1] - m[0, 1] * m[1, 0]
+        if det == 0.0 or not np.isfinite(det):
+            raise ValueError("singular PCi_j/CDELT matrix")
+        return np.array([[m[1, 1], -m[0, 1]], [-m[1, 0], m[0, 0]]], dtype=np.float64) / det
+
+    def as_array(self):
+        """Packed `CoregTanWcs` (include/coreg_b200.h): 11 doubles."""
+        return np.array([self.crpix1, self.crpix2, self.cdelt1, self.cdelt2,
+                         self.pc11, self.pc12, self.pc21, self.pc22,
+                         self.crval1, self.crval2, self.lonpole], dtype=np.float64)
+
+    # -- small-N host evaluation (closed form) ------------------------------------
+    def pixel_to_world(self, x, y):
+        """0-based pixel -> (lon, lat) in degrees; lon normalised like wcslib
+        ([0,360) when CRVAL1 >= 0, (-360,0] otherwise)."""
+        x = np.asarray(x, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        u1 = x + 1.0 - self.crpix1
+        u2 = y + 1.0 - self.crpix2
+        m = self.forward_matrix()
+        px = (m[0, 0] * u1 + m[0, 1] * u2) * D2R
+        py = (m[1, 0] * u1 + m[1, 1] * u2) * D2R
+        # unit vector in the native frame (pole at the reference point), rotated by LONPOLE
+        r = np.hypot(px, py)
+        phi = np.arctan2(px, -py) - self.lonpole * D2R
+        ct = r / np.sqrt(1.0 + r * r)
+        st = 1.0 / np.sqrt(1.0 + r * r)
+        s0, c0 = math.sin(self.crval2 * D2R), math.cos(self.crval2 * D2R)
+        xx = st * c0 - ct * s0 * np.cos(phi)
+        yy = -ct * np.sin(phi)
+        zz = st * s0 + ct * c0 * np.cos(phi)
+        lon = self.crval1 + np.arctan2(yy, xx) * R2D
+        if self.crval1 >= 0.0:
+            lon = np.where(lon < 0.0, lon + 360.0, lon)
+        else:
+            lon = np.where(lon > 0.0, lon - 360.0, lon)
+        lat = np.arctan2(zz, np.hypot(xx, yy)) * R2D
+        return lon, lat
+
+    def world_to_pixel(self, lon, lat):
+        """(lon, lat) in degrees -> 0-based pixel; NaN behind the tangent hemisphere."""
+        lon = np.asarray(lon, dtype=np.float64) * D2R
+        lat = np.asarray(lat, dtype=np.float64) * D2R
+        a0, d0 = self.crval1 * D2R, self.crval2 * D2R
+        da = lon - a0
+        sl, cl = np.sin(lat), np.cos(lat)
+        s0, c0 = math.sin(d0), math.cos(d0)
+        den = sl * s0 + cl * c0 * np.cos(da)
+        xs = sl * c0 - cl * s0 * np.cos(da)   # native x before LONPOLE
+        ys = -cl * np.sin(da)
+        phi = self.lonpole * D2R + np.arctan2(ys, xs)
+        rr = np.hypot(xs, ys) / den * R2D
+        px = rr * np.sin(phi)
+        py = -rr * np.cos(phi)
+        mi = self.inverse_matrix()
+        x = mi[0, 0] * px + mi[0, 1] * py + (self.crpix1 - 1.0)
+        y = mi[1, 0] * px + mi[1, 1] * py + (self.crpix2 - 1.0)
+        bad = den <= 0.0
+        return np.where(bad, np.nan, x), np.where(bad, np.nan, y)

@@ -1,0 +1,294 @@
+"""ctypes binding of `csrc/libcoreg_b200.so` (the C ABI declared in include/coreg_b200.h).
+
+PyTorch supplies device memory and the CUDA stream; every compute step goes through the C entry
+points below -- there is no CPU fallback and no alternative backend. If the shared library has not
+been built (`python -c "import __graft_entry__ as g; g.build()"`), importing this module still works
+(so host-only utilities and CPU tests can run) but the first compute call raises `CoregLibraryError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
+
+F32, F64 = 0, 1
+FLAG_FAST_MATH = 1
+
+
+class CoregLibraryError(RuntimeError):
+    pass
+
+
+class CoregTanWcs(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("crpix1", "crpix2", "cdelt1", "cdelt2", "pc11", "pc12", "pc21", "pc22",
+                                          "crval1", "crval2", "lonpole")]
+
+
+class CoregCarrington(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("lon0", "lat0", "roll", "dist", "cdelt1", "cdelt2")]
+
+
+LAG_TAN_DOUBLES = 10    # sizeof(CoregLagTan) / 8
+LAG_OFFSET_DOUBLES = 2  # sizeof(CoregLagOffset) / 8
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "coreg_last_error": (C.c_char_p, []),
+    "coreg_version": (C.c_int, []),
+    "coreg_device_sm_count": (C.c_int, []),
+    "coreg_tan_pix2world": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "coreg_tan_world2pix": (C.c_int, [C.POINTER(CoregTanWcs), _P, _P, C.c_int64, _P, _P, _P]),
+    "coreg_map_coordinates": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_double,
+                                        _P, C.c_int, _P]),
+    "coreg_tan_trig_planes": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
+    "coreg_finite_mean": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
+    "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
+    "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
+                                     C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
+                                        C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_synras_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
+                                     C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
+                                        C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "coreg_fp64_peak": (C.c_int, [C.POINTER(C.c_double), C.c_int, _P]),
+    "coreg_profile_begin": (C.c_int, []),
+    "coreg_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load(path: str | None = None):
+    """dlopen the C-ABI library and set the prototypes. Raises if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise CoregLibraryError(
+            f"{p} not found: the CUDA library is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). There is no CPU fallback for the pointing search.")
+    lib = C.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().coreg_last_error()
+        raise CoregLibraryError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def tan_struct(w) -> CoregTanWcs:
+    """`_compat.wcs.TanWcs` -> C struct."""
+    return CoregTanWcs(w.crpix1, w.crpix2, w.cdelt1, w.cdelt2, w.pc11, w.pc12, w.pc21, w.pc22,
+                       w.crval1, w.crval2, w.lonpole)
+
+
+# ------------------------------------------------------------------------------------------------
+# torch plumbing
+# ------------------------------------------------------------------------------------------------
+def _torch():
+    import torch
+    return torch
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _dt(t):
+    torch = _torch()
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise CoregLibraryError("device tensor expected (the pointing search has no CPU path)")
+        if not t.is_contiguous():
+            raise ValueError("contiguous tensor expected")
+
+
+def tan_pix2world(wcs, nx, ny, wrap_pipi=True, device=None):
+    """K3 -> (lng, lat) float64 device tensors [ny, nx], degrees."""
+    torch = _torch()
+    lib = load()
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    lng = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+    lat = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+    s = tan_struct(wcs)
+    with torch.cuda.device(dev):
+        _check(lib.coreg_tan_pix2world(C.byref(s), nx, ny, int(bool(wrap_pipi)), _ptr(lng), _ptr(lat), _stream()),
+               "coreg_tan_pix2world")
+    return lng, lat
+
+
+def tan_world2pix(wcs, lng, lat):
+    torch = _torch()
+    lib = load()
+    _require_cuda(lng, lat)
+    x = torch.empty_like(lng)
+    y = torch.empty_like(lat)
+    s = tan_struct(wcs)
+    with torch.cuda.device(lng.device):
+        _check(lib.coreg_tan_world2pix(C.byref(s), _ptr(lng), _ptr(lat), lng.numel(), _ptr(x), _ptr(y), _stream()),
+               "coreg_tan_world2pix")
+    return x, y
+
+
+def map_coordinates(img, y, x, order, cval, out_dtype):
+    """Device `map_coordinates(img, [y, x], order, mode='constant', cval, prefilter=False)`."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(img, y, x)
+    out = torch.empty(x.shape, dtype=out_dtype, device=img.device)
+    with torch.cuda.device(img.device):
+        _check(lib.coreg_map_coordinates(_ptr(img), _dt(img), img.shape[0], img.shape[1], _ptr(y), _ptr(x),
+                                         x.numel(), int(order), float(cval), _ptr(out), _dt(out), _stream()),
+               "coreg_map_coordinates")
+    return out
+
+
+def tan_trig_planes(lng, lat, alpha_ref_deg):
+    torch = _torch()
+    lib = load()
+    _require_cuda(lng, lat)
+    planes = torch.empty((3,) + tuple(lng.shape), dtype=torch.float64, device=lng.device)
+    with torch.cuda.device(lng.device):
+        _check(lib.coreg_tan_trig_planes(_ptr(lng), _ptr(lat), lng.numel(), float(alpha_ref_deg), _ptr(planes),
+                                         _stream()), "coreg_tan_trig_planes")
+    return planes
+
+
+def finite_mean(img, out):
+    """mean of finite values of `img` -> out[0] (device double, view into the pivots tensor)."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(img, out)
+    with torch.cuda.device(img.device):
+        _check(lib.coreg_finite_mean(_ptr(img), _dt(img), img.numel(), _ptr(out), _stream()), "coreg_finite_mean")
+
+
+def lag_corr_workspace_bytes(gnx, gny, n_lags):
+    return int(load().coreg_lag_corr_workspace_bytes(int(gnx), int(gny), int(n_lags)))
+
+
+def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid_out=None, fast_math=False):
+    """K1. `lags`: device float64 [n_lags, 10] (CoregLagTan rows). Writes corr_out[n_lags]."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(ref, small, planes, lags, pivots, work, corr_out)
+    if ref.dtype != torch.float32:
+        raise TypeError("ref must be float32 (the reference keeps the cut large image in float32)")
+    n_lags = lags.shape[0]
+    gny, gnx = ref.shape
+    with torch.cuda.device(ref.device):
+        _check(lib.coreg_hpc_lag_corr(_ptr(ref), _ptr(small), _dt(small), small.shape[1], small.shape[0], gnx, gny,
+                                      _ptr(planes), _ptr(lags), n_lags, int(order), _ptr(pivots), _ptr(work),
+                                      work.numel() * work.element_size(), _ptr(corr_out),
+                                      _ptr(nvalid_out) if nvalid_out is not None else None,
+                                      FLAG_FAST_MATH if fast_math else 0, _stream()), "coreg_hpc_lag_corr")
+
+
+def carrington_planes(c: CoregCarrington, sinlon, coslon, sinlat, coslat):
+    torch = _torch()
+    lib = load()
+    _require_cuda(sinlon, coslon, sinlat, coslat)
+    n_lon, n_lat = sinlon.numel(), sinlat.numel()
+    tx = torch.empty((n_lat, n_lon), dtype=torch.float64, device=sinlon.device)
+    ty = torch.empty_like(tx)
+    with torch.cuda.device(tx.device):
+        _check(lib.coreg_carrington_planes(C.byref(c), _ptr(sinlon), _ptr(coslon), n_lon, _ptr(sinlat), _ptr(coslat),
+                                           n_lat, _ptr(tx), _ptr(ty), _stream()), "coreg_carrington_planes")
+    return tx, ty
+
+
+def offset_lag_corr(ref, small, tx, ty, lags, order, pivots, work, corr_out, nvalid_out=None, fast_math=False):
+    """K4. `lags`: device float64 [n_lags, 2] (CoregLagOffset rows)."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(ref, small, tx, ty, lags, pivots, work, corr_out)
+    if ref.dtype != torch.float64:
+        raise TypeError("ref must be float64 (the reference keeps the Carrington-projected image in float64)")
+    gny, gnx = ref.shape
+    with torch.cuda.device(ref.device):
+        _check(lib.coreg_offset_lag_corr(_ptr(ref), _ptr(small), _dt(small), small.shape[1], small.shape[0], gnx, gny,
+                                         _ptr(tx), _ptr(ty), _ptr(lags), lags.shape[0], int(order), _ptr(pivots),
+                                         _ptr(work), work.numel() * work.element_size(), _ptr(corr_out),
+                                         _ptr(nvalid_out) if nvalid_out is not None else None,
+                                         FLAG_FAST_MATH if fast_math else 0, _stream()), "coreg_offset_lag_corr")
+
+
+def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):
+    """K6. frames: device [n_frames, fny, fnx]; lng/lat: device [n_rows, n_cols] degrees."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(frames, lng, lat)
+    n_frames, fny, fnx = frames.shape
+    n_rows, n_cols = lng.shape
+    arr = (CoregTanWcs * n_frames)(*[tan_struct(w) for w in wcs_list])
+    cols = (C.c_int * n_cols)(*[int(v) for v in frame_of_col])
+    out = torch.empty((n_rows, n_cols), dtype=torch.float64, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _check(lib.coreg_synras_build(_ptr(frames), _dt(frames), n_frames, fnx, fny, arr, cols, _ptr(lng), _ptr(lat),
+                                      n_rows, n_cols, int(order), _ptr(out), _stream()), "coreg_synras_build")
+        torch.cuda.current_stream().synchronize()  # `arr` / `cols` are host temporaries
+    return out
+
+
+def hpc_search_host(large, wcs_large, small, wcs_small, lags, order=2, fast_math=False):
+    """Whole helioprojective search from HOST numpy buffers (the C caller's entry point)."""
+    lib = load()
+    large = np.ascontiguousarray(large, dtype=np.float64)
+    small = np.ascontiguousarray(small, dtype=np.float64)
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    n_lags = lags.shape[0]
+    corr = np.empty(n_lags, dtype=np.float64)
+    nvalid = np.empty(n_lags, dtype=np.int64)
+    sl, ss = tan_struct(wcs_large), tan_struct(wcs_small)
+    _check(lib.coreg_hpc_search_host(large.ctypes.data_as(_P), large.shape[1], large.shape[0], C.byref(sl),
+                                     small.ctypes.data_as(_P), small.shape[1], small.shape[0], C.byref(ss),
+                                     lags.ctypes.data_as(_P), n_lags, int(order),
+                                     FLAG_FAST_MATH if fast_math else 0,
+                                     corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)), "coreg_hpc_search_host")
+    return corr, nvalid
+
+
+def fp64_peak(iters=20000):
+    lib = load()
+    v = C.c_double(0.0)
+    _check(lib.coreg_fp64_peak(C.byref(v), int(iters), None), "coreg_fp64_peak")
+    return v.value
+
+
+def profile_begin():
+    _check(load().coreg_profile_begin(), "coreg_profile_begin")
+
+
+def profile_end():
+    """-> (summed device ms of the fused lag kernel launches since profile_begin, their count)."""
+    ms, n = C.c_double(0.0), C.c_int(0)
+    _check(load().coreg_profile_end(C.byref(ms), C.byref(n)), "coreg_profile_end")
+    return ms.value, n.value

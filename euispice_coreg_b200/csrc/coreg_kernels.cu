@@ -1,0 +1,1043 @@
+// coreg_kernels.cu -- hand-written sm_100a kernels + the C ABI of include/coreg_b200.h.
+//
+// Hot path of adolliou/euispice_coreg's pointing search (hdrshift/alignment.py:509-549, 613-797):
+// per candidate header ("lag"), map every common-grid pixel into the small image, sample it with an order-k
+// B-spline exactly as scipy.ndimage.map_coordinates(prefilter=False) does, and score the pair of images with a
+// masked Pearson coefficient. Here all lags of a launch are evaluated by one kernel: a thread block owns a tile
+// of the common grid (its lag-independent per-pixel constants live in registers), walks the lag list, and emits
+// one 6-moment partial per (tile, lag); a second kernel folds the partials in a fixed order (deterministic,
+// independent of how lags are sharded over GPUs) and turns moments into r.
+//
+// FP64 throughout: the work is gather + FP64 arithmetic + reduction, there is no dense contraction, so no tensor
+// cores (tcgen05) are involved by design. Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/coreg_b200.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  return fail(COREG_ECUDA, "%s: %s", where, cudaGetErrorString(e));
+}
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
+  } while (0)
+#define CK_LAUNCH(name)                                       \
+  do {                                                        \
+    cudaError_t _e = cudaGetLastError();                      \
+    if (_e != cudaSuccess) return cuda_fail(_e, name);        \
+  } while (0)
+
+// optional per-launch timing of the fused lag kernel (bench.py): event pairs recorded around it while enabled
+struct ProfPair { cudaEvent_t a, b; };
+thread_local bool g_prof_on = false;
+thread_local ProfPair g_prof[4096];
+thread_local int g_prof_n = 0;
+
+constexpr double kD2R = 0.017453292519943295769236907684886;
+constexpr double kR2D = 57.295779513082320876798154814105;
+constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+
+// ---------------------------------------------------------------------------------------------------------
+// arithmetic helpers: `STRICT` keeps scipy's separate multiply / add (no FMA contraction)
+// ---------------------------------------------------------------------------------------------------------
+template <bool STRICT>
+__device__ __forceinline__ double mul_(double a, double b) {
+  return STRICT ? __dmul_rn(a, b) : a * b;
+}
+template <bool STRICT>
+__device__ __forceinline__ double add_(double a, double b) {
+  return STRICT ? __dadd_rn(a, b) : a + b;
+}
+template <bool STRICT>
+__device__ __forceinline__ double sub_(double a, double b) {
+  return STRICT ? __dsub_rn(a, b) : a - b;
+}
+
+// floor(s) for |s| < 2^31 on the FP64 pipe only (no F2F/F2I): add 1.5*2^52 rounding toward -inf, the integer
+// lands in the low mantissa word. Exact, i.e. identical to floor().
+__device__ __forceinline__ double floor_magic(double s, int& i) {
+  const double m = __dadd_rd(s, kMagic);
+  i = __double2loint(m);
+  return __dsub_rn(m, kMagic);
+}
+
+// Spline start index and weights of scipy's map_coordinates without prefilter (ni_splines.c), orders 0..3.
+template <int ORDER, bool STRICT>
+__device__ __forceinline__ void spline_weights(double t, int& start, double (&w)[ORDER + 1]) {
+  int i0;
+  if (ORDER == 0) {
+    floor_magic(__dadd_rn(t, 0.5), i0);
+    start = i0;
+    w[0] = 1.0;
+  } else if (ORDER == 1) {
+    const double fl = floor_magic(t, i0);
+    const double d = __dsub_rn(t, fl);
+    start = i0;
+    w[0] = __dsub_rn(1.0, d);
+    w[ORDER >= 1 ? 1 : 0] = __dsub_rn(1.0, w[0]);
+  } else if (ORDER == 2) {
+    const double fl = floor_magic(__dadd_rn(t, 0.5), i0);
+    const double d = __dsub_rn(t, fl);
+    start = i0 - 1;
+    const double u = __dsub_rn(0.5, d);
+    if (STRICT) {
+      w[ORDER >= 2 ? 1 : 0] = __dsub_rn(0.75, __dmul_rn(d, d));
+      w[0] = __dmul_rn(__dmul_rn(0.5, u), u);
+    } else {
+      w[ORDER >= 2 ? 1 : 0] = fma(-d, d, 0.75);
+      w[0] = (0.5 * u) * u;
+    }
+    w[ORDER >= 2 ? 2 : 0] = __dsub_rn(__dsub_rn(1.0, w[0]), w[ORDER >= 2 ? 1 : 0]);
+  } else {
+    const double fl = floor_magic(t, i0);
+    const double d = __dsub_rn(t, fl);
+    start = i0 - 1;
+    const double z = __dsub_rn(1.0, d);
+    const double w1 = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(d, d), __dsub_rn(d, 2.0)), 3.0), 4.0), 6.0);
+    const double w2 = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(z, z), __dsub_rn(z, 2.0)), 3.0), 4.0), 6.0);
+    const double w0 = __ddiv_rn(__dmul_rn(__dmul_rn(z, z), z), 6.0);
+    w[0] = w0;
+    w[ORDER >= 3 ? 1 : 0] = w1;
+    w[ORDER >= 3 ? 2 : 0] = w2;
+    w[ORDER >= 3 ? 3 : 0] = __dsub_rn(__dsub_rn(__dsub_rn(1.0, w0), w1), w2);
+  }
+}
+
+__device__ __forceinline__ int mirror_index(int i, int n) {
+  // scipy 'constant' mode keeps the full spline support near an edge by reflecting about the edge pixel centre
+  if (n == 1) return 0;
+  if (i < 0) i = -i;
+  if (i > n - 1) i = 2 * (n - 1) - i;
+  return min(max(i, 0), n - 1);
+}
+
+template <typename T>
+__device__ __forceinline__ double ldval(const T* p) {
+  return (double)__ldg(p);
+}
+
+// One sample of map_coordinates(img, (y, x), order=ORDER, mode='constant', prefilter=False).
+// Returns false when the point is outside [0, n-1] on either axis (NaN coordinates included) -> caller uses cval.
+template <int ORDER, bool STRICT, typename T>
+__device__ __forceinline__ bool spline_sample(const T* __restrict__ img, int ny, int nx, double y, double x,
+                                              double& out) {
+  const bool inside = (y >= 0.0) && (y <= (double)(ny - 1)) && (x >= 0.0) && (x <= (double)(nx - 1));
+  if (!inside) return false;
+  int sy, sx;
+  double wy[ORDER + 1], wx[ORDER + 1];
+  spline_weights<ORDER, STRICT>(y, sy, wy);
+  spline_weights<ORDER, STRICT>(x, sx, wx);
+  double t = 0.0;
+  const bool interior = (sy >= 0) && (sy + ORDER <= ny - 1) && (sx >= 0) && (sx + ORDER <= nx - 1);
+  if (interior) {
+    const T* p = img + (size_t)sy * nx + sx;
+    if (STRICT) {
+#pragma unroll
+      for (int a = 0; a <= ORDER; ++a) {
+#pragma unroll
+        for (int b = 0; b <= ORDER; ++b) {
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(ldval(p + (size_t)a * nx + b), wy[a]), wx[b]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a <= ORDER; ++a) {
+        double row = ldval(p + (size_t)a * nx) * wx[0];
+#pragma unroll
+        for (int b = 1; b <= ORDER; ++b) row = fma(ldval(p + (size_t)a * nx + b), wx[b], row);
+        t = fma(row, wy[a], t);
+      }
+    }
+  } else {
+    int iy[ORDER + 1], ix[ORDER + 1];
+#pragma unroll
+    for (int a = 0; a <= ORDER; ++a) {
+      iy[a] = mirror_index(sy + a, ny);
+      ix[a] = mirror_index(sx + a, nx);
+    }
+#pragma unroll
+    for (int a = 0; a <= ORDER; ++a) {
+#pragma unroll
+      for (int b = 0; b <= ORDER; ++b) {
+        const double v = ldval(img + (size_t)iy[a] * nx + ix[b]);
+        if (STRICT)
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(v, wy[a]), wx[b]));
+        else
+          t = fma(v * wy[a], wx[b], t);
+      }
+    }
+  }
+  out = t;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TAN (gnomonic) device math
+// ---------------------------------------------------------------------------------------------------------
+struct TanDev {
+  double crpix1, crpix2;
+  double f11, f12, f21, f22;  // cdelt_i * pc_ij * D2R : pixel offset -> projection plane [rad]
+  double i11, i12, i21, i22;  // inverse, projection plane [rad] -> pixel offset
+  double a0_deg, s0, c0;      // CRVAL1 [deg], sin/cos CRVAL2
+  double lonpole_rad;
+  double a0_rad;
+};
+
+int make_tan(const CoregTanWcs* w, TanDev* t) {
+  if (!w) return fail(COREG_EINVAL, "null CoregTanWcs");
+  const double f11 = w->cdelt1 * w->pc11, f12 = w->cdelt1 * w->pc12;
+  const double f21 = w->cdelt2 * w->pc21, f22 = w->cdelt2 * w->pc22;
+  const double det = f11 * f22 - f12 * f21;
+  if (!(det != 0.0) || det != det) return fail(COREG_EINVAL, "singular CDELT*PC matrix");
+  t->crpix1 = w->crpix1;
+  t->crpix2 = w->crpix2;
+  t->f11 = f11 * kD2R;
+  t->f12 = f12 * kD2R;
+  t->f21 = f21 * kD2R;
+  t->f22 = f22 * kD2R;
+  t->i11 = (f22 / det) * kR2D;
+  t->i12 = (-f12 / det) * kR2D;
+  t->i21 = (-f21 / det) * kR2D;
+  t->i22 = (f11 / det) * kR2D;
+  t->a0_deg = w->crval1;
+  t->a0_rad = w->crval1 * kD2R;
+  t->s0 = sin(w->crval2 * kD2R);
+  t->c0 = cos(w->crval2 * kD2R);
+  t->lonpole_rad = w->lonpole * kD2R;
+  return COREG_OK;
+}
+
+__device__ __forceinline__ double wrap_pipi_deg(double a) {
+  // -((-a + 180) % 360 - 180) with Python's floor-mod (utils/Util.py:76-80)
+  double m = fmod(-a + 180.0, 360.0);
+  if (m != 0.0 && m < 0.0) m += 360.0;
+  return -(m - 180.0);
+}
+
+__global__ void tan_pix2world_kernel(TanDev w, int nx, int ny, int wrap, double* __restrict__ lng,
+                                     double* __restrict__ lat) {
+  const int64_t n = (int64_t)nx * ny;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % nx), j = (int)(idx / nx);
+    const double u1 = ((double)i + 1.0) - w.crpix1;
+    const double u2 = ((double)j + 1.0) - w.crpix2;
+    const double px = w.f11 * u1 + w.f12 * u2;
+    const double py = w.f21 * u1 + w.f22 * u2;
+    const double r2 = px * px + py * py;
+    const double r = sqrt(r2);
+    const double phi = (r == 0.0) ? 0.0 : atan2(px, -py);
+    const double st = rsqrt(1.0 + r2);  // sin(theta), theta = atan2(1, r)
+    const double ct = r * st;
+    double sp, cp;
+    sincos(phi - w.lonpole_rad, &sp, &cp);
+    const double xx = st * w.c0 - ct * w.s0 * cp;
+    const double yy = -ct * sp;
+    const double zz = st * w.s0 + ct * w.c0 * cp;
+    double lo = w.a0_deg + atan2(yy, xx) * kR2D;
+    if (w.a0_deg >= 0.0) {
+      if (lo < 0.0) lo += 360.0;
+    } else {
+      if (lo > 0.0) lo -= 360.0;
+    }
+    double la = atan2(zz, sqrt(xx * xx + yy * yy)) * kR2D;
+    if (wrap) {
+      lo = wrap_pipi_deg(lo);
+      la = wrap_pipi_deg(la);
+    }
+    lng[idx] = lo;
+    lat[idx] = la;
+  }
+}
+
+__device__ __forceinline__ void tan_world2pix_dev(const TanDev& w, double lng_deg, double lat_deg, double& x,
+                                                  double& y) {
+  double sl, cl, sa, ca;
+  sincos(lat_deg * kD2R, &sl, &cl);
+  sincos(lng_deg * kD2R - w.a0_rad, &sa, &ca);
+  const double den = sl * w.s0 + cl * w.c0 * ca;
+  const double xs = sl * w.c0 - cl * w.s0 * ca;
+  const double ys = -cl * sa;
+  // phi = lonpole + atan2(ys, xs); plane = (r sin phi, -r cos phi), r = hypot(xs, ys) / den
+  double sp, cp;
+  sincos(w.lonpole_rad, &sp, &cp);
+  // sin(phi) * hypot = sp*xs + cp*ys ; cos(phi) * hypot = cp*xs - sp*ys
+  const double inv = 1.0 / den;
+  const double xi = (sp * xs + cp * ys) * inv;
+  const double eta = -(cp * xs - sp * ys) * inv;
+  x = w.i11 * xi + w.i12 * eta + (w.crpix1 - 1.0);
+  y = w.i21 * xi + w.i22 * eta + (w.crpix2 - 1.0);
+  if (!(den > 0.0)) {
+    x = CUDART_NAN;
+    y = CUDART_NAN;
+  }
+}
+
+__global__ void tan_world2pix_kernel(TanDev w, const double* __restrict__ lng, const double* __restrict__ lat,
+                                     int64_t n, double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double xx, yy;
+    tan_world2pix_dev(w, lng[idx], lat[idx], xx, yy);
+    x[idx] = xx;
+    y[idx] = yy;
+  }
+}
+
+__global__ void tan_trig_planes_kernel(const double* __restrict__ lng, const double* __restrict__ lat, int64_t n,
+                                       double alpha_ref_rad, double* __restrict__ planes) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double sl, cl, sa, ca;
+    sincos(lat[idx] * kD2R, &sl, &cl);
+    sincos(lng[idx] * kD2R - alpha_ref_rad, &sa, &ca);
+    planes[idx] = sl;
+    planes[n + idx] = cl * sa;
+    planes[2 * n + idx] = cl * ca;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// map_coordinates at explicit coordinates (one-shot resampling: K2, K5 large image, host API interpol2d)
+// ---------------------------------------------------------------------------------------------------------
+template <int ORDER, typename TI, typename TO>
+__global__ void map_coordinates_kernel(const TI* __restrict__ img, int ny, int nx, const double* __restrict__ yc,
+                                       const double* __restrict__ xc, int64_t n, double cval, TO* __restrict__ out) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double v;
+    if (!spline_sample<ORDER, true, TI>(img, ny, nx, yc[idx], xc[idx], v)) v = cval;
+    out[idx] = (TO)v;
+  }
+}
+
+template <typename TI, typename TO>
+int launch_map_coordinates(const TI* img, int ny, int nx, const double* y, const double* x, int64_t n, int order,
+                           double cval, TO* out, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
+  if (n == 0) return COREG_OK;
+  switch (order) {
+    case 0: map_coordinates_kernel<0, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    case 1: map_coordinates_kernel<1, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    case 2: map_coordinates_kernel<2, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    case 3: map_coordinates_kernel<3, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    default: return fail(COREG_EINVAL, "spline order must be 0..3");
+  }
+  CK_LAUNCH("map_coordinates_kernel");
+  return COREG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mean of finite values (pivot). One block, fixed traversal order -> deterministic.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void finite_mean_kernel(const T* __restrict__ img, int64_t n, double* __restrict__ mean) {
+  __shared__ double ssum[1024];
+  __shared__ unsigned long long scnt[1024];
+  double s = 0.0;
+  unsigned long long c = 0;
+  // coarse sample (every 4th element) is plenty for a pivot and keeps this one-block kernel short
+  for (int64_t i = (int64_t)threadIdx.x * 4; i < n; i += (int64_t)blockDim.x * 4) {
+    const double v = (double)img[i];
+    if (isfinite(v)) {
+      s += v;
+      ++c;
+    }
+  }
+  ssum[threadIdx.x] = s;
+  scnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + o];
+      scnt[threadIdx.x] += scnt[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mean[0] = scnt[0] ? ssum[0] / (double)scnt[0] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused lag search
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTileW = 64;
+constexpr int kTileH = 32;
+constexpr int kThreads = 256;
+constexpr int kPPT = (kTileW * kTileH) / kThreads;  // 8 pixels per thread
+constexpr int kWarps = kThreads / 32;
+constexpr int kLagSub = 64;  // lags staged in shared memory at a time
+constexpr int kMom = 8;      // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
+
+struct TanCoord {
+  typedef CoregLagTan Lag;
+  struct Planes {
+    const double* p;  // [3][n]
+    int64_t n;
+  };
+  struct Pix {
+    double p0, p1, p2;
+  };
+  __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx) {
+    Pix q;
+    q.p0 = __ldg(pl.p + idx);
+    q.p1 = __ldg(pl.p + pl.n + idx);
+    q.p2 = __ldg(pl.p + 2 * pl.n + idx);
+    return q;
+  }
+  __device__ static __forceinline__ Pix dead() {
+    Pix q;
+    q.p0 = q.p1 = q.p2 = CUDART_NAN;
+    return q;
+  }
+  // world -> pixel of the lag's header; NaN when behind the tangent hemisphere
+  __device__ static __forceinline__ void map(const Pix& q, const Lag& L, double& x, double& y) {
+    const double qs = fma(q.p1, L.cos_da, -(q.p2 * L.sin_da));  // cos(lat) sin(dA)
+    const double pc = fma(q.p2, L.cos_da, q.p1 * L.sin_da);     // cos(lat) cos(dA)
+    const double den = fma(pc, L.cos_d0, q.p0 * L.sin_d0);
+    const double en = fma(-pc, L.sin_d0, q.p0 * L.cos_d0);
+    const double inv = 1.0 / den;
+    const double xi = qs * inv, eta = en * inv;
+    x = fma(L.m11, xi, fma(L.m12, eta, L.x0));
+    y = fma(L.m21, xi, fma(L.m22, eta, L.y0));
+    if (!(den > 0.0)) x = CUDART_NAN;
+  }
+};
+
+struct OffsetCoord {
+  typedef CoregLagOffset Lag;
+  struct Planes {
+    const double* tx;
+    const double* ty;
+  };
+  struct Pix {
+    double tx, ty;
+  };
+  __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx) {
+    Pix q;
+    q.tx = __ldg(pl.tx + idx);
+    q.ty = __ldg(pl.ty + idx);
+    return q;
+  }
+  __device__ static __forceinline__ Pix dead() {
+    Pix q;
+    q.tx = q.ty = CUDART_NAN;
+    return q;
+  }
+  __device__ static __forceinline__ void map(const Pix& q, const Lag& L, double& x, double& y) {
+    x = __dadd_rn(L.x0, q.tx);
+    y = __dadd_rn(L.y0, q.ty);
+  }
+};
+
+// butterfly that leaves, in every lane, the warp total of value index (lane >> 2) & 7 : 9 shuffles instead of 40
+__device__ __forceinline__ double warp_transpose_reduce8(double (&v)[8], int lane) {
+  double w4[4], w2[2], w1;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double send = up ? v[i] : v[i + 4];
+      const double keep = up ? v[i + 4] : v[i];
+      w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double send = up ? w4[i] : w4[i + 2];
+      const double keep = up ? w4[i + 2] : w4[i];
+      w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+    const double send = up ? w2[0] : w2[1];
+    const double keep = up ? w2[1] : w2[0];
+    w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  return w1;  // value index = 4*bit4 + 2*bit3 + bit2 = (lane >> 2) & 7
+}
+
+// work layout: [tile][lag][kMom] doubles
+template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
+__global__ void __launch_bounds__(kThreads, 2)
+lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, int snx, int sny, int gnx, int gny,
+                typename Coord::Planes planes, const typename Coord::Lag* __restrict__ lags, int n_lags,
+                int lags_per_block, const double* __restrict__ pivots, double* __restrict__ work) {
+  typedef typename Coord::Lag Lag;
+  typedef typename Coord::Pix Pix;
+  __shared__ Lag s_lag[kLagSub];
+  __shared__ double s_part[kWarps][kLagSub][kMom];
+
+  const int tiles_x = (gnx + kTileW - 1) / kTileW;
+  const int tile = blockIdx.x;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & (kTileW - 1), ty0 = tid / kTileW;
+  const int gx = tile_x * kTileW + tx;
+  const double pivot_a = pivots[0], pivot_b = pivots[1];
+
+  // lag-independent per-pixel constants, held in registers for the whole lag walk
+  Pix pix[kPPT];
+  double a_c[kPPT];  // ref - pivot, NaN when the pair can never be valid
+#pragma unroll
+  for (int k = 0; k < kPPT; ++k) {
+    const int gy = tile_y * kTileH + ty0 + k * (kThreads / kTileW);
+    if (gx < gnx && gy < gny) {
+      const int64_t idx = (int64_t)gy * gnx + gx;
+      const double a = (double)ref[idx];
+      a_c[k] = isfinite(a) ? a - pivot_a : CUDART_NAN;
+      pix[k] = Coord::load(planes, idx);
+    } else {
+      a_c[k] = CUDART_NAN;
+      pix[k] = Coord::dead();
+    }
+  }
+
+  const int lag_begin = blockIdx.y * lags_per_block;
+  const int lag_end = min(n_lags, lag_begin + lags_per_block);
+  for (int l0 = lag_begin; l0 < lag_end; l0 += kLagSub) {
+    const int cnt = min(kLagSub, lag_end - l0);
+    __syncthreads();  // previous sub-chunk fully consumed
+    {
+      // stage lag constants: sizeof(Lag) is a multiple of 8
+      const double* src = reinterpret_cast<const double*>(lags + l0);
+      double* dst = reinterpret_cast<double*>(s_lag);
+      const int nd = cnt * (int)(sizeof(Lag) / sizeof(double));
+      for (int i = tid; i < nd; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (int l = 0; l < cnt; ++l) {
+      const Lag L = s_lag[l];
+      double m[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = 0.0;
+      int nv = 0;
+#pragma unroll
+      for (int k = 0; k < kPPT; ++k) {
+        double x, y, v;
+        Coord::map(pix[k], L, x, y);
+        bool ok = spline_sample<ORDER, STRICT, SmallT>(small, sny, snx, y, x, v);
+        double b;
+        if (ROUND32) {
+          const float bf = __double2float_rn(v);
+          ok = ok && isfinite(bf);
+          b = (double)bf;
+        } else {
+          ok = ok && isfinite(v) && (v != -32762.0);
+          b = v;
+        }
+        const double a = a_c[k];
+        ok = ok && (a == a);
+        if (ok) {
+          const double bc = b - pivot_b;
+          ++nv;
+          m[1] += a;
+          m[2] += bc;
+          m[3] = fma(a, a, m[3]);
+          m[4] = fma(bc, bc, m[4]);
+          m[5] = fma(a, bc, m[5]);
+        }
+      }
+      m[0] = (double)nv;
+      const double tot = warp_transpose_reduce8(m, lane);
+      if ((lane & 3) == 0) s_part[warp][l][lane >> 2] = tot;
+    }
+    __syncthreads();
+    // fold the warps in a fixed order and publish this tile's partials
+    for (int i = tid; i < cnt * kMom; i += kThreads) {
+      const int l = i / kMom, q = i % kMom;
+      double s = s_part[0][l][q];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) s += s_part[w][l][q];
+      work[((size_t)tile * n_lags + (l0 + l)) * kMom + q] = s;
+    }
+  }
+}
+
+// one block per lag: sum the tile partials in a fixed order, moments -> Pearson r
+__global__ void __launch_bounds__(128)
+lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lags, double* __restrict__ corr,
+                         int64_t* __restrict__ nvalid) {
+  __shared__ double s[128][6];
+  const int lag = blockIdx.x;
+  double m[6] = {0, 0, 0, 0, 0, 0};
+  for (int t = threadIdx.x; t < n_tiles; t += 128) {
+    const double* p = work + ((size_t)t * n_lags + lag) * kMom;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) m[q] += p[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s[threadIdx.x][q] = m[q];
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s[threadIdx.x][q] += s[threadIdx.x + o][q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = s[0][0], sa = s[0][1], sb = s[0][2], saa = s[0][3], sbb = s[0][4], sab = s[0][5];
+    double r = CUDART_NAN;
+    if (n > 0.0) {
+      const double cov = sab - sa * sb / n;
+      const double va = saa - sa * sa / n;
+      const double vb = sbb - sb * sb / n;
+      r = cov / sqrt(va * vb);
+    }
+    corr[lag] = r;
+    if (nvalid) nvalid[lag] = (int64_t)n;
+  }
+}
+
+template <class Coord, typename SmallT, typename RefT, bool ROUND32>
+int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int gnx, int gny,
+                    typename Coord::Planes planes, const typename Coord::Lag* lags, int64_t n_lags, int order,
+                    const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid, int flags,
+                    cudaStream_t s) {
+  if (n_lags <= 0) return COREG_OK;
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (gnx <= 0 || gny <= 0 || snx <= 0 || sny <= 0) return fail(COREG_EINVAL, "empty image");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + kTileH - 1) / kTileH);
+  // split the lag list over blockIdx.y until the grid has a few waves of (SMs x 2 resident blocks)
+  int sms = coreg_device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int want_blocks = sms * 2 * 4;
+  int splits = (want_blocks + tiles - 1) / tiles;
+  const int max_splits = (int)((n_lags + kLagSub - 1) / kLagSub);
+  splits = std::max(1, std::min(splits, max_splits));
+  int lags_per_block = (int)((n_lags + splits - 1) / splits);
+  lags_per_block = ((lags_per_block + kLagSub - 1) / kLagSub) * kLagSub;
+  splits = (int)((n_lags + lags_per_block - 1) / lags_per_block);
+  if (splits > 65535) return fail(COREG_EINVAL, "lag grid too large for one launch");
+  dim3 grid(tiles, splits);
+  const bool strict = !(flags & COREG_FLAG_FAST_MATH);
+  double* w = static_cast<double*>(work);
+  const bool prof = g_prof_on && g_prof_n < 4096;
+  if (prof) {
+    CK(cudaEventCreate(&g_prof[g_prof_n].a));
+    CK(cudaEventCreate(&g_prof[g_prof_n].b));
+    CK(cudaEventRecord(g_prof[g_prof_n].a, s));
+  }
+#define LAUNCH(ORD, STR)                                                                              \
+  lag_corr_kernel<Coord, ORD, STR, SmallT, RefT, ROUND32><<<grid, kThreads, 0, s>>>(                  \
+      ref, small, snx, sny, gnx, gny, planes, lags, (int)n_lags, lags_per_block, pivots, w)
+  switch (order * 2 + (strict ? 1 : 0)) {
+    case 1: LAUNCH(0, true); break;
+    case 0: LAUNCH(0, true); break;
+    case 3: LAUNCH(1, true); break;
+    case 2: LAUNCH(1, true); break;
+    case 5: LAUNCH(2, true); break;
+    case 4: LAUNCH(2, false); break;
+    case 7: LAUNCH(3, true); break;
+    case 6: LAUNCH(3, true); break;
+    default: return fail(COREG_EINVAL, "spline order must be 0..3");
+  }
+#undef LAUNCH
+  CK_LAUNCH("lag_corr_kernel");
+  if (prof) {
+    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+    ++g_prof_n;
+  }
+  lag_corr_finalize_kernel<<<(unsigned)n_lags, 128, 0, s>>>(w, tiles, (int)n_lags, corr, nvalid);
+  CK_LAUNCH("lag_corr_finalize_kernel");
+  return COREG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Carrington planes
+// ---------------------------------------------------------------------------------------------------------
+__global__ void carrington_planes_kernel(CoregCarrington c, double cosb0, double sinb0, double cosr, double sinr,
+                                         const double* __restrict__ sinlon, const double* __restrict__ coslon,
+                                         int n_lon, const double* __restrict__ sinlat,
+                                         const double* __restrict__ coslat, int n_lat, double* __restrict__ tx,
+                                         double* __restrict__ ty) {
+  const int64_t n = (int64_t)n_lon * n_lat;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % n_lon), j = (int)(idx / n_lon);
+    // utils/rectify.py:345-363, numpy evaluation order, no FMA
+    const double X = __dmul_rn(coslat[j], sinlon[i]);
+    const double Y = sinlat[j];
+    const double Z = __dmul_rn(coslat[j], coslon[i]);
+    const double zz = __dadd_rn(__dmul_rn(Z, cosb0), __dmul_rn(Y, sinb0));
+    const double yy = __dsub_rn(__dmul_rn(Y, cosb0), __dmul_rn(Z, sinb0));
+    double ox = CUDART_NAN, oy = CUDART_NAN;
+    if (zz >= 0.0) {
+      const double y2 = __dsub_rn(__dmul_rn(yy, cosr), __dmul_rn(X, sinr));
+      const double x2 = __dadd_rn(__dmul_rn(X, cosr), __dmul_rn(yy, sinr));
+      const double z2 = __dsub_rn(c.dist, zz);
+      ox = __ddiv_rn(__dmul_rn(__dmul_rn(atan(__ddiv_rn(x2, z2)), kR2D), 3600.0), c.cdelt1);
+      oy = __ddiv_rn(__dmul_rn(__dmul_rn(atan(__ddiv_rn(y2, z2)), kR2D), 3600.0), c.cdelt2);
+    }
+    tx[idx] = ox;
+    ty[idx] = oy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// synthetic raster
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxSynrasFrames = 64;
+struct SynrasWcs {
+  TanDev w[kMaxSynrasFrames];
+};
+
+template <int ORDER, typename T>
+__global__ void synras_kernel(const T* __restrict__ frames, int fnx, int fny, const TanDev* __restrict__ wcs,
+                              const int* __restrict__ frame_of_col, const double* __restrict__ lng,
+                              const double* __restrict__ lat, int n_rows, int n_cols, double* __restrict__ out) {
+  const int64_t n = (int64_t)n_rows * n_cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % n_cols);
+    const int f = frame_of_col[col];
+    double v = CUDART_NAN;
+    if (f >= 0) {
+      double x, y, s;
+      tan_world2pix_dev(wcs[f], lng[idx], lat[idx], x, y);
+      if (spline_sample<ORDER, true, T>(frames + (size_t)f * fnx * fny, fny, fnx, y, x, s)) v = s;
+    }
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP64 issue-rate microbenchmark
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+inline int grid_for(int64_t n, int threads = 256) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
+}
+
+}  // namespace
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C" {
+
+const char* coreg_last_error(void) { return g_err; }
+int coreg_version(void) { return 100; }
+
+int coreg_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return COREG_ECUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return COREG_ECUDA;
+  return sms;
+}
+
+int coreg_tan_pix2world(const CoregTanWcs* wcs, int nx, int ny, int wrap_pipi, double* lng, double* lat,
+                        void* stream) {
+  TanDev t;
+  int rc = make_tan(wcs, &t);
+  if (rc) return rc;
+  if (nx <= 0 || ny <= 0) return COREG_OK;
+  if (!lng || !lat) return fail(COREG_EINVAL, "null output plane");
+  const int64_t n = (int64_t)nx * ny;
+  tan_pix2world_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(t, nx, ny, wrap_pipi, lng, lat);
+  CK_LAUNCH("tan_pix2world_kernel");
+  return COREG_OK;
+}
+
+int coreg_tan_world2pix(const CoregTanWcs* wcs, const double* lng, const double* lat, int64_t n, double* x,
+                        double* y, void* stream) {
+  TanDev t;
+  int rc = make_tan(wcs, &t);
+  if (rc) return rc;
+  if (n <= 0) return COREG_OK;
+  if (!lng || !lat || !x || !y) return fail(COREG_EINVAL, "null pointer");
+  tan_world2pix_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(t, lng, lat, n, x, y);
+  CK_LAUNCH("tan_world2pix_kernel");
+  return COREG_OK;
+}
+
+int coreg_map_coordinates(const void* img, int img_dtype, int img_ny, int img_nx, const double* y, const double* x,
+                          int64_t n, int order, double cval, void* out, int out_dtype, void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!img || !y || !x || !out) return fail(COREG_EINVAL, "null pointer");
+  if (img_ny <= 0 || img_nx <= 0) return fail(COREG_EINVAL, "empty image");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (img_dtype == COREG_F32 && out_dtype == COREG_F32)
+    return launch_map_coordinates((const float*)img, img_ny, img_nx, y, x, n, order, cval, (float*)out, s);
+  if (img_dtype == COREG_F32 && out_dtype == COREG_F64)
+    return launch_map_coordinates((const float*)img, img_ny, img_nx, y, x, n, order, cval, (double*)out, s);
+  if (img_dtype == COREG_F64 && out_dtype == COREG_F32)
+    return launch_map_coordinates((const double*)img, img_ny, img_nx, y, x, n, order, cval, (float*)out, s);
+  if (img_dtype == COREG_F64 && out_dtype == COREG_F64)
+    return launch_map_coordinates((const double*)img, img_ny, img_nx, y, x, n, order, cval, (double*)out, s);
+  return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_tan_trig_planes(const double* lng, const double* lat, int64_t n, double alpha_ref_deg, double* planes,
+                          void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!lng || !lat || !planes) return fail(COREG_EINVAL, "null pointer");
+  tan_trig_planes_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(lng, lat, n, alpha_ref_deg * kD2R, planes);
+  CK_LAUNCH("tan_trig_planes_kernel");
+  return COREG_OK;
+}
+
+int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void* stream) {
+  if (!img || !mean || n <= 0) return fail(COREG_EINVAL, "coreg_finite_mean: bad argument");
+  if (dtype == COREG_F32)
+    finite_mean_kernel<float><<<1, 1024, 0, (cudaStream_t)stream>>>((const float*)img, n, mean);
+  else if (dtype == COREG_F64)
+    finite_mean_kernel<double><<<1, 1024, 0, (cudaStream_t)stream>>>((const double*)img, n, mean);
+  else
+    return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+  CK_LAUNCH("finite_mean_kernel");
+  return COREG_OK;
+}
+
+size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags) {
+  if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;
+  const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kTileH - 1) / kTileH);
+  return tiles * (size_t)n_lags * kMom * sizeof(double);
+}
+
+int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
+                       const double* planes, const CoregLagTan* lags, int64_t n_lags, int order,
+                       const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid, int flags,
+                       void* stream) {
+  if (!ref || !small || !planes || !lags || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr: null pointer");
+  TanCoord::Planes pl{planes, (int64_t)gnx * gny};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (small_dtype == COREG_F64)
+    return launch_lag_corr<TanCoord, double, float, true>(ref, (const double*)small, snx, sny, gnx, gny, pl, lags,
+                                                          n_lags, order, pivots, work, work_bytes, corr, nvalid,
+                                                          flags, s);
+  if (small_dtype == COREG_F32)
+    return launch_lag_corr<TanCoord, float, float, true>(ref, (const float*)small, snx, sny, gnx, gny, pl, lags,
+                                                         n_lags, order, pivots, work, work_bytes, corr, nvalid, flags,
+                                                         s);
+  return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_carrington_planes(const CoregCarrington* c, const double* sinlon, const double* coslon, int n_lon,
+                            const double* sinlat, const double* coslat, int n_lat, double* tx, double* ty,
+                            void* stream) {
+  if (!c || !sinlon || !coslon || !sinlat || !coslat || !tx || !ty)
+    return fail(COREG_EINVAL, "coreg_carrington_planes: null pointer");
+  if (n_lon <= 0 || n_lat <= 0) return COREG_OK;
+  const int64_t n = (int64_t)n_lon * n_lat;
+  carrington_planes_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+      *c, cos(c->lat0), sin(c->lat0), cos(c->roll), sin(c->roll), sinlon, coslon, n_lon, sinlat, coslat, n_lat, tx,
+      ty);
+  CK_LAUNCH("carrington_planes_kernel");
+  return COREG_OK;
+}
+
+int coreg_offset_lag_corr(const double* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
+                          const double* tx, const double* ty, const CoregLagOffset* lags, int64_t n_lags, int order,
+                          const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid,
+                          int flags, void* stream) {
+  if (!ref || !small || !tx || !ty || !lags || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_offset_lag_corr: null pointer");
+  OffsetCoord::Planes pl{tx, ty};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (small_dtype == COREG_F64)
+    return launch_lag_corr<OffsetCoord, double, double, false>(ref, (const double*)small, snx, sny, gnx, gny, pl,
+                                                               lags, n_lags, order, pivots, work, work_bytes, corr,
+                                                               nvalid, flags, s);
+  if (small_dtype == COREG_F32)
+    return launch_lag_corr<OffsetCoord, float, double, false>(ref, (const float*)small, snx, sny, gnx, gny, pl, lags,
+                                                              n_lags, order, pivots, work, work_bytes, corr, nvalid,
+                                                              flags, s);
+  return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_synras_build(const void* frames, int frame_dtype, int n_frames, int fnx, int fny, const CoregTanWcs* wcs,
+                       const int* frame_of_col, const double* lng, const double* lat, int n_rows, int n_cols,
+                       int order, double* out, void* stream) {
+  if (!frames || !wcs || !frame_of_col || !lng || !lat || !out)
+    return fail(COREG_EINVAL, "coreg_synras_build: null pointer");
+  if (n_frames <= 0 || n_frames > kMaxSynrasFrames) return fail(COREG_EINVAL, "n_frames must be in 1..64 per call");
+  if (n_rows <= 0 || n_cols <= 0) return COREG_OK;
+  if (order < 0 || order > 3) return fail(COREG_EINVAL, "spline order must be 0..3");
+  cudaStream_t s = (cudaStream_t)stream;
+  TanDev hw[kMaxSynrasFrames];
+  for (int f = 0; f < n_frames; ++f) {
+    int rc = make_tan(wcs + f, hw + f);
+    if (rc) return rc;
+  }
+  for (int c = 0; c < n_cols; ++c)
+    if (frame_of_col[c] >= n_frames) return fail(COREG_EINVAL, "frame_of_col entry out of range");
+  TanDev* dw = nullptr;
+  int* dcol = nullptr;
+  CK(cudaMallocAsync(&dw, sizeof(TanDev) * n_frames, s));
+  CK(cudaMallocAsync(&dcol, sizeof(int) * n_cols, s));
+  CK(cudaMemcpyAsync(dw, hw, sizeof(TanDev) * n_frames, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dcol, frame_of_col, sizeof(int) * n_cols, cudaMemcpyHostToDevice, s));
+  // hw / frame_of_col are pageable: the async copies above have consumed them when the call returns
+  const int64_t n = (int64_t)n_rows * n_cols;
+  const int g = grid_for(n);
+#define SYN(ORD, T) \
+  synras_kernel<ORD, T><<<g, 256, 0, s>>>((const T*)frames, fnx, fny, dw, dcol, lng, lat, n_rows, n_cols, out)
+  if (frame_dtype == COREG_F32) {
+    switch (order) { case 0: SYN(0, float); break; case 1: SYN(1, float); break; case 2: SYN(2, float); break; default: SYN(3, float); }
+  } else if (frame_dtype == COREG_F64) {
+    switch (order) { case 0: SYN(0, double); break; case 1: SYN(1, double); break; case 2: SYN(2, double); break; default: SYN(3, double); }
+  } else {
+    return fail(COREG_EINVAL, "frame_dtype must be COREG_F32 or COREG_F64");
+  }
+#undef SYN
+  CK_LAUNCH("synras_kernel");
+  CK(cudaFreeAsync(dw, s));
+  CK(cudaFreeAsync(dcol, s));
+  return COREG_OK;
+}
+
+int coreg_hpc_search_host(const double* large, int lnx, int lny, const CoregTanWcs* wcs_large, const double* small,
+                          int snx, int sny, const CoregTanWcs* wcs_small, const CoregLagTan* lags, int64_t n_lags,
+                          int order, int flags, double* corr, int64_t* nvalid) {
+  if (!large || !small || !wcs_large || !wcs_small || !lags || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_search_host: null pointer");
+  if (lnx <= 0 || lny <= 0 || snx <= 0 || sny <= 0 || n_lags <= 0)
+    return fail(COREG_EINVAL, "coreg_hpc_search_host: empty input");
+  const int64_t ns = (int64_t)snx * sny, nl = (int64_t)lnx * lny;
+  const size_t work_bytes = coreg_lag_corr_workspace_bytes(snx, sny, n_lags);
+  double *d_large = nullptr, *d_small = nullptr, *d_lng = nullptr, *d_lat = nullptr, *d_x = nullptr, *d_y = nullptr,
+         *d_planes = nullptr, *d_piv = nullptr, *d_corr = nullptr;
+  float* d_ref = nullptr;
+  CoregLagTan* d_lags = nullptr;
+  int64_t* d_nv = nullptr;
+  void* d_work = nullptr;
+  cudaStream_t s = nullptr;
+  int rc = COREG_OK;
+#define TRY(call)                       \
+  do {                                  \
+    cudaError_t _e = (call);            \
+    if (_e != cudaSuccess) {            \
+      rc = cuda_fail(_e, #call);        \
+      goto done;                        \
+    }                                   \
+  } while (0)
+#define TRYRC(call)      \
+  do {                   \
+    rc = (call);         \
+    if (rc) goto done;   \
+  } while (0)
+  TRY(cudaMalloc(&d_large, nl * sizeof(double)));
+  TRY(cudaMalloc(&d_small, ns * sizeof(double)));
+  TRY(cudaMalloc(&d_lng, ns * sizeof(double)));
+  TRY(cudaMalloc(&d_lat, ns * sizeof(double)));
+  TRY(cudaMalloc(&d_x, ns * sizeof(double)));
+  TRY(cudaMalloc(&d_y, ns * sizeof(double)));
+  TRY(cudaMalloc(&d_planes, 3 * ns * sizeof(double)));
+  TRY(cudaMalloc(&d_ref, ns * sizeof(float)));
+  TRY(cudaMalloc(&d_piv, 2 * sizeof(double)));
+  TRY(cudaMalloc(&d_corr, n_lags * sizeof(double)));
+  TRY(cudaMalloc(&d_nv, n_lags * sizeof(int64_t)));
+  TRY(cudaMalloc(&d_lags, n_lags * sizeof(CoregLagTan)));
+  TRY(cudaMalloc(&d_work, work_bytes));
+  TRY(cudaMemcpyAsync(d_large, large, nl * sizeof(double), cudaMemcpyHostToDevice, s));
+  TRY(cudaMemcpyAsync(d_small, small, ns * sizeof(double), cudaMemcpyHostToDevice, s));
+  TRY(cudaMemcpyAsync(d_lags, lags, n_lags * sizeof(CoregLagTan), cudaMemcpyHostToDevice, s));
+  TRYRC(coreg_tan_pix2world(wcs_small, snx, sny, 1, d_lng, d_lat, s));
+  TRYRC(coreg_tan_world2pix(wcs_large, d_lng, d_lat, ns, d_x, d_y, s));
+  TRYRC(coreg_map_coordinates(d_large, COREG_F64, lny, lnx, d_y, d_x, ns, order, (double)NAN, d_ref, COREG_F32, s));
+  TRYRC(coreg_tan_trig_planes(d_lng, d_lat, ns, wcs_small->crval1, d_planes, s));
+  TRYRC(coreg_finite_mean(d_ref, COREG_F32, ns, d_piv, s));
+  TRYRC(coreg_finite_mean(d_small, COREG_F64, ns, d_piv + 1, s));
+  TRYRC(coreg_hpc_lag_corr(d_ref, d_small, COREG_F64, snx, sny, snx, sny, d_planes, d_lags, n_lags, order, d_piv,
+                           d_work, work_bytes, d_corr, d_nv, flags, s));
+  TRY(cudaMemcpyAsync(corr, d_corr, n_lags * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (nvalid) TRY(cudaMemcpyAsync(nvalid, d_nv, n_lags * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  TRY(cudaStreamSynchronize(s));
+done:
+  cudaFree(d_large); cudaFree(d_small); cudaFree(d_lng); cudaFree(d_lat); cudaFree(d_x); cudaFree(d_y);
+  cudaFree(d_planes); cudaFree(d_ref); cudaFree(d_piv); cudaFree(d_corr); cudaFree(d_nv); cudaFree(d_lags);
+  cudaFree(d_work);
+#undef TRY
+#undef TRYRC
+  return rc;
+}
+
+int coreg_profile_begin(void) {
+  for (int i = 0; i < g_prof_n; ++i) {
+    cudaEventDestroy(g_prof[i].a);
+    cudaEventDestroy(g_prof[i].b);
+  }
+  g_prof_n = 0;
+  g_prof_on = true;
+  return COREG_OK;
+}
+
+int coreg_profile_end(double* lag_kernel_ms_total, int* launches) {
+  g_prof_on = false;
+  double tot = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    CK(cudaEventSynchronize(g_prof[i].b));
+    CK(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+    tot += ms;
+    cudaEventDestroy(g_prof[i].a);
+    cudaEventDestroy(g_prof[i].b);
+  }
+  if (lag_kernel_ms_total) *lag_kernel_ms_total = tot;
+  if (launches) *launches = g_prof_n;
+  g_prof_n = 0;
+  return COREG_OK;
+}
+
+int coreg_fp64_peak(double* fma_per_s, int iters, void* stream) {
+  if (!fma_per_s || iters <= 0) return fail(COREG_EINVAL, "coreg_fp64_peak: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int sms = coreg_device_sm_count();
+  if (sms <= 0) return fail(COREG_ECUDA, "no device");
+  const int blocks = sms * 8, threads = 256;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  fp64_peak_kernel<<<blocks, threads, 0, s>>>(out, iters / 8 + 1, 1.0);  // warm-up
+  CK(cudaEventRecord(e0, s));
+  fp64_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 1.0);
+  CK(cudaEventRecord(e1, s));
+  CK(cudaEventSynchronize(e1));
+  CK_LAUNCH("fp64_peak_kernel");
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  *fma_per_s = (double)blocks * threads * 8.0 * (double)iters / ((double)ms * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return COREG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+"""`Alignment` -- same public API as the reference's `hdrshift/alignment.py`, B200 engine underneath.
+
+Public signatures mirror `hdrshift/alignment.py:47-55, 144-148, 263-269`. What changes is everything
+below `_find_best_header_parameters` (`:613-797`): instead of forking `counts_cpu_max` workers that each
+rebuild two WCS objects, call scipy and numba per lag, the lag grid is turned into a table of per-lag
+constants and evaluated by the fused CUDA kernels of `csrc/coreg_kernels.cu` (see `engine.py`).
+
+Semantics follow the reference's `parallelism=True` branch (the contract of SURVEY.md section 0):
+the common grid of the helioprojective search is the UNSHIFTED small grid. `parallelism`,
+`counts_cpu_max` and `display_progress_bar` are accepted and ignored. Never-evaluated lags (the ones
+that kill the reference's worker, App. B1) are reported as 0.0 exactly like the reference's cube.
+"""
+from __future__ import annotations
+
+import copy
+import warnings
+
+import numpy as np
+
+from .._compat import fits_lite, units
+from .._compat.wcs import TanWcs
+from ..utils import Util
+from . import engine as _engine
+from .AlignmentResults import AlignmentResults
+
+
+def _open_fits(path):
+    return Util._fits().open(path)
+
+
+class _Refs:
+    pass
+
+
+class Alignment:
+
+    def __init__(self, large_fov_known_pointing: str, small_fov_to_correct: str, lag_crval1: np.array,
+                 lag_crval2: np.array, lag_cdelt1: object, lag_cdelt2: object, lag_crota: object,
+                 lag_solar_r: object = None,
+                 small_fov_value_min: object = None,
+                 parallelism: object = False, display_progress_bar: bool = False,
+                 small_fov_value_max: object = None, counts_cpu_max: int = 40, large_fov_window: object = -1,
+                 small_fov_window: object = -1,
+                 path_save_figure: str = None, reprojection_order=2, force_crota_0=False,
+                 unit_lag="arcsec", cdelt_semantics="reference", fast_math=False):
+        """Same parameters as the reference (`hdrshift/alignment.py:47-83`). Two additions:
+
+        cdelt_semantics: "reference" reproduces the reference's handling of CDELT lags (a CDELT1 lag only
+            rebuilds PCi_j, a non-zero CDELT2 lag leaves 0.0 in the cube because the reference's worker dies,
+            SURVEY App. B1); "intended" applies CDELTi = ref + lag before the PCi_j rebuild.
+        fast_math: let the spline weights / taps use fused multiply-add (differences ~1e-16 per sample).
+        """
+        self.large_fov_known_pointing = large_fov_known_pointing
+        self.small_fov_to_correct = small_fov_to_correct
+        self.lag_crval1 = lag_crval1
+        self.lag_crval2 = lag_crval2
+        self.lag_cdelt1 = lag_cdelt1
+        self.lag_cdelt2 = lag_cdelt2
+        self.lag_crota = lag_crota
+        self.lag_solar_r = lag_solar_r
+        self.unit_lag = unit_lag
+        self.unit_lag_input = copy.deepcopy(unit_lag)
+
+        self.lonlims = None
+        self.latlims = None
+        self.shape = None
+        self.reference_date = None
+        self.parallelism = parallelism            # accepted, ignored: the GPU path is always "parallel"
+        self.small_fov_window = small_fov_window
+        self.large_fov_window = large_fov_window
+
+        self.crval1_ref = None
+        self.crval2_ref = None
+        self.crota_ref = None
+        self.cdelt1_ref = None
+        self.cdelt2_ref = None
+        self.data_large = None
+        self.counts = counts_cpu_max              # accepted, ignored
+        self.data_small = None
+        self.hdr_small = None
+        self.hdr_large = None
+        self.method = None
+        self.small_fov_value_min = small_fov_value_min
+        self.small_fov_value_max = small_fov_value_max
+        self.path_save_figure = path_save_figure
+        self.display_progress_bar = display_progress_bar
+        self.force_crota_0 = force_crota_0
+        self.method_carrington_reprojection = None
+        self.use_pcij = not ((lag_crota is None) and (lag_cdelt1 is None) and (lag_cdelt2 is None))
+        self.order = reprojection_order
+        self.lon_ctype = None
+        self.lat_ctype = None
+        self.use_sunpy = False
+        self.cdelt_semantics = cdelt_semantics
+        self.fast_math = fast_math
+        self.engine = None
+        self.nvalid = None
+        for lag_name in ("lag_crval1", "lag_crval2", "lag_crota", "lag_cdelt1", "lag_cdelt2"):
+            if getattr(self, lag_name) is None:
+                setattr(self, lag_name, np.array([0.0]))
+
+    # ------------------------------------------------------------------------------------------------
+    # public entry points
+    # ------------------------------------------------------------------------------------------------
+    def align_using_helioprojective(self, method: str = 'correlation', return_type: str = 'AlignmentResults',
+                                    fov_limits=None, remove_fov_limits=None):
+        """Co-alignment in the helioprojective frame (`hdrshift/alignment.py:263-342`)."""
+        self.lonlims = None
+        self.latlims = None
+        self.shape = None
+        self.reference_date = None
+        self.method = method
+        self.coordinate_frame = "final_helioprojective"
+        self.lon_ctype = "HPLN-TAN"
+        self.lat_ctype = "HPLT-TAN"
+        self.ang2pipi = True
+        self._load_pair()
+        results = self._find_best_header_parameters(fov_limits=fov_limits, remove_fov_limits=remove_fov_limits)
+        return self._wrap_results(results, return_type)
+
+    def align_using_carrington(self, lonlims=None, latlims=None, size_deg_carrington=None, shape=None,
+                               reference_date=None, method='correlation', method_carrington_reprojection="fa",
+                               return_type='AlignmentResults'):
+        """Co-alignment on a user Carrington grid (`hdrshift/alignment.py:144-261`), "fa" reprojection."""
+        self.method = method
+        self.coordinate_frame = "final_carrington"
+        self.lon_ctype = "HPLN-TAN"
+        self.lat_ctype = "HPLT-TAN"
+        self.ang2pipi = True
+        self.method_carrington_reprojection = method_carrington_reprojection
+        if method_carrington_reprojection == "sunpy":
+            raise NotImplementedError("the sunpy reprojection (alignment.py:939-985) is outside the device path")
+        if method_carrington_reprojection != "fa":
+            raise ValueError("method_carrington_reprojection must be either 'fa' or 'sunpy")
+        self._load_pair()
+        if reference_date is None:
+            if "DATE-AVG" not in self.hdr_large:
+                raise ValueError(
+                    "Either provide a reference date manualy or the reference file header must have a DATE-AVG keyword.")
+            self.reference_date = self.hdr_large["DATE-AVG"]
+        else:
+            self.reference_date = reference_date
+        if (lonlims is None) and (latlims is None) & (size_deg_carrington is not None):
+            crln, crlt = self.hdr_small["CRLN_OBS"], self.hdr_small["CRLT_OBS"]
+            self.lonlims = [crln - 0.5 * size_deg_carrington[0], crln + 0.5 * size_deg_carrington[0]]
+            self.latlims = [crlt - 0.5 * size_deg_carrington[1], crlt + 0.5 * size_deg_carrington[1]]
+            self.shape = [self.hdr_small["NAXIS1"], self.hdr_small["NAXIS2"]]
+        elif (lonlims is not None) and (latlims is not None) & (shape is not None):
+            self.lonlims = lonlims
+            self.latlims = latlims
+            self.shape = shape
+        else:
+            raise ValueError("either set lonlims as None, or not. no in between.")
+        if self.shape[0] * self.shape[1] > 25000000:
+            warnings.warn(f"shape parameter is shape={shape}, which is very large."
+                          "Computational time might significantly increase")
+        results = self._find_best_header_parameters()
+        return self._wrap_results(results, return_type)
+
+    def align_using_initial_carrington(self, method='correlation', return_type='AlignmentResults'):
+        raise NotImplementedError("CRLN-CAR inputs (alignment.py:344-399) are outside the device path (SURVEY 8f-4)")
+
+    # ------------------------------------------------------------------------------------------------
+    # host preparation (mirrors alignment.py:299-316, 580-611, 799-887)
+    # ------------------------------------------------------------------------------------------------
+    def _load_pair(self):
+        f_large = _open_fits(self.large_fov_known_pointing)
+        f_small = _open_fits(self.small_fov_to_correct)
+        self.data_large = np.array(f_large[self.large_fov_window].data.copy(), dtype=np.float64)
+        self.hdr_large = f_large[self.large_fov_window].header.copy()
+        self.hdr_small = f_small[self.small_fov_window].header.copy()
+        self._check_ant_create_pcij_matrix(self.hdr_small)
+        self._check_ant_create_pcij_matrix(self.hdr_large)
+        self.data_small = np.array(f_small[self.small_fov_window].data.copy(), dtype=np.float64)
+        f_large.close()
+        f_small.close()
+
+    def _wrap_results(self, results, return_type):
+        if return_type == "corr":
+            return results
+        if return_type == "AlignmentResults":
+            conv = lambda v: units.convert(units.ang2pipi(v, self.unit_lag), self.unit_lag, self.unit_lag_input)  # noqa: E731
+            self.lag_crval1 = conv(self.lag_crval1)
+            self.lag_crval2 = conv(self.lag_crval2)
+            self.lag_cdelt1 = conv(self.lag_cdelt1)
+            self.lag_cdelt2 = conv(self.lag_cdelt2)
+            self.unit_lag = self.unit_lag_input
+            return AlignmentResults(corr=results, lag_crval1=self.lag_crval1, lag_crval2=self.lag_crval2,
+                                    lag_cdelt1=self.lag_cdelt1, lag_cdelt2=self.lag_cdelt2, lag_crota=self.lag_crota,
+                                    unit_lag=self.unit_lag_input, image_to_align_path=self.small_fov_to_correct,
+                                    image_to_align_window=self.small_fov_window,
+                                    reference_image_path=self.large_fov_known_pointing,
+                                    reference_image_window=self.large_fov_window)
+        return results
+
+    def _check_ant_create_pcij_matrix(self, hdr):
+        """`alignment.py:580-611`."""
+        if "PC1_1" not in hdr:
+            warnings.warn("PCi_j matrix not found in header of the FITS file to align. Adding it to the header.")
+            if "CROTA" in hdr:
+                crot = hdr["CROTA"]
+            elif "CROTA2" in hdr:
+                crot = hdr["CROTA2"]
+            elif self.force_crota_0:
+                crot = 0.0
+                hdr["CROTA"] = 0.0
+            else:
+                raise ValueError("No, CROTA, CROTA2 or PCi_j matrix in your FITS file. If want to force a CROTA=0, "
+                                 "please set the force_crota_0 to True when initializing Alignment ")
+            rho = np.deg2rad(crot)
+            lam = hdr["CDELT2"] / hdr["CDELT1"]
+            hdr["PC1_1"] = float(np.cos(rho))
+            hdr["PC2_2"] = float(np.cos(rho))
+            hdr["PC1_2"] = float(-lam * np.sin(rho))
+            hdr["PC2_1"] = float((1 / lam) * np.sin(rho))
+        if hdr["PC1_1"] >= 1.0:
+            warnings.warn(f'hdr["PC1_1"]={hdr["PC1_1"]}, setting to  1.0.')
+            hdr["PC1_1"] = 1.0
+            hdr["PC2_2"] = 1.0
+            hdr["PC1_2"] = 0.0
+            hdr["PC2_1"] = 0.0
+            hdr["CROTA"] = 0.0
+        if "CROTA" not in hdr:
+            s = -np.sign(hdr["PC1_2"]) + (hdr["PC1_2"] == 0)
+            hdr["CROTA"] = float(s * np.rad2deg(np.arccos(hdr["PC1_1"])))
+
+    def _set_initial_header_values(self, ang2pipi):
+        """`alignment.py:799-842`."""
+        self.crval1_ref = self.hdr_small['CRVAL1']
+        self.crval2_ref = self.hdr_small['CRVAL2']
+        if 'CROTA' in self.hdr_small:
+            self.crota_ref = self.hdr_small['CROTA']
+        elif 'CROTA2' in self.hdr_small:
+            self.crota_ref = self.hdr_small['CROTA2']
+        else:
+            s = -np.sign(self.hdr_small['PC1_2']) + (self.hdr_small['PC1_2'] == 0)
+            self.crota_ref = float(np.rad2deg(np.arccos(self.hdr_small['PC1_1'])) * s)
+            self.hdr_small["CROTA"] = float(np.rad2deg(np.arccos(self.hdr_small['PC1_1'])))
+        self.cdelt1_ref = self.hdr_small['CDELT1']
+        self.cdelt2_ref = self.hdr_small['CDELT2']
+        self.unit1 = self.hdr_small["CUNIT1"]
+        self.unit2 = self.hdr_small["CUNIT2"]
+        if self.unit_lag in self.unit1:
+            pass
+        else:
+            warnings.warn("Units of headers in deg: Modyfying inputs units to deg.")
+            conv = _engine.lag_unit_to_header_unit
+            self.lag_crval1 = conv(self.lag_crval1, self.unit_lag, self.unit1, ang2pipi)
+            self.lag_crval2 = conv(self.lag_crval2, self.unit_lag, self.unit2, ang2pipi)
+            self.lag_cdelt1 = conv(self.lag_cdelt1, self.unit_lag, self.unit1, ang2pipi)
+            self.lag_cdelt2 = conv(self.lag_cdelt2, self.unit_lag, self.unit2, ang2pipi)
+            self.unit_lag = self.unit1
+        if self.unit1 != self.unit2:
+            raise ValueError("CUNIT1 and CUNIT2 must be equal")
+        if self.lag_solar_r is None:
+            self.lag_solar_r = np.array([1.004])
+
+    def _set_threshold_minmax_to_nan(self):
+        """`alignment.py:876-887`."""
+        c1 = np.ones(self.data_small.shape, dtype=bool)
+        c2 = np.ones(self.data_small.shape, dtype=bool)
+        with np.errstate(invalid="ignore"):
+            if self.small_fov_value_min is not None:
+                c1[np.abs(self.data_small) < self.small_fov_value_min] = False
+            if self.small_fov_value_max is not None:
+                c2[np.abs(self.data_small) > self.small_fov_value_max] = False
+        self.data_small[np.logical_not(np.logical_and(c1, c2))] = np.nan
+
+    def _set_remove_fov_limits_to_nan(self, remove_fov_limits):
+        """`alignment.py:862-874`; limits are [[lonmin, lonmax], [latmin, latmax]] in arcsec (plain numbers or
+        astropy quantities)."""
+        lon, lat = Util.AlignEUIUtil.extract_EUI_coordinates(self.hdr_small, dsun=False)
+        lims = []
+        for pair in remove_fov_limits:
+            v, unit = units.strip(pair, "arcsec")
+            lims.append(units.convert(np.asarray(v, dtype=np.float64), unit, "deg"))
+        lonl, latl = lims
+        mask = (lon >= lonl[0]) & (lon <= lonl[1]) & (lat >= latl[0]) & (lat <= latl[1])
+        self.data_small[mask] = np.nan
+
+    def _set_removed_values_to_nan_in_datasmall(self, fov_limits, remove_fov_limits):
+        """`alignment.py:844-861`."""
+        self._set_threshold_minmax_to_nan()
+        if remove_fov_limits is not None:
+            self._set_remove_fov_limits_to_nan(remove_fov_limits)
+        if fov_limits is not None:
+            raise NotImplementedError("fov_limits (regular-grid re-sampling of the small image, "
+                                      "alignment.py:1082-1127) is not on the device path yet")
+
+    # ------------------------------------------------------------------------------------------------
+    # the seam: lag grid -> correlation cube
+    # ------------------------------------------------------------------------------------------------
+    def _find_best_header_parameters(self, ang2pipi: bool = True, fov_limits=None, remove_fov_limits=None):
+        """Correlation cube float64 [n_crval1, n_crval2, n_cdelt1, n_cdelt2, n_crota, n_solar_r]
+        (`alignment.py:613-797`, parallel branch)."""
+        if self.method != 'correlation':
+            raise NotImplementedError("only method='correlation' is on the device path")
+        self._set_removed_values_to_nan_in_datasmall(fov_limits=fov_limits, remove_fov_limits=remove_fov_limits)
+        self._set_initial_header_values(ang2pipi)
+        if np.isnan(self.data_small).all():
+            raise ValueError("minimum or maximum value have set all small FOV to nan")
+        if self.unit_lag != self.hdr_small["CUNIT1"] or self.unit_lag != self.hdr_small["CUNIT2"]:
+            raise ValueError("lag.unit and cUNIT are not the same")
+        shape5 = (len(self.lag_crval1), len(self.lag_crval2), len(self.lag_cdelt1), len(self.lag_cdelt2),
+                  len(self.lag_crota))
+        d1, d2, d3, d4, d5 = _engine.flat_lag_grid(self.lag_crval1, self.lag_crval2, self.lag_cdelt1,
+                                                   self.lag_cdelt2, self.lag_crota)
+        refs = _Refs()
+        refs.crval1_ref, refs.crval2_ref, refs.crota_ref = self.crval1_ref, self.crval2_ref, self.crota_ref
+        refs.cdelt1_ref, refs.cdelt2_ref = self.cdelt1_ref, self.cdelt2_ref
+
+        eng = _engine.LagSearchEngine(order=self.order, fast_math=self.fast_math)
+        self.engine = eng
+        eng.set_small(self.data_small)
+        n_r = len(self.lag_solar_r)
+        cube = np.zeros(shape5 + (n_r,), dtype=np.float64)
+        if self.coordinate_frame == "final_helioprojective":
+            w_small = TanWcs.from_header(self.hdr_small)
+            w_large = TanWcs.from_header(self.hdr_large)
+            eng.prepare_hpc(self.data_large, w_large, w_small)
+            self.hdr_large = self.hdr_small.copy()   # alignment.py:1000
+            table, dead = _engine.tan_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, eng.alpha_ref_deg,
+                                                self.cdelt_semantics)
+            corr, nvalid = eng.search(table, return_nvalid=True)
+            corr = np.where(dead, 0.0, corr)
+            for kk in range(n_r):
+                cube[..., kk] = corr.reshape(shape5)
+            self.nvalid = nvalid.reshape(shape5)
+        elif self.coordinate_frame == "final_carrington":
+            if n_r != 1:
+                raise ValueError("lag_solar_r must hold exactly one value (the reference breaks on more, "
+                                 "alignment.py:646-660)")
+            corr, nvalid = self._carrington_search(eng, refs, d1, d2, d3, d4, d5, float(self.lag_solar_r[0]))
+            cube[..., 0] = corr.reshape(shape5)
+            self.nvalid = nvalid.reshape(shape5)
+        else:
+            raise NotImplementedError(self.coordinate_frame)
+        self.data_large = None
+        return cube
+
+    def _carrington_search(self, eng, refs, d1, d2, d3, d4, d5, d_solar_r):
+        """Per CROTA-lag value one pair of detector planes; CRVAL lags are pure offsets on them
+        (`alignment.py:889-901`, `utils/rectify.py:377-423`)."""
+        for hdr in (self.hdr_small, self.hdr_large):
+            if str(hdr["CUNIT1"]).strip() != "arcsec":
+                warnings.warn("the 'fa' Carrington transform assumes arcsec headers (utils/rectify.py:362-363)")
+        eng.prepare_carrington_large(self.data_large, self.hdr_large, d_solar_r, self.lonlims, self.latlims,
+                                     self.shape)
+        n = d1.size
+        corr = np.zeros(n, dtype=np.float64)
+        nvalid = np.zeros(n, dtype=np.int64)
+        dead = np.zeros(n, dtype=bool)
+        if self.cdelt_semantics == "reference":
+            dead = d4 != 0.0
+        elif (np.any(d3 != 0.0) or np.any(d4 != 0.0)):
+            raise NotImplementedError("CDELT lags in the Carrington frame need cdelt_semantics='reference'")
+        roll_ref = self.hdr_small["CROTA"] if "CROTA" in self.hdr_small else self.hdr_small["CROTA2"]
+        for dc in np.unique(d5):
+            sel = np.nonzero((d5 == dc) & ~dead)[0]
+            if sel.size == 0:
+                continue
+            hdr = self.hdr_small.copy()
+            roll = roll_ref
+            if dc != 0.0:
+                roll = refs.crota_ref + dc
+                hdr["CROTA" if "CROTA" in hdr else "CROTA2"] = float(roll)
+            planes = eng.carrington_planes(hdr, d_solar_r, self.lonlims, self.latlims, self.shape)
+            x0, y0 = eng.carrington_offset(hdr, refs.crval1_ref + d1[sel], refs.crval2_ref + d2[sel], roll)
+            table = np.stack([x0, y0], axis=1).astype(np.float64)
+            c, nv = eng.search(table, planes=planes, return_nvalid=True)
+            corr[sel] = c
+            nvalid[sel] = nv
+        return corr, nvalid

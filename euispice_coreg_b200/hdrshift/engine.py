@@ -1,0 +1,306 @@
+"""Device engine under `Alignment._find_best_header_parameters` (the seam of SURVEY.md section 8b).
+
+The reference fans the flattened lag list out over `multiprocessing.Process` workers that share the
+two images through POSIX shared memory (`hdrshift/alignment.py:634-756`). Here the images are uploaded
+once and stay resident in HBM, the lag list becomes a table of per-lag constants, and one fused kernel
+launch (per <= `max_lags_per_launch` lags) evaluates the whole table. With `torch.distributed`
+initialised (one process per GPU), every rank holds both images, evaluates a contiguous slice of the
+C-ordered lag list -- the same decomposition as `np.array_split` at `alignment.py:677-687` -- and one
+all-gather assembles the cube.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .. import _ext
+from .._compat import units
+from .._compat.wcs import TanWcs
+
+R2D = 180.0 / math.pi
+D2R = math.pi / 180.0
+R_SUN_M = 695700000.0  # astropy.constants.R_sun.value (IAU 2015 nominal), utils/rectify.py:405
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def flat_lag_grid(lag_crval1, lag_crval2, lag_cdelt1, lag_cdelt2, lag_crota):
+    """C-order flattening of the 5-D lag meshgrid, crval1 slowest (`alignment.py:667-674`)."""
+    g = np.meshgrid(np.asarray(lag_crval1, dtype=np.float64), np.asarray(lag_crval2, dtype=np.float64),
+                    np.asarray(lag_cdelt1, dtype=np.float64), np.asarray(lag_cdelt2, dtype=np.float64),
+                    np.asarray(lag_crota, dtype=np.float64), indexing="ij")
+    return [a.ravel() for a in g]
+
+
+def shard_bounds(n_lags: int, world: int):
+    """Contiguous equal slices of the padded lag list: rank r owns [r*c, (r+1)*c) with c = ceil(n/world)."""
+    c = (n_lags + world - 1) // world if world > 0 else n_lags
+    return c, [(min(r * c, n_lags), min((r + 1) * c, n_lags)) for r in range(world)]
+
+
+def shifted_pc(hdr, crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1, cdelt2):
+    """PCi_j of the shifted header, vectorised over lags (`_shift_header`, `alignment.py:401-468`).
+    Lags that touch none of CDELT/CROTA keep the header's own PC."""
+    change = (d_cdelt1 != 0.0) | (d_cdelt2 != 0.0) | (d_crota != 0.0)
+    crot = np.where(d_crota != 0.0, crota_ref + d_crota, crota_ref)
+    rho = np.deg2rad(crot)
+    lam = cdelt2 / cdelt1
+    pc11 = np.where(change, np.cos(rho), hdr["PC1_1"])
+    pc22 = np.where(change, np.cos(rho), hdr["PC2_2"])
+    pc12 = np.where(change, -lam * np.sin(rho), hdr["PC1_2"])
+    pc21 = np.where(change, (1 / lam) * np.sin(rho), hdr["PC2_1"])
+    return pc11, pc12, pc21, pc22
+
+
+def tan_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, alpha_ref_deg,
+                  cdelt_semantics="reference"):
+    """[n_lags, 10] float64 rows of `CoregLagTan` + a mask of lags the reference cannot evaluate.
+
+    `refs` carries crval1_ref, crval2_ref, crota_ref, cdelt1_ref, cdelt2_ref (header units).
+    cdelt_semantics="reference": a CDELT1 lag only triggers the PC rebuild, a non-zero CDELT2 lag kills the
+    reference's worker (cube entry stays 0.0) -> reported in the returned `dead` mask.
+    cdelt_semantics="intended": CDELTi = ref + lag, then PC rebuild with the new CDELT2/CDELT1.
+    """
+    w0 = TanWcs.from_header(hdr_small)
+    s1, s2 = w0.unit_scale1, w0.unit_scale2
+    n = d_crval1.size
+    crval1 = (refs.crval1_ref + d_crval1) * s1
+    crval2 = (refs.crval2_ref + d_crval2) * s2
+    cdelt1_h = np.full(n, float(hdr_small["CDELT1"]))
+    cdelt2_h = np.full(n, float(hdr_small["CDELT2"]))
+    dead = np.zeros(n, dtype=bool)
+    if cdelt_semantics == "intended":
+        cdelt1_h = np.where(d_cdelt1 != 0.0, refs.cdelt1_ref + d_cdelt1, cdelt1_h)
+        cdelt2_h = np.where(d_cdelt2 != 0.0, refs.cdelt2_ref + d_cdelt2, cdelt2_h)
+    elif cdelt_semantics == "reference":
+        dead = d_cdelt2 != 0.0
+    else:
+        raise ValueError("cdelt_semantics must be 'reference' or 'intended'")
+    pc11, pc12, pc21, pc22 = shifted_pc(hdr_small, refs.crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1_h, cdelt2_h)
+    # forward matrix [deg/pixel] and its inverse, times 180/pi (the kernel's plane coordinates are radians)
+    f11, f12 = cdelt1_h * s1 * pc11, cdelt1_h * s1 * pc12
+    f21, f22 = cdelt2_h * s2 * pc21, cdelt2_h * s2 * pc22
+    det = f11 * f22 - f12 * f21
+    i11, i12, i21, i22 = f22 / det, -f12 / det, -f21 / det, f11 / det
+    # native-longitude rotation by LONPOLE folded in: (xp, yp) = (-cp xi + sp eta, -sp xi - cp eta)
+    sp, cp = math.sin(w0.lonpole * D2R), math.cos(w0.lonpole * D2R)
+    if w0.lonpole == 180.0:
+        sp, cp = 0.0, -1.0
+    m11 = (i11 * -cp + i12 * -sp) * R2D
+    m12 = (i11 * sp + i12 * -cp) * R2D
+    m21 = (i21 * -cp + i22 * -sp) * R2D
+    m22 = (i21 * sp + i22 * -cp) * R2D
+    tab = np.empty((n, _ext.LAG_TAN_DOUBLES), dtype=np.float64)
+    da = (crval1 - alpha_ref_deg) * D2R
+    tab[:, 0] = np.sin(da)
+    tab[:, 1] = np.cos(da)
+    tab[:, 2] = np.sin(crval2 * D2R)
+    tab[:, 3] = np.cos(crval2 * D2R)
+    tab[:, 4], tab[:, 5], tab[:, 6], tab[:, 7] = m11, m12, m21, m22
+    tab[:, 8] = w0.crpix1 - 1.0
+    tab[:, 9] = w0.crpix2 - 1.0
+    return tab, dead
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return None, 0, 1
+
+
+def gather_slices(local, n_total, chunk):
+    """All-gather equal `chunk`-sized slices (last ones padded) into one [n_total] tensor.
+    NCCL: a single `all_gather_into_tensor` (in place: every rank's slice is already at its offset).
+    gloo (CPU tests of the host logic): list-based `all_gather`."""
+    torch = _torch()
+    dist, rank, world = _dist_info()
+    if dist is None or world == 1:
+        return local[:n_total]
+    full = torch.empty(chunk * world, dtype=local.dtype, device=local.device)
+    send = local
+    if send.numel() != chunk:
+        pad = torch.full((chunk,), float("nan"), dtype=local.dtype, device=local.device)
+        pad[:send.numel()] = send
+        send = pad
+    if local.is_cuda:
+        dist.all_gather_into_tensor(full, send.contiguous())
+    else:
+        parts = [torch.empty(chunk, dtype=local.dtype) for _ in range(world)]
+        dist.all_gather(parts, send.contiguous())
+        full = torch.cat(parts)
+    return full[:n_total]
+
+
+class LagSearchEngine:
+    """Resident images + workspaces for one (large, small) pair on the current CUDA device."""
+
+    max_workspace_bytes = 1 << 30
+
+    def __init__(self, order=2, fast_math=False, device=None):
+        torch = _torch()
+        _ext.load()  # fail loudly when the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _ext.CoregLibraryError("no CUDA device: the pointing search has no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.order = int(order)
+        self.fast_math = bool(fast_math)
+        self.pivots = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.ref = None        # large image on the common grid
+        self.small = None
+        self.planes = None     # TAN: [3, gny, gnx]; Carrington: (tx, ty)
+        self._work = None
+        self.last_launches = 0
+
+    # ---- uploads -----------------------------------------------------------------------------
+    def _upload(self, arr, pinned=False):
+        torch = _torch()
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=pinned)
+
+    def set_small(self, data_small):
+        """Small image (float64 with NaN for masked pixels). Stored as float32 on the device when every
+        finite value is exactly representable (FITS BITPIX -32 data): half the gather traffic, same values."""
+        data_small = np.asarray(data_small)
+        with np.errstate(invalid="ignore", over="ignore"):
+            as32 = data_small.astype(np.float32)
+            exact = np.array_equal(as32.astype(np.float64), data_small, equal_nan=True)
+        self.small = self._upload(as32 if exact else data_small.astype(np.float64))
+        _ext.finite_mean(self.small, self.pivots[1:2])
+
+    # ---- helioprojective ------------------------------------------------------------------------
+    def prepare_hpc(self, data_large, wcs_large: TanWcs, wcs_small: TanWcs):
+        """One-time part of the helioprojective search: world grid of the unshifted small grid (K3), the
+        large image resampled onto it as float32 (K2, `_create_submap_of_large_data`,
+        `alignment.py:987-1016`), the lag-independent trig planes and the ref pivot."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            lng, lat = _ext.tan_pix2world(wcs_small, wcs_small.naxis1, wcs_small.naxis2, True, self.device)
+            x, y = _ext.tan_world2pix(wcs_large, lng, lat)
+            d_large = self._upload(np.asarray(data_large, dtype=np.float64))
+            self.ref = _ext.map_coordinates(d_large, y, x, self.order, float("nan"), torch.float32)
+            del d_large, x, y
+            self.planes = _ext.tan_trig_planes(lng, lat, wcs_small.crval1)
+            self.alpha_ref_deg = wcs_small.crval1
+            _ext.finite_mean(self.ref, self.pivots[0:1])
+        self.frame = "hpc"
+
+    # ---- Carrington --------------------------------------------------------------------------------
+    @staticmethod
+    def carrington_vectors(lonlims, latlims, shape, crln_obs):
+        """The float32 half of `Rectifier.__call__` + `SphericalTransform.forward` on the separable grid
+        (`utils/rectify.py:345-349, 876-877`), evaluated with NumPy exactly as the reference does."""
+        lon = np.linspace(lonlims[0], lonlims[1], shape[0], dtype=np.float32)
+        lat = np.linspace(latlims[0], latlims[1], shape[1], dtype=np.float32)
+        lon_r = np.radians(lon) - np.radians(crln_obs)      # float32 - float64 scalar -> float64
+        lat_r = np.radians(lat)                             # float32
+        return (np.sin(lon_r), np.cos(lon_r),
+                np.sin(lat_r).astype(np.float64), np.cos(lat_r).astype(np.float64))
+
+    def carrington_planes(self, hdr, d_solar_r, lonlims, latlims, shape):
+        """(tx, ty) detector-plane planes of one header on the Carrington grid (K5 coordinates)."""
+        roll_deg = hdr["CROTA"] if "CROTA" in hdr else hdr["CROTA2"]
+        c = _ext.CoregCarrington(float(np.radians(hdr["CRLN_OBS"])), float(np.radians(hdr["CRLT_OBS"])),
+                                 float(np.radians(roll_deg)),
+                                 float(hdr["DSUN_OBS"] / (d_solar_r * R_SUN_M)),
+                                 float(hdr["CDELT1"]), float(hdr["CDELT2"]))
+        vec = self.carrington_vectors(lonlims, latlims, shape, hdr["CRLN_OBS"])
+        sinlon, coslon, sinlat, coslat = (self._upload(v) for v in vec)
+        return _ext.carrington_planes(c, sinlon, coslon, sinlat, coslat)
+
+    @staticmethod
+    def carrington_offset(hdr, crval1, crval2, roll_deg):
+        """x0, y0 of `CarringtonTransform.__init__` (`utils/rectify.py:394-404`), vectorised over lags."""
+        cos = np.cos(np.radians(roll_deg))
+        sin = np.sin(np.radians(roll_deg))
+        dx = cos * crval1 + sin * crval2
+        dy = -sin * crval1 + cos * crval2
+        return (hdr["CRPIX1"] - 1) - dx / hdr["CDELT1"], (hdr["CRPIX2"] - 1) - dy / hdr["CDELT2"]
+
+    def prepare_carrington_large(self, data_large, hdr_large, d_solar_r, lonlims, latlims, shape):
+        """Large image -> Carrington grid, float64, -32762 fill -> NaN (`alignment.py:646-648, 889-901`)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            tx, ty = self.carrington_planes(hdr_large, d_solar_r, lonlims, latlims, shape)
+            roll = hdr_large["CROTA"] if "CROTA" in hdr_large else hdr_large["CROTA2"]
+            x0, y0 = self.carrington_offset(hdr_large, hdr_large["CRVAL1"], hdr_large["CRVAL2"], roll)
+            d_large = self._upload(np.asarray(data_large, dtype=np.float64))
+            nx = float(x0) + tx
+            ny = float(y0) + ty
+            ref = _ext.map_coordinates(d_large, ny, nx, self.order, -32762.0, torch.float64)
+            ref = torch.where(ref == -32762.0, torch.full_like(ref, float("nan")), ref)
+            self.ref = ref.contiguous()
+            _ext.finite_mean(self.ref, self.pivots[0:1])
+        self.frame = "carrington"
+
+    # ---- evaluation ------------------------------------------------------------------------------------
+    def _workspace(self, gnx, gny, n_lags):
+        torch = _torch()
+        need = _ext.lag_corr_workspace_bytes(gnx, gny, n_lags)
+        if self._work is None or self._work.numel() * 8 < need:
+            self._work = None
+            self._work = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        return self._work
+
+    def lags_per_launch(self, gnx, gny):
+        per_lag = max(1, _ext.lag_corr_workspace_bytes(gnx, gny, 1))
+        return max(64, (self.max_workspace_bytes // per_lag) // 64 * 64)
+
+    def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None):
+        """Run the fused kernel over a device lag table [n, k]; results into out_dev[n]."""
+        torch = _torch()
+        n = table_dev.shape[0]
+        gny, gnx = self.ref.shape
+        step = self.lags_per_launch(gnx, gny)
+        self.last_launches = 0
+        with torch.cuda.device(self.device):
+            work = self._workspace(gnx, gny, min(n, step))
+            for lo in range(0, n, step):
+                hi = min(n, lo + step)
+                nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
+                if self.frame == "hpc":
+                    _ext.hpc_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order, self.pivots,
+                                      work, out_dev[lo:hi], nv, self.fast_math)
+                else:
+                    tx, ty = planes
+                    _ext.offset_lag_corr(self.ref, self.small, tx, ty, table_dev[lo:hi], self.order, self.pivots,
+                                         work, out_dev[lo:hi], nv, self.fast_math)
+                self.last_launches += 2  # lag kernel + finalize
+        return out_dev
+
+    def search(self, table, planes=None, return_nvalid=False):
+        """Host lag table [n_lags, k] -> numpy corr[n_lags]; shards over ranks when torch.distributed is up."""
+        torch = _torch()
+        n = table.shape[0]
+        dist, rank, world = _dist_info()
+        chunk, bounds = shard_bounds(n, world)
+        lo, hi = bounds[rank]
+        with torch.cuda.device(self.device):
+            local = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
+            nvalid = torch.zeros(chunk, dtype=torch.int64, device=self.device) if return_nvalid else None
+            if hi > lo:
+                tab_dev = self._upload(table[lo:hi])
+                self.evaluate(tab_dev, local[:hi - lo], None if nvalid is None else nvalid[:hi - lo], planes)
+            full = gather_slices(local, n, chunk)
+            corr = full.cpu().numpy()
+            if return_nvalid:
+                nv_full = gather_slices(nvalid.to(torch.float64), n, chunk).cpu().numpy().astype(np.int64)
+                return corr, nv_full
+        return corr
+
+
+def lag_unit_to_header_unit(values, unit_lag, unit_hdr, wrap):
+    """`ang2pipi(Quantity(values, unit_lag)).to(unit_hdr).value` (`alignment.py:819-837`)."""
+    v = np.asarray(values, dtype=np.float64)
+    if wrap:
+        v = units.ang2pipi(v, unit_lag)
+    return units.convert(v, unit_lag, unit_hdr)

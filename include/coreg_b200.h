@@ -1,0 +1,189 @@
+/*
+ * coreg_b200.h -- C ABI of the B200-native lag-grid pointing search.
+ *
+ * Drop-in boundary for the hot path of adolliou/euispice_coreg v0.4.0 (pure Python; it has no FFI of
+ * its own, so each entry point below names the Python function it replaces, file:line relative to the
+ * reference checkout). Plain C types only: no torch / numpy / C++ types cross this boundary.
+ *
+ * Conventions
+ *  - "dev" pointers are CUDA device pointers owned by the caller; "host" pointers are ordinary memory.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream). Device entry points are
+ *    stream-ordered: they enqueue work and return; they never synchronise, allocate or free.
+ *  - Images are row-major [ny][nx] (FITS NAXIS2 x NAXIS1); pixel coordinates are 0-based (astropy origin 0).
+ *  - Angles in `CoregTanWcs` are DEGREES (what wcslib holds after wcsset rescales CUNIT).
+ *  - Return value: 0 on success, negative `COREG_E*` on error; `coreg_last_error()` gives the message of the
+ *    last failure on the calling thread.
+ */
+#ifndef COREG_B200_H
+#define COREG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COREG_OK 0
+#define COREG_EINVAL (-1)  /* bad argument */
+#define COREG_ECUDA (-2)   /* CUDA runtime error */
+#define COREG_ENOMEM (-3)  /* workspace too small / allocation failed */
+
+#define COREG_F32 0
+#define COREG_F64 1
+
+/* flags of the lag-correlation kernels */
+#define COREG_FLAG_FAST_MATH 1 /* allow FMA contraction in the spline weights / taps (default: scipy's op order) */
+
+/* Constants of a 2-axis gnomonic (TAN) WCS. Replaces `astropy.wcs.WCS(hdr)`:
+ * hdrshift/alignment.py:1041, utils/Util.py:284, synras/map_builder.py:119. */
+typedef struct CoregTanWcs {
+  double crpix1, crpix2; /* 1-based FITS reference pixel */
+  double cdelt1, cdelt2; /* deg / pixel */
+  double pc11, pc12, pc21, pc22;
+  double crval1, crval2; /* deg */
+  double lonpole;        /* deg (180 for TAN unless CRVAL2 >= 90) */
+} CoregTanWcs;
+
+/* One candidate ("lag") header in the helioprojective search, reduced on the host to the constants of its
+ * world->pixel map. Replaces the per-lag `_shift_header` + `WCS(hdr_shifted)`:
+ * hdrshift/alignment.py:401-468, 1041.  With (lng, lat) the world coordinate of a common-grid pixel and
+ * A = lng - alpha_ref (alpha_ref = longitude the trig planes were built with):
+ *   dA = A - (CRVAL1_lag - alpha_ref);  D = sin(lat) sin_d0 + cos(lat) cos_d0 cos(dA)
+ *   xi = cos(lat) sin(dA) / D;  eta = (sin(lat) cos_d0 - cos(lat) sin_d0 cos(dA)) / D      [radians]
+ *   x = m11 xi + m12 eta + x0;  y = m21 xi + m22 eta + y0                                  [0-based pixel]
+ */
+typedef struct CoregLagTan {
+  double sin_da, cos_da;     /* sin / cos of (CRVAL1_lag - alpha_ref) */
+  double sin_d0, cos_d0;     /* sin / cos of CRVAL2_lag */
+  double m11, m12, m21, m22; /* (diag(CDELT) PC)^-1 * 180/pi */
+  double x0, y0;             /* CRPIX - 1 */
+} CoregLagTan;
+
+/* One candidate header in the Carrington search whose only lag-dependent part is a detector-plane offset:
+ *   x = x0 + Tx[pixel], y = y0 + Ty[pixel].  Replaces rectify.CarringtonTransform(hdr_shifted) per lag:
+ * utils/rectify.py:377-404, hdrshift/alignment.py:889-901. */
+typedef struct CoregLagOffset {
+  double x0, y0;
+} CoregLagOffset;
+
+/* Per-image constants of the Carrington ("fa") transform. Replaces rectify.CarringtonTransform.__init__ /
+ * SphericalTransform.__init__: utils/rectify.py:314-338, 377-423. Angles in RADIANS (already converted on the
+ * host exactly as the reference does with np.radians), cdelt in arcsec/pixel. */
+typedef struct CoregCarrington {
+  double lon0, lat0, roll; /* radians(CRLN_OBS), radians(CRLT_OBS), radians(CROTA) */
+  double dist;             /* DSUN_OBS / (solar_r * R_sun) */
+  double cdelt1, cdelt2;   /* header units per pixel (arcsec assumed by the reference) */
+} CoregCarrington;
+
+const char* coreg_last_error(void);
+int coreg_version(void);
+/* number of SMs of the current device (grid sizing); negative on error */
+int coreg_device_sm_count(void);
+
+/* ---- K3: pixel -> world for every pixel of an nx x ny TAN image ------------------------------------------
+ * Replaces AlignEUIUtil.extract_EUI_coordinates (utils/Util.py:283-312) incl. ang2pipi (utils/Util.py:76-80).
+ * lng_dev/lat_dev: [ny*nx] float64 degrees. wrap_pipi != 0 applies -((-a+180)%360-180). */
+int coreg_tan_pix2world(const CoregTanWcs* wcs_host, int nx, int ny, int wrap_pipi, double* lng_dev,
+                        double* lat_dev, void* stream);
+
+/* ---- world -> pixel for n points through one TAN WCS -------------------------------------------------------
+ * Replaces WCS(hdr).world_to_pixel(lon, lat): hdrshift/alignment.py:1065, synras/map_builder.py:127.
+ * Points behind the tangent hemisphere give NaN. */
+int coreg_tan_world2pix(const CoregTanWcs* wcs_host, const double* lng_dev, const double* lat_dev, int64_t n,
+                        double* x_dev, double* y_dev, void* stream);
+
+/* ---- spline resampling at given coordinates -----------------------------------------------------------------
+ * Replaces AlignCommonUtil.interpol2d / rectify.interpol2d, i.e.
+ * scipy.ndimage.map_coordinates(img, [y, x], order, mode='constant', cval, prefilter=False):
+ * utils/Util.py:82-104, utils/rectify.py:22-56. order in 0..3. Same operation order as scipy (no FMA). */
+int coreg_map_coordinates(const void* img_dev, int img_dtype, int img_ny, int img_nx, const double* y_dev,
+                          const double* x_dev, int64_t n, int order, double cval, void* out_dev, int out_dtype,
+                          void* stream);
+
+/* ---- lag-independent per-pixel trig planes for the helioprojective search -----------------------------------
+ * planes_dev: [3][n] float64 = sin(lat), cos(lat) sin(lng - alpha_ref), cos(lat) cos(lng - alpha_ref).
+ * Hoists the lag-independent half of world_to_pixel out of the per-lag loop (hdrshift/alignment.py:1061-1065). */
+int coreg_tan_trig_planes(const double* lng_dev, const double* lat_dev, int64_t n, double alpha_ref_deg,
+                          double* planes_dev, void* stream);
+
+/* mean of the finite values of an image -> mean_dev[0] (device double); deterministic. Used as the pivot of the
+ * single-pass moments (the Pearson coefficient is invariant under it). */
+int coreg_finite_mean(const void* img_dev, int dtype, int64_t n, double* mean_dev, void* stream);
+
+/* ---- K1: fused helioprojective lag search ---------------------------------------------------------------------
+ * For every lag: shift header -> world->pixel of every common-grid pixel -> order-k spline sample of the small
+ * image -> round to float32 -> mask non-finite pairs -> Pearson r against `ref`.
+ * Replaces Alignment._step + _interpolate_on_large_data_grid + interpol2d + c_correlate for a list of lags:
+ * hdrshift/alignment.py:509-542, 1018-1029; utils/Util.py:82-104; hdrshift/c_correlate.py:39-72.
+ *   ref_dev     [gny*gnx] float32  large image already on the common grid (output of the one-time resampling)
+ *   small_dev   [sny*snx] small image, dtype small_dtype
+ *   planes_dev  [3][gny*gnx] from coreg_tan_trig_planes
+ *   lags_dev    [n_lags] CoregLagTan (device)
+ *   pivots_dev  [2] device doubles: pivot of ref, pivot of small
+ *   work_dev    scratch of at least coreg_lag_corr_workspace_bytes(gnx, gny, n_lags) bytes
+ *   corr_dev    [n_lags] float64 out; nvalid_dev [n_lags] int64 out (may be NULL)
+ */
+size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags);
+int coreg_hpc_lag_corr(const float* ref_dev, const void* small_dev, int small_dtype, int snx, int sny, int gnx,
+                       int gny, const double* planes_dev, const CoregLagTan* lags_dev, int64_t n_lags, int order,
+                       const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
+                       int64_t* nvalid_dev, int flags, void* stream);
+
+/* ---- K5 (coordinates): Carrington grid -> detector pixel of one header --------------------------------------------
+ * Replaces CarringtonTransform / SphericalTransform.forward on the Rectifier grid
+ * (utils/rectify.py:304-311, 340-363, 876-877). The Rectifier grid is separable (lon along x, lat along y) and the
+ * reference evaluates its float32 half (np.linspace(dtype=float32), np.radians, sin/cos of the float32 latitude)
+ * with NumPy; the host does exactly that on the two 1-D vectors and hands over, widened to float64:
+ *   sinlon/coslon [n_lon] = sin/cos(float64(radians_f32(lon)) - radians(CRLN_OBS))
+ *   sinlat/coslat [n_lat] = float64(sin_f32(radians_f32(lat))), float64(cos_f32(radians_f32(lat)))
+ * The device does the per-pixel float64 part in NumPy's operation order (no FMA). Output planes [n_lat*n_lon]:
+ * tx = degrees(atan(x2/z2))*3600/cdelt1, ty likewise (NaN where the point is behind the limb, zz < 0); the full
+ * detector coordinate is x0 + tx with x0 = (CRPIX1-1) - dx/CDELT1 added per lag. */
+int coreg_carrington_planes(const CoregCarrington* c_host, const double* sinlon_dev, const double* coslon_dev,
+                            int n_lon, const double* sinlat_dev, const double* coslat_dev, int n_lat,
+                            double* tx_dev, double* ty_dev, void* stream);
+
+/* ---- K4: fused Carrington lag search (offset lags) ------------------------------------------------------------------
+ * Replaces Alignment._step with function_to_apply=_carrington_transform_fa for lags that share `roll`:
+ * hdrshift/alignment.py:509-542, 889-901; utils/rectify.py:865-888. ref is float64 here (the reference keeps the
+ * Carrington-projected large image in float64), samples are NOT rounded to float32, and a sample equal to -32762
+ * is treated as missing, like `np.where(image == -32762, nan, image)`. */
+int coreg_offset_lag_corr(const double* ref_dev, const void* small_dev, int small_dtype, int snx, int sny, int gnx,
+                          int gny, const double* tx_dev, const double* ty_dev, const CoregLagOffset* lags_dev,
+                          int64_t n_lags, int order, const double* pivots_dev, void* work_dev, size_t work_bytes,
+                          double* corr_dev, int64_t* nvalid_dev, int flags, void* stream);
+
+/* ---- K6: synthetic raster ----------------------------------------------------------------------------------------
+ * Replaces the column loop of SPICEComposedMapBuilder._create_map_from_hdu (synras/map_builder.py:95-131):
+ * output pixel (row j, column i) = order-k sample of imager frame frame_of_col[i] at the pixel position of the sky
+ * point (lng[j,i], lat[j,i]) under that frame's TAN WCS; NaN outside. frames_dev: [n_frames][fny][fnx] float32/64,
+ * wcs_host: [n_frames]; frame_of_col_host: [n_cols] (negative = column left NaN). out_dev float64 [n_rows*n_cols]. */
+int coreg_synras_build(const void* frames_dev, int frame_dtype, int n_frames, int fnx, int fny,
+                       const CoregTanWcs* wcs_host, const int* frame_of_col_host, const double* lng_dev,
+                       const double* lat_dev, int n_rows, int n_cols, int order, double* out_dev, void* stream);
+
+/* ---- whole helioprojective search from HOST buffers (allocates, copies, runs, copies back, frees) ---------------
+ * The call a non-Python host would make: replaces Alignment._find_best_header_parameters for the
+ * helioprojective frame (hdrshift/alignment.py:613-797) given images and header constants.
+ *   large_host [lny*lnx] float64, small_host [sny*snx] float64 (NaN = masked), lags_host [n_lags] CoregLagTan built
+ *   against alpha_ref_deg = wcs_small->crval1. corr_host [n_lags] out. */
+int coreg_hpc_search_host(const double* large_host, int lnx, int lny, const CoregTanWcs* wcs_large,
+                          const double* small_host, int snx, int sny, const CoregTanWcs* wcs_small,
+                          const CoregLagTan* lags_host, int64_t n_lags, int order, int flags, double* corr_host,
+                          int64_t* nvalid_host);
+
+/* Measurement hooks (bench.py): between begin and end every fused lag-kernel launch made by the calling thread is
+ * bracketed by a CUDA event pair on its own stream; end() synchronises on them and returns the summed device time
+ * of those launches [ms] and their count. No effect on results. */
+int coreg_profile_begin(void);
+int coreg_profile_end(double* lag_kernel_ms_total, int* launches);
+
+/* FP64 issue-rate microbenchmark (dependent DFMA chains, all SMs): returns achieved FP64 FMA instructions/s in
+ * *fma_per_s (lane-instructions, i.e. multiply by 2 for FLOP/s). Used by bench.py as the roofline denominator. */
+int coreg_fp64_peak(double* fma_per_s, int iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COREG_B200_H */
