@@ -16,7 +16,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
 
 F32, F64 = 0, 1
-FLAG_FAST_MATH = 1
+FLAG_STRICT = 1
+
+
+def make_flags(strict=False, variant=0):
+    """flags word of the lag kernels: bit 0 strict scipy op order, bits 8..11 tuning variant."""
+    return (FLAG_STRICT if strict else 0) | ((int(variant) & 15) << 8)
 
 
 class CoregLibraryError(RuntimeError):
@@ -195,7 +200,7 @@ def lag_corr_workspace_bytes(gnx, gny, n_lags):
     return int(load().coreg_lag_corr_workspace_bytes(int(gnx), int(gny), int(n_lags)))
 
 
-def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid_out=None, fast_math=False):
+def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid_out=None, flags=0):
     """K1. `lags`: device float64 [n_lags, 10] (CoregLagTan rows). Writes corr_out[n_lags]."""
     torch = _torch()
     lib = load()
@@ -209,7 +214,7 @@ def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
                                       _ptr(planes), _ptr(lags), n_lags, int(order), _ptr(pivots), _ptr(work),
                                       work.numel() * work.element_size(), _ptr(corr_out),
                                       _ptr(nvalid_out) if nvalid_out is not None else None,
-                                      FLAG_FAST_MATH if fast_math else 0, _stream()), "coreg_hpc_lag_corr")
+                                      int(flags), _stream()), "coreg_hpc_lag_corr")
 
 
 def carrington_planes(c: CoregCarrington, sinlon, coslon, sinlat, coslat):
@@ -225,7 +230,7 @@ def carrington_planes(c: CoregCarrington, sinlon, coslon, sinlat, coslat):
     return tx, ty
 
 
-def offset_lag_corr(ref, small, tx, ty, lags, order, pivots, work, corr_out, nvalid_out=None, fast_math=False):
+def offset_lag_corr(ref, small, tx, ty, lags, order, pivots, work, corr_out, nvalid_out=None, flags=0):
     """K4. `lags`: device float64 [n_lags, 2] (CoregLagOffset rows)."""
     torch = _torch()
     lib = load()
@@ -238,7 +243,7 @@ def offset_lag_corr(ref, small, tx, ty, lags, order, pivots, work, corr_out, nva
                                          _ptr(tx), _ptr(ty), _ptr(lags), lags.shape[0], int(order), _ptr(pivots),
                                          _ptr(work), work.numel() * work.element_size(), _ptr(corr_out),
                                          _ptr(nvalid_out) if nvalid_out is not None else None,
-                                         FLAG_FAST_MATH if fast_math else 0, _stream()), "coreg_offset_lag_corr")
+                                         int(flags), _stream()), "coreg_offset_lag_corr")
 
 
 def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):
@@ -258,7 +263,7 @@ def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):
     return out
 
 
-def hpc_search_host(large, wcs_large, small, wcs_small, lags, order=2, fast_math=False):
+def hpc_search_host(large, wcs_large, small, wcs_small, lags, order=2, flags=0):
     """Whole helioprojective search from HOST numpy buffers (the C caller's entry point)."""
     lib = load()
     large = np.ascontiguousarray(large, dtype=np.float64)
@@ -271,7 +276,7 @@ def hpc_search_host(large, wcs_large, small, wcs_small, lags, order=2, fast_math
     _check(lib.coreg_hpc_search_host(large.ctypes.data_as(_P), large.shape[1], large.shape[0], C.byref(sl),
                                      small.ctypes.data_as(_P), small.shape[1], small.shape[0], C.byref(ss),
                                      lags.ctypes.data_as(_P), n_lags, int(order),
-                                     FLAG_FAST_MATH if fast_math else 0,
+                                     int(flags),
                                      corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)), "coreg_hpc_search_host")
     return corr, nvalid
 

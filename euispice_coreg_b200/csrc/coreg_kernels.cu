@@ -146,22 +146,24 @@ __device__ __forceinline__ bool spline_sample(const T* __restrict__ img, int ny,
   double t = 0.0;
   const bool interior = (sy >= 0) && (sy + ORDER <= ny - 1) && (sx >= 0) && (sx + ORDER <= nx - 1);
   if (interior) {
-    const T* p = img + (size_t)sy * nx + sx;
+    const T* p = img + (sy * nx + sx);  // callers guarantee ny*nx < 2^31
     if (STRICT) {
 #pragma unroll
       for (int a = 0; a <= ORDER; ++a) {
 #pragma unroll
         for (int b = 0; b <= ORDER; ++b) {
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(ldval(p + (size_t)a * nx + b), wy[a]), wx[b]));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(ldval(p + b), wy[a]), wx[b]));
         }
+        p += nx;
       }
     } else {
 #pragma unroll
       for (int a = 0; a <= ORDER; ++a) {
-        double row = ldval(p + (size_t)a * nx) * wx[0];
+        double row = ldval(p) * wx[0];
 #pragma unroll
-        for (int b = 1; b <= ORDER; ++b) row = fma(ldval(p + (size_t)a * nx + b), wx[b], row);
+        for (int b = 1; b <= ORDER; ++b) row = fma(ldval(p + b), wx[b], row);
         t = fma(row, wy[a], t);
+        p += nx;
       }
     }
   } else {
@@ -175,7 +177,7 @@ __device__ __forceinline__ bool spline_sample(const T* __restrict__ img, int ny,
     for (int a = 0; a <= ORDER; ++a) {
 #pragma unroll
       for (int b = 0; b <= ORDER; ++b) {
-        const double v = ldval(img + (size_t)iy[a] * nx + ix[b]);
+        const double v = ldval(img + (iy[a] * nx + ix[b]));
         if (STRICT)
           t = __dadd_rn(t, __dmul_rn(__dmul_rn(v, wy[a]), wx[b]));
         else
@@ -378,12 +380,12 @@ __global__ void finite_mean_kernel(const T* __restrict__ img, int64_t n, double*
 // fused lag search
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTileW = 64;
-constexpr int kTileH = 32;
 constexpr int kThreads = 256;
-constexpr int kPPT = (kTileW * kTileH) / kThreads;  // 8 pixels per thread
+constexpr int kRowsPerPass = kThreads / kTileW;  // 4 grid rows per pass of the block
 constexpr int kWarps = kThreads / 32;
-constexpr int kLagSub = 64;  // lags staged in shared memory at a time
-constexpr int kMom = 8;      // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
+constexpr int kLagSub = 64;   // lags staged in shared memory at a time
+constexpr int kMom = 8;       // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
+constexpr int kMinTileH = 16; // smallest tile height of any variant (workspace sizing)
 
 struct TanCoord {
   typedef CoregLagTan Lag;
@@ -478,14 +480,19 @@ __device__ __forceinline__ double warp_transpose_reduce8(double (&v)[8], int lan
   return w1;  // value index = 4*bit4 + 2*bit3 + bit2 = (lane >> 2) & 7
 }
 
-// work layout: [tile][lag][kMom] doubles
-template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
-__global__ void __launch_bounds__(kThreads, 2)
+// One block = one tile of the common grid (64 x 4*PPT pixels, PPT pixels per thread, their lag-independent
+// constants in registers) x one slice of the lag list. work layout: [tile][lag][kMom] doubles.
+// Moments: the sums over the reference image (Sa, Saa) are taken once over the pixels whose reference value is
+// finite and corrected, per lag, by the (rare) pixels whose small-image sample is missing; Sb, Sbb, Sab and the
+// count are accumulated per lag.
+template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32, int PPT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, int snx, int sny, int gnx, int gny,
                 typename Coord::Planes planes, const typename Coord::Lag* __restrict__ lags, int n_lags,
                 int lags_per_block, const double* __restrict__ pivots, double* __restrict__ work) {
   typedef typename Coord::Lag Lag;
   typedef typename Coord::Pix Pix;
+  constexpr int TILE_H = kRowsPerPass * PPT;
   __shared__ Lag s_lag[kLagSub];
   __shared__ double s_part[kWarps][kLagSub][kMom];
 
@@ -497,22 +504,28 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
   const int gx = tile_x * kTileW + tx;
   const double pivot_a = pivots[0], pivot_b = pivots[1];
 
-  // lag-independent per-pixel constants, held in registers for the whole lag walk
-  Pix pix[kPPT];
-  double a_c[kPPT];  // ref - pivot, NaN when the pair can never be valid
+  Pix pix[PPT];
+  double a_c[PPT];       // ref - pivot (0 where the reference pixel is missing)
+  unsigned a_ok = 0;     // bit k: reference pixel k is finite
+  double sa_all = 0.0, saa_all = 0.0;
 #pragma unroll
-  for (int k = 0; k < kPPT; ++k) {
-    const int gy = tile_y * kTileH + ty0 + k * (kThreads / kTileW);
+  for (int k = 0; k < PPT; ++k) {
+    const int gy = tile_y * TILE_H + ty0 + k * kRowsPerPass;
+    a_c[k] = 0.0;
+    pix[k] = Coord::dead();
     if (gx < gnx && gy < gny) {
       const int64_t idx = (int64_t)gy * gnx + gx;
       const double a = (double)ref[idx];
-      a_c[k] = isfinite(a) ? a - pivot_a : CUDART_NAN;
-      pix[k] = Coord::load(planes, idx);
-    } else {
-      a_c[k] = CUDART_NAN;
-      pix[k] = Coord::dead();
+      if (isfinite(a)) {
+        a_c[k] = a - pivot_a;
+        a_ok |= 1u << k;
+        pix[k] = Coord::load(planes, idx);
+        sa_all += a_c[k];
+        saa_all = fma(a_c[k], a_c[k], saa_all);
+      }
     }
   }
+  int n_all = __popc(a_ok);
 
   const int lag_begin = blockIdx.y * lags_per_block;
   const int lag_end = min(n_lags, lag_begin + lags_per_block);
@@ -520,7 +533,6 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
     const int cnt = min(kLagSub, lag_end - l0);
     __syncthreads();  // previous sub-chunk fully consumed
     {
-      // stage lag constants: sizeof(Lag) is a multiple of 8
       const double* src = reinterpret_cast<const double*>(lags + l0);
       double* dst = reinterpret_cast<double*>(s_lag);
       const int nd = cnt * (int)(sizeof(Lag) / sizeof(double));
@@ -529,14 +541,12 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
     __syncthreads();
     for (int l = 0; l < cnt; ++l) {
       const Lag L = s_lag[l];
-      double m[8];
+      double sb = 0.0, sbb = 0.0, sab = 0.0, sa_miss = 0.0, saa_miss = 0.0;
+      int n_miss = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = 0.0;
-      int nv = 0;
-#pragma unroll
-      for (int k = 0; k < kPPT; ++k) {
+      for (int k = 0; k < PPT; ++k) {
         double x, y, v;
-        Coord::map(pix[k], L, x, y);
+        Coord::map(pix[k], L, x, y);   // dead pixels carry NaN -> "outside"
         bool ok = spline_sample<ORDER, STRICT, SmallT>(small, sny, snx, y, x, v);
         double b;
         if (ROUND32) {
@@ -547,19 +557,26 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
           ok = ok && isfinite(v) && (v != -32762.0);
           b = v;
         }
-        const double a = a_c[k];
-        ok = ok && (a == a);
         if (ok) {
           const double bc = b - pivot_b;
-          ++nv;
-          m[1] += a;
-          m[2] += bc;
-          m[3] = fma(a, a, m[3]);
-          m[4] = fma(bc, bc, m[4]);
-          m[5] = fma(a, bc, m[5]);
+          sb += bc;
+          sbb = fma(bc, bc, sbb);
+          sab = fma(a_c[k], bc, sab);
+        } else if (a_ok & (1u << k)) {
+          ++n_miss;
+          sa_miss += a_c[k];
+          saa_miss = fma(a_c[k], a_c[k], saa_miss);
         }
       }
-      m[0] = (double)nv;
+      double m[8];
+      m[0] = (double)(n_all - n_miss);
+      m[1] = sa_all - sa_miss;
+      m[2] = sb;
+      m[3] = saa_all - saa_miss;
+      m[4] = sbb;
+      m[5] = sab;
+      m[6] = 0.0;
+      m[7] = 0.0;
       const double tot = warp_transpose_reduce8(m, lane);
       if ((lane & 3) == 0) s_part[warp][l][lane >> 2] = tot;
     }
@@ -611,20 +628,24 @@ lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lag
   }
 }
 
-template <class Coord, typename SmallT, typename RefT, bool ROUND32>
-int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int gnx, int gny,
-                    typename Coord::Planes planes, const typename Coord::Lag* lags, int64_t n_lags, int order,
-                    const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid, int flags,
-                    cudaStream_t s) {
-  if (n_lags <= 0) return COREG_OK;
-  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
-  if (gnx <= 0 || gny <= 0 || snx <= 0 || sny <= 0) return fail(COREG_EINVAL, "empty image");
-  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
-  const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + kTileH - 1) / kTileH);
-  // split the lag list over blockIdx.y until the grid has a few waves of (SMs x 2 resident blocks)
-  int sms = coreg_device_sm_count();
-  if (sms <= 0) sms = 148;
-  const int want_blocks = sms * 2 * 4;
+// tuning variants (flags bits 8..11): tile height = 4*PPT, MINB resident blocks per SM
+template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
+int launch_lag_variant(int variant, dim3 grid_tiles_of, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s,
+                       const RefT* ref, const SmallT* small, int snx, int sny, typename Coord::Planes planes,
+                       const typename Coord::Lag* lags, const double* pivots, double* w, int* tiles_out) {
+  (void)grid_tiles_of;
+  int ppt, minb;
+  switch (variant) {  // measured on config 1 (profiles/r1_k1_tuning.md): 0 is the fastest
+    case 1: ppt = 8; minb = 2; break;
+    case 2: ppt = 8; minb = 3; break;
+    case 3: ppt = 4; minb = 3; break;
+    default: ppt = 4; minb = 4; break;
+  }
+  const int tile_h = kRowsPerPass * ppt;
+  const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
+  *tiles_out = tiles;
+  // split the lag list over blockIdx.y until the grid has a few waves of resident blocks
+  const int want_blocks = sms * minb * 4;
   int splits = (want_blocks + tiles - 1) / tiles;
   const int max_splits = (int)((n_lags + kLagSub - 1) / kLagSub);
   splits = std::max(1, std::min(splits, max_splits));
@@ -633,7 +654,33 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
   splits = (int)((n_lags + lags_per_block - 1) / lags_per_block);
   if (splits > 65535) return fail(COREG_EINVAL, "lag grid too large for one launch");
   dim3 grid(tiles, splits);
-  const bool strict = !(flags & COREG_FLAG_FAST_MATH);
+#define LV(PPT_, MINB_)                                                                                     \
+  lag_corr_kernel<Coord, ORDER, STRICT, SmallT, RefT, ROUND32, PPT_, MINB_><<<grid, kThreads, 0, s>>>(      \
+      ref, small, snx, sny, gnx, gny, planes, lags, (int)n_lags, lags_per_block, pivots, w)
+  switch (variant) {
+    case 1: LV(8, 2); break;
+    case 2: LV(8, 3); break;
+    case 3: LV(4, 3); break;
+    default: LV(4, 4); break;
+  }
+#undef LV
+  return COREG_OK;
+}
+
+template <class Coord, typename SmallT, typename RefT, bool ROUND32>
+int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int gnx, int gny,
+                    typename Coord::Planes planes, const typename Coord::Lag* lags, int64_t n_lags, int order,
+                    const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid, int flags,
+                    cudaStream_t s) {
+  if (n_lags <= 0) return COREG_OK;
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (gnx <= 0 || gny <= 0 || snx <= 0 || sny <= 0) return fail(COREG_EINVAL, "empty image");
+  if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  int sms = coreg_device_sm_count();
+  if (sms <= 0) sms = 148;
+  const bool strict = (flags & COREG_FLAG_STRICT) != 0;
+  const int variant = (flags >> 8) & 15;
   double* w = static_cast<double*>(work);
   const bool prof = g_prof_on && g_prof_n < 4096;
   if (prof) {
@@ -641,21 +688,19 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
     CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
-#define LAUNCH(ORD, STR)                                                                              \
-  lag_corr_kernel<Coord, ORD, STR, SmallT, RefT, ROUND32><<<grid, kThreads, 0, s>>>(                  \
-      ref, small, snx, sny, gnx, gny, planes, lags, (int)n_lags, lags_per_block, pivots, w)
-  switch (order * 2 + (strict ? 1 : 0)) {
-    case 1: LAUNCH(0, true); break;
+  int tiles = 0, rc = COREG_OK;
+#define LAUNCH(ORD, STR)                                                                                          \
+  rc = launch_lag_variant<Coord, ORD, STR, SmallT, RefT, ROUND32>(variant, dim3(), gnx, gny, n_lags, sms, s, ref, \
+                                                                   small, snx, sny, planes, lags, pivots, w, &tiles)
+  switch (order) {
     case 0: LAUNCH(0, true); break;
-    case 3: LAUNCH(1, true); break;
-    case 2: LAUNCH(1, true); break;
-    case 5: LAUNCH(2, true); break;
-    case 4: LAUNCH(2, false); break;
-    case 7: LAUNCH(3, true); break;
-    case 6: LAUNCH(3, true); break;
+    case 1: LAUNCH(1, true); break;
+    case 2: if (strict) LAUNCH(2, true); else LAUNCH(2, false); break;
+    case 3: LAUNCH(3, true); break;
     default: return fail(COREG_EINVAL, "spline order must be 0..3");
   }
 #undef LAUNCH
+  if (rc) return rc;
   CK_LAUNCH("lag_corr_kernel");
   if (prof) {
     CK(cudaEventRecord(g_prof[g_prof_n].b, s));
@@ -824,7 +869,7 @@ int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void*
 
 size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags) {
   if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;
-  const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kTileH - 1) / kTileH);
+  const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kMinTileH - 1) / kMinTileH);
   return tiles * (size_t)n_lags * kMom * sizeof(double);
 }
 

@@ -42,13 +42,14 @@ class Alignment:
                  small_fov_value_max: object = None, counts_cpu_max: int = 40, large_fov_window: object = -1,
                  small_fov_window: object = -1,
                  path_save_figure: str = None, reprojection_order=2, force_crota_0=False,
-                 unit_lag="arcsec", cdelt_semantics="reference", fast_math=False):
+                 unit_lag="arcsec", cdelt_semantics="reference", strict_arithmetic=False):
         """Same parameters as the reference (`hdrshift/alignment.py:47-83`). Two additions:
 
         cdelt_semantics: "reference" reproduces the reference's handling of CDELT lags (a CDELT1 lag only
             rebuilds PCi_j, a non-zero CDELT2 lag leaves 0.0 in the cube because the reference's worker dies,
             SURVEY App. B1); "intended" applies CDELTi = ref + lag before the PCi_j rebuild.
-        fast_math: let the spline weights / taps use fused multiply-add (differences ~1e-16 per sample).
+        strict_arithmetic: evaluate the spline weights / tap sums in scipy's exact operation order (separate
+            multiply and add) instead of fused multiply-add; per-sample bit-faithful, ~1e-15 in r, slower.
         """
         self.large_fov_known_pointing = large_fov_known_pointing
         self.small_fov_to_correct = small_fov_to_correct
@@ -92,7 +93,7 @@ class Alignment:
         self.lat_ctype = None
         self.use_sunpy = False
         self.cdelt_semantics = cdelt_semantics
-        self.fast_math = fast_math
+        self.strict_arithmetic = strict_arithmetic
         self.engine = None
         self.nvalid = None
         for lag_name in ("lag_crval1", "lag_crval2", "lag_crota", "lag_cdelt1", "lag_cdelt2"):
@@ -309,7 +310,7 @@ class Alignment:
         refs.crval1_ref, refs.crval2_ref, refs.crota_ref = self.crval1_ref, self.crval2_ref, self.crota_ref
         refs.cdelt1_ref, refs.cdelt2_ref = self.cdelt1_ref, self.cdelt2_ref
 
-        eng = _engine.LagSearchEngine(order=self.order, fast_math=self.fast_math)
+        eng = _engine.LagSearchEngine(order=self.order, strict=self.strict_arithmetic)
         self.engine = eng
         eng.set_small(self.data_small)
         n_r = len(self.lag_solar_r)

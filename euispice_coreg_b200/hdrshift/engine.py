@@ -144,14 +144,16 @@ class LagSearchEngine:
 
     max_workspace_bytes = 1 << 30
 
-    def __init__(self, order=2, fast_math=False, device=None):
+    def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64"):
         torch = _torch()
         _ext.load()  # fail loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _ext.CoregLibraryError("no CUDA device: the pointing search has no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.order = int(order)
-        self.fast_math = bool(fast_math)
+        self.strict = bool(strict)
+        self.flags = _ext.make_flags(strict, variant)
+        self.small_storage = small_storage
         self.pivots = torch.zeros(2, dtype=torch.float64, device=self.device)
         self.ref = None        # large image on the common grid
         self.small = None
@@ -168,12 +170,16 @@ class LagSearchEngine:
         return t.to(self.device, non_blocking=pinned)
 
     def set_small(self, data_small):
-        """Small image (float64 with NaN for masked pixels). Stored as float32 on the device when every
-        finite value is exactly representable (FITS BITPIX -32 data): half the gather traffic, same values."""
+        """Small image (float64 with NaN for masked pixels). small_storage="f64" (default) keeps it float64 on
+        the device; "auto" stores float32 when every finite value is exactly representable (FITS BITPIX -32
+        data): half the gather traffic, same values, but 9 f32->f64 conversions per sample on the quarter-rate
+        conversion pipe -- measured slower on B200 (profiles/r1_k1_tuning.md)."""
         data_small = np.asarray(data_small)
         with np.errstate(invalid="ignore", over="ignore"):
             as32 = data_small.astype(np.float32)
             exact = np.array_equal(as32.astype(np.float64), data_small, equal_nan=True)
+        if self.small_storage == "f64":
+            exact = False
         self.small = self._upload(as32 if exact else data_small.astype(np.float64))
         _ext.finite_mean(self.small, self.pivots[1:2])
 
@@ -269,11 +275,11 @@ class LagSearchEngine:
                 nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
                 if self.frame == "hpc":
                     _ext.hpc_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order, self.pivots,
-                                      work, out_dev[lo:hi], nv, self.fast_math)
+                                      work, out_dev[lo:hi], nv, self.flags)
                 else:
                     tx, ty = planes
                     _ext.offset_lag_corr(self.ref, self.small, tx, ty, table_dev[lo:hi], self.order, self.pivots,
-                                         work, out_dev[lo:hi], nv, self.fast_math)
+                                         work, out_dev[lo:hi], nv, self.flags)
                 self.last_launches += 2  # lag kernel + finalize
         return out_dev
 

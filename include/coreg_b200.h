@@ -32,8 +32,12 @@ extern "C" {
 #define COREG_F32 0
 #define COREG_F64 1
 
-/* flags of the lag-correlation kernels */
-#define COREG_FLAG_FAST_MATH 1 /* allow FMA contraction in the spline weights / taps (default: scipy's op order) */
+/* flags of the lag-correlation kernels.
+ * Default arithmetic: FP64 with fused multiply-add in the spline weights / tap sums (|dr| ~ 1e-15 vs strict).
+ * COREG_FLAG_STRICT: scipy's exact operation order (separate multiply / add), bit-faithful per sample.
+ * bits 8..11: tuning variant of the fused kernel (0 = default tile / occupancy). */
+#define COREG_FLAG_STRICT 1
+#define COREG_FLAG_VARIANT(v) (((v) & 15) << 8)
 
 /* Constants of a 2-axis gnomonic (TAN) WCS. Replaces `astropy.wcs.WCS(hdr)`:
  * hdrshift/alignment.py:1041, utils/Util.py:284, synras/map_builder.py:119. */

@@ -97,7 +97,7 @@ def _oracle_cube(pair, **kw):
     kw = dict(kw)
     kw["order"] = kw.pop("reprojection_order", 2)
     kw["cdelt_mode"] = kw.pop("cdelt_semantics", "reference")
-    kw.pop("fast_math", None)
+    kw.pop("strict_arithmetic", None)
     s = HpcSearch(dl, hl, ds, hs, **kw)
     return s.cube(), s
 
@@ -176,8 +176,11 @@ def test_hpc_cube_deg_units(torch_cuda, toy_pair, tmp_path):
     assert (LAGS["lag_crval1"][i], LAGS["lag_crval2"][j]) == (24.0, 6.0)
 
 
-def test_fast_math_within_tolerance(torch_cuda, toy_pair):
-    gpu, _ = _gpu_cube(toy_pair, fast_math=True, **LAGS)
+def test_strict_arithmetic_mode(torch_cuda, toy_pair):
+    """scipy's exact tap arithmetic; the default FMA mode differs from it by far less than the tolerance."""
+    gpu, _ = _gpu_cube(toy_pair, strict_arithmetic=True, **LAGS)
+    fma, _ = _gpu_cube(toy_pair, **LAGS)
+    assert np.nanmax(np.abs(gpu - fma)) < 1e-12
     ref, _ = _oracle_cube(toy_pair, **LAGS)
     _assert_parity(gpu, ref)
 
