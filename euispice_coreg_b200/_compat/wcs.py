@@ -198,3 +198,90 @@ class TanWcs:
         y = mi[1, 0] * px + mi[1, 1] * py + (self.crpix2 - 1.0)
         bad = den <= 0.0
         return np.where(bad, np.nan, x), np.where(bad, np.nan, y)
+
+
+# ------------------------------------------------------------------------------------------------------
+# SPICE-style 4-axis headers (x = HPLN-TAN, y = HPLT-TAN, dispersion, time)
+# ------------------------------------------------------------------------------------------------------
+class SpiceWcs:
+    """The pieces of a 4-axis SPICE L2 WCS that the pointing search needs, replacing the astropy calls
+    `WCS(hdr).dropaxis(2)`, `.pixel_to_world(x, y, t)`, `.sub(['spectral'])` and `w_xy.to_header()` in
+    `hdrshift/alignment_spice.py:250-261` and `synras/map_builder.py:249-294`.
+
+    Axis roles are found from CTYPEi. The celestial pair may only couple to itself through PCi_j (SPICE
+    files satisfy this); the time axis may depend on the x pixel through PC<t>_<x> (the raster scan).
+    """
+
+    def __init__(self, hdr):
+        n = int(hdr.get("WCSAXES", hdr.get("NAXIS", 4)))
+        self.n = n
+        self.ilon, self.ilat = celestial_axes(hdr, naxis=n)
+        self.iwave = self.itime = None
+        for i in range(1, n + 1):
+            ct = str(hdr.get("CTYPE%d" % i, "")).upper()
+            if ct.startswith("WAVE") or ct.startswith("AWAV") or ct.startswith("FREQ"):
+                self.iwave = i
+            elif ct in ("UTC", "TIME", "TAI", "TT"):
+                self.itime = i
+        self.hdr = hdr
+        self.pc = np.eye(n)
+        for i in range(1, n + 1):
+            for j in range(1, n + 1):
+                k = "PC%d_%d" % (i, j)
+                if k in hdr:
+                    self.pc[i - 1, j - 1] = float(hdr[k])
+        self.crpix = np.array([float(hdr.get("CRPIX%d" % i, 0.0)) for i in range(1, n + 1)])
+        self.cdelt = np.array([float(hdr.get("CDELT%d" % i, 1.0)) for i in range(1, n + 1)])
+        self.crval = np.array([float(hdr.get("CRVAL%d" % i, 0.0)) for i in range(1, n + 1)])
+        for i in (self.ilon, self.ilat):
+            for j in range(1, n + 1):
+                if j not in (self.ilon, self.ilat) and self.pc[i - 1, j - 1] != 0.0:
+                    raise NotImplementedError(f"PC{i}_{j} couples a celestial axis to a non-celestial one")
+
+    def celestial(self) -> TanWcs:
+        return TanWcs.from_header(self.hdr, self.ilon, self.ilat)
+
+    def time_seconds(self, x, t=0.0, y=0.0):
+        """Seconds relative to DATE-REF of pixel (x, y, t), 0-based, with the dispersion axis dropped
+        (`w_spice.dropaxis(2)` removes its row and column of PCi_j)."""
+        if self.itime is None:
+            raise ValueError("no time axis in header")
+        it = self.itime - 1
+        off = (self.pc[it, self.ilon - 1] * (np.asarray(x, dtype=np.float64) + 1.0 - self.crpix[self.ilon - 1])
+               + self.pc[it, self.ilat - 1] * (np.asarray(y, dtype=np.float64) + 1.0 - self.crpix[self.ilat - 1])
+               + self.pc[it, it] * (np.asarray(t, dtype=np.float64) + 1.0 - self.crpix[it]))
+        unit = str(self.hdr.get("CUNIT%d" % self.itime, "s")).strip()
+        scale = {"s": 1.0, "min": 60.0, "h": 3600.0, "d": 86400.0}.get(unit, 1.0)
+        return (self.crval[it] + self.cdelt[it] * off) * scale
+
+    def wavelength(self, z):
+        """World value of dispersion pixel z (0-based) in the header's CUNIT (`w_spice.sub(['spectral'])`)."""
+        if self.iwave is None:
+            raise ValueError("no spectral axis in header")
+        iw = self.iwave - 1
+        return self.crval[iw] + self.cdelt[iw] * self.pc[iw, iw] * (np.asarray(z, dtype=np.float64) + 1.0
+                                                                    - self.crpix[iw])
+
+    def xy_header(self):
+        """What `w_xy.to_header()` yields for the celestial pair: degrees, PCi_j only where they differ from
+        the identity, axes renumbered 1, 2."""
+        from .fits_lite import Header
+        w = self.celestial()
+        h = Header()
+        h["WCSAXES"] = 2
+        h["CRPIX1"], h["CRPIX2"] = w.crpix1, w.crpix2
+        for key, val, default in (("PC1_1", w.pc11, 1.0), ("PC1_2", w.pc12, 0.0), ("PC2_1", w.pc21, 0.0),
+                                  ("PC2_2", w.pc22, 1.0)):
+            if val != default:
+                h[key] = val
+        h["CDELT1"], h["CDELT2"] = w.cdelt1, w.cdelt2
+        h["CUNIT1"], h["CUNIT2"] = "deg", "deg"
+        h["CTYPE1"] = str(self.hdr["CTYPE%d" % self.ilon])
+        h["CTYPE2"] = str(self.hdr["CTYPE%d" % self.ilat])
+        h["CRVAL1"], h["CRVAL2"] = w.crval1, w.crval2
+        h["LONPOLE"] = w.lonpole
+        h["LATPOLE"] = float(self.hdr.get("LATPOLE", w.crval2))
+        for k in ("DATE-OBS", "DATE-BEG", "DATE-AVG", "DATE-END", "RSUN_REF", "DSUN_OBS", "HGLN_OBS", "HGLT_OBS"):
+            if k in self.hdr:
+                h[k] = self.hdr[k]
+        return h

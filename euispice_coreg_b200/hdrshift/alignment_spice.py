@@ -1,0 +1,139 @@
+"""`AlignmentSpice` -- the reference's `hdrshift/alignment_spice.py:13-120, 182-323` on top of the device engine.
+
+Host preparation (slit-edge rows -> NaN, spectral sum of the chosen wavelength interval, 2-D header from the
+4-axis WCS) is numpy; the search itself is `Alignment._find_best_header_parameters`. Like the reference
+ the 2-D header comes out in degrees, `_check_ant_create_pcij_matrix` is not called, and
+`reprojection_order`, value thresholds and `force_crota_0` are not forwarded.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .._compat import units
+from .._compat.wcs import SpiceWcs
+from ..utils import Util
+from .alignment import Alignment, _open_fits
+
+
+def _value_in(q, unit):
+    """Plain number (already in `unit`) or astropy-like quantity -> float in `unit`."""
+    if hasattr(q, "to"):
+        return float(q.to(unit).value)
+    return float(q)
+
+
+class AlignmentSpice(Alignment):
+
+    def __init__(self, large_fov_known_pointing: str, small_fov_to_correct: str, lag_crval1=None, lag_crval2=None,
+                 lag_cdelt1=None, lag_cdelt2=None, lag_crota=None, lag_solar_r=None, large_fov_window=-1,
+                 small_fov_window=-1, parallelism: bool = False, counts_cpu_max: int = 40,
+                 display_progress_bar: bool = False, path_save_figure=None, wavelength_interval_to_sum="all",
+                 sub_fov_window="all"):
+        """Same parameters as `hdrshift/alignment_spice.py:14-49`. `wavelength_interval_to_sum` is "all" or
+        [wave_min, wave_max] in the header's dispersion unit (or astropy quantities); `sub_fov_window` is "all" or
+        [lon_min, lon_max, lat_min, lat_max] in arcsec (or quantities)."""
+        super().__init__(large_fov_known_pointing=large_fov_known_pointing, small_fov_to_correct=small_fov_to_correct,
+                         lag_crval1=lag_crval1, lag_crval2=lag_crval2, lag_cdelt1=lag_cdelt1, lag_cdelt2=lag_cdelt2,
+                         lag_crota=lag_crota, display_progress_bar=display_progress_bar, lag_solar_r=lag_solar_r,
+                         parallelism=parallelism, counts_cpu_max=counts_cpu_max, large_fov_window=large_fov_window,
+                         small_fov_window=small_fov_window, path_save_figure=path_save_figure)
+        self.sub_fov_window = sub_fov_window
+        self.coordinate_frame = None
+        self.extend_pixel_size = None
+        self.cut_from_center = None
+        self.wavelength_interval_to_sum = wavelength_interval_to_sum
+
+    def align_using_helioprojective(self, method='correlation', extend_pixel_size=False, cut_from_center=None,
+                                    return_type="AlignmentResults", coefficient_l3: int = None):
+        """`hdrshift/alignment_spice.py:66-120`."""
+        self.lonlims = None
+        self.latlims = None
+        self.shape = None
+        self.reference_date = None
+        self.method = method
+        self.coordinate_frame = "final_helioprojective"
+        self.extend_pixel_size = extend_pixel_size
+        self.cut_from_center = cut_from_center
+        self.ang2pipi = True
+        self._extract_imager_data_header()
+        self.lon_ctype = "HPLN-TAN"
+        self.lat_ctype = "HPLT-TAN"
+        level = None
+        if "L2" in self.small_fov_to_correct:
+            level = 2
+        elif "L3" in self.small_fov_to_correct:
+            level = 3
+        self._extract_spice_data_header(level=level, coeff=coefficient_l3)
+        results = self._find_best_header_parameters()
+        return self._wrap_results(results, return_type)
+
+    def align_using_carrington(self, *args, **kwargs):
+        raise NotImplementedError("AlignmentSpice.align_using_carrington calls a method that does not exist in the "
+                                  "reference (alignment_spice.py:146); it is outside the device path")
+
+    # ------------------------------------------------------------------------------------------------
+    def _extract_imager_data_header(self):
+        """`alignment_spice.py:182-187`: the large image is read as is (no PCi_j check)."""
+        with _open_fits(self.large_fov_known_pointing) as hdul_large:
+            self.data_large = np.array(hdul_large[self.large_fov_window].data.copy(), dtype=np.float64)
+            self.hdr_large = hdul_large[self.large_fov_window].header.copy()
+
+    def _extract_spice_data_header(self, level: int, coeff: int = None):
+        """`alignment_spice.py:189-221`."""
+        with _open_fits(self.small_fov_to_correct) as hdul_small:
+            hdu = hdul_small[self.small_fov_window]
+            dt = hdu.header.copy()["PC4_1"]
+            if level == 2:
+                self._prepare_spice_from_l2(hdu)
+            elif level == 3:
+                raise NotImplementedError("level 3 (fitted) SPICE files are outside the device path")
+            else:
+                raise ValueError("level must be 2 or 3")
+            for k in ("SOLAR_B0", "RSUN_REF", "DSUN_OBS", "CROTA"):
+                self.hdr_small[k] = hdu.header[k]
+            if self.extend_pixel_size:
+                raise NotImplementedError("extend_pixel_size (solar-rotation CDELT1 correction, "
+                                          f"alignment_spice.py:223-248, dt={dt}) is not on the device path")
+
+    def _prepare_spice_from_l2(self, hdu):
+        """`alignment_spice.py:250-323`: 4-D L2 cube -> 2-D image + 2-D header."""
+        data_small = np.array(hdu.data.copy(), dtype=np.float64)
+        header_spice = hdu.header
+        ymin, ymax = Util.AlignSpiceUtil.vertical_edges_limits(header_spice)
+        sw = SpiceWcs(header_spice)
+        self.hdr_small = sw.xy_header().copy()
+        data_small[:, :, :ymin, :] = np.nan
+        data_small[:, :, ymax:, :] = np.nan
+        if isinstance(self.wavelength_interval_to_sum, str) and self.wavelength_interval_to_sum == "all":
+            self.data_small = np.nansum(data_small[0, :, :, :], axis=0)
+        elif type(self.wavelength_interval_to_sum).__name__ == "list":
+            unit = str(header_spice.get("CUNIT%d" % sw.iwave, "nm")).strip()
+            wave = sw.wavelength(np.arange(data_small.shape[1]))
+            lo = _value_in(self.wavelength_interval_to_sum[0], unit)
+            hi = _value_in(self.wavelength_interval_to_sum[1], unit)
+            sel = np.logical_and(wave >= lo, wave <= hi)
+            self.data_small = np.nansum(data_small[0, sel, :, :], axis=0)
+        else:
+            raise ValueError("wavelength_interval_to_sum must be a [wave_min * u.angstrom, wave_max * u.angstrom] "
+                             "or 'all' str ")
+        self.data_small[:ymin, :] = np.nan
+        self.data_small[ymax:, :] = np.nan
+        if self.cut_from_center is not None:
+            xlen = self.cut_from_center
+            xmid = self.data_small.shape[1] // 2
+            self.data_small[:, :(xmid - xlen // 2 - 1)] = np.nan
+            self.data_small[:, (xmid + xlen // 2):] = np.nan
+        if isinstance(self.sub_fov_window, str) and self.sub_fov_window == "all":
+            pass
+        elif type(self.sub_fov_window).__name__ == "list":
+            w = sw.celestial()
+            x, y = np.meshgrid(np.arange(data_small.shape[3]), np.arange(data_small.shape[2]))
+            lon, lat = w.pixel_to_world(x, y)     # degrees, wcslib's longitude range
+            lims = [_value_in(v, "arcsec") * units.factor("arcsec", "deg") for v in self.sub_fov_window]
+            sel = (lon >= lims[0]) & (lon <= lims[1]) & (lat >= lims[2]) & (lat <= lims[3])
+            self.data_small[~sel] = np.nan
+        else:
+            raise ValueError("sub_fov_window must be a [lon_min * u.arcsec, lon_max * u.arcsec,"
+                             " lat_min * u.arcsec, lat_max * u.arcsec] or 'all' str ")
+        self.hdr_small["NAXIS1"] = self.data_small.shape[1]
+        self.hdr_small["NAXIS2"] = self.data_small.shape[0]

@@ -49,10 +49,11 @@ def shifted_pc(hdr, crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1, cdelt2):
     crot = np.where(d_crota != 0.0, crota_ref + d_crota, crota_ref)
     rho = np.deg2rad(crot)
     lam = cdelt2 / cdelt1
-    pc11 = np.where(change, np.cos(rho), hdr["PC1_1"])
-    pc22 = np.where(change, np.cos(rho), hdr["PC2_2"])
-    pc12 = np.where(change, -lam * np.sin(rho), hdr["PC1_2"])
-    pc21 = np.where(change, (1 / lam) * np.sin(rho), hdr["PC2_1"])
+    own = TanWcs.from_header(hdr)   # PCi_j as wcslib would read them (identity when absent)
+    pc11 = np.where(change, np.cos(rho), own.pc11)
+    pc22 = np.where(change, np.cos(rho), own.pc22)
+    pc12 = np.where(change, -lam * np.sin(rho), own.pc12)
+    pc21 = np.where(change, (1 / lam) * np.sin(rho), own.pc21)
     return pc11, pc12, pc21, pc22
 
 

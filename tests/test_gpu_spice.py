@@ -1,0 +1,80 @@
+"""GPU parity of the synthetic-raster builder (K6) and the SPICE helioprojective search (config 3 path)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+R_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def spice_case(tmp_path_factory):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from euispice_coreg_b200._synth.spice import make_spice_case, small_spice_spec
+    d = tmp_path_factory.mktemp("spice")
+    return make_spice_case(str(d), small_spice_spec(nbin2=8, pxbeg2=192), tag="toy") + (str(d),)
+
+
+def _load(path):
+    from euispice_coreg_b200._compat import fits_lite
+    h = fits_lite.open(path)[0]
+    return h.data, dict(h.header.items())
+
+
+def test_synras_matches_oracle(spice_case):
+    from euispice_coreg_b200._compat import fits_lite
+    from euispice_coreg_b200.synras import SPICEComposedMapBuilder
+    from oracle.synras import build_synras
+    p_spice, imagers, spec, d = spice_case
+    b = SPICEComposedMapBuilder(p_spice, imagers, threshold_time=100.0)
+    name = b.process(folder_path_output=d, basename_output="synras.fits", print_filename=False,
+                     return_synras_name=True)
+    assert name == os.path.join(d, "synras.fits") == b.get_path_to_composed_map()
+    out = fits_lite.open(name)[0]
+    _, h4 = _load(p_spice)
+    frames, hdrs = zip(*[_load(p) for p in imagers])
+    ref, chosen = build_synras(h4, frames, hdrs, 100.0)
+    assert len(set(chosen.tolist())) >= 3            # the raster really spans several imager frames
+    assert out.data.shape == ref.shape == (spec.n_y, spec.n_x) and out.data.dtype == np.float64
+    assert np.array_equal(np.isnan(out.data), np.isnan(ref))
+    assert np.nanmax(np.abs(out.data - ref) / np.abs(ref)) < 1e-10
+    # header: SPICE WCS keys in degrees on top of the middle imager header
+    assert out.header["CUNIT1"] == "deg" and out.header["CRVAL1"] == h4["CRVAL1"] * (1.0 / 3600.0)
+    assert out.header["CDELT2"] == h4["CDELT2"] * (1.0 / 3600.0) and out.header["PC1_2"] == h4["PC1_2"]
+    assert out.header["DATE-AVG"] == h4["DATE-AVG"] and out.header["SPECPATH"] == os.path.basename(p_spice)
+    with pytest.raises(ValueError):
+        SPICEComposedMapBuilder(p_spice, imagers, threshold_time=1.0).process(print_filename=False)
+
+
+def test_alignment_spice_parity_and_recovers_shift(spice_case):
+    from euispice_coreg_b200.hdrshift import AlignmentSpice
+    from euispice_coreg_b200.synras import SPICEComposedMapBuilder
+    from oracle.hpc import HpcSearch
+    from oracle.synras import spice_l2_image
+    p_spice, imagers, spec, d = spice_case
+    synras = SPICEComposedMapBuilder(p_spice, imagers, threshold_time=100.0).process(
+        folder_path_output=d, basename_output="synras2.fits", print_filename=False, return_synras_name=True)
+    lags = dict(lag_crval1=np.arange(-14, -1, 2.0), lag_crval2=np.arange(6, 19, 2.0), lag_cdelt1=[0], lag_cdelt2=[0],
+                lag_crota=[0])
+    a = AlignmentSpice(synras, p_spice, parallelism=True, small_fov_window=0, large_fov_window=-1, **lags)
+    gpu = a.align_using_helioprojective(return_type="corr")
+    d4, h4 = _load(p_spice)
+    img, hdr = spice_l2_image(d4, h4)
+    assert np.array_equal(np.isnan(img), np.isnan(a.data_small)) and np.nanmax(np.abs(img - a.data_small)) == 0.0
+    dl, hl = _load(synras)
+    # the reference's AlignmentSpice skips the PCi_j check; both headers carry PCi_j here so the oracle's check is a no-op
+    ref = HpcSearch(dl, hl, img, hdr, **lags).cube()
+    assert np.array_equal(np.isnan(gpu), np.isnan(ref))
+    assert np.nanmax(np.abs(gpu - ref)) <= R_TOL
+    am = np.unravel_index(np.nanargmax(gpu), gpu.shape)
+    assert am == np.unravel_index(np.nanargmax(ref), ref.shape)
+    assert (lags["lag_crval1"][am[0]], lags["lag_crval2"][am[1]]) == spec.true_shift
+    # wavelength interval + results object
+    a2 = AlignmentSpice(synras, p_spice, small_fov_window=0, wavelength_interval_to_sum=[97.68, 97.72], **lags)
+    res = a2.align_using_helioprojective()
+    img2, _ = spice_l2_image(d4, h4, (97.68, 97.72))
+    assert np.nanmax(np.abs(img2 - a2.data_small)) == 0.0 and not np.array_equal(img2, img, equal_nan=True)
+    assert abs(res.shift_arcsec[0] - spec.true_shift[0]) < 2.0 and abs(res.shift_arcsec[1] - spec.true_shift[1]) < 2.0
