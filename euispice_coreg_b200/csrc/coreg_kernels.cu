@@ -763,7 +763,10 @@ __global__ void synras_kernel(const T* __restrict__ frames, int fnx, int fny, co
     if (f >= 0) {
       double x, y, s;
       tan_world2pix_dev(wcs[f], lng[idx], lat[idx], x, y);
-      if (spline_sample<ORDER, true, T>(frames + (size_t)f * fnx * fny, fny, fnx, y, x, s)) v = s;
+      // interpol2d(dst=None) returns the imager's dtype (utils/Util.py:95-97): float32 frames give float32-rounded
+      // samples, which the reference then stores into its float64 raster
+      if (spline_sample<ORDER, true, T>(frames + (size_t)f * fnx * fny, fny, fnx, y, x, s))
+        v = (sizeof(T) == 4) ? (double)__double2float_rn(s) : s;
     }
     out[idx] = v;
   }

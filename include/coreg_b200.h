@@ -162,7 +162,8 @@ int coreg_offset_lag_corr(const double* ref_dev, const void* small_dev, int smal
  * Replaces the column loop of SPICEComposedMapBuilder._create_map_from_hdu (synras/map_builder.py:95-131):
  * output pixel (row j, column i) = order-k sample of imager frame frame_of_col[i] at the pixel position of the sky
  * point (lng[j,i], lat[j,i]) under that frame's TAN WCS; NaN outside. frames_dev: [n_frames][fny][fnx] float32/64,
- * wcs_host: [n_frames]; frame_of_col_host: [n_cols] (negative = column left NaN). out_dev float64 [n_rows*n_cols]. */
+ * wcs_host: [n_frames]; frame_of_col_host: [n_cols] (negative = column left NaN). out_dev float64 [n_rows*n_cols];
+ * with float32 frames every sample is rounded to float32 first, as interpol2d(dst=None) returns the image dtype. */
 int coreg_synras_build(const void* frames_dev, int frame_dtype, int n_frames, int fnx, int fny,
                        const CoregTanWcs* wcs_host, const int* frame_of_col_host, const double* lng_dev,
                        const double* lat_dev, int n_rows, int n_cols, int order, double* out_dev, void* stream);
