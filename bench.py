@@ -168,7 +168,9 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
     pl, ps = ensure_config1(rank, barrier)
@@ -253,12 +255,14 @@ def run_gpu(args):
     h2d = a.data_large.nbytes + small_bytes + table[lo:hi].nbytes
     d2h = n_lags * 8
 
+    # full public API once on every rank (FITS read + host prep + sharded search + all-gather + Gaussian fit):
+    # the "align() wall time" metric. It contains a collective, so all ranks take part.
+    barrier()
+    t0 = time.perf_counter()
+    res = Alignment(pl, ps, parallelism=True, **LAGS).align_using_helioprojective()
+    torch.cuda.synchronize()
+    align_wall = time.perf_counter() - t0
     if rank == 0:
-        # full public API once (FITS read + host prep + search + Gaussian fit), for the "align() wall time" metric
-        t0 = time.perf_counter()
-        res = Alignment(pl, ps, parallelism=True, **LAGS).align_using_helioprojective()
-        torch.cuda.synchronize()
-        align_wall = time.perf_counter() - t0
         am = tuple(int(v) for v in res.max_index[:2])
         best = (float(LAGS["lag_crval1"][am[0]]), float(LAGS["lag_crval2"][am[1]]))
         assert np.array_equal(np.nan_to_num(cube), np.nan_to_num(res.corr.ravel())), "e2e cube != public API cube"
