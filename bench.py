@@ -187,11 +187,13 @@ def run_gpu(args):
     gny, gnx = a.data_small.shape
     n_pix = gnx * gny
 
-    eng = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage)
+    eng = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage,
+                            no_fast=args.no_fast)
     eng.set_small(a.data_small)
     eng.prepare_hpc(a.data_large, w_large, w_small)
     chunk, bounds = E.shard_bounds(n_lags, world)
     lo, hi = bounds[rank]
+    eng.flags = _ext.make_flags(args.strict, args.variant, small_angle=eng._small_angle(table), no_fast=args.no_fast)
     tab_dev = eng._upload(table[lo:hi])
     local_out = torch.full((chunk,), float("nan"), dtype=torch.float64, device=eng.device)
     full = torch.empty(chunk * world, dtype=torch.float64, device=eng.device)
@@ -233,7 +235,8 @@ def run_gpu(args):
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_step():
-        e = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage)
+        e = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage,
+                              no_fast=args.no_fast)
         e.set_small(h_small)
         e.prepare_hpc(h_large, w_large, w_small)
         return e.search(table)
@@ -285,7 +288,7 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "lags": n_lags, "grid": [gny, gnx], "spline_order": 2,
-                       "arithmetic": "strict (scipy op order)" if args.strict else "fp64 fma", "variant": args.variant, "small_storage": str(eng.small.dtype).replace("torch.", ""),
+                       "arithmetic": "strict (scipy op order)" if args.strict else "fp64 fma", "variant": args.variant, "kernel": "generic" if (args.no_fast or args.strict) else "fast", "small_storage": str(eng.small.dtype).replace("torch.", ""),
                        "parallelism": f"lag-sharded x{world}",
                        "l2": "no explicit flush: per-step working set (images+planes+partials workspace "
                              f"{(eng._work.numel() * 8 + 3 * n_pix * 8 + n_pix * 4 + small_bytes) / 1e6:.0f} MB) "
@@ -328,6 +331,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--strict", action="store_true", help="scipy operation order in the spline (no FMA)")
     ap.add_argument("--variant", type=int, default=0, help="kernel tuning variant (tile/occupancy)")
+    ap.add_argument("--no-fast", action="store_true", help="force the generic fused kernel")
     ap.add_argument("--small-storage", default="f64", choices=["auto", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -17,11 +17,15 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
 
 F32, F64 = 0, 1
 FLAG_STRICT = 1
+FLAG_SMALL_ANGLE = 2
+FLAG_NO_FAST = 4
 
 
-def make_flags(strict=False, variant=0):
-    """flags word of the lag kernels: bit 0 strict scipy op order, bits 8..11 tuning variant."""
-    return (FLAG_STRICT if strict else 0) | ((int(variant) & 15) << 8)
+def make_flags(strict=False, variant=0, small_angle=False, no_fast=False):
+    """flags word of the lag kernels: bit 0 strict scipy op order, bit 1 small-angle guarantee (fast TAN kernel),
+    bit 2 force the generic kernel, bits 8..11 tuning variant."""
+    return ((FLAG_STRICT if strict else 0) | (FLAG_SMALL_ANGLE if small_angle else 0)
+            | (FLAG_NO_FAST if no_fast else 0) | ((int(variant) & 15) << 8))
 
 
 class CoregLibraryError(RuntimeError):

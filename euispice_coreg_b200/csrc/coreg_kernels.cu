@@ -14,6 +14,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -385,7 +386,12 @@ constexpr int kRowsPerPass = kThreads / kTileW;  // 4 grid rows per pass of the 
 constexpr int kWarps = kThreads / 32;
 constexpr int kLagSub = 64;   // lags staged in shared memory at a time
 constexpr int kMom = 8;       // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
-constexpr int kMinTileH = 16; // smallest tile height of any variant (workspace sizing)
+constexpr int kMinTileH = 8;  // smallest tile height of any variant (workspace sizing)
+
+inline size_t partials_bytes(int gnx, int gny, int64_t n_lags) {
+  const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kMinTileH - 1) / kMinTileH);
+  return tiles * (size_t)n_lags * kMom * sizeof(double);
+}
 
 struct TanCoord {
   typedef CoregLagTan Lag;
@@ -592,6 +598,317 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast variant of the fused lag kernel: order-2 spline, FMA arithmetic, float64 small image.
+//  * coordinates come out already offset by +0.5 so that floor(x + 0.5) is one magic-number add;
+//  * TAN: the reciprocal of the gnomonic denominator D = cos(angular distance to the lag's reference point) is the
+//    product form of the geometric series (1+e)(1+e^2)(1+e^4), e = 1 - D, exact to 2^-56 for |e| <= 2^-7
+//    (7.1 deg) -- the caller guarantees that bound (COREG_FLAG_SMALL_ANGLE, checked on the host from the FOV);
+//  * "strictly interior" (all taps inside the image, so no closed-bound test and no mirroring) is one unsigned
+//    integer compare per axis on the floor index; the PPT pixels of a thread take the branch-free path together,
+//    anything else (image borders, missing reference pixels, NaN coordinates) falls back to the exact generic
+//    per-pixel code, so results differ from the generic kernel only by FMA-level rounding.
+// ---------------------------------------------------------------------------------------------------------
+// Fast-path lag constants of the helioprojective search: with u = (sin lat, cos lat sin A, cos lat cos A) the unit
+// vector of a pixel's sky direction (the three trig planes), the gnomonic map of a lag's header is one 3x3 matrix
+// per lag followed by a perspective divide:  (nx, ny, D) = R u,  x = x0 + nx / D,  y = y0 + ny / D.
+// R is built once per lag from CoregLagTan by tan_fast_table_kernel (rows: nx, ny, D; then x0 + 0.5, y0 + 0.5).
+struct TanFastLag {
+  double a0, a1, a2, b0, b1, b2, d0, d1, d2, x0h, y0h, pad;
+};
+
+__global__ void tan_fast_table_kernel(const CoregLagTan* __restrict__ lags, int n, TanFastLag* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const CoregLagTan L = lags[i];
+  TanFastLag f;
+  // qs = p1 cda - p2 sda ; pc = p2 cda + p1 sda ; D = pc cd0 + p0 sd0 ; en = p0 cd0 - pc sd0
+  // nx = m11 qs + m12 en ; ny = m21 qs + m22 en
+  f.a0 = L.m12 * L.cos_d0;
+  f.a1 = L.m11 * L.cos_da - L.m12 * L.sin_da * L.sin_d0;
+  f.a2 = -L.m11 * L.sin_da - L.m12 * L.cos_da * L.sin_d0;
+  f.b0 = L.m22 * L.cos_d0;
+  f.b1 = L.m21 * L.cos_da - L.m22 * L.sin_da * L.sin_d0;
+  f.b2 = -L.m21 * L.sin_da - L.m22 * L.cos_da * L.sin_d0;
+  f.d0 = L.sin_d0;
+  f.d1 = L.sin_da * L.cos_d0;
+  f.d2 = L.cos_da * L.cos_d0;
+  f.x0h = L.x0 + 0.5;
+  f.y0h = L.y0 + 0.5;
+  f.pad = 0.0;
+  out[i] = f;
+}
+
+struct TanFast {
+  typedef TanCoord Base;
+  typedef TanFastLag LagC;
+  __device__ static __forceinline__ void map_half(const TanCoord::Pix& q, const LagC& L, double& sx, double& sy) {
+    const double den = fma(q.p2, L.d2, fma(q.p1, L.d1, q.p0 * L.d0));
+    const double nx = fma(q.p2, L.a2, fma(q.p1, L.a1, q.p0 * L.a0));
+    const double ny = fma(q.p2, L.b2, fma(q.p1, L.b1, q.p0 * L.b0));
+    // 1/D for |1 - D| <= 2^-7: (1+e)(1+e^2)(1+e^4), e = 1 - D
+    const double e = 1.0 - den;
+    const double e2 = e * e;
+    double inv = 1.0 + e;
+    inv = fma(e2, inv, inv);
+    const double e4 = e2 * e2;
+    inv = fma(e4, inv, inv);
+    sx = fma(nx, inv, L.x0h);
+    sy = fma(ny, inv, L.y0h);
+  }
+};
+
+struct OffsetFastLag {
+  double x0h, y0h;
+};
+
+__global__ void offset_fast_table_kernel(const CoregLagOffset* __restrict__ lags, int n, OffsetFastLag* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  OffsetFastLag f;
+  f.x0h = lags[i].x0 + 0.5;
+  f.y0h = lags[i].y0 + 0.5;
+  out[i] = f;
+}
+
+struct OffsetFast {
+  typedef OffsetCoord Base;
+  typedef OffsetFastLag LagC;
+  __device__ static __forceinline__ void map_half(const OffsetCoord::Pix& q, const LagC& L, double& sx, double& sy) {
+    sx = L.x0h + q.tx;
+    sy = L.y0h + q.ty;
+  }
+};
+
+// butterfly for 4 values: every lane ends with the warp total of value index (lane >> 3) & 3 (6 shuffles)
+__device__ __forceinline__ double warp_transpose_reduce4(double (&v)[4], int lane) {
+  double w2[2], w1;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double send = up ? v[i] : v[i + 2];
+      const double keep = up ? v[i + 2] : v[i];
+      w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+    const double send = up ? w2[0] : w2[1];
+    const double keep = up ? w2[1] : w2[0];
+    w1 = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 4);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  return w1;  // value index = 2*bit4 + bit3
+}
+
+constexpr int kFastLagSub = 16;  // lags per shared-memory stage of the fast kernel (small: leaves L1 to the taps)
+
+template <class Fast, typename SmallT, typename RefT, bool ROUND32, int PPT, int MINB, int GROUP>
+__global__ void __launch_bounds__(kThreads, MINB)
+lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, int snx, int sny, int gnx, int gny,
+                     typename Fast::Base::Planes planes, const typename Fast::Base::Lag* __restrict__ lags,
+                     const typename Fast::LagC* __restrict__ fast_lags, int n_lags, int lags_per_block,
+                     const double* __restrict__ pivots, double* __restrict__ work) {
+  typedef typename Fast::Base Coord;
+  typedef typename Coord::Lag Lag;
+  typedef typename Coord::Pix Pix;
+  typedef typename Fast::LagC LagC;
+  constexpr int TILE_H = kRowsPerPass * PPT;
+  // GROUP = pixels whose dependency chains are interleaved (their coordinates / indices are live together)
+  static_assert(PPT % GROUP == 0, "PPT must be a multiple of GROUP");
+  __shared__ __align__(16) LagC s_lag[kFastLagSub];
+  __shared__ double s_part[kWarps][kFastLagSub][kMom];
+
+  const int tiles_x = (gnx + kTileW - 1) / kTileW;
+  const int tile = blockIdx.x;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & (kTileW - 1), ty0 = tid / kTileW;
+  const int gx = tile_x * kTileW + tx;
+  const double pivot_a = pivots[0], pivot_b = pivots[1];
+  const unsigned ux = (unsigned)(snx - 2), uy = (unsigned)(sny - 2);  // launcher guarantees snx, sny >= 3
+  const size_t row_bytes = (size_t)snx * sizeof(SmallT);
+
+  Pix pix[PPT];
+  double a_c[PPT];
+  unsigned a_ok = 0;
+  double sa_all = 0.0, saa_all = 0.0;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int gy = tile_y * TILE_H + ty0 + k * kRowsPerPass;
+    a_c[k] = 0.0;
+    pix[k] = Coord::dead();
+    if (gx < gnx && gy < gny) {
+      const int64_t idx = (int64_t)gy * gnx + gx;
+      const double a = (double)ref[idx];
+      if (isfinite(a)) {
+        a_c[k] = a - pivot_a;
+        a_ok |= 1u << k;
+        pix[k] = Coord::load(planes, idx);
+        sa_all += a_c[k];
+        saa_all = fma(a_c[k], a_c[k], saa_all);
+      }
+    }
+  }
+  const int n_all = __popc(a_ok);
+  // warp totals of the lag-independent reference moments (used when no sample of the warp is missing)
+  double wsa = sa_all, wsaa = saa_all;
+  int wn = n_all;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
+    wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
+    wn += __shfl_xor_sync(0xffffffffu, wn, o);
+  }
+
+  const int lag_begin = blockIdx.y * lags_per_block;
+  const int lag_end = min(n_lags, lag_begin + lags_per_block);
+  for (int l0 = lag_begin; l0 < lag_end; l0 += kFastLagSub) {
+    const int cnt = min(kFastLagSub, lag_end - l0);
+    __syncthreads();
+    {
+      const double* src = reinterpret_cast<const double*>(fast_lags + l0);
+      double* dst = reinterpret_cast<double*>(s_lag);
+      const int nd = cnt * (int)(sizeof(LagC) / sizeof(double));
+      for (int i = tid; i < nd; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (int l = 0; l < cnt; ++l) {
+      const LagC C = s_lag[l];
+      double sb = 0.0, sbb = 0.0, sab = 0.0, sa_miss = 0.0, saa_miss = 0.0;
+      int n_miss = 0;
+#pragma unroll
+      for (int g = 0; g < PPT; g += GROUP) {
+        // phase A: coordinates (+0.5), floor indices, fractional parts; branch-free
+        double vx[GROUP], vy[GROUP];
+        int ix[GROUP], iy[GROUP];
+        bool interior = true;
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+          double sx, sy;
+          Fast::map_half(pix[g + j], C, sx, sy);
+          const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+          ix[j] = __double2loint(mx);
+          iy[j] = __double2loint(my);
+          vx[j] = sx - (mx - kMagic);   // = d + 0.5 in [0, 1)
+          vy[j] = sy - (my - kMagic);
+          interior = interior && ((unsigned)(ix[j] - 1) < ux) && ((unsigned)(iy[j] - 1) < uy);
+        }
+        if (interior) {
+          // phase B: weights, 9 taps, float32 rounding, moments
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j) {
+            // order-2 B-spline weights from v = d + 0.5: w2 = v^2/2, w0 = w2 - d, w1 = 1 - w0 - w2
+            const double wx2 = (0.5 * vx[j]) * vx[j];
+            const double wx0 = (wx2 + 0.5) - vx[j];
+            const double wx1 = fma(-2.0, wx2, vx[j] + 0.5);
+            const double wy2 = (0.5 * vy[j]) * vy[j];
+            const double wy0 = (wy2 + 0.5) - vy[j];
+            const double wy1 = fma(-2.0, wy2, vy[j] + 0.5);
+            const char* p0 = reinterpret_cast<const char*>(small + ((iy[j] - 1) * snx + (ix[j] - 1)));
+            const SmallT* r0p = reinterpret_cast<const SmallT*>(p0);
+            const SmallT* r1p = reinterpret_cast<const SmallT*>(p0 + row_bytes);
+            const SmallT* r2p = reinterpret_cast<const SmallT*>(p0 + 2 * row_bytes);
+            const double r0 = fma(ldval(r0p + 2), wx2, fma(ldval(r0p + 1), wx1, ldval(r0p) * wx0));
+            const double r1 = fma(ldval(r1p + 2), wx2, fma(ldval(r1p + 1), wx1, ldval(r1p) * wx0));
+            const double r2 = fma(ldval(r2p + 2), wx2, fma(ldval(r2p + 1), wx1, ldval(r2p) * wx0));
+            const double t = fma(r2, wy2, fma(r1, wy1, r0 * wy0));
+            double b;
+            bool ok;
+            if (ROUND32) {
+              const float bf = __double2float_rn(t);
+              ok = isfinite(bf);
+              b = (double)bf;
+            } else {
+              ok = isfinite(t) && (t != -32762.0);
+              b = t;
+            }
+            if (ok) {
+              const double bc = b - pivot_b;
+              sb += bc;
+              sbb = fma(bc, bc, sbb);
+              sab = fma(a_c[g + j], bc, sab);
+            } else {
+              ++n_miss;   // interior => the reference pixel is present (dead pixels carry NaN coordinates)
+              sa_miss += a_c[g + j];
+              saa_miss = fma(a_c[g + j], a_c[g + j], saa_miss);
+            }
+          }
+        } else {
+          // generic exact path (image borders, missing reference pixels)
+          const Lag L = lags[l0 + l];
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j) {
+            double x, y, v;
+            Coord::map(pix[g + j], L, x, y);
+            bool ok = spline_sample<2, false, SmallT>(small, sny, snx, y, x, v);
+            double b;
+            if (ROUND32) {
+              const float bf = __double2float_rn(v);
+              ok = ok && isfinite(bf);
+              b = (double)bf;
+            } else {
+              ok = ok && isfinite(v) && (v != -32762.0);
+              b = v;
+            }
+            if (ok) {
+              const double bc = b - pivot_b;
+              sb += bc;
+              sbb = fma(bc, bc, sbb);
+              sab = fma(a_c[g + j], bc, sab);
+            } else if (a_ok & (1u << (g + j))) {
+              ++n_miss;
+              sa_miss += a_c[g + j];
+              saa_miss = fma(a_c[g + j], a_c[g + j], saa_miss);
+            }
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, n_miss != 0)) {
+        double m[8];
+        m[0] = (double)(n_all - n_miss);
+        m[1] = sa_all - sa_miss;
+        m[2] = sb;
+        m[3] = saa_all - saa_miss;
+        m[4] = sbb;
+        m[5] = sab;
+        m[6] = 0.0;
+        m[7] = 0.0;
+        const double tot = warp_transpose_reduce8(m, lane);
+        if ((lane & 3) == 0) s_part[warp][l][lane >> 2] = tot;
+      } else {
+        // common case: nothing missing in this warp -> only the three lag-dependent sums need the butterfly
+        double m[4];
+        m[0] = sb;
+        m[1] = sbb;
+        m[2] = sab;
+        m[3] = 0.0;
+        const double tot = warp_transpose_reduce4(m, lane);
+        if ((lane & 7) == 0) {
+          const int q = lane >> 3;  // 0: Sb, 1: Sbb, 2: Sab, 3: unused
+          if (q < 3) s_part[warp][l][q == 0 ? 2 : (q == 1 ? 4 : 5)] = tot;
+        }
+        if (lane == 1) s_part[warp][l][0] = (double)wn;
+        if (lane == 2) s_part[warp][l][1] = wsa;
+        if (lane == 3) s_part[warp][l][3] = wsaa;
+        if (lane == 4) s_part[warp][l][6] = 0.0;
+        if (lane == 5) s_part[warp][l][7] = 0.0;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < cnt * kMom; i += kThreads) {
+      const int l = i / kMom, q = i % kMom;
+      double s = s_part[0][l][q];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) s += s_part[w][l][q];
+      work[((size_t)tile * n_lags + (l0 + l)) * kMom + q] = s;
+    }
+  }
+}
+
 // one block per lag: sum the tile partials in a fixed order, moments -> Pearson r
 __global__ void __launch_bounds__(128)
 lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lags, double* __restrict__ corr,
@@ -629,6 +946,73 @@ lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lag
 }
 
 // tuning variants (flags bits 8..11): tile height = 4*PPT, MINB resident blocks per SM
+template <class Coord> struct FastOf;
+template <> struct FastOf<TanCoord> { typedef TanFast type; };
+template <> struct FastOf<OffsetCoord> { typedef OffsetFast type; };
+
+// grid for a (ppt, minb) variant; returns false when the lag list does not fit one launch
+inline bool lag_grid(int ppt, int minb, int gnx, int gny, int64_t n_lags, int sms, dim3* grid, int* lags_per_block,
+                     int* tiles_out) {
+  const int tile_h = kRowsPerPass * ppt;
+  const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
+  *tiles_out = tiles;
+  const int want_blocks = sms * minb * 4;   // a few waves of resident blocks
+  int splits = (want_blocks + tiles - 1) / tiles;
+  const int max_splits = (int)((n_lags + kLagSub - 1) / kLagSub);
+  splits = std::max(1, std::min(splits, max_splits));
+  int lpb = (int)((n_lags + splits - 1) / splits);
+  lpb = ((lpb + kLagSub - 1) / kLagSub) * kLagSub;
+  splits = (int)((n_lags + lpb - 1) / lpb);
+  if (splits > 65535) return false;
+  *grid = dim3(tiles, splits);
+  *lags_per_block = lpb;
+  return true;
+}
+
+inline void build_fast_table(const CoregLagTan* lags, int n, TanFastLag* out, cudaStream_t s) {
+  tan_fast_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(lags, n, out);
+}
+inline void build_fast_table(const CoregLagOffset* lags, int n, OffsetFastLag* out, cudaStream_t s) {
+  offset_fast_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(lags, n, out);
+}
+
+template <class Coord, typename SmallT, typename RefT, bool ROUND32>
+int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
+                    const SmallT* small, int snx, int sny, typename Coord::Planes planes,
+                    const typename Coord::Lag* lags, const double* pivots, double* w, void* fast_table,
+                    int* tiles_out) {
+  typedef typename FastOf<Coord>::type Fast;
+  typedef typename Fast::LagC LagC;
+  // (pixels per thread, resident CTAs per SM, interleave group); 0 = fastest measured on config 1
+  static const int kVar[10][3] = {{4, 3, 2}, {8, 2, 2}, {4, 2, 2}, {2, 3, 2}, {4, 4, 2},
+                                  {2, 4, 2}, {6, 2, 2}, {6, 3, 2}, {4, 2, 4}, {4, 3, 1}};
+  if (variant < 0 || variant > 9) variant = 0;
+  const int ppt = kVar[variant][0], minb = kVar[variant][1];
+  dim3 grid;
+  int lpb;
+  if (!lag_grid(ppt, minb, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out))
+    return fail(COREG_EINVAL, "lag grid too large for one launch");
+  LagC* ft = static_cast<LagC*>(fast_table);
+  build_fast_table(lags, (int)n_lags, ft, s);
+#define LF(PPT_, MINB_, G_)                                                                     \
+  lag_corr_fast_kernel<Fast, SmallT, RefT, ROUND32, PPT_, MINB_, G_><<<grid, kThreads, 0, s>>>( \
+      ref, small, snx, sny, gnx, gny, planes, lags, ft, (int)n_lags, lpb, pivots, w)
+  switch (variant) {
+    case 1: LF(8, 2, 2); break;
+    case 2: LF(4, 2, 2); break;
+    case 3: LF(2, 3, 2); break;
+    case 4: LF(4, 4, 2); break;
+    case 5: LF(2, 4, 2); break;
+    case 6: LF(6, 2, 2); break;
+    case 7: LF(6, 3, 2); break;
+    case 8: LF(4, 2, 4); break;
+    case 9: LF(4, 3, 1); break;
+    default: LF(4, 3, 2); break;
+  }
+#undef LF
+  return COREG_OK;
+}
+
 template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
 int launch_lag_variant(int variant, dim3 grid_tiles_of, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s,
                        const RefT* ref, const SmallT* small, int snx, int sny, typename Coord::Planes planes,
@@ -689,6 +1073,26 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
     CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
   int tiles = 0, rc = COREG_OK;
+  // fast kernel: order 2, FMA arithmetic, float64 small image of at least 3x3; TAN additionally needs the
+  // caller's small-angle guarantee (the offset functor has no reciprocal)
+  const bool fast_ok = (order == 2) && !strict && snx >= 3 && sny >= 3 &&
+                       !(flags & COREG_FLAG_NO_FAST) &&
+                       (std::is_same<Coord, OffsetCoord>::value || (flags & COREG_FLAG_SMALL_ANGLE));
+  if (fast_ok) {
+    // the per-lag fast table lives in the tail of the workspace (after the [tiles][lags][8] partials)
+    char* tail = static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags);
+    rc = launch_lag_fast<Coord, SmallT, RefT, ROUND32>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny, planes,
+                                                       lags, pivots, w, tail, &tiles);
+    if (rc) return rc;
+    CK_LAUNCH("lag_corr_fast_kernel");
+    if (prof) {
+      CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+      ++g_prof_n;
+    }
+    lag_corr_finalize_kernel<<<(unsigned)n_lags, 128, 0, s>>>(w, tiles, (int)n_lags, corr, nvalid);
+    CK_LAUNCH("lag_corr_finalize_kernel");
+    return COREG_OK;
+  }
 #define LAUNCH(ORD, STR)                                                                                          \
   rc = launch_lag_variant<Coord, ORD, STR, SmallT, RefT, ROUND32>(variant, dim3(), gnx, gny, n_lags, sms, s, ref, \
                                                                    small, snx, sny, planes, lags, pivots, w, &tiles)
@@ -872,8 +1276,7 @@ int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void*
 
 size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags) {
   if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;
-  const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kMinTileH - 1) / kMinTileH);
-  return tiles * (size_t)n_lags * kMom * sizeof(double);
+  return partials_bytes(gnx, gny, n_lags) + (size_t)n_lags * sizeof(TanFastLag);
 }
 
 int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,

@@ -145,7 +145,9 @@ class LagSearchEngine:
 
     max_workspace_bytes = 1 << 30
 
-    def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64"):
+    small_angle_limit_deg = 6.5   # the fast TAN kernel's reciprocal series is exact to 2^-56 within 7.1 deg
+
+    def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64", no_fast=False):
         torch = _torch()
         _ext.load()  # fail loudly when the CUDA library is missing
         if not torch.cuda.is_available():
@@ -153,7 +155,9 @@ class LagSearchEngine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.order = int(order)
         self.strict = bool(strict)
-        self.flags = _ext.make_flags(strict, variant)
+        self.variant, self.no_fast = int(variant), bool(no_fast)
+        self.flags = _ext.make_flags(strict, variant, no_fast=no_fast)
+        self.fov_radius_deg = None
         self.small_storage = small_storage
         self.pivots = torch.zeros(2, dtype=torch.float64, device=self.device)
         self.ref = None        # large image on the common grid
@@ -198,8 +202,27 @@ class LagSearchEngine:
             del d_large, x, y
             self.planes = _ext.tan_trig_planes(lng, lat, wcs_small.crval1)
             self.alpha_ref_deg = wcs_small.crval1
+            self.delta_ref_deg = wcs_small.crval2
             _ext.finite_mean(self.ref, self.pivots[0:1])
+        # largest angular distance of a common-grid pixel from the unshifted reference point (corners suffice for a
+        # convex gnomonic footprint)
+        cx = np.array([0.0, wcs_small.naxis1 - 1.0, 0.0, wcs_small.naxis1 - 1.0])
+        cy = np.array([0.0, 0.0, wcs_small.naxis2 - 1.0, wcs_small.naxis2 - 1.0])
+        lon, lat = wcs_small.pixel_to_world(cx, cy)
+        cosd = (np.sin(lat * D2R) * math.sin(wcs_small.crval2 * D2R)
+                + np.cos(lat * D2R) * math.cos(wcs_small.crval2 * D2R) * np.cos((lon - wcs_small.crval1) * D2R))
+        self.fov_radius_deg = float(np.max(np.arccos(np.clip(cosd, -1.0, 1.0))) * R2D)
         self.frame = "hpc"
+
+    def _small_angle(self, table):
+        """True when every (pixel, lag) pair is within `small_angle_limit_deg` of the lag's reference point:
+        FOV radius + largest displacement of the reference point over the lag table (triangle inequality)."""
+        if self.fov_radius_deg is None:
+            return False
+        da = np.abs(np.arctan2(table[:, 0], table[:, 1])) * R2D
+        d0 = np.abs(np.arctan2(table[:, 2], table[:, 3]) * R2D - self.delta_ref_deg)
+        shift = float(np.max(da + d0)) if table.shape[0] else 0.0
+        return bool(np.isfinite(shift) and self.fov_radius_deg + shift < self.small_angle_limit_deg)
 
     # ---- Carrington --------------------------------------------------------------------------------
     @staticmethod
@@ -291,6 +314,9 @@ class LagSearchEngine:
         dist, rank, world = _dist_info()
         chunk, bounds = shard_bounds(n, world)
         lo, hi = bounds[rank]
+        if self.frame == "hpc":
+            self.flags = _ext.make_flags(self.strict, self.variant, small_angle=self._small_angle(table),
+                                         no_fast=self.no_fast)
         with torch.cuda.device(self.device):
             local = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
             nvalid = torch.zeros(chunk, dtype=torch.int64, device=self.device) if return_nvalid else None

@@ -37,6 +37,13 @@ extern "C" {
  * COREG_FLAG_STRICT: scipy's exact operation order (separate multiply / add), bit-faithful per sample.
  * bits 8..11: tuning variant of the fused kernel (0 = default tile / occupancy). */
 #define COREG_FLAG_STRICT 1
+/* COREG_FLAG_SMALL_ANGLE (helioprojective kernel): the caller guarantees that every common-grid pixel lies within
+ * 7 degrees of every lag's reference point (CRVAL of the shifted header). It enables the fast order-2 kernel, whose
+ * gnomonic reciprocal is a 3-factor geometric-series product exact to 2^-56 under that bound. Always true for
+ * HRIEUV/FSI/SPICE fields; euispice_coreg_b200.hdrshift.engine checks it from the header geometry. */
+#define COREG_FLAG_SMALL_ANGLE 2
+/* COREG_FLAG_NO_FAST: force the generic kernel (testing / comparison). */
+#define COREG_FLAG_NO_FAST 4
 #define COREG_FLAG_VARIANT(v) (((v) & 15) << 8)
 
 /* Constants of a 2-axis gnomonic (TAN) WCS. Replaces `astropy.wcs.WCS(hdr)`:

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--variants", default="0,1,2,3")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--out", default="gpurun_out/k1_tune.json")
+    ap.add_argument("--only-fast", action="store_true")
     args = ap.parse_args()
     pl, ps = bench.ensure_config1()
     a = Alignment(pl, ps, parallelism=True, **bench.LAGS)
@@ -34,12 +35,16 @@ def main():
     table, _ = E.tan_lag_table(a.hdr_small, a, *d, w_small.crval1)
     results = []
     base = None
-    for storage in ("auto", "f64"):
-        for strict in (False, True):
+    combos = (("f64", False, False), ("f64", False, True), ("f64", True, True))
+    if args.only_fast:
+        combos = (("f64", False, False),)
+    for storage, strict, no_fast in combos:
+        if True:
             for v in [int(x) for x in args.variants.split(",")]:
-                eng = E.LagSearchEngine(order=2, strict=strict, variant=v, small_storage=storage)
+                eng = E.LagSearchEngine(order=2, strict=strict, variant=v, small_storage=storage, no_fast=no_fast)
                 eng.set_small(a.data_small)
                 eng.prepare_hpc(a.data_large, w_large, w_small)
+                eng.flags = _ext.make_flags(strict, v, small_angle=eng._small_angle(table), no_fast=no_fast)
                 tab = eng._upload(table)
                 out = torch.empty(table.shape[0], dtype=torch.float64, device=eng.device)
                 eng.evaluate(tab, out)
@@ -51,7 +56,7 @@ def main():
                 c = out.cpu().numpy()
                 if base is None:
                     base = c
-                rec = {"storage": storage, "strict": strict, "variant": v, "k1_ms": ms / n,
+                rec = {"storage": storage, "strict": strict, "fast_kernel": not (no_fast or strict), "variant": v, "k1_ms": ms / n,
                        "max_abs_diff_vs_first": float(np.nanmax(np.abs(c - base))),
                        "argmax": int(np.nanargmax(c))}
                 print(json.dumps(rec), flush=True)
