@@ -182,8 +182,6 @@ def run_gpu(args):
     a._set_initial_header_values(True)
     w_small, w_large = TanWcs.from_header(a.hdr_small), TanWcs.from_header(a.hdr_large)
     d = E.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
-    table, _ = E.tan_lag_table(a.hdr_small, a, *d, w_small.crval1)
-    n_lags = table.shape[0]
     gny, gnx = a.data_small.shape
     n_pix = gnx * gny
 
@@ -191,9 +189,13 @@ def run_gpu(args):
                             no_fast=args.no_fast)
     eng.set_small(a.data_small)
     eng.prepare_hpc(a.data_large, w_large, w_small)
+    table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
+    n_lags = table.shape[0]
+    fast = table.shape[1] == _ext.TAN_WCS_DOUBLES
     chunk, bounds = E.shard_bounds(n_lags, world)
     lo, hi = bounds[rank]
-    eng.flags = _ext.make_flags(args.strict, args.variant, small_angle=eng._small_angle(table), no_fast=args.no_fast)
+    eng.flags = _ext.make_flags(args.strict, args.variant, small_angle=fast and eng._small_angle(table),
+                                no_fast=args.no_fast)
     tab_dev = eng._upload(table[lo:hi])
     local_out = torch.full((chunk,), float("nan"), dtype=torch.float64, device=eng.device)
     full = torch.empty(chunk * world, dtype=torch.float64, device=eng.device)

@@ -42,6 +42,7 @@ class CoregCarrington(C.Structure):
 
 
 LAG_TAN_DOUBLES = 10    # sizeof(CoregLagTan) / 8
+TAN_WCS_DOUBLES = 11    # sizeof(CoregTanWcs) / 8
 LAG_OFFSET_DOUBLES = 2  # sizeof(CoregLagOffset) / 8
 
 _P = C.c_void_p
@@ -58,13 +59,15 @@ _SIGNATURES = {
     "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
+                                         _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
                                         C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_synras_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                      C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
-    "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
-                                        C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
     "coreg_fp64_peak": (C.c_int, [C.POINTER(C.c_double), C.c_int, _P]),
     "coreg_profile_begin": (C.c_int, []),
     "coreg_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -221,6 +224,24 @@ def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
                                       int(flags), _stream()), "coreg_hpc_lag_corr")
 
 
+def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_out, nvalid_out=None, flags=0):
+    """K1, homography form. `lag_wcs`: device float64 [n_lags, 11] (CoregTanWcs rows of the shifted headers);
+    `grid_wcs`: `_compat.wcs.TanWcs` of the common grid."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(ref, small, lag_wcs, pivots, work, corr_out)
+    if ref.dtype != torch.float32:
+        raise TypeError("ref must be float32 (the reference keeps the cut large image in float32)")
+    gny, gnx = ref.shape
+    g = tan_struct(grid_wcs)
+    with torch.cuda.device(ref.device):
+        _check(lib.coreg_hpc_lag_corr_wcs(_ptr(ref), _ptr(small), _dt(small), small.shape[1], small.shape[0], gnx, gny,
+                                          C.byref(g), _ptr(lag_wcs), lag_wcs.shape[0], int(order), _ptr(pivots),
+                                          _ptr(work), work.numel() * work.element_size(), _ptr(corr_out),
+                                          _ptr(nvalid_out) if nvalid_out is not None else None, int(flags),
+                                          _stream()), "coreg_hpc_lag_corr_wcs")
+
+
 def carrington_planes(c: CoregCarrington, sinlon, coslon, sinlat, coslat):
     torch = _torch()
     lib = load()
@@ -267,21 +288,32 @@ def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):
     return out
 
 
-def hpc_search_host(large, wcs_large, small, wcs_small, lags, order=2, flags=0):
-    """Whole helioprojective search from HOST numpy buffers (the C caller's entry point)."""
+def _np_dt(a):
+    if a.dtype == np.float32:
+        return F32
+    if a.dtype == np.float64:
+        return F64
+    raise TypeError(f"unsupported dtype {a.dtype}")
+
+
+def hpc_search_host(large, wcs_large, small, wcs_small, lag_wcs, order=2, flags=0):
+    """Whole helioprojective search from HOST numpy buffers (the C caller's entry point). `large` / `small`:
+    float32 or float64 arrays; `lag_wcs`: [n_lags, 11] float64 `CoregTanWcs` rows (`engine.tan_wcs_table`)."""
     lib = load()
-    large = np.ascontiguousarray(large, dtype=np.float64)
-    small = np.ascontiguousarray(small, dtype=np.float64)
-    lags = np.ascontiguousarray(lags, dtype=np.float64)
-    n_lags = lags.shape[0]
+    large = np.ascontiguousarray(large, dtype=None if large.dtype in (np.float32, np.float64) else np.float64)
+    small = np.ascontiguousarray(small, dtype=None if small.dtype in (np.float32, np.float64) else np.float64)
+    lag_wcs = np.ascontiguousarray(lag_wcs, dtype=np.float64)
+    if lag_wcs.ndim != 2 or lag_wcs.shape[1] != TAN_WCS_DOUBLES:
+        raise ValueError("lag_wcs must be [n_lags, 11] CoregTanWcs rows")
+    n_lags = lag_wcs.shape[0]
     corr = np.empty(n_lags, dtype=np.float64)
     nvalid = np.empty(n_lags, dtype=np.int64)
     sl, ss = tan_struct(wcs_large), tan_struct(wcs_small)
-    _check(lib.coreg_hpc_search_host(large.ctypes.data_as(_P), large.shape[1], large.shape[0], C.byref(sl),
-                                     small.ctypes.data_as(_P), small.shape[1], small.shape[0], C.byref(ss),
-                                     lags.ctypes.data_as(_P), n_lags, int(order),
-                                     int(flags),
-                                     corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)), "coreg_hpc_search_host")
+    _check(lib.coreg_hpc_search_host(large.ctypes.data_as(_P), _np_dt(large), large.shape[1], large.shape[0],
+                                     C.byref(sl), small.ctypes.data_as(_P), _np_dt(small), small.shape[1],
+                                     small.shape[0], C.byref(ss), lag_wcs.ctypes.data_as(_P), n_lags, int(order),
+                                     int(flags), corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)),
+           "coreg_hpc_search_host")
     return corr, nvalid
 
 

@@ -386,7 +386,7 @@ constexpr int kRowsPerPass = kThreads / kTileW;  // 4 grid rows per pass of the 
 constexpr int kWarps = kThreads / 32;
 constexpr int kLagSub = 64;   // lags staged in shared memory at a time
 constexpr int kMom = 8;       // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
-constexpr int kMinTileH = 8;  // smallest tile height of any variant (workspace sizing)
+constexpr int kMinTileH = 16; // smallest tile height of any variant (workspace sizing)
 
 inline size_t partials_bytes(int gnx, int gny, int64_t n_lags) {
   const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kMinTileH - 1) / kMinTileH);
@@ -599,62 +599,164 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fast variant of the fused lag kernel: order-2 spline, FMA arithmetic, float64 small image.
-//  * coordinates come out already offset by +0.5 so that floor(x + 0.5) is one magic-number add;
-//  * TAN: the reciprocal of the gnomonic denominator D = cos(angular distance to the lag's reference point) is the
-//    product form of the geometric series (1+e)(1+e^2)(1+e^4), e = 1 - D, exact to 2^-56 for |e| <= 2^-7
-//    (7.1 deg) -- the caller guarantees that bound (COREG_FLAG_SMALL_ANGLE, checked on the host from the FOV);
-//  * "strictly interior" (all taps inside the image, so no closed-bound test and no mirroring) is one unsigned
-//    integer compare per axis on the floor index; the PPT pixels of a thread take the branch-free path together,
-//    anything else (image borders, missing reference pixels, NaN coordinates) falls back to the exact generic
-//    per-pixel code, so results differ from the generic kernel only by FMA-level rounding.
+// Fast variant of the fused lag kernel: order-2 spline, FMA arithmetic.
+//
+// Helioprojective frame = homography. The common grid and every candidate header are gnomonic (TAN) projections
+// of the same sphere from its centre, so pixel (i, j) of the common grid maps to the candidate's pixel through a
+// plane projective transformation, exactly:
+//      (nx, ny, D) = H (i, j, 1)^T ,   x = x0 + nx / D ,   y = y0 + ny / D ,
+// H = [plane'->pixel'] . E(lag)^T Rz(alpha0 - alpha') E(grid) . [pixel->plane]   (3x3, one per lag, built by
+// tan_homography_kernel from the two CoregTanWcs). No per-pixel trig, no world-coordinate planes; per sample the
+// map costs 3 FMA + the reciprocal. D = cos(angle to the lag's reference point) * sqrt(1 + r^2) is within 2^-7 of 1
+// for fields smaller than ~6 deg, where 1/D is the product form of the geometric series (1+e)(1+e^2)(1+e^4),
+// e = 1 - D, exact to 2^-56 (COREG_FLAG_SMALL_ANGLE, guaranteed by the caller); otherwise a true division is used.
+//
+// Both functors deliver coordinates already offset by +0.5, so floor(x + 0.5) is one magic-number add, and
+// "strictly interior" (all 9 taps inside the image: no closed-bound test, no mirroring) is one unsigned integer
+// compare per axis on the floor index. Groups of pixels take the branch-free path together; anything else (image
+// borders, missing reference pixels) falls back to the exact generic sampler with the same coordinates.
 // ---------------------------------------------------------------------------------------------------------
-// Fast-path lag constants of the helioprojective search: with u = (sin lat, cos lat sin A, cos lat cos A) the unit
-// vector of a pixel's sky direction (the three trig planes), the gnomonic map of a lag's header is one 3x3 matrix
-// per lag followed by a perspective divide:  (nx, ny, D) = R u,  x = x0 + nx / D,  y = y0 + ny / D.
-// R is built once per lag from CoregLagTan by tan_fast_table_kernel (rows: nx, ny, D; then x0 + 0.5, y0 + 0.5).
-struct TanFastLag {
-  double a0, a1, a2, b0, b1, b2, d0, d1, d2, x0h, y0h, pad;
+struct HomLag {
+  double hx0, hx1, hx2, hy0, hy1, hy2, he0, he1, he2, x0h, y0h, pad;  // he = (0,0,1) - (denominator row)
 };
 
-__global__ void tan_fast_table_kernel(const CoregLagTan* __restrict__ lags, int n, TanFastLag* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const CoregLagTan L = lags[i];
-  TanFastLag f;
-  // qs = p1 cda - p2 sda ; pc = p2 cda + p1 sda ; D = pc cd0 + p0 sd0 ; en = p0 cd0 - pc sd0
-  // nx = m11 qs + m12 en ; ny = m21 qs + m22 en
-  f.a0 = L.m12 * L.cos_d0;
-  f.a1 = L.m11 * L.cos_da - L.m12 * L.sin_da * L.sin_d0;
-  f.a2 = -L.m11 * L.sin_da - L.m12 * L.cos_da * L.sin_d0;
-  f.b0 = L.m22 * L.cos_d0;
-  f.b1 = L.m21 * L.cos_da - L.m22 * L.sin_da * L.sin_d0;
-  f.b2 = -L.m21 * L.sin_da - L.m22 * L.cos_da * L.sin_d0;
-  f.d0 = L.sin_d0;
-  f.d1 = L.sin_da * L.cos_d0;
-  f.d2 = L.cos_da * L.cos_d0;
-  f.x0h = L.x0 + 0.5;
-  f.y0h = L.y0 + 0.5;
-  f.pad = 0.0;
-  out[i] = f;
+struct HomGrid {  // pixel (i, j, 1) -> native direction (-Y, X, 1), and the grid's Euler matrix
+  double c[3][3];
+  double e[3][3];
+  double a0_rad;
+};
+
+// E(delta0, lonpole): native unit vector -> celestial frame whose x axis points at longitude alpha0
+__host__ __device__ inline void euler_matrix(double sin_d, double cos_d, double sin_lp, double cos_lp, double (&e)[3][3]) {
+  e[0][0] = -sin_d * cos_lp; e[0][1] = -sin_d * sin_lp; e[0][2] = cos_d;
+  e[1][0] = sin_lp;          e[1][1] = -cos_lp;         e[1][2] = 0.0;
+  e[2][0] = cos_d * cos_lp;  e[2][1] = cos_d * sin_lp;  e[2][2] = sin_d;
 }
 
-struct TanFast {
-  typedef TanCoord Base;
-  typedef TanFastLag LagC;
-  __device__ static __forceinline__ void map_half(const TanCoord::Pix& q, const LagC& L, double& sx, double& sy) {
-    const double den = fma(q.p2, L.d2, fma(q.p1, L.d1, q.p0 * L.d0));
-    const double nx = fma(q.p2, L.a2, fma(q.p1, L.a1, q.p0 * L.a0));
-    const double ny = fma(q.p2, L.b2, fma(q.p1, L.b1, q.p0 * L.b0));
-    // 1/D for |1 - D| <= 2^-7: (1+e)(1+e^2)(1+e^4), e = 1 - D
-    const double e = 1.0 - den;
-    const double e2 = e * e;
-    double inv = 1.0 + e;
-    inv = fma(e2, inv, inv);
-    const double e4 = e2 * e2;
-    inv = fma(e4, inv, inv);
-    sx = fma(nx, inv, L.x0h);
-    sy = fma(ny, inv, L.y0h);
+int make_hom_grid(const CoregTanWcs* w, HomGrid* g) {
+  TanDev t;
+  int rc = make_tan(w, &t);
+  if (rc) return rc;
+  const double cx = t.f11 * (1.0 - t.crpix1) + t.f12 * (1.0 - t.crpix2);
+  const double cy = t.f21 * (1.0 - t.crpix1) + t.f22 * (1.0 - t.crpix2);
+  // d_native = (-Y, X, 1) with X = f11 i + f12 j + cx, Y = f21 i + f22 j + cy
+  g->c[0][0] = -t.f21; g->c[0][1] = -t.f22; g->c[0][2] = -cy;
+  g->c[1][0] = t.f11;  g->c[1][1] = t.f12;  g->c[1][2] = cx;
+  g->c[2][0] = 0.0;    g->c[2][1] = 0.0;    g->c[2][2] = 1.0;
+  euler_matrix(t.s0, t.c0, sin(t.lonpole_rad), cos(t.lonpole_rad), g->e);
+  g->a0_rad = t.a0_rad;
+  return COREG_OK;
+}
+
+__global__ void tan_homography_kernel(HomGrid g, const CoregTanWcs* __restrict__ lag_wcs, int n,
+                                      HomLag* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const CoregTanWcs w = lag_wcs[idx];
+  double sd, cd, sl, cl, sa, ca;
+  sincos(w.crval2 * kD2R, &sd, &cd);
+  sincos(w.lonpole * kD2R, &sl, &cl);
+  sincos(g.a0_rad - w.crval1 * kD2R, &sa, &ca);  // Rz(alpha0 - alpha')
+  double e2[3][3];
+  euler_matrix(sd, cd, sl, cl, e2);
+  // m = Rz * E(grid) * C   (celestial direction in the lag's alpha frame, as a function of (i, j, 1))
+  double ec[3][3], m[3][3], r[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) ec[a][b] = g.e[a][0] * g.c[0][b] + g.e[a][1] * g.c[1][b] + g.e[a][2] * g.c[2][b];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    m[0][b] = ca * ec[0][b] - sa * ec[1][b];
+    m[1][b] = sa * ec[0][b] + ca * ec[1][b];
+    m[2][b] = ec[2][b];
+  }
+  // r = E(lag)^T m : native direction of the lag's projection
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) r[a][b] = e2[0][a] * m[0][b] + e2[1][a] * m[1][b] + e2[2][a] * m[2][b];
+  // plane' = (r1 / r2, -r0 / r2) [rad]; pixel' = inv(cdelt pc) plane' + crpix - 1
+  const double f11 = w.cdelt1 * w.pc11 * kD2R, f12 = w.cdelt1 * w.pc12 * kD2R;
+  const double f21 = w.cdelt2 * w.pc21 * kD2R, f22 = w.cdelt2 * w.pc22 * kD2R;
+  const double det = f11 * f22 - f12 * f21;
+  const double i11 = f22 / det, i12 = -f12 / det, i21 = -f21 / det, i22 = f11 / det;
+  HomLag h;
+  h.hx0 = i11 * r[1][0] - i12 * r[0][0]; h.hx1 = i11 * r[1][1] - i12 * r[0][1]; h.hx2 = i11 * r[1][2] - i12 * r[0][2];
+  h.hy0 = i21 * r[1][0] - i22 * r[0][0]; h.hy1 = i21 * r[1][1] - i22 * r[0][1]; h.hy2 = i21 * r[1][2] - i22 * r[0][2];
+  h.he0 = -r[2][0]; h.he1 = -r[2][1]; h.he2 = 1.0 - r[2][2];
+  h.x0h = (w.crpix1 - 1.0) + 0.5;
+  h.y0h = (w.crpix2 - 1.0) + 0.5;
+  h.pad = 0.0;
+  out[idx] = h;
+}
+
+// CoregLagTan rows of the generic kernel from the candidate headers (same formulas as the host's
+// hdrshift/engine.py:tan_lag_table): used by coreg_hpc_search_host when the homography kernel does not apply.
+__global__ void tan_lag_from_wcs_kernel(const CoregTanWcs* __restrict__ lag_wcs, int n, double alpha_ref_deg,
+                                        double grid_lonpole_deg, CoregLagTan* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const CoregTanWcs w = lag_wcs[idx];
+  const double f11 = w.cdelt1 * w.pc11, f12 = w.cdelt1 * w.pc12;
+  const double f21 = w.cdelt2 * w.pc21, f22 = w.cdelt2 * w.pc22;
+  const double det = f11 * f22 - f12 * f21;
+  const double i11 = f22 / det, i12 = -f12 / det, i21 = -f21 / det, i22 = f11 / det;
+  double sp, cp;
+  sincos(grid_lonpole_deg * kD2R, &sp, &cp);
+  if (grid_lonpole_deg == 180.0) { sp = 0.0; cp = -1.0; }
+  CoregLagTan L;
+  sincos((w.crval1 - alpha_ref_deg) * kD2R, &L.sin_da, &L.cos_da);
+  sincos(w.crval2 * kD2R, &L.sin_d0, &L.cos_d0);
+  L.m11 = (i11 * -cp + i12 * -sp) * kR2D;
+  L.m12 = (i11 * sp + i12 * -cp) * kR2D;
+  L.m21 = (i21 * -cp + i22 * -sp) * kR2D;
+  L.m22 = (i21 * sp + i22 * -cp) * kR2D;
+  L.x0 = w.crpix1 - 1.0;
+  L.y0 = w.crpix2 - 1.0;
+  out[idx] = L;
+}
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)in[i];
+}
+
+template <bool SERIES>
+struct TanHom {
+  typedef HomLag LagC;
+  struct Planes {};
+  struct Thread { double di; };
+  struct Pix { double dj; };
+  struct TL { double cx, cy, ce; };
+  static constexpr bool kCoordsAlwaysFinite = true;  // dead reference pixels must be masked explicitly
+  __device__ static __forceinline__ Thread thread_init(int gx) { Thread t; t.di = (double)gx; return t; }
+  __device__ static __forceinline__ Pix load(const Planes&, int64_t, int gy) { Pix q; q.dj = (double)gy; return q; }
+  __device__ static __forceinline__ Pix dead() { Pix q; q.dj = 0.0; return q; }
+  __device__ static __forceinline__ TL thread_lag(const LagC& C, const Thread& t) {
+    TL v;
+    v.cx = fma(C.hx0, t.di, C.hx2);
+    v.cy = fma(C.hy0, t.di, C.hy2);
+    v.ce = fma(C.he0, t.di, C.he2);
+    return v;
+  }
+  __device__ static __forceinline__ void map_half(const Pix& q, const TL& t, const LagC& C, double& sx, double& sy) {
+    const double nx = fma(C.hx1, q.dj, t.cx);
+    const double ny = fma(C.hy1, q.dj, t.cy);
+    const double e = fma(C.he1, q.dj, t.ce);
+    double inv;
+    if (SERIES) {
+      const double e2 = e * e;
+      inv = 1.0 + e;
+      inv = fma(e2, inv, inv);
+      const double e4 = e2 * e2;
+      inv = fma(e4, inv, inv);
+    } else {
+      const double den = 1.0 - e;
+      inv = (den > 0.0) ? 1.0 / den : CUDART_NAN;  // behind the tangent hemisphere -> invalid
+    }
+    sx = fma(nx, inv, C.x0h);
+    sy = fma(ny, inv, C.y0h);
   }
 };
 
@@ -672,11 +774,19 @@ __global__ void offset_fast_table_kernel(const CoregLagOffset* __restrict__ lags
 }
 
 struct OffsetFast {
-  typedef OffsetCoord Base;
   typedef OffsetFastLag LagC;
-  __device__ static __forceinline__ void map_half(const OffsetCoord::Pix& q, const LagC& L, double& sx, double& sy) {
-    sx = L.x0h + q.tx;
-    sy = L.y0h + q.ty;
+  typedef OffsetCoord::Planes Planes;
+  struct Thread {};
+  typedef OffsetCoord::Pix Pix;
+  struct TL {};
+  static constexpr bool kCoordsAlwaysFinite = false;  // dead pixels carry NaN offsets -> never interior
+  __device__ static __forceinline__ Thread thread_init(int) { return Thread(); }
+  __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx, int) { return OffsetCoord::load(pl, idx); }
+  __device__ static __forceinline__ Pix dead() { return OffsetCoord::dead(); }
+  __device__ static __forceinline__ TL thread_lag(const LagC&, const Thread&) { return TL(); }
+  __device__ static __forceinline__ void map_half(const Pix& q, const TL&, const LagC& C, double& sx, double& sy) {
+    sx = C.x0h + q.tx;
+    sy = C.y0h + q.ty;
   }
 };
 
@@ -704,23 +814,22 @@ __device__ __forceinline__ double warp_transpose_reduce4(double (&v)[4], int lan
   return w1;  // value index = 2*bit4 + bit3
 }
 
-constexpr int kFastLagSub = 16;  // lags per shared-memory stage of the fast kernel (small: leaves L1 to the taps)
+constexpr int kFastLagSub = 32;  // lags per shared-memory stage of the fast kernel (small: leaves L1 to the taps)
 
 template <class Fast, typename SmallT, typename RefT, bool ROUND32, int PPT, int MINB, int GROUP>
 __global__ void __launch_bounds__(kThreads, MINB)
 lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, int snx, int sny, int gnx, int gny,
-                     typename Fast::Base::Planes planes, const typename Fast::Base::Lag* __restrict__ lags,
-                     const typename Fast::LagC* __restrict__ fast_lags, int n_lags, int lags_per_block,
-                     const double* __restrict__ pivots, double* __restrict__ work) {
-  typedef typename Fast::Base Coord;
-  typedef typename Coord::Lag Lag;
-  typedef typename Coord::Pix Pix;
+                     typename Fast::Planes planes, const typename Fast::LagC* __restrict__ fast_lags, int n_lags,
+                     int lags_per_block, const double* __restrict__ pivots, double* __restrict__ work) {
+  typedef typename Fast::Pix Pix;
   typedef typename Fast::LagC LagC;
   constexpr int TILE_H = kRowsPerPass * PPT;
   // GROUP = pixels whose dependency chains are interleaved (their coordinates / indices are live together)
   static_assert(PPT % GROUP == 0, "PPT must be a multiple of GROUP");
   __shared__ __align__(16) LagC s_lag[kFastLagSub];
   __shared__ double s_part[kWarps][kFastLagSub][kMom];
+  __shared__ double s_wconst[kWarps][3];                 // per warp: n, Sa, Saa over its finite reference pixels
+  __shared__ unsigned char s_miss[kWarps][kFastLagSub];  // 1 when the (warp, lag) slot carries its own n, Sa, Saa
 
   const int tiles_x = (gnx + kTileW - 1) / kTileW;
   const int tile = blockIdx.x;
@@ -730,8 +839,9 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
   const int gx = tile_x * kTileW + tx;
   const double pivot_a = pivots[0], pivot_b = pivots[1];
   const unsigned ux = (unsigned)(snx - 2), uy = (unsigned)(sny - 2);  // launcher guarantees snx, sny >= 3
-  const size_t row_bytes = (size_t)snx * sizeof(SmallT);
+  const unsigned row_elems = (unsigned)snx;
 
+  const typename Fast::Thread tstate = Fast::thread_init(gx);
   Pix pix[PPT];
   double a_c[PPT];
   unsigned a_ok = 0;
@@ -740,14 +850,14 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
   for (int k = 0; k < PPT; ++k) {
     const int gy = tile_y * TILE_H + ty0 + k * kRowsPerPass;
     a_c[k] = 0.0;
-    pix[k] = Coord::dead();
+    pix[k] = Fast::dead();
     if (gx < gnx && gy < gny) {
       const int64_t idx = (int64_t)gy * gnx + gx;
       const double a = (double)ref[idx];
       if (isfinite(a)) {
         a_c[k] = a - pivot_a;
         a_ok |= 1u << k;
-        pix[k] = Coord::load(planes, idx);
+        pix[k] = Fast::load(planes, idx, gy);
         sa_all += a_c[k];
         saa_all = fma(a_c[k], a_c[k], saa_all);
       }
@@ -762,6 +872,11 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
     wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
     wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
     wn += __shfl_xor_sync(0xffffffffu, wn, o);
+  }
+  if (lane == 0) {
+    s_wconst[warp][0] = (double)wn;
+    s_wconst[warp][1] = wsa;
+    s_wconst[warp][2] = wsaa;
   }
 
   const int lag_begin = blockIdx.y * lags_per_block;
@@ -778,25 +893,26 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
     __syncthreads();
     for (int l = 0; l < cnt; ++l) {
       const LagC C = s_lag[l];
+      const typename Fast::TL tl = Fast::thread_lag(C, tstate);
       double sb = 0.0, sbb = 0.0, sab = 0.0, sa_miss = 0.0, saa_miss = 0.0;
       int n_miss = 0;
 #pragma unroll
       for (int g = 0; g < PPT; g += GROUP) {
         // phase A: coordinates (+0.5), floor indices, fractional parts; branch-free
-        double vx[GROUP], vy[GROUP];
+        double sxs[GROUP], sys[GROUP], vx[GROUP], vy[GROUP];
         int ix[GROUP], iy[GROUP];
         bool interior = true;
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
-          double sx, sy;
-          Fast::map_half(pix[g + j], C, sx, sy);
-          const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+          Fast::map_half(pix[g + j], tl, C, sxs[j], sys[j]);
+          const double mx = __dadd_rd(sxs[j], kMagic), my = __dadd_rd(sys[j], kMagic);
           ix[j] = __double2loint(mx);
           iy[j] = __double2loint(my);
-          vx[j] = sx - (mx - kMagic);   // = d + 0.5 in [0, 1)
-          vy[j] = sy - (my - kMagic);
+          vx[j] = sxs[j] - (mx - kMagic);   // = d + 0.5 in [0, 1)
+          vy[j] = sys[j] - (my - kMagic);
           interior = interior && ((unsigned)(ix[j] - 1) < ux) && ((unsigned)(iy[j] - 1) < uy);
         }
+        if (Fast::kCoordsAlwaysFinite) interior = interior && (((a_ok >> g) & ((1u << GROUP) - 1u)) == ((1u << GROUP) - 1u));
         if (interior) {
           // phase B: weights, 9 taps, float32 rounding, moments
 #pragma unroll
@@ -808,10 +924,11 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
             const double wy2 = (0.5 * vy[j]) * vy[j];
             const double wy0 = (wy2 + 0.5) - vy[j];
             const double wy1 = fma(-2.0, wy2, vy[j] + 0.5);
-            const char* p0 = reinterpret_cast<const char*>(small + ((iy[j] - 1) * snx + (ix[j] - 1)));
-            const SmallT* r0p = reinterpret_cast<const SmallT*>(p0);
-            const SmallT* r1p = reinterpret_cast<const SmallT*>(p0 + row_bytes);
-            const SmallT* r2p = reinterpret_cast<const SmallT*>(p0 + 2 * row_bytes);
+            // interior => 1 <= ix, iy, so the first tap index is a non-negative 32-bit number
+            const unsigned tap0 = (unsigned)(iy[j] - 1) * row_elems + (unsigned)(ix[j] - 1);
+            const SmallT* r0p = small + tap0;
+            const SmallT* r1p = r0p + row_elems;
+            const SmallT* r2p = r1p + row_elems;
             const double r0 = fma(ldval(r0p + 2), wx2, fma(ldval(r0p + 1), wx1, ldval(r0p) * wx0));
             const double r1 = fma(ldval(r1p + 2), wx2, fma(ldval(r1p + 1), wx1, ldval(r1p) * wx0));
             const double r2 = fma(ldval(r2p + 2), wx2, fma(ldval(r2p + 1), wx1, ldval(r2p) * wx0));
@@ -832,19 +949,18 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
               sbb = fma(bc, bc, sbb);
               sab = fma(a_c[g + j], bc, sab);
             } else {
-              ++n_miss;   // interior => the reference pixel is present (dead pixels carry NaN coordinates)
+              ++n_miss;   // interior => the reference pixel is present
               sa_miss += a_c[g + j];
               saa_miss = fma(a_c[g + j], a_c[g + j], saa_miss);
             }
           }
         } else {
-          // generic exact path (image borders, missing reference pixels)
-          const Lag L = lags[l0 + l];
+          // exact generic sampler with the same coordinates (image borders, missing reference pixels)
 #pragma unroll
           for (int j = 0; j < GROUP; ++j) {
-            double x, y, v;
-            Coord::map(pix[g + j], L, x, y);
-            bool ok = spline_sample<2, false, SmallT>(small, sny, snx, y, x, v);
+            if (!(a_ok & (1u << (g + j)))) continue;
+            double v;
+            bool ok = spline_sample<2, false, SmallT>(small, sny, snx, sys[j] - 0.5, sxs[j] - 0.5, v);
             double b;
             if (ROUND32) {
               const float bf = __double2float_rn(v);
@@ -859,7 +975,7 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
               sb += bc;
               sbb = fma(bc, bc, sbb);
               sab = fma(a_c[g + j], bc, sab);
-            } else if (a_ok & (1u << (g + j))) {
+            } else {
               ++n_miss;
               sa_miss += a_c[g + j];
               saa_miss = fma(a_c[g + j], a_c[g + j], saa_miss);
@@ -879,31 +995,30 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
         m[7] = 0.0;
         const double tot = warp_transpose_reduce8(m, lane);
         if ((lane & 3) == 0) s_part[warp][l][lane >> 2] = tot;
+        if (lane == 0) s_miss[warp][l] = 1;
       } else {
-        // common case: nothing missing in this warp -> only the three lag-dependent sums need the butterfly
+        // common case: nothing missing in this warp -> only the three lag-dependent sums need the butterfly;
+        // n, Sa, Saa are the warp constants
         double m[4];
         m[0] = sb;
         m[1] = sbb;
         m[2] = sab;
         m[3] = 0.0;
         const double tot = warp_transpose_reduce4(m, lane);
-        if ((lane & 7) == 0) {
-          const int q = lane >> 3;  // 0: Sb, 1: Sbb, 2: Sab, 3: unused
-          if (q < 3) s_part[warp][l][q == 0 ? 2 : (q == 1 ? 4 : 5)] = tot;
-        }
-        if (lane == 1) s_part[warp][l][0] = (double)wn;
-        if (lane == 2) s_part[warp][l][1] = wsa;
-        if (lane == 3) s_part[warp][l][3] = wsaa;
-        if (lane == 4) s_part[warp][l][6] = 0.0;
-        if (lane == 5) s_part[warp][l][7] = 0.0;
+        // lanes 0, 8, 16 hold Sb, Sbb, Sab -> slots 2, 4, 5
+        if ((lane & 7) == 0 && lane < 24) s_part[warp][l][(lane >> 3) + 2 + (lane != 0)] = tot;
+        if (lane == 1) s_miss[warp][l] = 0;
       }
     }
     __syncthreads();
     for (int i = tid; i < cnt * kMom; i += kThreads) {
       const int l = i / kMom, q = i % kMom;
-      double s = s_part[0][l][q];
+      double s = 0.0;
+      if (q < 6) {
+        const int c = (q == 0) ? 0 : ((q == 1) ? 1 : ((q == 3) ? 2 : -1));  // slot of a warp constant, or -1
 #pragma unroll
-      for (int w = 1; w < kWarps; ++w) s += s_part[w][l][q];
+        for (int w = 0; w < kWarps; ++w) s += (c >= 0 && !s_miss[w][l]) ? s_wconst[w][c] : s_part[w][l][q];
+      }
       work[((size_t)tile * n_lags + (l0 + l)) * kMom + q] = s;
     }
   }
@@ -946,22 +1061,18 @@ lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lag
 }
 
 // tuning variants (flags bits 8..11): tile height = 4*PPT, MINB resident blocks per SM
-template <class Coord> struct FastOf;
-template <> struct FastOf<TanCoord> { typedef TanFast type; };
-template <> struct FastOf<OffsetCoord> { typedef OffsetFast type; };
-
 // grid for a (ppt, minb) variant; returns false when the lag list does not fit one launch
 inline bool lag_grid(int ppt, int minb, int gnx, int gny, int64_t n_lags, int sms, dim3* grid, int* lags_per_block,
-                     int* tiles_out) {
+                     int* tiles_out, int lag_sub) {
   const int tile_h = kRowsPerPass * ppt;
   const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
   *tiles_out = tiles;
   const int want_blocks = sms * minb * 4;   // a few waves of resident blocks
   int splits = (want_blocks + tiles - 1) / tiles;
-  const int max_splits = (int)((n_lags + kLagSub - 1) / kLagSub);
+  const int max_splits = (int)((n_lags + lag_sub - 1) / lag_sub);
   splits = std::max(1, std::min(splits, max_splits));
   int lpb = (int)((n_lags + splits - 1) / splits);
-  lpb = ((lpb + kLagSub - 1) / kLagSub) * kLagSub;
+  lpb = ((lpb + lag_sub - 1) / lag_sub) * lag_sub;
   splits = (int)((n_lags + lpb - 1) / lpb);
   if (splits > 65535) return false;
   *grid = dim3(tiles, splits);
@@ -969,40 +1080,29 @@ inline bool lag_grid(int ppt, int minb, int gnx, int gny, int64_t n_lags, int sm
   return true;
 }
 
-inline void build_fast_table(const CoregLagTan* lags, int n, TanFastLag* out, cudaStream_t s) {
-  tan_fast_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(lags, n, out);
-}
-inline void build_fast_table(const CoregLagOffset* lags, int n, OffsetFastLag* out, cudaStream_t s) {
-  offset_fast_table_kernel<<<(n + 127) / 128, 128, 0, s>>>(lags, n, out);
-}
-
-template <class Coord, typename SmallT, typename RefT, bool ROUND32>
+// launch the fast kernel over an already-built fast lag table
+template <class Fast, typename SmallT, typename RefT, bool ROUND32>
 int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
-                    const SmallT* small, int snx, int sny, typename Coord::Planes planes,
-                    const typename Coord::Lag* lags, const double* pivots, double* w, void* fast_table,
-                    int* tiles_out) {
-  typedef typename FastOf<Coord>::type Fast;
-  typedef typename Fast::LagC LagC;
+                    const SmallT* small, int snx, int sny, typename Fast::Planes planes,
+                    const typename Fast::LagC* ft, const double* pivots, double* w, int* tiles_out) {
   // (pixels per thread, resident CTAs per SM, interleave group); 0 = fastest measured on config 1
-  static const int kVar[10][3] = {{4, 3, 2}, {8, 2, 2}, {4, 2, 2}, {2, 3, 2}, {4, 4, 2},
-                                  {2, 4, 2}, {6, 2, 2}, {6, 3, 2}, {4, 2, 4}, {4, 3, 1}};
+  static const int kVar[10][3] = {{4, 3, 2}, {8, 2, 2}, {4, 2, 2}, {8, 2, 4}, {4, 4, 2},
+                                  {8, 3, 2}, {6, 2, 2}, {6, 3, 2}, {4, 2, 4}, {4, 3, 1}};
   if (variant < 0 || variant > 9) variant = 0;
   const int ppt = kVar[variant][0], minb = kVar[variant][1];
   dim3 grid;
   int lpb;
-  if (!lag_grid(ppt, minb, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out))
+  if (!lag_grid(ppt, minb, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out, kFastLagSub))
     return fail(COREG_EINVAL, "lag grid too large for one launch");
-  LagC* ft = static_cast<LagC*>(fast_table);
-  build_fast_table(lags, (int)n_lags, ft, s);
 #define LF(PPT_, MINB_, G_)                                                                     \
   lag_corr_fast_kernel<Fast, SmallT, RefT, ROUND32, PPT_, MINB_, G_><<<grid, kThreads, 0, s>>>( \
-      ref, small, snx, sny, gnx, gny, planes, lags, ft, (int)n_lags, lpb, pivots, w)
+      ref, small, snx, sny, gnx, gny, planes, ft, (int)n_lags, lpb, pivots, w)
   switch (variant) {
     case 1: LF(8, 2, 2); break;
     case 2: LF(4, 2, 2); break;
-    case 3: LF(2, 3, 2); break;
+    case 3: LF(8, 2, 4); break;
     case 4: LF(4, 4, 2); break;
-    case 5: LF(2, 4, 2); break;
+    case 5: LF(8, 3, 2); break;
     case 6: LF(6, 2, 2); break;
     case 7: LF(6, 3, 2); break;
     case 8: LF(4, 2, 4); break;
@@ -1011,6 +1111,22 @@ int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
   }
 #undef LF
   return COREG_OK;
+}
+
+template <typename SmallT, typename RefT, bool ROUND32>
+int launch_offset_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
+                       const SmallT* small, int snx, int sny, OffsetCoord::Planes planes, const CoregLagOffset* lags,
+                       const double* pivots, double* w, void* work, int* tiles_out) {
+  // the per-lag fast table lives in the tail of the workspace (after the [tiles][lags][8] partials)
+  OffsetFastLag* ft = reinterpret_cast<OffsetFastLag*>(static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags));
+  offset_fast_table_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(lags, (int)n_lags, ft);
+  return launch_lag_fast<OffsetFast, SmallT, RefT, ROUND32>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny,
+                                                            planes, ft, pivots, w, tiles_out);
+}
+template <typename SmallT, typename RefT, bool ROUND32>
+int launch_offset_fast(int, int, int, int64_t, int, cudaStream_t, const RefT*, const SmallT*, int, int,
+                       TanCoord::Planes, const CoregLagTan*, const double*, double*, void*, int*) {
+  return fail(COREG_EINVAL, "internal: offset fast path requested for the TAN functor");
 }
 
 template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
@@ -1073,16 +1189,12 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
     CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
   int tiles = 0, rc = COREG_OK;
-  // fast kernel: order 2, FMA arithmetic, float64 small image of at least 3x3; TAN additionally needs the
-  // caller's small-angle guarantee (the offset functor has no reciprocal)
-  const bool fast_ok = (order == 2) && !strict && snx >= 3 && sny >= 3 &&
-                       !(flags & COREG_FLAG_NO_FAST) &&
-                       (std::is_same<Coord, OffsetCoord>::value || (flags & COREG_FLAG_SMALL_ANGLE));
+  // fast kernel for the offset (Carrington) functor: order 2, FMA arithmetic, image of at least 3x3
+  const bool fast_ok = std::is_same<Coord, OffsetCoord>::value && (order == 2) && !strict && snx >= 3 && sny >= 3 &&
+                       !(flags & COREG_FLAG_NO_FAST);
   if (fast_ok) {
-    // the per-lag fast table lives in the tail of the workspace (after the [tiles][lags][8] partials)
-    char* tail = static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags);
-    rc = launch_lag_fast<Coord, SmallT, RefT, ROUND32>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny, planes,
-                                                       lags, pivots, w, tail, &tiles);
+    rc = launch_offset_fast<SmallT, RefT, ROUND32>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny, planes,
+                                                   lags, pivots, w, work, &tiles);
     if (rc) return rc;
     CK_LAUNCH("lag_corr_fast_kernel");
     if (prof) {
@@ -1194,6 +1306,45 @@ inline int grid_for(int64_t n, int threads = 256) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
 }
 
+template <typename SmallT>
+int hpc_lag_corr_wcs_impl(const float* ref, const SmallT* small, int snx, int sny, int gnx, int gny,
+                          const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags,
+                          const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s) {
+  HomGrid g;
+  int rc = make_hom_grid(grid_wcs, &g);
+  if (rc) return rc;
+  int sms = coreg_device_sm_count();
+  if (sms <= 0) sms = 148;
+  double* w = static_cast<double*>(work);
+  HomLag* ft = reinterpret_cast<HomLag*>(static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags));
+  tan_homography_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(g, lag_wcs, (int)n_lags, ft);
+  CK_LAUNCH("tan_homography_kernel");
+  const bool prof = g_prof_on && g_prof_n < 4096;
+  if (prof) {
+    CK(cudaEventCreate(&g_prof[g_prof_n].a));
+    CK(cudaEventCreate(&g_prof[g_prof_n].b));
+    CK(cudaEventRecord(g_prof[g_prof_n].a, s));
+  }
+  const int variant = (flags >> 8) & 15;
+  int tiles = 0;
+  TanHom<true>::Planes none;
+  if (flags & COREG_FLAG_SMALL_ANGLE)
+    rc = launch_lag_fast<TanHom<true>, SmallT, float, true>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny,
+                                                            none, ft, pivots, w, &tiles);
+  else
+    rc = launch_lag_fast<TanHom<false>, SmallT, float, true>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny,
+                                                             TanHom<false>::Planes(), ft, pivots, w, &tiles);
+  if (rc) return rc;
+  CK_LAUNCH("lag_corr_fast_kernel");
+  if (prof) {
+    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+    ++g_prof_n;
+  }
+  lag_corr_finalize_kernel<<<(unsigned)n_lags, 128, 0, s>>>(w, tiles, (int)n_lags, corr, nvalid);
+  CK_LAUNCH("lag_corr_finalize_kernel");
+  return COREG_OK;
+}
+
 }  // namespace
 
 // =============================================================================================================
@@ -1276,7 +1427,7 @@ int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void*
 
 size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags) {
   if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;
-  return partials_bytes(gnx, gny, n_lags) + (size_t)n_lags * sizeof(TanFastLag);
+  return partials_bytes(gnx, gny, n_lags) + (size_t)n_lags * sizeof(HomLag);
 }
 
 int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
@@ -1295,6 +1446,29 @@ int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int
     return launch_lag_corr<TanCoord, float, float, true>(ref, (const float*)small, snx, sny, gnx, gny, pl, lags,
                                                          n_lags, order, pivots, work, work_bytes, corr, nvalid, flags,
                                                          s);
+  return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_hpc_lag_corr_wcs(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
+                           const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags, int order,
+                           const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid,
+                           int flags, void* stream) {
+  if (!ref || !small || !grid_wcs || !lag_wcs || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  if (order != 2 || (flags & COREG_FLAG_STRICT))
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs: only order 2 with FMA arithmetic; use coreg_hpc_lag_corr");
+  if (gnx <= 0 || gny <= 0 || snx < 3 || sny < 3) return fail(COREG_EINVAL, "image too small for the fast kernel");
+  if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (small_dtype == COREG_F64)
+    return hpc_lag_corr_wcs_impl<double>(ref, (const double*)small, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags,
+                                         pivots, work, corr, nvalid, flags, s);
+  if (small_dtype == COREG_F32)
+    return hpc_lag_corr_wcs_impl<float>(ref, (const float*)small, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags,
+                                        pivots, work, corr, nvalid, flags, s);
   return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
 }
 
@@ -1372,18 +1546,25 @@ int coreg_synras_build(const void* frames, int frame_dtype, int n_frames, int fn
   return COREG_OK;
 }
 
-int coreg_hpc_search_host(const double* large, int lnx, int lny, const CoregTanWcs* wcs_large, const double* small,
-                          int snx, int sny, const CoregTanWcs* wcs_small, const CoregLagTan* lags, int64_t n_lags,
-                          int order, int flags, double* corr, int64_t* nvalid) {
-  if (!large || !small || !wcs_large || !wcs_small || !lags || !corr)
+int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, const CoregTanWcs* wcs_large,
+                          const void* small, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,
+                          const CoregTanWcs* lag_wcs, int64_t n_lags, int order, int flags, double* corr,
+                          int64_t* nvalid) {
+  if (!large || !small || !wcs_large || !wcs_small || !lag_wcs || !corr)
     return fail(COREG_EINVAL, "coreg_hpc_search_host: null pointer");
   if (lnx <= 0 || lny <= 0 || snx <= 0 || sny <= 0 || n_lags <= 0)
     return fail(COREG_EINVAL, "coreg_hpc_search_host: empty input");
+  if ((large_dtype != COREG_F32 && large_dtype != COREG_F64) || (small_dtype != COREG_F32 && small_dtype != COREG_F64))
+    return fail(COREG_EINVAL, "coreg_hpc_search_host: dtype must be COREG_F32 or COREG_F64");
   const int64_t ns = (int64_t)snx * sny, nl = (int64_t)lnx * lny;
+  const size_t lsz = large_dtype == COREG_F32 ? 4 : 8, ssz = small_dtype == COREG_F32 ? 4 : 8;
   const size_t work_bytes = coreg_lag_corr_workspace_bytes(snx, sny, n_lags);
-  double *d_large = nullptr, *d_small = nullptr, *d_lng = nullptr, *d_lat = nullptr, *d_x = nullptr, *d_y = nullptr,
-         *d_planes = nullptr, *d_piv = nullptr, *d_corr = nullptr;
+  const bool fast = (order == 2) && !(flags & (COREG_FLAG_STRICT | COREG_FLAG_NO_FAST)) && snx >= 3 && sny >= 3;
+  void *d_large = nullptr, *d_small_in = nullptr;
+  double *d_small = nullptr, *d_lng = nullptr, *d_lat = nullptr, *d_x = nullptr, *d_y = nullptr, *d_planes = nullptr,
+         *d_piv = nullptr, *d_corr = nullptr;
   float* d_ref = nullptr;
+  CoregTanWcs* d_lagw = nullptr;
   CoregLagTan* d_lags = nullptr;
   int64_t* d_nv = nullptr;
   void* d_work = nullptr;
@@ -1402,37 +1583,52 @@ int coreg_hpc_search_host(const double* large, int lnx, int lny, const CoregTanW
     rc = (call);         \
     if (rc) goto done;   \
   } while (0)
-  TRY(cudaMalloc(&d_large, nl * sizeof(double)));
+  TRY(cudaMalloc(&d_large, nl * lsz));
   TRY(cudaMalloc(&d_small, ns * sizeof(double)));
   TRY(cudaMalloc(&d_lng, ns * sizeof(double)));
   TRY(cudaMalloc(&d_lat, ns * sizeof(double)));
   TRY(cudaMalloc(&d_x, ns * sizeof(double)));
   TRY(cudaMalloc(&d_y, ns * sizeof(double)));
-  TRY(cudaMalloc(&d_planes, 3 * ns * sizeof(double)));
   TRY(cudaMalloc(&d_ref, ns * sizeof(float)));
   TRY(cudaMalloc(&d_piv, 2 * sizeof(double)));
   TRY(cudaMalloc(&d_corr, n_lags * sizeof(double)));
   TRY(cudaMalloc(&d_nv, n_lags * sizeof(int64_t)));
-  TRY(cudaMalloc(&d_lags, n_lags * sizeof(CoregLagTan)));
+  TRY(cudaMalloc(&d_lagw, n_lags * sizeof(CoregTanWcs)));
   TRY(cudaMalloc(&d_work, work_bytes));
-  TRY(cudaMemcpyAsync(d_large, large, nl * sizeof(double), cudaMemcpyHostToDevice, s));
-  TRY(cudaMemcpyAsync(d_small, small, ns * sizeof(double), cudaMemcpyHostToDevice, s));
-  TRY(cudaMemcpyAsync(d_lags, lags, n_lags * sizeof(CoregLagTan), cudaMemcpyHostToDevice, s));
+  TRY(cudaMemcpyAsync(d_large, large, nl * lsz, cudaMemcpyHostToDevice, s));
+  if (small_dtype == COREG_F64) {
+    TRY(cudaMemcpyAsync(d_small, small, ns * sizeof(double), cudaMemcpyHostToDevice, s));
+  } else {
+    // the lag kernels run fastest on float64 storage (no per-tap conversion): widen once on the device
+    TRY(cudaMalloc(&d_small_in, ns * sizeof(float)));
+    TRY(cudaMemcpyAsync(d_small_in, small, ns * sizeof(float), cudaMemcpyHostToDevice, s));
+    f32_to_f64_kernel<<<grid_for(ns), 256, 0, s>>>((const float*)d_small_in, ns, d_small);
+  }
+  TRY(cudaMemcpyAsync(d_lagw, lag_wcs, n_lags * sizeof(CoregTanWcs), cudaMemcpyHostToDevice, s));
   TRYRC(coreg_tan_pix2world(wcs_small, snx, sny, 1, d_lng, d_lat, s));
   TRYRC(coreg_tan_world2pix(wcs_large, d_lng, d_lat, ns, d_x, d_y, s));
-  TRYRC(coreg_map_coordinates(d_large, COREG_F64, lny, lnx, d_y, d_x, ns, order, (double)NAN, d_ref, COREG_F32, s));
-  TRYRC(coreg_tan_trig_planes(d_lng, d_lat, ns, wcs_small->crval1, d_planes, s));
+  TRYRC(coreg_map_coordinates(d_large, large_dtype, lny, lnx, d_y, d_x, ns, order, (double)NAN, d_ref, COREG_F32, s));
   TRYRC(coreg_finite_mean(d_ref, COREG_F32, ns, d_piv, s));
   TRYRC(coreg_finite_mean(d_small, COREG_F64, ns, d_piv + 1, s));
-  TRYRC(coreg_hpc_lag_corr(d_ref, d_small, COREG_F64, snx, sny, snx, sny, d_planes, d_lags, n_lags, order, d_piv,
-                           d_work, work_bytes, d_corr, d_nv, flags, s));
+  if (fast) {
+    TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, COREG_F64, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv,
+                                 d_work, work_bytes, d_corr, d_nv, flags, s));
+  } else {
+    TRY(cudaMalloc(&d_planes, 3 * ns * sizeof(double)));
+    TRY(cudaMalloc(&d_lags, n_lags * sizeof(CoregLagTan)));
+    TRYRC(coreg_tan_trig_planes(d_lng, d_lat, ns, wcs_small->crval1, d_planes, s));
+    tan_lag_from_wcs_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(d_lagw, (int)n_lags, wcs_small->crval1,
+                                                                     wcs_small->lonpole, d_lags);
+    TRYRC(coreg_hpc_lag_corr(d_ref, d_small, COREG_F64, snx, sny, snx, sny, d_planes, d_lags, n_lags, order, d_piv,
+                             d_work, work_bytes, d_corr, d_nv, flags, s));
+  }
   TRY(cudaMemcpyAsync(corr, d_corr, n_lags * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (nvalid) TRY(cudaMemcpyAsync(nvalid, d_nv, n_lags * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   TRY(cudaStreamSynchronize(s));
 done:
-  cudaFree(d_large); cudaFree(d_small); cudaFree(d_lng); cudaFree(d_lat); cudaFree(d_x); cudaFree(d_y);
-  cudaFree(d_planes); cudaFree(d_ref); cudaFree(d_piv); cudaFree(d_corr); cudaFree(d_nv); cudaFree(d_lags);
-  cudaFree(d_work);
+  cudaFree(d_large); cudaFree(d_small_in); cudaFree(d_small); cudaFree(d_lng); cudaFree(d_lat); cudaFree(d_x);
+  cudaFree(d_y); cudaFree(d_planes); cudaFree(d_ref); cudaFree(d_piv); cudaFree(d_corr); cudaFree(d_nv);
+  cudaFree(d_lagw); cudaFree(d_lags); cudaFree(d_work);
 #undef TRY
 #undef TRYRC
   return rc;

@@ -320,8 +320,7 @@ class Alignment:
             w_large = TanWcs.from_header(self.hdr_large)
             eng.prepare_hpc(self.data_large, w_large, w_small)
             self.hdr_large = self.hdr_small.copy()   # alignment.py:1000
-            table, dead = _engine.tan_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, eng.alpha_ref_deg,
-                                                self.cdelt_semantics)
+            table, dead = eng.hpc_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, self.cdelt_semantics)
             corr, nvalid = eng.search(table, return_nvalid=True)
             corr = np.where(dead, 0.0, corr)
             for kk in range(n_r):

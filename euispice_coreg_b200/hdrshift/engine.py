@@ -57,15 +57,8 @@ def shifted_pc(hdr, crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1, cdelt2):
     return pc11, pc12, pc21, pc22
 
 
-def tan_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, alpha_ref_deg,
-                  cdelt_semantics="reference"):
-    """[n_lags, 10] float64 rows of `CoregLagTan` + a mask of lags the reference cannot evaluate.
-
-    `refs` carries crval1_ref, crval2_ref, crota_ref, cdelt1_ref, cdelt2_ref (header units).
-    cdelt_semantics="reference": a CDELT1 lag only triggers the PC rebuild, a non-zero CDELT2 lag kills the
-    reference's worker (cube entry stays 0.0) -> reported in the returned `dead` mask (SURVEY App. B1).
-    cdelt_semantics="intended": CDELTi = ref + lag, then PC rebuild with the new CDELT2/CDELT1.
-    """
+def _shifted_header_constants(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics):
+    """Per-lag constants of `_shift_header` (`alignment.py:401-468`) in degrees, vectorised over lags."""
     w0 = TanWcs.from_header(hdr_small)
     s1, s2 = w0.unit_scale1, w0.unit_scale2
     n = d_crval1.size
@@ -81,10 +74,25 @@ def tan_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_cro
         dead = d_cdelt2 != 0.0
     else:
         raise ValueError("cdelt_semantics must be 'reference' or 'intended'")
-    pc11, pc12, pc21, pc22 = shifted_pc(hdr_small, refs.crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1_h, cdelt2_h)
+    pc = shifted_pc(hdr_small, refs.crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1_h, cdelt2_h)
+    return w0, crval1, crval2, cdelt1_h * s1, cdelt2_h * s2, pc, dead
+
+
+def tan_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, alpha_ref_deg,
+                  cdelt_semantics="reference"):
+    """[n_lags, 10] float64 rows of `CoregLagTan` + a mask of lags the reference cannot evaluate.
+
+    `refs` carries crval1_ref, crval2_ref, crota_ref, cdelt1_ref, cdelt2_ref (header units).
+    cdelt_semantics="reference": a CDELT1 lag only triggers the PC rebuild, a non-zero CDELT2 lag kills the
+    reference's worker (cube entry stays 0.0) -> reported in the returned `dead` mask (SURVEY App. B1).
+    cdelt_semantics="intended": CDELTi = ref + lag, then PC rebuild with the new CDELT2/CDELT1.
+    """
+    w0, crval1, crval2, cd1, cd2, (pc11, pc12, pc21, pc22), dead = _shifted_header_constants(
+        hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics)
+    n = d_crval1.size
     # forward matrix [deg/pixel] and its inverse, times 180/pi (the kernel's plane coordinates are radians)
-    f11, f12 = cdelt1_h * s1 * pc11, cdelt1_h * s1 * pc12
-    f21, f22 = cdelt2_h * s2 * pc21, cdelt2_h * s2 * pc22
+    f11, f12 = cd1 * pc11, cd1 * pc12
+    f21, f22 = cd2 * pc21, cd2 * pc22
     det = f11 * f22 - f12 * f21
     i11, i12, i21, i22 = f22 / det, -f12 / det, -f21 / det, f11 / det
     # native-longitude rotation by LONPOLE folded in: (xp, yp) = (-cp xi + sp eta, -sp xi - cp eta)
@@ -104,6 +112,22 @@ def tan_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_cro
     tab[:, 4], tab[:, 5], tab[:, 6], tab[:, 7] = m11, m12, m21, m22
     tab[:, 8] = w0.crpix1 - 1.0
     tab[:, 9] = w0.crpix2 - 1.0
+    return tab, dead
+
+
+def tan_wcs_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics="reference"):
+    """[n_lags, 11] float64 rows of `CoregTanWcs`: the candidate headers themselves (output of `_shift_header`,
+    `alignment.py:401-468`, as wcslib would hold them, degrees). Input of the homography kernel
+    (`coreg_hpc_lag_corr_wcs`), which derives its per-lag 3x3 matrix on the device."""
+    w0, crval1, crval2, cd1, cd2, (pc11, pc12, pc21, pc22), dead = _shifted_header_constants(
+        hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics)
+    n = d_crval1.size
+    tab = np.empty((n, _ext.TAN_WCS_DOUBLES), dtype=np.float64)
+    tab[:, 0], tab[:, 1] = w0.crpix1, w0.crpix2
+    tab[:, 2], tab[:, 3] = cd1, cd2
+    tab[:, 4], tab[:, 5], tab[:, 6], tab[:, 7] = pc11, pc12, pc21, pc22
+    tab[:, 8], tab[:, 9] = crval1, crval2
+    tab[:, 10] = w0.lonpole
     return tab, dead
 
 
@@ -199,8 +223,9 @@ class LagSearchEngine:
             x, y = _ext.tan_world2pix(wcs_large, lng, lat)
             d_large = self._upload(np.asarray(data_large, dtype=np.float64))
             self.ref = _ext.map_coordinates(d_large, y, x, self.order, float("nan"), torch.float32)
-            del d_large, x, y
-            self.planes = _ext.tan_trig_planes(lng, lat, wcs_small.crval1)
+            del d_large, x, y, lng, lat
+            self.planes = None          # trig planes of the generic kernel: built on first use (`_hpc_planes`)
+            self.grid_wcs = wcs_small
             self.alpha_ref_deg = wcs_small.crval1
             self.delta_ref_deg = wcs_small.crval2
             _ext.finite_mean(self.ref, self.pivots[0:1])
@@ -214,15 +239,39 @@ class LagSearchEngine:
         self.fov_radius_deg = float(np.max(np.arccos(np.clip(cosd, -1.0, 1.0))) * R2D)
         self.frame = "hpc"
 
-    def _small_angle(self, table):
+    def _hpc_planes(self):
+        """Lag-independent trig planes of the generic helioprojective kernel (101 MB at 2048^2), built lazily:
+        the homography kernel does not need them."""
+        if self.planes is None:
+            torch = _torch()
+            w = self.grid_wcs
+            with torch.cuda.device(self.device):
+                lng, lat = _ext.tan_pix2world(w, w.naxis1, w.naxis2, True, self.device)
+                self.planes = _ext.tan_trig_planes(lng, lat, w.crval1)
+        return self.planes
+
+    def _small_angle(self, wcs_table):
         """True when every (pixel, lag) pair is within `small_angle_limit_deg` of the lag's reference point:
         FOV radius + largest displacement of the reference point over the lag table (triangle inequality)."""
         if self.fov_radius_deg is None:
             return False
-        da = np.abs(np.arctan2(table[:, 0], table[:, 1])) * R2D
-        d0 = np.abs(np.arctan2(table[:, 2], table[:, 3]) * R2D - self.delta_ref_deg)
-        shift = float(np.max(da + d0)) if table.shape[0] else 0.0
+        da = np.abs(wcs_table[:, 8] - self.alpha_ref_deg)
+        da = np.minimum(da, 360.0 - da)
+        d0 = np.abs(wcs_table[:, 9] - self.delta_ref_deg)
+        shift = float(np.max(da + d0)) if wcs_table.shape[0] else 0.0
         return bool(np.isfinite(shift) and self.fov_radius_deg + shift < self.small_angle_limit_deg)
+
+    def hpc_fast_eligible(self):
+        """The homography kernel covers spline order 2 with FMA arithmetic on images of at least 3x3 pixels."""
+        return (self.order == 2 and not self.strict and not self.no_fast and self.small is not None
+                and min(self.small.shape) >= 3)
+
+    def hpc_lag_table(self, hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics="reference"):
+        """Host lag table for `search` in the helioprojective frame + the mask of lags the reference cannot
+        evaluate: candidate-header rows for the homography kernel when it applies, `CoregLagTan` rows otherwise."""
+        if self.hpc_fast_eligible():
+            return tan_wcs_table(hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics)
+        return tan_lag_table(hdr_small, refs, d1, d2, d3, d4, d5, self.alpha_ref_deg, cdelt_semantics)
 
     # ---- Carrington --------------------------------------------------------------------------------
     @staticmethod
@@ -286,7 +335,9 @@ class LagSearchEngine:
         return max(64, (self.max_workspace_bytes // per_lag) // 64 * 64)
 
     def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None):
-        """Run the fused kernel over a device lag table [n, k]; results into out_dev[n]."""
+        """Run the fused kernel over a device lag table [n, k]; results into out_dev[n]. Helioprojective frame:
+        k = 11 (`CoregTanWcs` rows, `tan_wcs_table`) selects the homography kernel, k = 10 (`CoregLagTan` rows,
+        `tan_lag_table`) the generic one."""
         torch = _torch()
         n = table_dev.shape[0]
         gny, gnx = self.ref.shape
@@ -297,9 +348,12 @@ class LagSearchEngine:
             for lo in range(0, n, step):
                 hi = min(n, lo + step)
                 nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
-                if self.frame == "hpc":
-                    _ext.hpc_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order, self.pivots,
-                                      work, out_dev[lo:hi], nv, self.flags)
+                if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
+                    _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
+                                          self.pivots, work, out_dev[lo:hi], nv, self.flags)
+                elif self.frame == "hpc":
+                    _ext.hpc_lag_corr(self.ref, self.small, self._hpc_planes(), table_dev[lo:hi], self.order,
+                                      self.pivots, work, out_dev[lo:hi], nv, self.flags)
                 else:
                     tx, ty = planes
                     _ext.offset_lag_corr(self.ref, self.small, tx, ty, table_dev[lo:hi], self.order, self.pivots,
@@ -315,8 +369,9 @@ class LagSearchEngine:
         chunk, bounds = shard_bounds(n, world)
         lo, hi = bounds[rank]
         if self.frame == "hpc":
-            self.flags = _ext.make_flags(self.strict, self.variant, small_angle=self._small_angle(table),
-                                         no_fast=self.no_fast)
+            wcs_rows = table.shape[1] == _ext.TAN_WCS_DOUBLES
+            self.flags = _ext.make_flags(self.strict, self.variant,
+                                         small_angle=wcs_rows and self._small_angle(table), no_fast=self.no_fast)
         with torch.cuda.device(self.device):
             local = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
             nvalid = torch.zeros(chunk, dtype=torch.int64, device=self.device) if return_nvalid else None

@@ -183,7 +183,8 @@ def test_strict_arithmetic_mode(torch_cuda, toy_pair):
     """scipy's exact tap arithmetic; the default FMA mode differs from it by far less than the tolerance."""
     gpu, _ = _gpu_cube(toy_pair, strict_arithmetic=True, **LAGS)
     fma, _ = _gpu_cube(toy_pair, **LAGS)
-    assert np.nanmax(np.abs(gpu - fma)) < 1e-12
+    # default path = homography kernel with FMA arithmetic; strict = generic kernel, scipy operation order
+    assert np.nanmax(np.abs(gpu - fma)) < 1e-10
     ref, _ = _oracle_cube(toy_pair, **LAGS)
     _assert_parity(gpu, ref)
 
@@ -197,11 +198,20 @@ def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     dl, hl, ds, hs = load_pair(*toy_pair[:2])
     d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
     w_small = TanWcs.from_header(a.hdr_small)
-    table, _ = engine.tan_lag_table(a.hdr_small, a, *d, w_small.crval1)
+    table, _ = engine.tan_wcs_table(a.hdr_small, a, *d)
+    flags = _ext.make_flags(small_angle=True)
     corr, nvalid = _ext.hpc_search_host(dl.astype(np.float64), TanWcs.from_header(hl), ds.astype(np.float64), w_small,
-                                        table)
+                                        table, flags=flags)
     assert np.array_equal(corr.reshape(gpu.shape), gpu)
     assert np.array_equal(nvalid.reshape(a.nvalid.shape), a.nvalid)
+    # float32 payloads (what FITS BITPIX -32 files hold) go up as they are: same bits
+    assert dl.dtype == np.float32 and ds.dtype == np.float32
+    corr32, _ = _ext.hpc_search_host(dl, TanWcs.from_header(hl), ds, w_small, table, flags=flags)
+    assert np.array_equal(corr32, corr)
+    # the generic kernel from the same candidate headers (lag constants derived on the device)
+    corr_g, nv_g = _ext.hpc_search_host(dl, TanWcs.from_header(hl), ds, w_small, table,
+                                        flags=_ext.make_flags(no_fast=True))
+    assert np.nanmax(np.abs(corr_g - corr)) < 1e-11 and np.array_equal(nv_g, nvalid)
 
 
 def test_results_and_written_header_match_oracle_cube(torch_cuda, toy_pair, tmp_path):
@@ -238,6 +248,15 @@ def test_determinism_and_lag_sharding_invariance(torch_cuda, toy_pair):
     assert np.array_equal(gpu, gpu2)
     eng = a.engine
     d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
-    table, _ = engine.tan_lag_table(a.hdr_small, a, *d, eng.alpha_ref_deg)
+    table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
+    assert table.shape[1] == 11     # candidate-header rows: the homography kernel is the default path
     parts = [eng.search(table[lo:hi]) for lo, hi in ((0, 7), (7, 8), (8, 25))]
     assert np.array_equal(np.concatenate(parts), gpu.ravel())
+    # the generic kernel (separate world-coordinate planes + trig per lag) agrees far inside the tolerance
+    eng_g = engine.LagSearchEngine(order=2, no_fast=True)
+    eng_g.set_small(eng.small.cpu().numpy())
+    eng_g.ref, eng_g.frame, eng_g.grid_wcs, eng_g.pivots = eng.ref, "hpc", eng.grid_wcs, eng.pivots
+    eng_g.alpha_ref_deg, eng_g.delta_ref_deg = eng.alpha_ref_deg, eng.delta_ref_deg
+    table_g, _ = eng_g.hpc_lag_table(a.hdr_small, a, *d)
+    assert table_g.shape[1] == 10
+    assert np.nanmax(np.abs(eng_g.search(table_g) - gpu.ravel())) < 1e-11

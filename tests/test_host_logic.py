@@ -98,6 +98,64 @@ def test_lag_table_reproduces_oracle_shifted_headers(toy_pair, sem):
         assert np.max(np.abs(x - xo)) < 1e-9 and np.max(np.abs(y - yo)) < 1e-9
 
 
+def _homography_map(grid_row, lag_row, i, j):
+    """numpy restatement of csrc `make_hom_grid` + `tan_homography_kernel` + `TanHom::map_half` (division form):
+    common-grid pixel (i, j) -> 0-based pixel of the candidate header."""
+    d2r = np.pi / 180.0
+
+    def euler(dec, lonpole):
+        sd, cd, sl, cl = np.sin(dec * d2r), np.cos(dec * d2r), np.sin(lonpole * d2r), np.cos(lonpole * d2r)
+        return np.array([[-sd * cl, -sd * sl, cd], [sl, -cl, 0.0], [cd * cl, cd * sl, sd]])
+
+    def fmat(r):
+        return np.array([[r[2] * r[4], r[2] * r[5]], [r[3] * r[6], r[3] * r[7]]]) * d2r
+
+    f = fmat(grid_row)
+    c = f @ (1.0 - grid_row[0:2])
+    cmat = np.array([[-f[1, 0], -f[1, 1], -c[1]], [f[0, 0], f[0, 1], c[0]], [0.0, 0.0, 1.0]])
+    a = (grid_row[8] - lag_row[8]) * d2r
+    rz = np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    r = euler(lag_row[9], lag_row[10]).T @ rz @ euler(grid_row[9], grid_row[10]) @ cmat
+    inv = np.linalg.inv(fmat(lag_row))
+    hx = inv[0, 0] * r[1] - inv[0, 1] * r[0]
+    hy = inv[1, 0] * r[1] - inv[1, 1] * r[0]
+    v = np.stack([i, j, np.ones_like(i)])
+    den = np.tensordot(r[2], v, 1)
+    return (np.tensordot(hx, v, 1) / den + lag_row[0] - 1.0, np.tensordot(hy, v, 1) / den + lag_row[1] - 1.0, den)
+
+
+@pytest.mark.parametrize("sem", ["reference", "intended"])
+def test_homography_of_candidate_headers_reproduces_oracle_world_to_pixel(toy_pair, sem):
+    """Two gnomonic projections of one sphere are related by a plane homography: the per-lag 3x3 matrix the fast
+    kernel derives from `tan_wcs_table` rows maps common-grid pixels where the oracle's pixel->world->pixel
+    round trip (wcslib-structured, per lag) puts them, within 1e-9 px, for CRVAL / CROTA / CDELT lags."""
+    from euispice_coreg_b200.hdrshift import engine
+    from oracle import hpc, wcs_tan
+    _, _, _, hs = load_pair(*toy_pair[:2])
+    hs = dict(hs)
+    hpc.check_and_create_pcij(hs)
+    refs = hpc.Refs(hs, [0.0], [0.0], [0.0], [0.0], [0.0], None)
+    lags = [(24.0, 6.0, 0.0, 0.0, 0.0), (-30.0, 12.5, 0.0, 0.0, 0.75), (3.0, -4.0, 0.004, 0.0, 0.0),
+            (5.0, 5.0, 0.002, -0.003, -0.5), (3000.0, -2000.0, 0.0, 0.0, 10.0)]
+    d = [np.array(c, dtype=np.float64) for c in zip(*lags)]
+    table, dead = engine.tan_wcs_table(hs, refs, *d, sem)
+    grid, _ = engine.tan_wcs_table(hs, refs, *[np.zeros(1)] * 5, sem)
+    assert table.shape == (len(lags), 11)
+    lng, lat = wcs_tan.extract_coordinates(hs)
+    jj, ii = np.mgrid[0:lng.shape[0], 0:lng.shape[1]].astype(np.float64)
+    for k, lag in enumerate(lags):
+        h = dict(hs)
+        try:
+            hpc.shift_header(h, refs, *lag, cdelt_mode=sem)
+        except hpc.LagKillsWorker:
+            assert dead[k] and sem == "reference"
+            continue
+        xo, yo = wcs_tan.WcsTan(h).world_to_pixel(lng, lat)
+        x, y, den = _homography_map(grid[0], table[k], ii, jj)
+        assert np.max(np.abs(x - xo)) < 1e-9 and np.max(np.abs(y - yo)) < 1e-9
+        assert np.all(den > 0.9)    # e = 1 - den stays tiny: the small-angle reciprocal series applies
+
+
 def test_flat_lag_grid_and_shard_bounds_match_array_split():
     from euispice_coreg_b200.hdrshift import engine
     d = engine.flat_lag_grid([1, 2, 3], [10, 20], [0], [0], [0.0, 0.5])
@@ -245,7 +303,8 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert lib.coreg_version() >= 100
     lib.coreg_lag_corr_workspace_bytes.restype = ctypes.c_size_t
     lib.coreg_lag_corr_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64]
-    assert lib.coreg_lag_corr_workspace_bytes(2048, 2048, 3600) == 32 * 128 * 3600 * 64
+    # [tiles of 64x16][lags][8 doubles] partials + one 96-byte fast-path row per lag
+    assert lib.coreg_lag_corr_workspace_bytes(2048, 2048, 3600) == 32 * 128 * 3600 * 64 + 3600 * 96
     assert lib.coreg_lag_corr_workspace_bytes(0, 5, 5) == 0
 
 

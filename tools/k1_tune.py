@@ -32,7 +32,6 @@ def main():
     a._set_initial_header_values(True)
     w_small, w_large = TanWcs.from_header(a.hdr_small), TanWcs.from_header(a.hdr_large)
     d = E.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
-    table, _ = E.tan_lag_table(a.hdr_small, a, *d, w_small.crval1)
     results = []
     base = None
     combos = (("f64", False, False), ("f64", False, True), ("f64", True, True))
@@ -44,7 +43,9 @@ def main():
                 eng = E.LagSearchEngine(order=2, strict=strict, variant=v, small_storage=storage, no_fast=no_fast)
                 eng.set_small(a.data_small)
                 eng.prepare_hpc(a.data_large, w_large, w_small)
-                eng.flags = _ext.make_flags(strict, v, small_angle=eng._small_angle(table), no_fast=no_fast)
+                table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
+                fast = table.shape[1] == _ext.TAN_WCS_DOUBLES
+                eng.flags = _ext.make_flags(strict, v, small_angle=fast and eng._small_angle(table), no_fast=no_fast)
                 tab = eng._upload(table)
                 out = torch.empty(table.shape[0], dtype=torch.float64, device=eng.device)
                 eng.evaluate(tab, out)
@@ -56,7 +57,8 @@ def main():
                 c = out.cpu().numpy()
                 if base is None:
                     base = c
-                rec = {"storage": storage, "strict": strict, "fast_kernel": not (no_fast or strict), "variant": v, "k1_ms": ms / n,
+                rec = {"storage": storage, "strict": strict, "fast_kernel": bool(fast), "variant": v,
+                       "k1_ms_per_search": ms / args.steps, "launches_per_search": n // args.steps,
                        "max_abs_diff_vs_first": float(np.nanmax(np.abs(c - base))),
                        "argmax": int(np.nanargmax(c))}
                 print(json.dumps(rec), flush=True)
