@@ -194,8 +194,6 @@ def run_gpu(args):
     fast = table.shape[1] == _ext.TAN_WCS_DOUBLES
     chunk, bounds = E.shard_bounds(n_lags, world)
     lo, hi = bounds[rank]
-    eng.flags = _ext.make_flags(args.strict, args.variant, small_angle=fast and eng._small_angle(table),
-                                no_fast=args.no_fast)
     tab_dev = eng._upload(table[lo:hi])
     local_out = torch.full((chunk,), float("nan"), dtype=torch.float64, device=eng.device)
     full = torch.empty(chunk * world, dtype=torch.float64, device=eng.device)

@@ -17,15 +17,13 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
 
 F32, F64 = 0, 1
 FLAG_STRICT = 1
-FLAG_SMALL_ANGLE = 2
 FLAG_NO_FAST = 4
 
 
-def make_flags(strict=False, variant=0, small_angle=False, no_fast=False):
-    """flags word of the lag kernels: bit 0 strict scipy op order, bit 1 small-angle guarantee (fast TAN kernel),
-    bit 2 force the generic kernel, bits 8..11 tuning variant."""
-    return ((FLAG_STRICT if strict else 0) | (FLAG_SMALL_ANGLE if small_angle else 0)
-            | (FLAG_NO_FAST if no_fast else 0) | ((int(variant) & 15) << 8))
+def make_flags(strict=False, variant=0, no_fast=False):
+    """flags word of the lag kernels: bit 0 strict scipy op order, bit 2 force the generic kernel,
+    bits 8..11 tuning variant."""
+    return (FLAG_STRICT if strict else 0) | (FLAG_NO_FAST if no_fast else 0) | ((int(variant) & 15) << 8)
 
 
 class CoregLibraryError(RuntimeError):
@@ -59,7 +57,7 @@ _SIGNATURES = {
     "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
-    "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
+    "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                          _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
@@ -232,10 +230,12 @@ def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_ou
     _require_cuda(ref, small, lag_wcs, pivots, work, corr_out)
     if ref.dtype != torch.float32:
         raise TypeError("ref must be float32 (the reference keeps the cut large image in float32)")
+    if small.dtype != torch.float64:
+        raise TypeError("the homography kernel reads a float64 small image")
     gny, gnx = ref.shape
     g = tan_struct(grid_wcs)
     with torch.cuda.device(ref.device):
-        _check(lib.coreg_hpc_lag_corr_wcs(_ptr(ref), _ptr(small), _dt(small), small.shape[1], small.shape[0], gnx, gny,
+        _check(lib.coreg_hpc_lag_corr_wcs(_ptr(ref), _ptr(small), small.shape[1], small.shape[0], gnx, gny,
                                           C.byref(g), _ptr(lag_wcs), lag_wcs.shape[0], int(order), _ptr(pivots),
                                           _ptr(work), work.numel() * work.element_size(), _ptr(corr_out),
                                           _ptr(nvalid_out) if nvalid_out is not None else None, int(flags),

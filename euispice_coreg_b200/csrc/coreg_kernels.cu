@@ -617,13 +617,15 @@ lag_corr_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, 
 // borders, missing reference pixels) falls back to the exact generic sampler with the same coordinates.
 // ---------------------------------------------------------------------------------------------------------
 struct HomLag {
-  double hx0, hx1, hx2, hy0, hy1, hy2, he0, he1, he2, x0h, y0h, pad;  // he = (0,0,1) - (denominator row)
+  double hx0, hx1, hx2, hy0, hy1, hy2, he0, he1, he2, x0h, y0h;  // he = (0,0,1) - (denominator row)
+  double emax;  // max |e| over the common grid (e is linear in (i, j): attained at a corner); +inf if not finite
 };
 
 struct HomGrid {  // pixel (i, j, 1) -> native direction (-Y, X, 1), and the grid's Euler matrix
   double c[3][3];
   double e[3][3];
   double a0_rad;
+  double xmax, ymax;  // gnx - 1, gny - 1
 };
 
 // E(delta0, lonpole): native unit vector -> celestial frame whose x axis points at longitude alpha0
@@ -633,7 +635,7 @@ __host__ __device__ inline void euler_matrix(double sin_d, double cos_d, double 
   e[2][0] = cos_d * cos_lp;  e[2][1] = cos_d * sin_lp;  e[2][2] = sin_d;
 }
 
-int make_hom_grid(const CoregTanWcs* w, HomGrid* g) {
+int make_hom_grid(const CoregTanWcs* w, int gnx, int gny, HomGrid* g) {
   TanDev t;
   int rc = make_tan(w, &t);
   if (rc) return rc;
@@ -645,6 +647,8 @@ int make_hom_grid(const CoregTanWcs* w, HomGrid* g) {
   g->c[2][0] = 0.0;    g->c[2][1] = 0.0;    g->c[2][2] = 1.0;
   euler_matrix(t.s0, t.c0, sin(t.lonpole_rad), cos(t.lonpole_rad), g->e);
   g->a0_rad = t.a0_rad;
+  g->xmax = (double)(gnx - 1);
+  g->ymax = (double)(gny - 1);
   return COREG_OK;
 }
 
@@ -687,7 +691,12 @@ __global__ void tan_homography_kernel(HomGrid g, const CoregTanWcs* __restrict__
   h.he0 = -r[2][0]; h.he1 = -r[2][1]; h.he2 = 1.0 - r[2][2];
   h.x0h = (w.crpix1 - 1.0) + 0.5;
   h.y0h = (w.crpix2 - 1.0) + 0.5;
-  h.pad = 0.0;
+  // e = he0 i + he1 j + he2 is linear over the grid: its extreme values sit at the four corners
+  const double e00 = h.he2, e10 = fma(h.he0, g.xmax, h.he2), e01 = fma(h.he1, g.ymax, h.he2),
+               e11 = fma(h.he0, g.xmax, fma(h.he1, g.ymax, h.he2));
+  double em = fmax(fmax(fabs(e00), fabs(e10)), fmax(fabs(e01), fabs(e11)));
+  if (!(em == em) || !isfinite(h.hx0 + h.hx1 + h.hx2 + h.hy0 + h.hy1 + h.hy2)) em = CUDART_INF;
+  h.emax = em;
   out[idx] = h;
 }
 
@@ -722,43 +731,54 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, doubl
     out[i] = (double)in[i];
 }
 
-template <bool SERIES>
-struct TanHom {
-  typedef HomLag LagC;
-  struct Planes {};
-  struct Thread { double di; };
-  struct Pix { double dj; };
-  struct TL { double cx, cy, ce; };
-  static constexpr bool kCoordsAlwaysFinite = true;  // dead reference pixels must be masked explicitly
-  __device__ static __forceinline__ Thread thread_init(int gx) { Thread t; t.di = (double)gx; return t; }
-  __device__ static __forceinline__ Pix load(const Planes&, int64_t, int gy) { Pix q; q.dj = (double)gy; return q; }
-  __device__ static __forceinline__ Pix dead() { Pix q; q.dj = 0.0; return q; }
-  __device__ static __forceinline__ TL thread_lag(const LagC& C, const Thread& t) {
-    TL v;
-    v.cx = fma(C.hx0, t.di, C.hx2);
-    v.cy = fma(C.hy0, t.di, C.hy2);
-    v.ce = fma(C.he0, t.di, C.he2);
-    return v;
+// reciprocal of the projective denominator D = 1 - e, chosen per lag (block-uniform) from the lag's emax:
+//   |e| <= 2^-18 : 1 + e + e^2                    (2 ops, truncation e^3 <= 2^-54)
+//   |e| <= 2^-7  : (1 + e)(1 + e^2)(1 + e^4)      (5 ops, truncation e^8 <= 2^-56)
+//   otherwise    : true division; D <= 0 (behind the tangent hemisphere) -> NaN
+constexpr double kTinyE = 3.814697265625e-06;  // 2^-18
+constexpr double kSmallE = 0.0078125;          // 2^-7
+
+__device__ __forceinline__ double recip_1me_tiny(double e) { return fma(e, e, 1.0 + e); }
+__device__ __forceinline__ double recip_1me_small(double e) {
+  const double e2 = e * e;
+  double inv = 1.0 + e;
+  inv = fma(e2, inv, inv);
+  const double e4 = e2 * e2;
+  return fma(e4, inv, inv);
+}
+__device__ __forceinline__ double recip_1me_div(double e) {
+  const double den = 1.0 - e;
+  return (den > 0.0) ? 1.0 / den : CUDART_NAN;
+}
+
+// v in [0, 1)  <=>  sign bit clear and biased exponent < 1023: one unsigned compare on the high word
+// (false for negatives, -0.0, NaN and Inf)
+__device__ __forceinline__ bool in_unit_interval(double v) {
+  return (unsigned)__double2hiint(v) < 0x3FF00000u;
+}
+
+// |v| < 2^30 (false for NaN / Inf): the range in which the magic-number floor of the fast kernels is exact
+__device__ __forceinline__ bool small_magnitude(double v) {
+  return (unsigned)(__double2hiint(v) & 0x7FFFFFFF) < 0x41D00000u;
+}
+
+// exact order-2 sample at (sx - 0.5, sy - 0.5) with float32 rounding / masking, kept out of line: only image
+// borders, irregular columns and missing reference pixels come here
+template <bool ROUND32>
+__device__ __noinline__ bool sample_exact_half(const double* __restrict__ small, int sny, int snx, double sy,
+                                               double sx, double* out) {
+  double v;
+  bool ok = spline_sample<2, false, double>(small, sny, snx, sy - 0.5, sx - 0.5, v);
+  if (ROUND32) {
+    const float bf = __double2float_rn(v);
+    ok = ok && isfinite(bf);
+    v = (double)bf;
+  } else {
+    ok = ok && isfinite(v) && (v != -32762.0);
   }
-  __device__ static __forceinline__ void map_half(const Pix& q, const TL& t, const LagC& C, double& sx, double& sy) {
-    const double nx = fma(C.hx1, q.dj, t.cx);
-    const double ny = fma(C.hy1, q.dj, t.cy);
-    const double e = fma(C.he1, q.dj, t.ce);
-    double inv;
-    if (SERIES) {
-      const double e2 = e * e;
-      inv = 1.0 + e;
-      inv = fma(e2, inv, inv);
-      const double e4 = e2 * e2;
-      inv = fma(e4, inv, inv);
-    } else {
-      const double den = 1.0 - e;
-      inv = (den > 0.0) ? 1.0 / den : CUDART_NAN;  // behind the tangent hemisphere -> invalid
-    }
-    sx = fma(nx, inv, C.x0h);
-    sy = fma(ny, inv, C.y0h);
-  }
-};
+  *out = v;
+  return ok;
+}
 
 struct OffsetFastLag {
   double x0h, y0h;
@@ -814,7 +834,8 @@ __device__ __forceinline__ double warp_transpose_reduce4(double (&v)[4], int lan
   return w1;  // value index = 2*bit4 + bit3
 }
 
-constexpr int kFastLagSub = 32;  // lags per shared-memory stage of the fast kernel (small: leaves L1 to the taps)
+constexpr int kFastLagSub = 32;
+constexpr int kRollLagSub = 8;  // = kRollChunk (lag-list granularity of the rolling kernel's grid)  // lags per shared-memory stage of the fast kernel (small: leaves L1 to the taps)
 
 template <class Fast, typename SmallT, typename RefT, bool ROUND32, int PPT, int MINB, int GROUP>
 __global__ void __launch_bounds__(kThreads, MINB)
@@ -910,7 +931,8 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
           iy[j] = __double2loint(my);
           vx[j] = sxs[j] - (mx - kMagic);   // = d + 0.5 in [0, 1)
           vy[j] = sys[j] - (my - kMagic);
-          interior = interior && ((unsigned)(ix[j] - 1) < ux) && ((unsigned)(iy[j] - 1) < uy);
+          interior = interior && ((unsigned)(ix[j] - 1) < ux) && ((unsigned)(iy[j] - 1) < uy) &&
+                     small_magnitude(sxs[j]) && small_magnitude(sys[j]);
         }
         if (Fast::kCoordsAlwaysFinite) interior = interior && (((a_ok >> g) & ((1u << GROUP) - 1u)) == ((1u << GROUP) - 1u));
         if (interior) {
@@ -1024,6 +1046,303 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Column-rolling form of the fused helioprojective lag kernel (order-2 spline, FMA arithmetic, float64 small image).
+//
+// A thread owns P CONSECUTIVE rows of one common-grid column. Under a candidate header the homography moves that
+// column segment almost rigidly: x is constant to a small fraction of a pixel and y advances by one pixel per row,
+// so floor(x + 0.5) is shared by the P pixels and floor(y + 0.5) increases by exactly one per row ("regular"
+// column). The 3x3 tap windows of consecutive pixels then overlap in two of their three rows: the thread keeps a
+// rolling window of three tap rows in registers and loads 3 new taps per pixel instead of 9 (3 (P + 2) / P per pixel
+// overall) -- the L1 data pipe, not FP64 issue, bounded the per-pixel kernel. The fractional parts come from the
+// shared floors (x - floor_x0, y - (floor_y0 + p)); whether they really lie in [0, 1) is checked per pixel with one
+// integer compare on the high word, and a pixel that fails (a floor changed inside the segment: rotated lags, or a
+// coordinate within 1e-7 of a half-integer) is re-evaluated by the exact out-of-line sampler, as is every pixel of
+// a thread whose window touches the image border or whose reference pixels are not all finite. Results therefore
+// equal the per-pixel kernel's up to the rounding of the reciprocal series.
+// ---------------------------------------------------------------------------------------------------------
+// The P pixels of a regular window, fully unrolled and free of branches, selects and predicates so that the
+// independent dependency chains of consecutive pixels interleave (the FP64 pipe has an 8-cycle dependent-issue
+// latency). MODE selects the reciprocal series (0: 1 + e + e^2, 1: three-factor product). Validity is tracked for the
+// segment as a whole with two integer maxima: `vmax` over the high words of the fractional parts (all in [0, 1) <=>
+// vmax < 0x3FF00000) and `bmax` over the magnitude bits of the float32 samples (all finite <=> bmax < 0x7F800000);
+// the caller discards the sums and re-evaluates the segment pixel by pixel when either test fails.
+template <int MODE, bool ROUND32, int P>
+__device__ __forceinline__ void roll_segment(const double* __restrict__ small, unsigned tap, unsigned row_elems,
+                                             double be, double bnx, double bny, double he1, double hx1, double hy1,
+                                             double inv0, double xoff, double yoff, double pivot_b,
+                                             const double (&a_c)[P], double& sb, double& sbb, double& sab,
+                                             unsigned& vmax, unsigned& bmax) {
+  const double* rp = small + tap;
+  double r0a = __ldg(rp), r0b = __ldg(rp + 1), r0c = __ldg(rp + 2);
+  rp = small + (tap += row_elems);
+  double r1a = __ldg(rp), r1b = __ldg(rp + 1), r1c = __ldg(rp + 2);
+  rp = small + (tap += row_elems);
+  double r2a = __ldg(rp), r2b = __ldg(rp + 1), r2c = __ldg(rp + 2);
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    // next row's taps first: they are consumed one pixel later
+    double r3a = 0.0, r3b = 0.0, r3c = 0.0;
+    if (p + 1 < P) {
+      rp = small + (tap += row_elems);
+      r3a = __ldg(rp); r3b = __ldg(rp + 1); r3c = __ldg(rp + 2);
+    }
+    const double e = (p == 0) ? be : fma(he1, (double)p, be);
+    const double inv = (p == 0) ? inv0 : ((MODE == 0) ? recip_1me_tiny(e) : recip_1me_small(e));
+    const double nx = (p == 0) ? bnx : fma(hx1, (double)p, bnx);
+    const double ny = (p == 0) ? bny : fma(hy1, (double)p, bny);
+    // fractional parts (+0.5) relative to the shared floors: v = d + 0.5 in [0, 1) on a regular column
+    const double vx = fma(nx, inv, xoff);
+    const double vy = fma(ny, inv, yoff - (double)p);
+    vmax = max(vmax, max((unsigned)__double2hiint(vx), (unsigned)__double2hiint(vy)));
+    // order-2 B-spline weights: w2 = v^2/2, w0 = w2 + 1/2 - v, w1 = 1 - w0 - w2
+    const double wx2 = (0.5 * vx) * vx;
+    const double wx0 = (wx2 + 0.5) - vx;
+    const double wx1 = fma(-2.0, wx2, vx + 0.5);
+    const double wy2 = (0.5 * vy) * vy;
+    const double wy0 = (wy2 + 0.5) - vy;
+    const double wy1 = fma(-2.0, wy2, vy + 0.5);
+    const double q0 = fma(r0c, wx2, fma(r0b, wx1, r0a * wx0));
+    const double q1 = fma(r1c, wx2, fma(r1b, wx1, r1a * wx0));
+    const double q2 = fma(r2c, wx2, fma(r2b, wx1, r2a * wx0));
+    const double t = fma(q2, wy2, fma(q1, wy1, q0 * wy0));
+    double b;
+    if (ROUND32) {
+      const float bf = __double2float_rn(t);
+      bmax = max(bmax, (unsigned)__float_as_int(bf) & 0x7FFFFFFFu);
+      b = (double)bf;
+    } else {
+      // finite and not the -32762 fill: fold both into the same flag (the fill marks the sample as missing)
+      const unsigned hi = (unsigned)__double2hiint(t) & 0x7FFFFFFFu;
+      bmax = max(bmax, (t == -32762.0) ? 0x7F800000u : ((hi >= 0x7FF00000u) ? 0x7F800000u : 0u));
+      b = t;
+    }
+    const double bc = b - pivot_b;
+    sb += bc;
+    sbb = fma(bc, bc, sbb);
+    sab = fma(a_c[p], bc, sab);
+    r0a = r1a; r0b = r1b; r0c = r1c;
+    r1a = r2a; r1b = r2b; r1c = r2c;
+    r2a = r3a; r2b = r3b; r2c = r3c;
+  }
+}
+
+// One pixel by the per-pixel rules: own floors, 9 taps when they are all inside the image, otherwise the exact
+// out-of-line sampler. (sx, sy) are the coordinates + 0.5. Returns false when the sample is missing.
+template <bool ROUND32>
+__device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ small, int sny, int snx,
+                                                  unsigned row_elems, double sx, double sy, double* out) {
+  const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+  const int ix = __double2loint(mx), iy = __double2loint(my);
+  const bool interior = small_magnitude(sx) && small_magnitude(sy) && ((unsigned)(ix - 1) < (unsigned)(snx - 2)) &&
+                        ((unsigned)(iy - 1) < (unsigned)(sny - 2));
+  if (!interior) return sample_exact_half<ROUND32>(small, sny, snx, sy, sx, out);
+  const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);
+  const double wx2 = (0.5 * vx) * vx;
+  const double wx0 = (wx2 + 0.5) - vx;
+  const double wx1 = fma(-2.0, wx2, vx + 0.5);
+  const double wy2 = (0.5 * vy) * vy;
+  const double wy0 = (wy2 + 0.5) - vy;
+  const double wy1 = fma(-2.0, wy2, vy + 0.5);
+  const double* r0p = small + ((unsigned)(iy - 1) * row_elems + (unsigned)(ix - 1));
+  const double* r1p = r0p + row_elems;
+  const double* r2p = r1p + row_elems;
+  const double q0 = fma(__ldg(r0p + 2), wx2, fma(__ldg(r0p + 1), wx1, __ldg(r0p) * wx0));
+  const double q1 = fma(__ldg(r1p + 2), wx2, fma(__ldg(r1p + 1), wx1, __ldg(r1p) * wx0));
+  const double q2 = fma(__ldg(r2p + 2), wx2, fma(__ldg(r2p + 1), wx1, __ldg(r2p) * wx0));
+  const double t = fma(q2, wy2, fma(q1, wy1, q0 * wy0));
+  if (ROUND32) {
+    const float bf = __double2float_rn(t);
+    *out = (double)bf;
+    return isfinite(bf);
+  }
+  *out = t;
+  return isfinite(t) && (t != -32762.0);
+}
+
+constexpr int kRollChunk = 8;  // lags whose per-thread sums wait in shared memory for one block-wide reduction
+
+// Shared memory of the rolling kernel, per block: per-thread (Sb, Sbb, Sab) of kRollChunk lags, transposed so that
+// both the stores and the reduction reads are conflict-free; per-warp corrections (n, Sa, Saa of the pixels that
+// have a reference value but no sample) for the rare lags that have any.
+struct RollShared {
+  double acc[kRollChunk][3][kThreads];
+  double corr[kRollChunk][kWarps][3];
+  HomLag lag[kRollChunk];
+  double tile_const[3];  // n, Sa, Saa over the tile's finite reference pixels
+  double warp_const[kWarps][3];
+};
+
+template <typename RefT, bool ROUND32, int P, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small, int snx, int sny, int gnx,
+                     int gny, const HomLag* __restrict__ lags, int n_lags, int lags_per_block,
+                     const double* __restrict__ pivots, double* __restrict__ work) {
+  constexpr int TILE_H = kRowsPerPass * P;  // 4 row groups of P consecutive rows
+  extern __shared__ __align__(16) unsigned char roll_smem[];
+  RollShared& S = *reinterpret_cast<RollShared*>(roll_smem);
+
+  const int tiles_x = (gnx + kTileW - 1) / kTileW;
+  const int tile = blockIdx.x;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & (kTileW - 1), rg = tid / kTileW;
+  const int gx = tile_x * kTileW + tx;
+  const int gy0 = tile_y * TILE_H + rg * P;
+  const double pivot_a = pivots[0], pivot_b = pivots[1];
+  const unsigned row_elems = (unsigned)snx;
+  const double di = (double)gx, dj0 = (double)gy0;
+
+  double a_c[P];
+  unsigned a_ok = 0;
+  double sa_all = 0.0, saa_all = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int gy = gy0 + p;
+    a_c[p] = 0.0;
+    if (gx < gnx && gy < gny) {
+      const double a = (double)ref[(int64_t)gy * gnx + gx];
+      if (isfinite(a)) {
+        a_c[p] = a - pivot_a;
+        a_ok |= 1u << p;
+        sa_all += a_c[p];
+        saa_all = fma(a_c[p], a_c[p], saa_all);
+      }
+    }
+  }
+  const bool all_ref = a_ok == ((1u << P) - 1u);
+  {
+    // lag-independent reference moments of the tile: warp butterflies, then a fixed-order fold over the warps
+    double wsa = sa_all, wsaa = saa_all;
+    int wn = __popc(a_ok);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
+      wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
+      wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    }
+    if (lane == 0) {
+      S.warp_const[warp][0] = (double)wn;
+      S.warp_const[warp][1] = wsa;
+      S.warp_const[warp][2] = wsaa;
+    }
+    __syncthreads();
+    if (tid < 3) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += S.warp_const[w][tid];
+      S.tile_const[tid] = t;
+    }
+  }
+
+  const int lag_begin = blockIdx.y * lags_per_block;
+  const int lag_end = min(n_lags, lag_begin + lags_per_block);
+  for (int l0 = lag_begin; l0 < lag_end; l0 += kRollChunk) {
+    const int cnt = min(kRollChunk, lag_end - l0);
+    __syncthreads();  // previous chunk fully reduced
+    {
+      const double* src = reinterpret_cast<const double*>(lags + l0);
+      double* dst = reinterpret_cast<double*>(S.lag);
+      const int nd = cnt * (int)(sizeof(HomLag) / sizeof(double));
+      for (int i = tid; i < nd; i += kThreads) dst[i] = src[i];
+      for (int i = tid; i < kRollChunk * kWarps * 3; i += kThreads) (&S.corr[0][0][0])[i] = 0.0;
+    }
+    __syncthreads();
+    for (int l = 0; l < cnt; ++l) {
+      const HomLag& C = S.lag[l];
+      const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
+      const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
+      // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
+      const double bnx = fma(hx1, dj0, fma(C.hx0, di, C.hx2));
+      const double bny = fma(hy1, dj0, fma(C.hy0, di, C.hy2));
+      const double be = fma(he1, dj0, fma(C.he0, di, C.he2));
+      const double inv0 = (mode == 0) ? recip_1me_tiny(be) : ((mode == 1) ? recip_1me_small(be) : recip_1me_div(be));
+      const double sx0 = fma(bnx, inv0, x0h), sy0 = fma(bny, inv0, y0h);  // coordinates + 0.5
+      // floors shared by the segment
+      const double mx0 = __dadd_rd(sx0, kMagic), my0 = __dadd_rd(sy0, kMagic);
+      const int ix0 = __double2loint(mx0), iy0 = __double2loint(my0);
+      const double xoff = x0h - (mx0 - kMagic), yoff = y0h - (my0 - kMagic);
+      double sb = 0.0, sbb = 0.0, sab = 0.0;
+      // whole window inside the image: columns ix0-1 .. ix0+1, rows iy0-1 .. iy0+P; |coordinate| < 2^30 keeps the
+      // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
+      bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
+                  ((unsigned)(ix0 - 1) < (unsigned)(snx - 2)) && (iy0 >= 1) && (iy0 + P <= sny - 1);
+      if (fast) {
+        const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
+        unsigned vmax = 0, bmax = 0;
+        if (mode == 0)
+          roll_segment<0, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
+                                      a_c, sb, sbb, sab, vmax, bmax);
+        else
+          roll_segment<1, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
+                                      a_c, sb, sbb, sab, vmax, bmax);
+        fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u);
+      }
+      unsigned miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
+      if (!fast && a_ok) {
+        // image borders, irregular columns (rotated lags), missing pixels: the segment pixel by pixel
+        sb = sbb = sab = 0.0;
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+          if (!(a_ok & (1u << p))) continue;
+          const double e = fma(he1, (double)p, be);
+          const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
+          const double sx = fma(fma(hx1, (double)p, bnx), inv, x0h);
+          const double sy = fma(fma(hy1, (double)p, bny), inv, y0h);
+          double ac = a_c[0];
+#pragma unroll
+          for (int q = 1; q < P; ++q)
+            if (q == p) ac = a_c[q];
+          double b;
+          if (sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, &b)) {
+            const double bc = b - pivot_b;
+            sb += bc;
+            sbb = fma(bc, bc, sbb);
+            sab = fma(ac, bc, sab);
+          } else {
+            miss |= 1u << p;
+          }
+        }
+      }
+      S.acc[l][0][tid] = sb;
+      S.acc[l][1][tid] = sbb;
+      S.acc[l][2][tid] = sab;
+      if (__any_sync(0xffffffffu, miss != 0)) {
+        double m[4] = {(double)__popc(miss), 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (miss & (1u << p)) {
+            m[1] += a_c[p];
+            m[2] = fma(a_c[p], a_c[p], m[2]);
+          }
+        const double tot = warp_transpose_reduce4(m, lane);  // lanes 0, 8, 16: n, Sa, Saa of the missing pixels
+        if ((lane & 7) == 0 && lane < 24) S.corr[l][warp][lane >> 3] = tot;
+      }
+    }
+    __syncthreads();
+    // block-wide reduction of the chunk in a fixed order: warp w takes (lag, moment) pairs w, w + 8, ...;
+    // every lane folds its 8 strided values, then one butterfly
+    for (int pair = warp; pair < cnt * 3; pair += kWarps) {
+      const int l = pair / 3, v = pair % 3;
+      const double* src = &S.acc[l][v][0];
+      double t = src[lane];
+#pragma unroll
+      for (int k = 1; k < kThreads / 32; ++k) t += src[lane + 32 * k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) {
+        double c = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) c += S.corr[l][w][v];
+        double* dst = work + ((size_t)tile * n_lags + (l0 + l)) * kMom;
+        // slots: n, Sa, Sb, Saa, Sbb, Sab
+        dst[v == 0 ? 2 : (v == 1 ? 4 : 5)] = t;
+        dst[v == 0 ? 0 : (v == 1 ? 1 : 3)] = S.tile_const[v] - c;
+      }
+    }
+  }
+}
+
 // one block per lag: sum the tile partials in a fixed order, moments -> Pearson r
 __global__ void __launch_bounds__(128)
 lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lags, double* __restrict__ corr,
@@ -1060,14 +1379,13 @@ lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lag
   }
 }
 
-// tuning variants (flags bits 8..11): tile height = 4*PPT, MINB resident blocks per SM
-// grid for a (ppt, minb) variant; returns false when the lag list does not fit one launch
-inline bool lag_grid(int ppt, int minb, int gnx, int gny, int64_t n_lags, int sms, dim3* grid, int* lags_per_block,
+// grid for a (rows per tile, resident blocks per SM) choice: blockIdx.x = tile, blockIdx.y = slice of the lag list,
+// enough slices for a few waves of resident blocks; returns false when the lag list does not fit one launch
+inline bool lag_grid(int tile_h, int minb, int gnx, int gny, int64_t n_lags, int sms, dim3* grid, int* lags_per_block,
                      int* tiles_out, int lag_sub) {
-  const int tile_h = kRowsPerPass * ppt;
   const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
   *tiles_out = tiles;
-  const int want_blocks = sms * minb * 4;   // a few waves of resident blocks
+  const int want_blocks = sms * minb * 4;
   int splits = (want_blocks + tiles - 1) / tiles;
   const int max_splits = (int)((n_lags + lag_sub - 1) / lag_sub);
   splits = std::max(1, std::min(splits, max_splits));
@@ -1080,37 +1398,58 @@ inline bool lag_grid(int ppt, int minb, int gnx, int gny, int64_t n_lags, int sm
   return true;
 }
 
-// launch the fast kernel over an already-built fast lag table
+// tuning variants (flags bits 8..11) of the per-pixel fast kernel: (pixels per thread, resident CTAs per SM, group)
 template <class Fast, typename SmallT, typename RefT, bool ROUND32>
 int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
                     const SmallT* small, int snx, int sny, typename Fast::Planes planes,
                     const typename Fast::LagC* ft, const double* pivots, double* w, int* tiles_out) {
-  // (pixels per thread, resident CTAs per SM, interleave group); 0 = fastest measured on config 1
-  static const int kVar[10][3] = {{4, 3, 2}, {8, 2, 2}, {4, 2, 2}, {8, 2, 4}, {4, 4, 2},
-                                  {8, 3, 2}, {6, 2, 2}, {6, 3, 2}, {4, 2, 4}, {4, 3, 1}};
-  if (variant < 0 || variant > 9) variant = 0;
-  const int ppt = kVar[variant][0], minb = kVar[variant][1];
+  static const int kVar[3][2] = {{4, 3}, {8, 2}, {4, 4}};
+  if (variant < 0 || variant > 2) variant = 0;
   dim3 grid;
   int lpb;
-  if (!lag_grid(ppt, minb, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out, kFastLagSub))
+  if (!lag_grid(kRowsPerPass * kVar[variant][0], kVar[variant][1], gnx, gny, n_lags, sms, &grid, &lpb, tiles_out,
+                kFastLagSub))
     return fail(COREG_EINVAL, "lag grid too large for one launch");
 #define LF(PPT_, MINB_, G_)                                                                     \
   lag_corr_fast_kernel<Fast, SmallT, RefT, ROUND32, PPT_, MINB_, G_><<<grid, kThreads, 0, s>>>( \
       ref, small, snx, sny, gnx, gny, planes, ft, (int)n_lags, lpb, pivots, w)
   switch (variant) {
     case 1: LF(8, 2, 2); break;
-    case 2: LF(4, 2, 2); break;
-    case 3: LF(8, 2, 4); break;
-    case 4: LF(4, 4, 2); break;
-    case 5: LF(8, 3, 2); break;
-    case 6: LF(6, 2, 2); break;
-    case 7: LF(6, 3, 2); break;
-    case 8: LF(4, 2, 4); break;
-    case 9: LF(4, 3, 1); break;
+    case 2: LF(4, 4, 2); break;
     default: LF(4, 3, 2); break;
   }
 #undef LF
   return COREG_OK;
+}
+
+// tuning variants of the column-rolling kernel: (consecutive rows per thread, resident CTAs per SM)
+#ifndef COREG_ROLL_VARIANTS
+#define COREG_ROLL_VARIANTS X(0, 8, 2) X(1, 6, 3) X(2, 12, 2) X(3, 4, 3)
+#endif
+template <typename RefT, bool ROUND32>
+int launch_lag_roll(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
+                    const double* small, int snx, int sny, const HomLag* ft, const double* pivots, double* w,
+                    int* tiles_out) {
+  dim3 grid;
+  int lpb;
+  bool done = false;
+#define X(V_, P_, MINB_)                                                                                        \
+  if (!done && variant == V_) {                                                                                 \
+    if (!lag_grid(kRowsPerPass * P_, MINB_, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out, kRollLagSub))        \
+      return fail(COREG_EINVAL, "lag grid too large for one launch");                                           \
+    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, MINB_>;                                                 \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollShared));           \
+    kern<<<grid, kThreads, sizeof(RollShared), s>>>(ref, small, snx, sny, gnx, gny, ft, (int)n_lags, lpb,       \
+                                                    pivots, w);                                                 \
+    done = true;                                                                                                \
+  }
+  COREG_ROLL_VARIANTS
+  if (!done) {
+    variant = 0;
+    COREG_ROLL_VARIANTS
+  }
+#undef X
+  return done ? COREG_OK : fail(COREG_EINVAL, "no such kernel variant");
 }
 
 template <typename SmallT, typename RefT, bool ROUND32>
@@ -1129,40 +1468,21 @@ int launch_offset_fast(int, int, int, int64_t, int, cudaStream_t, const RefT*, c
   return fail(COREG_EINVAL, "internal: offset fast path requested for the TAN functor");
 }
 
+// generic kernel: variant 1 = 8 pixels per thread, 2 CTAs / SM; anything else 4 pixels per thread, 4 CTAs / SM
 template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
 int launch_lag_variant(int variant, dim3 grid_tiles_of, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s,
                        const RefT* ref, const SmallT* small, int snx, int sny, typename Coord::Planes planes,
                        const typename Coord::Lag* lags, const double* pivots, double* w, int* tiles_out) {
   (void)grid_tiles_of;
-  int ppt, minb;
-  switch (variant) {  // measured on config 1 (profiles/r1_k1_tuning.md): 0 is the fastest
-    case 1: ppt = 8; minb = 2; break;
-    case 2: ppt = 8; minb = 3; break;
-    case 3: ppt = 4; minb = 3; break;
-    default: ppt = 4; minb = 4; break;
-  }
-  const int tile_h = kRowsPerPass * ppt;
-  const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
-  *tiles_out = tiles;
-  // split the lag list over blockIdx.y until the grid has a few waves of resident blocks
-  const int want_blocks = sms * minb * 4;
-  int splits = (want_blocks + tiles - 1) / tiles;
-  const int max_splits = (int)((n_lags + kLagSub - 1) / kLagSub);
-  splits = std::max(1, std::min(splits, max_splits));
-  int lags_per_block = (int)((n_lags + splits - 1) / splits);
-  lags_per_block = ((lags_per_block + kLagSub - 1) / kLagSub) * kLagSub;
-  splits = (int)((n_lags + lags_per_block - 1) / lags_per_block);
-  if (splits > 65535) return fail(COREG_EINVAL, "lag grid too large for one launch");
-  dim3 grid(tiles, splits);
+  const int ppt = (variant == 1) ? 8 : 4, minb = (variant == 1) ? 2 : 4;
+  dim3 grid;
+  int lags_per_block;
+  if (!lag_grid(kRowsPerPass * ppt, minb, gnx, gny, n_lags, sms, &grid, &lags_per_block, tiles_out, kLagSub))
+    return fail(COREG_EINVAL, "lag grid too large for one launch");
 #define LV(PPT_, MINB_)                                                                                     \
   lag_corr_kernel<Coord, ORDER, STRICT, SmallT, RefT, ROUND32, PPT_, MINB_><<<grid, kThreads, 0, s>>>(      \
       ref, small, snx, sny, gnx, gny, planes, lags, (int)n_lags, lags_per_block, pivots, w)
-  switch (variant) {
-    case 1: LV(8, 2); break;
-    case 2: LV(8, 3); break;
-    case 3: LV(4, 3); break;
-    default: LV(4, 4); break;
-  }
+  if (variant == 1) LV(8, 2); else LV(4, 4);
 #undef LV
   return COREG_OK;
 }
@@ -1306,12 +1626,11 @@ inline int grid_for(int64_t n, int threads = 256) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
 }
 
-template <typename SmallT>
-int hpc_lag_corr_wcs_impl(const float* ref, const SmallT* small, int snx, int sny, int gnx, int gny,
+int hpc_lag_corr_wcs_impl(const float* ref, const double* small, int snx, int sny, int gnx, int gny,
                           const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags,
                           const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s) {
   HomGrid g;
-  int rc = make_hom_grid(grid_wcs, &g);
+  int rc = make_hom_grid(grid_wcs, gnx, gny, &g);
   if (rc) return rc;
   int sms = coreg_device_sm_count();
   if (sms <= 0) sms = 148;
@@ -1325,17 +1644,11 @@ int hpc_lag_corr_wcs_impl(const float* ref, const SmallT* small, int snx, int sn
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
     CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
-  const int variant = (flags >> 8) & 15;
   int tiles = 0;
-  TanHom<true>::Planes none;
-  if (flags & COREG_FLAG_SMALL_ANGLE)
-    rc = launch_lag_fast<TanHom<true>, SmallT, float, true>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny,
-                                                            none, ft, pivots, w, &tiles);
-  else
-    rc = launch_lag_fast<TanHom<false>, SmallT, float, true>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny,
-                                                             TanHom<false>::Planes(), ft, pivots, w, &tiles);
+  rc = launch_lag_roll<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, w,
+                                    &tiles);
   if (rc) return rc;
-  CK_LAUNCH("lag_corr_fast_kernel");
+  CK_LAUNCH("lag_corr_roll_kernel");
   if (prof) {
     CK(cudaEventRecord(g_prof[g_prof_n].b, s));
     ++g_prof_n;
@@ -1449,7 +1762,7 @@ int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int
   return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
 }
 
-int coreg_hpc_lag_corr_wcs(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
+int coreg_hpc_lag_corr_wcs(const float* ref, const double* small, int snx, int sny, int gnx, int gny,
                            const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags, int order,
                            const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid,
                            int flags, void* stream) {
@@ -1462,14 +1775,8 @@ int coreg_hpc_lag_corr_wcs(const float* ref, const void* small, int small_dtype,
   if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
   if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
   if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (small_dtype == COREG_F64)
-    return hpc_lag_corr_wcs_impl<double>(ref, (const double*)small, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags,
-                                         pivots, work, corr, nvalid, flags, s);
-  if (small_dtype == COREG_F32)
-    return hpc_lag_corr_wcs_impl<float>(ref, (const float*)small, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags,
-                                        pivots, work, corr, nvalid, flags, s);
-  return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
+  return hpc_lag_corr_wcs_impl(ref, small, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr, nvalid,
+                               flags, (cudaStream_t)stream);
 }
 
 int coreg_carrington_planes(const CoregCarrington* c, const double* sinlon, const double* coslon, int n_lon,
@@ -1611,8 +1918,8 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   TRYRC(coreg_finite_mean(d_ref, COREG_F32, ns, d_piv, s));
   TRYRC(coreg_finite_mean(d_small, COREG_F64, ns, d_piv + 1, s));
   if (fast) {
-    TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, COREG_F64, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv,
-                                 d_work, work_bytes, d_corr, d_nv, flags, s));
+    TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv, d_work,
+                                 work_bytes, d_corr, d_nv, flags, s));
   } else {
     TRY(cudaMalloc(&d_planes, 3 * ns * sizeof(double)));
     TRY(cudaMalloc(&d_lags, n_lags * sizeof(CoregLagTan)));

@@ -169,8 +169,6 @@ class LagSearchEngine:
 
     max_workspace_bytes = 1 << 30
 
-    small_angle_limit_deg = 6.5   # the fast TAN kernel's reciprocal series is exact to 2^-56 within 7.1 deg
-
     def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64", no_fast=False):
         torch = _torch()
         _ext.load()  # fail loudly when the CUDA library is missing
@@ -250,21 +248,11 @@ class LagSearchEngine:
                 self.planes = _ext.tan_trig_planes(lng, lat, w.crval1)
         return self.planes
 
-    def _small_angle(self, wcs_table):
-        """True when every (pixel, lag) pair is within `small_angle_limit_deg` of the lag's reference point:
-        FOV radius + largest displacement of the reference point over the lag table (triangle inequality)."""
-        if self.fov_radius_deg is None:
-            return False
-        da = np.abs(wcs_table[:, 8] - self.alpha_ref_deg)
-        da = np.minimum(da, 360.0 - da)
-        d0 = np.abs(wcs_table[:, 9] - self.delta_ref_deg)
-        shift = float(np.max(da + d0)) if wcs_table.shape[0] else 0.0
-        return bool(np.isfinite(shift) and self.fov_radius_deg + shift < self.small_angle_limit_deg)
-
     def hpc_fast_eligible(self):
         """The homography kernel covers spline order 2 with FMA arithmetic on images of at least 3x3 pixels."""
+        torch = _torch()
         return (self.order == 2 and not self.strict and not self.no_fast and self.small is not None
-                and min(self.small.shape) >= 3)
+                and self.small.dtype == torch.float64 and min(self.small.shape) >= 3)
 
     def hpc_lag_table(self, hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics="reference"):
         """Host lag table for `search` in the helioprojective frame + the mask of lags the reference cannot
@@ -368,10 +356,6 @@ class LagSearchEngine:
         dist, rank, world = _dist_info()
         chunk, bounds = shard_bounds(n, world)
         lo, hi = bounds[rank]
-        if self.frame == "hpc":
-            wcs_rows = table.shape[1] == _ext.TAN_WCS_DOUBLES
-            self.flags = _ext.make_flags(self.strict, self.variant,
-                                         small_angle=wcs_rows and self._small_angle(table), no_fast=self.no_fast)
         with torch.cuda.device(self.device):
             local = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
             nvalid = torch.zeros(chunk, dtype=torch.int64, device=self.device) if return_nvalid else None

@@ -37,13 +37,7 @@ extern "C" {
  * COREG_FLAG_STRICT: scipy's exact operation order (separate multiply / add), bit-faithful per sample.
  * bits 8..11: tuning variant of the fused kernel (0 = default tile / occupancy). */
 #define COREG_FLAG_STRICT 1
-/* COREG_FLAG_SMALL_ANGLE (coreg_hpc_lag_corr_wcs): the caller guarantees that every common-grid pixel lies within
- * 6 degrees of the common grid's own reference point and of every lag's reference point (CRVAL of the shifted
- * header). The reciprocal of the projective denominator is then a 3-factor geometric-series product exact to
- * 2^-56; without the flag a true division is used. Always true for HRIEUV/FSI/SPICE fields;
- * euispice_coreg_b200.hdrshift.engine checks it from the header geometry. */
-#define COREG_FLAG_SMALL_ANGLE 2
-/* COREG_FLAG_NO_FAST: force the generic kernel (testing / comparison). */
+/* COREG_FLAG_NO_FAST (value 4; 2 is reserved): force the generic kernel (testing / comparison). */
 #define COREG_FLAG_NO_FAST 4
 #define COREG_FLAG_VARIANT(v) (((v) & 15) << 8)
 
@@ -143,14 +137,17 @@ int coreg_hpc_lag_corr(const float* ref_dev, const void* small_dev, int small_dt
                        int64_t* nvalid_dev, int flags, void* stream);
 
 /* ---- K1 (fast form): fused helioprojective lag search from headers --------------------------------------------------
- * Same computation and outputs as coreg_hpc_lag_corr for spline order 2 with FMA arithmetic, but each lag is given
- * as the candidate header itself (CoregTanWcs = the output of _shift_header, hdrshift/alignment.py:401-468) and the
- * common grid as its own CoregTanWcs: two gnomonic projections of one sphere are related by a plane homography, so
- * the per-pixel map is three FMAs and a reciprocal on integer pixel indices -- no world-coordinate planes.
+ * Same computation and outputs as coreg_hpc_lag_corr for spline order 2 with FMA arithmetic and a float64 small image,
+ * but each lag is given as the candidate header itself (CoregTanWcs = the output of _shift_header,
+ * hdrshift/alignment.py:401-468) and the common grid as its own CoregTanWcs: two gnomonic projections of one sphere
+ * are related by a plane homography, so the per-pixel map is three FMAs and a reciprocal on integer pixel indices --
+ * no world-coordinate planes. The reciprocal is a 2- or 5-term series or a true division, chosen per lag on the
+ * device from the exact range of the denominator over the grid (no caller guarantee needed). Threads walk grid
+ * columns and share spline tap rows between consecutive pixels (column-rolling kernel).
  *   grid_wcs_host  the common grid (the UNSHIFTED small header)          lag_wcs_dev  [n_lags] device array
  * Returns COREG_EINVAL for other orders / COREG_FLAG_STRICT (use coreg_hpc_lag_corr then). */
-int coreg_hpc_lag_corr_wcs(const float* ref_dev, const void* small_dev, int small_dtype, int snx, int sny, int gnx,
-                           int gny, const CoregTanWcs* grid_wcs_host, const CoregTanWcs* lag_wcs_dev, int64_t n_lags,
+int coreg_hpc_lag_corr_wcs(const float* ref_dev, const double* small_dev, int snx, int sny, int gnx, int gny,
+                           const CoregTanWcs* grid_wcs_host, const CoregTanWcs* lag_wcs_dev, int64_t n_lags,
                            int order, const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
                            int64_t* nvalid_dev, int flags, void* stream);
 
@@ -194,8 +191,8 @@ int coreg_synras_build(const void* frames_dev, int frame_dtype, int n_frames, in
  *   large_host [lny*lnx], small_host [sny*snx] (NaN = masked): COREG_F32 or COREG_F64 as given by *_dtype (float32
  *   FITS payloads need no widening on the host; the small image is widened once on the device).
  *   lag_wcs_host [n_lags] CoregTanWcs = the candidate headers (output of _shift_header, alignment.py:401-468).
- *   Order 2 without COREG_FLAG_STRICT / COREG_FLAG_NO_FAST runs the homography kernel (coreg_hpc_lag_corr_wcs; pass
- *   COREG_FLAG_SMALL_ANGLE when its guarantee holds), anything else the generic kernel (coreg_hpc_lag_corr).
+ *   Order 2 without COREG_FLAG_STRICT / COREG_FLAG_NO_FAST runs the homography kernel (coreg_hpc_lag_corr_wcs),
+ *   anything else the generic kernel (coreg_hpc_lag_corr).
  *   corr_host [n_lags] out, nvalid_host [n_lags] out (may be NULL). */
 int coreg_hpc_search_host(const void* large_host, int large_dtype, int lnx, int lny, const CoregTanWcs* wcs_large,
                           const void* small_host, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,

@@ -199,7 +199,7 @@ def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
     w_small = TanWcs.from_header(a.hdr_small)
     table, _ = engine.tan_wcs_table(a.hdr_small, a, *d)
-    flags = _ext.make_flags(small_angle=True)
+    flags = _ext.make_flags()
     corr, nvalid = _ext.hpc_search_host(dl.astype(np.float64), TanWcs.from_header(hl), ds.astype(np.float64), w_small,
                                         table, flags=flags)
     assert np.array_equal(corr.reshape(gpu.shape), gpu)
@@ -260,3 +260,35 @@ def test_determinism_and_lag_sharding_invariance(torch_cuda, toy_pair):
     table_g, _ = eng_g.hpc_lag_table(a.hdr_small, a, *d)
     assert table_g.shape[1] == 10
     assert np.nanmax(np.abs(eng_g.search(table_g) - gpu.ravel())) < 1e-11
+
+
+def test_config1_full_size_bounded_sample_vs_oracle(torch_cuda):
+    """BASELINE.json configs[0] at full size (2048^2 vs 3072^2, 60x60 CRVAL lags): the whole GPU cube through the
+    public API against the oracle on a bounded sample of lags (the oracle needs ~5 s per lag per core).
+
+    The lag (0, 0) is the known knife edge: the candidate header equals the grid's own header,
+    every pixel maps onto itself to ~1e-11 px, and whether the four border rows / columns pass map_coordinates'
+    closed bound [0, n-1] is decided by the last bits of the pixel->world->pixel round trip -- in the reference too.
+    There only the membership of border pixels may differ: |dr| < 1e-3 and at most two border rows + columns."""
+    import os
+    import bench
+    from euispice_coreg_b200.hdrshift import Alignment
+    from oracle.hpc import HpcSearch, cube_multiprocess
+    pl, ps = bench.ensure_config1()
+    a = Alignment(pl, ps, parallelism=True, **bench.LAGS)
+    cube = a.align_using_helioprojective(return_type="corr")
+    assert cube.shape == (60, 60, 1, 1, 1, 1)
+    gpu = cube.ravel()
+    nvalid = a.nvalid.ravel()
+    dl, hl, ds, hs = load_pair(pl, ps)
+    search = HpcSearch(dl, hl, ds, hs, **bench.LAGS)
+    zero = 30 * 60 + 30
+    sel = np.array([0, 59, 3540, 3599, 54 * 60 + 36, 1000, 2500, zero])   # corners, the peak (24, 6), interior, (0, 0)
+    assert bench.LAGS["lag_crval1"][30] == 0.0
+    cores = max(1, min(len(sel), len(os.sched_getaffinity(0))))
+    ref = cube_multiprocess(search, cores, sel)
+    err = np.abs(gpu[sel] - ref)
+    assert np.all(err[:-1] <= R_TOL), err
+    assert err[:-1].max() < 1e-10
+    assert err[-1] < 1e-3 and 2048 * 2048 - nvalid[zero] <= 2 * (2048 + 2048)
+    assert int(np.nanargmax(gpu)) == 54 * 60 + 36

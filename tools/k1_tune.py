@@ -45,7 +45,6 @@ def main():
                 eng.prepare_hpc(a.data_large, w_large, w_small)
                 table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
                 fast = table.shape[1] == _ext.TAN_WCS_DOUBLES
-                eng.flags = _ext.make_flags(strict, v, small_angle=fast and eng._small_angle(table), no_fast=no_fast)
                 tab = eng._upload(table)
                 out = torch.empty(table.shape[0], dtype=torch.float64, device=eng.device)
                 eng.evaluate(tab, out)
