@@ -29,7 +29,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "config1: HRIEUV-like 2048x2048 vs FSI174-like 3072x3072, helioprojective, 60x60 CRVAL lags @1arcsec"
-FP64_INSTR_PER_SAMPLE = 69.0   # algorithmic FP64 instructions per pixel-sample (HPC)
+FP64_INSTR_PER_SAMPLE = 69.0   # algorithmic FP64 instructions per pixel-sample (HPC), counted
+#                                on the reference's formulation (pixel -> world -> pixel per lag)
+FP64_EXECUTED_PER_SAMPLE = 37.5  # FP64 thread-instructions the column-rolling kernel actually executes per pixel-sample
+#                                  (ncu: DADD + DMUL + DFMA of one launch / pixel-samples, profiles/r1_roll_kernel.md)
 BYTES_PER_SAMPLE = 8.0         # un-amortised: one f32 sample of each image per pixel-sample
 LAGS = dict(lag_crval1=np.arange(-30, 30, 1.0), lag_crval2=np.arange(-30, 30, 1.0), lag_cdelt1=np.array([0.0]),
             lag_cdelt2=np.array([0.0]), lag_crota=np.array([0.0]))
@@ -230,6 +233,7 @@ def run_gpu(args):
     value = n_lags * args.steps / (ms_total * 1e-3)
 
     # ---- end to end: host buffers -> cube on the host, every step -------------------------------------------
+    # host inputs of the end-to-end arm: the images as the FITS files hold them (float32), in pinned memory
     h_large = torch.from_numpy(np.ascontiguousarray(a.data_large)).pin_memory().numpy()
     h_small = torch.from_numpy(np.ascontiguousarray(a.data_small)).pin_memory().numpy()
     e2e_steps = max(1, min(args.steps, 5))
@@ -255,7 +259,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     small_bytes = eng.small.numel() * eng.small.element_size()
-    h2d = a.data_large.nbytes + small_bytes + table[lo:hi].nbytes
+    h2d = h_large.nbytes + h_small.nbytes + table[lo:hi].nbytes
     d2h = n_lags * 8
 
     # full public API once on every rank (FITS read + host prep + sharded search + all-gather + Gaussian fit):
@@ -296,17 +300,26 @@ def run_gpu(args):
             "pixel_samples_per_s": value * n_pix,
             "e2e": {"value": n_lags * e2e_steps / e2e_s, "unit": "lag-evals/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "what": "LagSearchEngine from pinned host arrays: H2D images+lag table, one-time resampling, "
-                            "search, all-gather, D2H cube"},
+                    "what": f"LagSearchEngine from pinned host arrays ({h_large.dtype} large, {h_small.dtype} small, as "
+                            "the FITS files hold them): H2D images + lag table, one-time resampling, search, "
+                            "all-gather, D2H cube"},
             "align_wall_s": align_wall, "argmax_lag_arcsec": best,
             "gpu_launches": int(k1_launches + k1_launches),  # fused lag kernel + finalize per launch pair
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": ach_instr / 1e12, "peak": fp64_peak / 1e12,
                          "unit": "T FP64-instr/s", "frac": ach_instr / fp64_peak, "traffic": None,
-                         "kernel": "lag_corr_kernel<TanCoord,2>", "kernel_ms": k1_avg_ms,
-                         "algorithmic": f"{FP64_INSTR_PER_SAMPLE:.0f} FP64 instr/pixel-sample x "
-                                        f"{samples_per_launch:.3e} pixel-samples/launch",
+                         "kernel": "lag_corr_roll_kernel" if fast else "lag_corr_kernel<TanCoord>",
+                         "kernel_ms": k1_avg_ms,
+                         "algorithmic": f"{FP64_INSTR_PER_SAMPLE:.0f} FP64 instr/pixel-sample (SURVEY 8d, reference "
+                                        f"formulation) x {samples_per_launch:.3e} pixel-samples/launch",
                          "peak_source": "coreg_fp64_peak DFMA microbenchmark, this run"},
+            "roofline_executed": {"bound": "fp64", "unit": "T FP64-instr/s", "peak": fp64_peak / 1e12,
+                                  "achieved": (FP64_EXECUTED_PER_SAMPLE if fast else None) and
+                                  FP64_EXECUTED_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3) / 1e12,
+                                  "frac": (FP64_EXECUTED_PER_SAMPLE if fast else None) and
+                                  FP64_EXECUTED_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3) / fp64_peak,
+                                  "what": "FP64 instructions the kernel really issues (the homography + shared-floor "
+                                          "formulation needs 37.5 per pixel-sample, not 69) against the same peak"},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                              "algorithmic": f"{BYTES_PER_SAMPLE:.0f} B/pixel-sample (un-amortised)"},

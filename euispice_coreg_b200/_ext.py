@@ -53,6 +53,7 @@ _SIGNATURES = {
     "coreg_map_coordinates": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_double,
                                         _P, C.c_int, _P]),
     "coreg_tan_trig_planes": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
+    "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_finite_mean": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
     "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
@@ -190,6 +191,19 @@ def tan_trig_planes(lng, lat, alpha_ref_deg):
         _check(lib.coreg_tan_trig_planes(_ptr(lng), _ptr(lat), lng.numel(), float(alpha_ref_deg), _ptr(planes),
                                          _stream()), "coreg_tan_trig_planes")
     return planes
+
+
+def widen_f32(img):
+    """float32 device image -> float64 (exact), on the device."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(img)
+    if img.dtype != torch.float32:
+        raise TypeError("float32 tensor expected")
+    out = torch.empty(img.shape, dtype=torch.float64, device=img.device)
+    with torch.cuda.device(img.device):
+        _check(lib.coreg_widen_f32(_ptr(img), img.numel(), _ptr(out), _stream()), "coreg_widen_f32")
+    return out
 
 
 def finite_mean(img, out):

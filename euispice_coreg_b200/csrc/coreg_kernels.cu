@@ -1726,6 +1726,14 @@ int coreg_tan_trig_planes(const double* lng, const double* lat, int64_t n, doubl
   return COREG_OK;
 }
 
+int coreg_widen_f32(const float* in, int64_t n, double* out, void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!in || !out) return fail(COREG_EINVAL, "coreg_widen_f32: null pointer");
+  f32_to_f64_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, n, out);
+  CK_LAUNCH("f32_to_f64_kernel");
+  return COREG_OK;
+}
+
 int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void* stream) {
   if (!img || !mean || n <= 0) return fail(COREG_EINVAL, "coreg_finite_mean: bad argument");
   if (dtype == COREG_F32)

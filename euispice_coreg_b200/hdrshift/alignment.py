@@ -167,14 +167,23 @@ class Alignment:
     def _load_pair(self):
         f_large = _open_fits(self.large_fov_known_pointing)
         f_small = _open_fits(self.small_fov_to_correct)
-        self.data_large = np.array(f_large[self.large_fov_window].data.copy(), dtype=np.float64)
+        # the reference widens both images to float64 on the host (alignment.py:299-316); float32 payloads are kept
+        # as they are here (float32 -> float64 is exact) and widened on the device where a kernel wants float64
+        self.data_large = self._float_image(f_large[self.large_fov_window].data)
         self.hdr_large = f_large[self.large_fov_window].header.copy()
         self.hdr_small = f_small[self.small_fov_window].header.copy()
         self._check_ant_create_pcij_matrix(self.hdr_small)
         self._check_ant_create_pcij_matrix(self.hdr_large)
-        self.data_small = np.array(f_small[self.small_fov_window].data.copy(), dtype=np.float64)
+        self.data_small = self._float_image(f_small[self.small_fov_window].data)
         f_large.close()
         f_small.close()
+
+    @staticmethod
+    def _float_image(data):
+        data = np.asarray(data)
+        if data.dtype in (np.float32, np.float64) and data.dtype.isnative:
+            return np.array(data)      # private, writable copy
+        return np.array(data, dtype=np.float64)
 
     def _wrap_results(self, results, return_type):
         if return_type == "corr":
@@ -258,6 +267,9 @@ class Alignment:
 
     def _set_threshold_minmax_to_nan(self):
         """`alignment.py:876-887`."""
+        if self.small_fov_value_min is None and self.small_fov_value_max is None:
+            return
+        self.data_small = self.data_small.astype(np.float64)   # compare in float64 like the reference
         c1 = np.ones(self.data_small.shape, dtype=bool)
         c2 = np.ones(self.data_small.shape, dtype=bool)
         with np.errstate(invalid="ignore"):

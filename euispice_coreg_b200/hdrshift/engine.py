@@ -179,7 +179,6 @@ class LagSearchEngine:
         self.strict = bool(strict)
         self.variant, self.no_fast = int(variant), bool(no_fast)
         self.flags = _ext.make_flags(strict, variant, no_fast=no_fast)
-        self.fov_radius_deg = None
         self.small_storage = small_storage
         self.pivots = torch.zeros(2, dtype=torch.float64, device=self.device)
         self.ref = None        # large image on the common grid
@@ -196,18 +195,24 @@ class LagSearchEngine:
             t = t.pin_memory()
         return t.to(self.device, non_blocking=pinned)
 
+    @staticmethod
+    def _native_float(arr):
+        """float32 / float64 arrays go up as they are (float32 -> float64 is exact, so FITS BITPIX -32 payloads need
+        no widening on the host); anything else is converted to float64 like the reference does."""
+        arr = np.asarray(arr)
+        if arr.dtype not in (np.float32, np.float64) or not arr.dtype.isnative:
+            arr = arr.astype(np.float64)
+        return arr
+
     def set_small(self, data_small):
-        """Small image (float64 with NaN for masked pixels). small_storage="f64" (default) keeps it float64 on
-        the device; "auto" stores float32 when every finite value is exactly representable (FITS BITPIX -32
-        data): half the gather traffic, same values, but 9 f32->f64 conversions per sample on the quarter-rate
-        conversion pipe -- measured slower on B200 (profiles/r1_k1_tuning.md)."""
-        data_small = np.asarray(data_small)
-        with np.errstate(invalid="ignore", over="ignore"):
-            as32 = data_small.astype(np.float32)
-            exact = np.array_equal(as32.astype(np.float64), data_small, equal_nan=True)
-        if self.small_storage == "f64":
-            exact = False
-        self.small = self._upload(as32 if exact else data_small.astype(np.float64))
+        """Small image (NaN for masked pixels), float32 or float64 on the host. small_storage="f64" (default): kept
+        as float64 on the device (a float32 input is uploaded as float32 and widened there); "auto": kept as float32
+        when the input is float32 -- half the gather traffic, same values, but 9 f32->f64 conversions per sample on the
+        quarter-rate conversion pipe and no homography kernel: measured slower on B200 (profiles/r1_k1_tuning.md)."""
+        small = self._upload(self._native_float(data_small))
+        if small.dtype == _torch().float32 and self.small_storage == "f64":
+            small = _ext.widen_f32(small)
+        self.small = small
         _ext.finite_mean(self.small, self.pivots[1:2])
 
     # ---- helioprojective ------------------------------------------------------------------------
@@ -219,7 +224,7 @@ class LagSearchEngine:
         with torch.cuda.device(self.device):
             lng, lat = _ext.tan_pix2world(wcs_small, wcs_small.naxis1, wcs_small.naxis2, True, self.device)
             x, y = _ext.tan_world2pix(wcs_large, lng, lat)
-            d_large = self._upload(np.asarray(data_large, dtype=np.float64))
+            d_large = self._upload(self._native_float(data_large))
             self.ref = _ext.map_coordinates(d_large, y, x, self.order, float("nan"), torch.float32)
             del d_large, x, y, lng, lat
             self.planes = None          # trig planes of the generic kernel: built on first use (`_hpc_planes`)
@@ -227,14 +232,6 @@ class LagSearchEngine:
             self.alpha_ref_deg = wcs_small.crval1
             self.delta_ref_deg = wcs_small.crval2
             _ext.finite_mean(self.ref, self.pivots[0:1])
-        # largest angular distance of a common-grid pixel from the unshifted reference point (corners suffice for a
-        # convex gnomonic footprint)
-        cx = np.array([0.0, wcs_small.naxis1 - 1.0, 0.0, wcs_small.naxis1 - 1.0])
-        cy = np.array([0.0, 0.0, wcs_small.naxis2 - 1.0, wcs_small.naxis2 - 1.0])
-        lon, lat = wcs_small.pixel_to_world(cx, cy)
-        cosd = (np.sin(lat * D2R) * math.sin(wcs_small.crval2 * D2R)
-                + np.cos(lat * D2R) * math.cos(wcs_small.crval2 * D2R) * np.cos((lon - wcs_small.crval1) * D2R))
-        self.fov_radius_deg = float(np.max(np.arccos(np.clip(cosd, -1.0, 1.0))) * R2D)
         self.frame = "hpc"
 
     def _hpc_planes(self):
@@ -300,7 +297,7 @@ class LagSearchEngine:
             tx, ty = self.carrington_planes(hdr_large, d_solar_r, lonlims, latlims, shape)
             roll = hdr_large["CROTA"] if "CROTA" in hdr_large else hdr_large["CROTA2"]
             x0, y0 = self.carrington_offset(hdr_large, hdr_large["CRVAL1"], hdr_large["CRVAL2"], roll)
-            d_large = self._upload(np.asarray(data_large, dtype=np.float64))
+            d_large = self._upload(self._native_float(data_large))
             nx = float(x0) + tx
             ny = float(y0) + ty
             ref = _ext.map_coordinates(d_large, ny, nx, self.order, -32762.0, torch.float64)

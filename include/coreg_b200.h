@@ -113,6 +113,11 @@ int coreg_map_coordinates(const void* img_dev, int img_dtype, int img_ny, int im
 int coreg_tan_trig_planes(const double* lng_dev, const double* lat_dev, int64_t n, double alpha_ref_deg,
                           double* planes_dev, void* stream);
 
+/* float32 image -> float64 on the device (exact). FITS BITPIX -32 payloads go up as float32 (half the H2D bytes of the
+ * reference's host-side np.array(..., dtype=float64), hdrshift/alignment.py:299-316) and are widened once here: the lag
+ * kernels read the small image fastest as float64 (no per-tap conversion). */
+int coreg_widen_f32(const float* in_dev, int64_t n, double* out_dev, void* stream);
+
 /* mean of the finite values of an image -> mean_dev[0] (device double); deterministic. Used as the pivot of the
  * single-pass moments (the Pearson coefficient is invariant under it). */
 int coreg_finite_mean(const void* img_dev, int dtype, int64_t n, double* mean_dev, void* stream);
