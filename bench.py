@@ -31,8 +31,9 @@ if ROOT not in sys.path:
 WORKLOAD = "config1: HRIEUV-like 2048x2048 vs FSI174-like 3072x3072, helioprojective, 60x60 CRVAL lags @1arcsec"
 FP64_INSTR_PER_SAMPLE = 69.0   # algorithmic FP64 instructions per pixel-sample (HPC), counted
 #                                on the reference's formulation (pixel -> world -> pixel per lag)
-FP64_EXECUTED_PER_SAMPLE = 37.5  # FP64 thread-instructions the column-rolling kernel actually executes per pixel-sample
-#                                  (ncu: DADD + DMUL + DFMA of one launch / pixel-samples, profiles/r1_roll_kernel.md)
+FP64_EXECUTED_PER_SAMPLE = 36.7  # FP64 thread-instructions the column-rolling kernel executes per pixel-sample = the
+#                                  algorithmic count of ITS formulation (ncu: DADD + DMUL + DFMA of
+#                                  one launch / pixel-samples, profiles/r1_roll_kernel.md)
 BYTES_PER_SAMPLE = 8.0         # un-amortised: one f32 sample of each image per pixel-sample
 LAGS = dict(lag_crval1=np.arange(-30, 30, 1.0), lag_crval2=np.arange(-30, 30, 1.0), lag_cdelt1=np.array([0.0]),
             lag_cdelt2=np.array([0.0]), lag_crota=np.array([0.0]))
@@ -285,6 +286,8 @@ def run_gpu(args):
         k1_avg_ms = k1_ms / max(1, k1_launches)
         samples_per_launch = n_pix * (hi - lo) / max(1, k1_launches // args.steps)
         ach_instr = FP64_INSTR_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3)
+        per_sample = FP64_EXECUTED_PER_SAMPLE if fast else FP64_INSTR_PER_SAMPLE
+        ach_exec = per_sample * samples_per_launch / (k1_avg_ms * 1e-3)
         ach_gbs = BYTES_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3) / 1e9
         line = {
             "metric": "lag_evals_per_s", "value": value, "unit": "lag-evals/s", "n_gpus": world,
@@ -306,20 +309,22 @@ def run_gpu(args):
             "align_wall_s": align_wall, "argmax_lag_arcsec": best,
             "gpu_launches": int(k1_launches + k1_launches),  # fused lag kernel + finalize per launch pair
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": ach_instr / 1e12, "peak": fp64_peak / 1e12,
-                         "unit": "T FP64-instr/s", "frac": ach_instr / fp64_peak, "traffic": None,
+            "roofline": {"bound": "fp64", "achieved": ach_exec / 1e12, "peak": fp64_peak / 1e12,
+                         "unit": "T FP64-instr/s", "frac": ach_exec / fp64_peak, "traffic": None,
                          "kernel": "lag_corr_roll_kernel" if fast else "lag_corr_kernel<TanCoord>",
                          "kernel_ms": k1_avg_ms,
-                         "algorithmic": f"{FP64_INSTR_PER_SAMPLE:.0f} FP64 instr/pixel-sample (SURVEY 8d, reference "
-                                        f"formulation) x {samples_per_launch:.3e} pixel-samples/launch",
-                         "peak_source": "coreg_fp64_peak DFMA microbenchmark, this run"},
-            "roofline_executed": {"bound": "fp64", "unit": "T FP64-instr/s", "peak": fp64_peak / 1e12,
-                                  "achieved": (FP64_EXECUTED_PER_SAMPLE if fast else None) and
-                                  FP64_EXECUTED_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3) / 1e12,
-                                  "frac": (FP64_EXECUTED_PER_SAMPLE if fast else None) and
-                                  FP64_EXECUTED_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3) / fp64_peak,
-                                  "what": "FP64 instructions the kernel really issues (the homography + shared-floor "
-                                          "formulation needs 37.5 per pixel-sample, not 69) against the same peak"},
+                         "algorithmic": f"{per_sample:.1f} FP64 instr/pixel-sample x {samples_per_launch:.3e} "
+                                        "pixel-samples/launch (homography + shared-floor formulation, DESIGN.md 5)"
+                                        if fast else f"{per_sample:.0f} FP64 instr/pixel-sample (SURVEY 8d)",
+                         "peak_source": "coreg_fp64_peak DFMA microbenchmark, this run",
+                         "note": "the FP64 pipe is the binding unit but a DFMA blocks the warp scheduler's dispatch "
+                                 "port for 2 cycles and every other instruction for 1, so the reachable fraction "
+                                 "for this instruction mix is about 0.8 (profiles/r1_roll_kernel.md)"},
+            "roofline_survey": {"bound": "fp64", "achieved": ach_instr / 1e12, "peak": fp64_peak / 1e12,
+                                "unit": "T FP64-instr/s", "frac": ach_instr / fp64_peak,
+                                "algorithmic": f"{FP64_INSTR_PER_SAMPLE:.0f} FP64 instr/pixel-sample: SURVEY 8d's count "
+                                               "for the reference's pixel->world->pixel formulation; > 1 means the "
+                                               "kernel needs fewer instructions than that formulation's minimum"},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": ach_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                              "algorithmic": f"{BYTES_PER_SAMPLE:.0f} B/pixel-sample (un-amortised)"},

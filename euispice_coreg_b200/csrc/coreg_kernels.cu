@@ -18,6 +18,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/coreg_b200.h"
@@ -835,7 +836,7 @@ __device__ __forceinline__ double warp_transpose_reduce4(double (&v)[4], int lan
 }
 
 constexpr int kFastLagSub = 32;
-constexpr int kRollLagSub = 8;  // = kRollChunk (lag-list granularity of the rolling kernel's grid)  // lags per shared-memory stage of the fast kernel (small: leaves L1 to the taps)
+
 
 template <class Fast, typename SmallT, typename RefT, bool ROUND32, int PPT, int MINB, int GROUP>
 __global__ void __launch_bounds__(kThreads, MINB)
@@ -1160,7 +1161,10 @@ __device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ sma
   return isfinite(t) && (t != -32762.0);
 }
 
-constexpr int kRollChunk = 8;  // lags whose per-thread sums wait in shared memory for one block-wide reduction
+#ifndef COREG_ROLL_CHUNK
+#define COREG_ROLL_CHUNK 8
+#endif
+constexpr int kRollChunk = COREG_ROLL_CHUNK;  // lags whose per-thread sums wait in shared memory for one block-wide reduction
 
 // Shared memory of the rolling kernel, per block: per-thread (Sb, Sbb, Sab) of kRollChunk lags, transposed so that
 // both the stores and the reduction reads are conflict-free; per-warp corrections (n, Sa, Saa of the pixels that
@@ -1385,7 +1389,10 @@ inline bool lag_grid(int tile_h, int minb, int gnx, int gny, int64_t n_lags, int
                      int* tiles_out, int lag_sub) {
   const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
   *tiles_out = tiles;
-  const int want_blocks = sms * minb * 4;
+  // many more blocks than resident slots: border tiles take the per-pixel path and run longer, so a fine
+  // granularity keeps the last wave short (COREG_WAVES overrides the default for tuning)
+  static const int waves = []() { const char* e = getenv("COREG_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
+  const int want_blocks = sms * minb * waves;
   int splits = (want_blocks + tiles - 1) / tiles;
   const int max_splits = (int)((n_lags + lag_sub - 1) / lag_sub);
   splits = std::max(1, std::min(splits, max_splits));
@@ -1424,7 +1431,7 @@ int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
 
 // tuning variants of the column-rolling kernel: (consecutive rows per thread, resident CTAs per SM)
 #ifndef COREG_ROLL_VARIANTS
-#define COREG_ROLL_VARIANTS X(0, 8, 2) X(1, 6, 3) X(2, 12, 2) X(3, 4, 3)
+#define COREG_ROLL_VARIANTS X(0, 12, 2) X(1, 8, 2) X(2, 16, 2) X(3, 6, 3)
 #endif
 template <typename RefT, bool ROUND32>
 int launch_lag_roll(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
@@ -1435,7 +1442,7 @@ int launch_lag_roll(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
   bool done = false;
 #define X(V_, P_, MINB_)                                                                                        \
   if (!done && variant == V_) {                                                                                 \
-    if (!lag_grid(kRowsPerPass * P_, MINB_, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out, kRollLagSub))        \
+    if (!lag_grid(kRowsPerPass * P_, MINB_, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out, kRollChunk))        \
       return fail(COREG_EINVAL, "lag grid too large for one launch");                                           \
     auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, MINB_>;                                                 \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollShared));           \
