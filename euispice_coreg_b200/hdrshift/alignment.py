@@ -164,9 +164,15 @@ class Alignment:
     # ------------------------------------------------------------------------------------------------
     # host preparation (mirrors alignment.py:299-316, 580-611, 799-887)
     # ------------------------------------------------------------------------------------------------
+    def _open_large(self):
+        return _open_fits(self.large_fov_known_pointing)
+
+    def _open_small(self):
+        return _open_fits(self.small_fov_to_correct)
+
     def _load_pair(self):
-        f_large = _open_fits(self.large_fov_known_pointing)
-        f_small = _open_fits(self.small_fov_to_correct)
+        f_large = self._open_large()
+        f_small = self._open_small()
         # the reference widens both images to float64 on the host (alignment.py:299-316); float32 payloads are kept
         # as they are here (float32 -> float64 is exact) and widened on the device where a kernel wants float64
         self.data_large = self._float_image(f_large[self.large_fov_window].data)

@@ -185,6 +185,8 @@ class LagSearchEngine:
         self.small = None
         self.planes = None     # TAN: [3, gny, gnx]; Carrington: (tx, ty)
         self._work = None
+        self.d_large = None
+        self.wcs_large = None
         self.last_launches = 0
 
     # ---- uploads -----------------------------------------------------------------------------
@@ -216,23 +218,35 @@ class LagSearchEngine:
         _ext.finite_mean(self.small, self.pivots[1:2])
 
     # ---- helioprojective ------------------------------------------------------------------------
-    def prepare_hpc(self, data_large, wcs_large: TanWcs, wcs_small: TanWcs):
-        """One-time part of the helioprojective search: world grid of the unshifted small grid (K3), the
-        large image resampled onto it as float32 (K2, `_create_submap_of_large_data`,
-        `alignment.py:987-1016`), the lag-independent trig planes and the ref pivot."""
+    def set_large(self, data_large, wcs_large: TanWcs):
+        """Upload the large image once; it stays resident for any number of `cut_large` calls (frame sequences)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            self.d_large = self._upload(self._native_float(data_large))
+        self.wcs_large = wcs_large
+
+    def cut_large(self, wcs_small: TanWcs):
+        """One-time part of a helioprojective search: world grid of the unshifted small grid (K3), the resident
+        large image resampled onto it as float32 (K2, `_create_submap_of_large_data`, `alignment.py:987-1016`) and
+        the ref pivot. The common grid of the search is this unshifted small grid (`alignment.py:649-651, 1000`)."""
         torch = _torch()
         with torch.cuda.device(self.device):
             lng, lat = _ext.tan_pix2world(wcs_small, wcs_small.naxis1, wcs_small.naxis2, True, self.device)
-            x, y = _ext.tan_world2pix(wcs_large, lng, lat)
-            d_large = self._upload(self._native_float(data_large))
-            self.ref = _ext.map_coordinates(d_large, y, x, self.order, float("nan"), torch.float32)
-            del d_large, x, y, lng, lat
+            x, y = _ext.tan_world2pix(self.wcs_large, lng, lat)
+            self.ref = _ext.map_coordinates(self.d_large, y, x, self.order, float("nan"), torch.float32)
+            del x, y, lng, lat
             self.planes = None          # trig planes of the generic kernel: built on first use (`_hpc_planes`)
             self.grid_wcs = wcs_small
             self.alpha_ref_deg = wcs_small.crval1
             self.delta_ref_deg = wcs_small.crval2
             _ext.finite_mean(self.ref, self.pivots[0:1])
         self.frame = "hpc"
+
+    def prepare_hpc(self, data_large, wcs_large: TanWcs, wcs_small: TanWcs):
+        """`set_large` + `cut_large` for a single pair; the large image is released afterwards."""
+        self.set_large(data_large, wcs_large)
+        self.cut_large(wcs_small)
+        self.d_large = None
 
     def _hpc_planes(self):
         """Lag-independent trig planes of the generic helioprojective kernel (101 MB at 2048^2), built lazily:
