@@ -794,6 +794,35 @@ __global__ void offset_fast_table_kernel(const CoregLagOffset* __restrict__ lags
   out[i] = f;
 }
 
+// per lag slice (blockIdx.y of the fast kernel): range of the offsets, so that a tile whose whole bounding box
+// falls outside the small image for every lag of the slice can be skipped
+__global__ void offset_lag_range_kernel(const OffsetFastLag* __restrict__ ft, int n_lags, int lags_per_block,
+                                        double* __restrict__ ranges) {
+  __shared__ double s[4][128];
+  const int lo = blockIdx.x * lags_per_block, hi = min(n_lags, lo + lags_per_block);
+  double x0 = CUDART_INF, x1 = -CUDART_INF, y0 = CUDART_INF, y1 = -CUDART_INF;
+  bool bad = false;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const OffsetFastLag f = ft[i];
+    bad = bad || !(f.x0h == f.x0h) || !(f.y0h == f.y0h);
+    x0 = fmin(x0, f.x0h); x1 = fmax(x1, f.x0h);
+    y0 = fmin(y0, f.y0h); y1 = fmax(y1, f.y0h);
+  }
+  if (bad) { x0 = y0 = -CUDART_INF; x1 = y1 = CUDART_INF; }   // NaN offsets: never skip
+  s[0][threadIdx.x] = x0; s[1][threadIdx.x] = x1; s[2][threadIdx.x] = y0; s[3][threadIdx.x] = y1;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + o]);
+      s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + o]);
+      s[2][threadIdx.x] = fmin(s[2][threadIdx.x], s[2][threadIdx.x + o]);
+      s[3][threadIdx.x] = fmax(s[3][threadIdx.x], s[3][threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) ranges[blockIdx.x * 4 + threadIdx.x] = s[threadIdx.x][0];
+}
+
 struct OffsetFast {
   typedef OffsetFastLag LagC;
   typedef OffsetCoord::Planes Planes;
@@ -805,6 +834,8 @@ struct OffsetFast {
   __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx, int) { return OffsetCoord::load(pl, idx); }
   __device__ static __forceinline__ Pix dead() { return OffsetCoord::dead(); }
   __device__ static __forceinline__ TL thread_lag(const LagC&, const Thread&) { return TL(); }
+  __device__ static __forceinline__ double plane_x(const Pix& q) { return q.tx; }
+  __device__ static __forceinline__ double plane_y(const Pix& q) { return q.ty; }
   __device__ static __forceinline__ void map_half(const Pix& q, const TL&, const LagC& C, double& sx, double& sy) {
     sx = C.x0h + q.tx;
     sy = C.y0h + q.ty;
@@ -842,10 +873,12 @@ template <class Fast, typename SmallT, typename RefT, bool ROUND32, int PPT, int
 __global__ void __launch_bounds__(kThreads, MINB)
 lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, int snx, int sny, int gnx, int gny,
                      typename Fast::Planes planes, const typename Fast::LagC* __restrict__ fast_lags, int n_lags,
-                     int lags_per_block, const double* __restrict__ pivots, double* __restrict__ work) {
+                     int lags_per_block, const double* __restrict__ pivots, double* __restrict__ work,
+                     const double* __restrict__ ranges) {
   typedef typename Fast::Pix Pix;
   typedef typename Fast::LagC LagC;
   constexpr int TILE_H = kRowsPerPass * PPT;
+  __shared__ double s_box[4][kWarps];
   // GROUP = pixels whose dependency chains are interleaved (their coordinates / indices are live together)
   static_assert(PPT % GROUP == 0, "PPT must be a multiple of GROUP");
   __shared__ __align__(16) LagC s_lag[kFastLagSub];
@@ -903,6 +936,42 @@ lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ sm
 
   const int lag_begin = blockIdx.y * lags_per_block;
   const int lag_end = min(n_lags, lag_begin + lags_per_block);
+  if (ranges != nullptr) {
+    // A Carrington grid is usually far larger than the small image's footprint: when the bounding box of this
+    // tile's detector-plane offsets cannot reach the image under any lag of the slice (or the tile has no finite
+    // reference pixel), every sample is missing, all six moments are zero, and the lag walk is skipped.
+    double bx0 = CUDART_INF, bx1 = -CUDART_INF, by0 = CUDART_INF, by1 = -CUDART_INF;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+      if (a_ok & (1u << k)) {
+        const double px = Fast::plane_x(pix[k]), py = Fast::plane_y(pix[k]);
+        bx0 = fmin(bx0, px); bx1 = fmax(bx1, px);
+        by0 = fmin(by0, py); by1 = fmax(by1, py);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bx0 = fmin(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+      bx1 = fmax(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+      by0 = fmin(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      by1 = fmax(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    if (lane == 0) { s_box[0][warp] = bx0; s_box[1][warp] = bx1; s_box[2][warp] = by0; s_box[3][warp] = by1; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      bx0 = fmin(bx0, s_box[0][w]); bx1 = fmax(bx1, s_box[1][w]);
+      by0 = fmin(by0, s_box[2][w]); by1 = fmax(by1, s_box[3][w]);
+    }
+    const double* rg = ranges + 4 * blockIdx.y;   // min / max of x0 + 0.5, y0 + 0.5 over the slice
+    // sample valid <=> 0 <= x <= n - 1 <=> 0.5 <= x + 0.5 <= n - 0.5 (one pixel of slack for rounding)
+    const bool reach = (bx1 + rg[1] >= -0.5) && (bx0 + rg[0] <= (double)snx + 0.5) &&
+                       (by1 + rg[3] >= -0.5) && (by0 + rg[2] <= (double)sny + 0.5);
+    if (!reach) {   // also taken when the tile has no live pixel (box stays empty: +inf / -inf)
+      for (int i = tid; i < (lag_end - lag_begin) * kMom; i += kThreads)
+        work[((size_t)tile * n_lags + lag_begin) * kMom + i] = 0.0;
+      return;
+    }
+  }
   for (int l0 = lag_begin; l0 < lag_end; l0 += kFastLagSub) {
     const int cnt = min(kFastLagSub, lag_end - l0);
     __syncthreads();
@@ -1409,7 +1478,8 @@ inline bool lag_grid(int tile_h, int minb, int gnx, int gny, int64_t n_lags, int
 template <class Fast, typename SmallT, typename RefT, bool ROUND32>
 int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
                     const SmallT* small, int snx, int sny, typename Fast::Planes planes,
-                    const typename Fast::LagC* ft, const double* pivots, double* w, int* tiles_out) {
+                    const typename Fast::LagC* ft, const double* pivots, double* w, int* tiles_out,
+                    double* ranges) {
   static const int kVar[3][2] = {{4, 3}, {8, 2}, {4, 4}};
   if (variant < 0 || variant > 2) variant = 0;
   dim3 grid;
@@ -1417,9 +1487,10 @@ int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
   if (!lag_grid(kRowsPerPass * kVar[variant][0], kVar[variant][1], gnx, gny, n_lags, sms, &grid, &lpb, tiles_out,
                 kFastLagSub))
     return fail(COREG_EINVAL, "lag grid too large for one launch");
+  if (ranges) offset_lag_range_kernel<<<grid.y, 128, 0, s>>>(ft, (int)n_lags, lpb, ranges);
 #define LF(PPT_, MINB_, G_)                                                                     \
   lag_corr_fast_kernel<Fast, SmallT, RefT, ROUND32, PPT_, MINB_, G_><<<grid, kThreads, 0, s>>>( \
-      ref, small, snx, sny, gnx, gny, planes, ft, (int)n_lags, lpb, pivots, w)
+      ref, small, snx, sny, gnx, gny, planes, ft, (int)n_lags, lpb, pivots, w, ranges)
   switch (variant) {
     case 1: LF(8, 2, 2); break;
     case 2: LF(4, 4, 2); break;
@@ -1466,8 +1537,10 @@ int launch_offset_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, c
   // the per-lag fast table lives in the tail of the workspace (after the [tiles][lags][8] partials)
   OffsetFastLag* ft = reinterpret_cast<OffsetFastLag*>(static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags));
   offset_fast_table_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(lags, (int)n_lags, ft);
+  // per-slice offset ranges right behind the table (the tail reserves 96 B per lag; the table uses 16)
+  double* ranges = reinterpret_cast<double*>(ft + n_lags);
   return launch_lag_fast<OffsetFast, SmallT, RefT, ROUND32>(variant, gnx, gny, n_lags, sms, s, ref, small, snx, sny,
-                                                            planes, ft, pivots, w, tiles_out);
+                                                            planes, ft, pivots, w, tiles_out, ranges);
 }
 template <typename SmallT, typename RefT, bool ROUND32>
 int launch_offset_fast(int, int, int, int64_t, int, cudaStream_t, const RefT*, const SmallT*, int, int,
