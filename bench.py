@@ -31,6 +31,8 @@ if ROOT not in sys.path:
 WORKLOAD = "config1: HRIEUV-like 2048x2048 vs FSI174-like 3072x3072, helioprojective, 60x60 CRVAL lags @1arcsec"
 FP64_INSTR_PER_SAMPLE = 69.0   # algorithmic FP64 instructions per pixel-sample (HPC), counted
 #                                on the reference's formulation (pixel -> world -> pixel per lag)
+K1_DRAM_BYTES_PER_LAUNCH = 613.9e6  # dram__bytes_read.sum + dram__bytes_write.sum of one config-1 launch of the rolling
+#                                     kernel (ncu --set full, profiles/r1_ncu_roll_v5_raw.csv): 309.4 MB + 304.5 MB
 FP64_EXECUTED_PER_SAMPLE = 36.7  # FP64 thread-instructions the column-rolling kernel executes per pixel-sample = the
 #                                  algorithmic count of ITS formulation (ncu: DADD + DMUL + DFMA of
 #                                  one launch / pixel-samples, profiles/r1_roll_kernel.md)
@@ -107,15 +109,28 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm (reference-structured oracle port)
 # ---------------------------------------------------------------------------------------------------------
+_CPU_SEARCH = None
+
+
+def cpu_search():
+    """The CPU arm's one-time preparation (FITS read, PCi_j checks, the one-time cut of the large image), done once
+    per process -- like the reference does it once per `align_using_helioprojective` call, outside the lag loop."""
+    global _CPU_SEARCH
+    if _CPU_SEARCH is None:
+        from oracle.hpc import HpcSearch
+        pl, ps = ensure_config1()
+        dl, hl, ds, hs = load_pair(pl, ps)
+        _CPU_SEARCH = HpcSearch(dl, dict(hl.items()), ds, dict(hs.items()), **LAGS)
+    return _CPU_SEARCH
+
+
 def cpu_sample(n_lags_per_core=1, cores=None):
     """Evaluate a bounded sample of the config-1 lag grid the way the reference does (per lag: pixel->world and
     world->pixel of the full grid, scipy map_coordinates, NaN compaction, two-pass Pearson) with one forked
-    process per host core. Returns (lag_evals_per_s, seconds, n_lags, cores, search)."""
-    from oracle.hpc import HpcSearch, cube_multiprocess
-    pl, ps = ensure_config1()
-    dl, hl, ds, hs = load_pair(pl, ps)
+    process per host core. Returns (lag_evals_per_s, seconds, n_lags, cores)."""
+    from oracle.hpc import cube_multiprocess
     cores = cores or len(os.sched_getaffinity(0))
-    search = HpcSearch(dl, dict(hl.items()), ds, dict(hs.items()), **LAGS)
+    search = cpu_search()
     n_total = 3600
     n = cores * n_lags_per_core
     sel = np.linspace(0, n_total - 1, n).astype(int)   # spread over the grid: in- and out-of-overlap lags alike
@@ -130,20 +145,22 @@ def run_reference(args):
     if rank != 0:
         return 0
     per_core = 1
-    vals, secs = [], []
+    secs = []
     cores = len(os.sched_getaffinity(0))
+    cpu_search()
     for i in range(args.warmup + args.steps):
         v, dt, n, cores = cpu_sample(per_core, cores)
         if i >= args.warmup:
-            vals.append(v)
             secs.append(dt)
     total_lags = cores * per_core * args.steps
     value = total_lags / sum(secs)
-    sample = f"{cores * per_core} of 3600 lags per step (1 per core, spread over the grid), {args.steps} steps"
+    sample = (f"{cores * per_core} of 3600 lags per step (1 per core, spread over the grid), {args.steps} steps, "
+              f"{sum(secs):.1f} s; one-time cut of the large image outside the timed region")
     line = {"impl": "reference", "metric": "lag_evals_per_s", "value": value, "unit": "lag-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "lags": 3600, "grid": [2048, 2048], "spline_order": 2},
             "cpu_baseline": {"value": value, "unit": "lag-evals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "lag-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -310,7 +327,10 @@ def run_gpu(args):
             "gpu_launches": int(k1_launches + k1_launches),  # fused lag kernel + finalize per launch pair
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": ach_exec / 1e12, "peak": fp64_peak / 1e12,
-                         "unit": "T FP64-instr/s", "frac": ach_exec / fp64_peak, "traffic": None,
+                         "unit": "T FP64-instr/s", "frac": ach_exec / fp64_peak,
+                         "traffic": K1_DRAM_BYTES_PER_LAUNCH * (hi - lo) / 3600.0 if (fast and n_lags == 3600) else None,
+                         "traffic_unit": "B per launch (ncu DRAM read + write of one full 3600-lag launch, scaled by "
+                                         "this rank's share of the lags)",
                          "kernel": "lag_corr_roll_kernel" if fast else "lag_corr_kernel<TanCoord>",
                          "kernel_ms": k1_avg_ms,
                          "algorithmic": f"{per_sample:.1f} FP64 instr/pixel-sample x {samples_per_launch:.3e} "
