@@ -219,7 +219,12 @@ def run_gpu(args):
     local_out = torch.full((chunk,), float("nan"), dtype=torch.float64, device=eng.device)
     full = torch.empty(chunk * world, dtype=torch.float64, device=eng.device)
 
+    # L2 hygiene: a 256 MiB buffer (> the 126 MB L2) is rewritten before every step, inside the timed region
+    # (~0.05 ms per step), so no step starts with the previous step's images or partials in L2
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+
     def step():
+        l2_flush.zero_()
         eng.evaluate(tab_dev, local_out[:hi - lo])
         if world > 1:
             dist.all_gather_into_tensor(full, local_out)
@@ -314,9 +319,9 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "lags": n_lags, "grid": [gny, gnx], "spline_order": 2,
                        "arithmetic": "strict (scipy op order)" if args.strict else "fp64 fma", "variant": args.variant, "kernel": "generic" if (args.no_fast or args.strict) else "fast", "small_storage": str(eng.small.dtype).replace("torch.", ""),
                        "parallelism": f"lag-sharded x{world}",
-                       "l2": "no explicit flush: per-step working set (images+planes+partials workspace "
-                             f"{(eng._work.numel() * 8 + 3 * n_pix * 8 + n_pix * 4 + small_bytes) / 1e6:.0f} MB) "
-                             "exceeds the 126 MB L2"},
+                       "l2": "flushed: a 256 MiB device buffer is rewritten before every timed step (inside the timed "
+                             f"region); every step also rewrites its {eng._work.numel() * 8 / 1e6:.0f} MB partials "
+                             "workspace"},
             "pixel_samples_per_s": value * n_pix,
             "e2e": {"value": n_lags * e2e_steps / e2e_s, "unit": "lag-evals/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
@@ -324,7 +329,9 @@ def run_gpu(args):
                             "the FITS files hold them): H2D images + lag table, one-time resampling, search, "
                             "all-gather, D2H cube"},
             "align_wall_s": align_wall, "argmax_lag_arcsec": best,
-            "gpu_launches": int(k1_launches + k1_launches),  # fused lag kernel + finalize per launch pair
+            # own kernels inside the timed region: per lag-kernel launch the homography table (fast path), the fused
+            # lag kernel and the finalize kernel (the L2 flush memset and the NCCL all-gather are not ours)
+            "gpu_launches": int(k1_launches * (3 if fast else 2)),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": ach_exec / 1e12, "peak": fp64_peak / 1e12,
                          "unit": "T FP64-instr/s", "frac": ach_exec / fp64_peak,
