@@ -60,6 +60,7 @@ _SIGNATURES = {
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                          _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_tan_homography_emax": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P]),
     "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
                                         C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
@@ -254,6 +255,21 @@ def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_ou
                                           _ptr(work), work.numel() * work.element_size(), _ptr(corr_out),
                                           _ptr(nvalid_out) if nvalid_out is not None else None, int(flags),
                                           _stream()), "coreg_hpc_lag_corr_wcs")
+
+
+def homography_emax(grid_wcs, lag_wcs, gnx, gny):
+    """max |1 - D| of each candidate header's homography over the common grid (device float64 [n_lags])."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(lag_wcs)
+    n = lag_wcs.shape[0]
+    scratch = torch.empty(12 * max(n, 1), dtype=torch.float64, device=lag_wcs.device)
+    out = torch.empty(n, dtype=torch.float64, device=lag_wcs.device)
+    g = tan_struct(grid_wcs)
+    with torch.cuda.device(lag_wcs.device):
+        _check(lib.coreg_tan_homography_emax(C.byref(g), int(gnx), int(gny), _ptr(lag_wcs), n, _ptr(scratch), _ptr(out),
+                                             _stream()), "coreg_tan_homography_emax")
+    return out
 
 
 def carrington_planes(c: CoregCarrington, sinlon, coslon, sinlat, coslat):

@@ -1867,6 +1867,22 @@ int coreg_hpc_lag_corr_wcs(const float* ref, const double* small, int snx, int s
                                flags, (cudaStream_t)stream);
 }
 
+int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs, int gnx, int gny, const CoregTanWcs* lag_wcs, int64_t n_lags,
+                              void* scratch, double* emax, void* stream) {
+  if (!grid_wcs || !lag_wcs || !scratch || !emax) return fail(COREG_EINVAL, "coreg_tan_homography_emax: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  HomGrid g;
+  int rc = make_hom_grid(grid_wcs, gnx, gny, &g);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  HomLag* ft = static_cast<HomLag*>(scratch);
+  tan_homography_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(g, lag_wcs, (int)n_lags, ft);
+  CK_LAUNCH("tan_homography_kernel");
+  CK(cudaMemcpy2DAsync(emax, sizeof(double), &ft[0].emax, sizeof(HomLag), sizeof(double), (size_t)n_lags,
+                       cudaMemcpyDeviceToDevice, s));
+  return COREG_OK;
+}
+
 int coreg_carrington_planes(const CoregCarrington* c, const double* sinlon, const double* coslon, int n_lon,
                             const double* sinlat, const double* coslat, int n_lat, double* tx, double* ty,
                             void* stream) {

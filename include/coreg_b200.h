@@ -156,6 +156,12 @@ int coreg_hpc_lag_corr_wcs(const float* ref_dev, const double* small_dev, int sn
                            int order, const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
                            int64_t* nvalid_dev, int flags, void* stream);
 
+/* Diagnostic: max |e| = max |1 - D| of each candidate header's homography over the gnx x gny common grid (what selects
+ * the reciprocal form per lag inside coreg_hpc_lag_corr_wcs). scratch_dev: at least 96 * n_lags bytes.
+ * emax_dev: [n_lags] float64 out. */
+int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs_host, int gnx, int gny, const CoregTanWcs* lag_wcs_dev,
+                              int64_t n_lags, void* scratch_dev, double* emax_dev, void* stream);
+
 /* ---- K5 (coordinates): Carrington grid -> detector pixel of one header --------------------------------------------
  * Replaces CarringtonTransform / SphericalTransform.forward on the Rectifier grid
  * (utils/rectify.py:304-311, 340-363, 876-877). The Rectifier grid is separable (lon along x, lat along y) and the

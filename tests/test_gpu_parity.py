@@ -292,3 +292,67 @@ def test_config1_full_size_bounded_sample_vs_oracle(torch_cuda):
     assert err[:-1].max() < 1e-10
     assert err[-1] < 1e-3 and 2048 * 2048 - nvalid[zero] <= 2 * (2048 + 2048)
     assert int(np.nanargmax(gpu)) == 54 * 60 + 36
+
+
+@pytest.fixture(scope="module")
+def wide_pair(tmp_path_factory):
+    """A wide-field toy pair (small image 96 px x 300 arcsec = 8 deg): shifts of degrees make the projective
+    denominator of the homography leave the ranges of the two reciprocal series."""
+    from euispice_coreg_b200._synth.scene import make_pair, small_spec
+    d = tmp_path_factory.mktemp("wide")
+    spec = small_spec(96, 160, small_cdelt=300.0, true_crval=(-3000.0, 2000.0), true_shift=(2400.0, 600.0))
+    return make_pair(str(d), spec, tag="wide")
+
+
+def test_hpc_cube_parity_all_three_reciprocal_modes(torch_cuda, wide_pair):
+    """Per lag the rolling kernel picks 1 + e + e^2 (|e| <= 2^-18), the three-factor product (|e| <= 2^-7) or a true
+    division from the exact range of e = 1 - D over the grid. One cube that needs all three, against the oracle."""
+    import torch
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200.hdrshift import engine
+    # (no exact (0, 0, 0) lag: that one is the closed-bound knife edge of DESIGN.md section 4)
+    kw = dict(lag_crval1=np.array([0.5, 3.0, 600.0, 2400.0, 9000.0, 30000.0]), lag_crval2=np.array([0.0, 600.0, -20000.0]),
+              lag_cdelt1=None, lag_cdelt2=None, lag_crota=[0.0, 2.0])
+    gpu, a = _gpu_cube(wide_pair, **kw)
+    ref, _ = _oracle_cube(wide_pair, **kw)
+    _assert_parity(gpu, ref)
+    # which series each lag got: e_max of the device-built homographies
+    d = engine.flat_lag_grid(kw["lag_crval1"], kw["lag_crval2"], [0.0], [0.0], kw["lag_crota"])
+    table, _ = a.engine.hpc_lag_table(a.hdr_small, a, *d)
+    emax = _ext.homography_emax(a.engine.grid_wcs, torch.from_numpy(table).cuda(), a.engine.ref.shape[1],
+                                a.engine.ref.shape[0]).cpu().numpy()
+    modes = np.where(emax <= 2.0 ** -18, 0, np.where(emax <= 2.0 ** -7, 1, 2))
+    assert set(modes.tolist()) == {0, 1, 2}, (emax.min(), emax.max())
+    # and the generic kernel (per-lag trig, true division everywhere) agrees with all of them
+    gen, _ = _gpu_cube(wide_pair, strict_arithmetic=True, **kw)
+    assert np.nanmax(np.abs(gen - gpu)) < 1e-9
+
+
+def test_small_image_with_holes_and_all_nan(torch_cuda, toy_pair, tmp_path):
+    """NaN holes in the small image (segments with a non-finite sample leave the rolling path) and the
+    reference's ValueError when the thresholds mask everything (alignment.py:656)."""
+    from euispice_coreg_b200._compat import fits_lite
+    from euispice_coreg_b200.hdrshift import Alignment
+    hd = fits_lite.open(toy_pair[1])[0]
+    data = hd.data.copy()
+    rng = np.random.default_rng(5)
+    data[rng.integers(0, data.shape[0], 40), rng.integers(0, data.shape[1], 40)] = np.nan
+    data[30:34, 10:50] = np.inf
+    p = str(tmp_path / "holes_small.fits")
+    fits_lite.writeto(p, [fits_lite.PrimaryHDU(data, hd.header)], overwrite=True)
+    pair = (toy_pair[0], p)
+    gpu, _ = _gpu_cube(pair, **LAGS)
+    ref, _ = _oracle_cube(pair, **LAGS)
+    _assert_parity(gpu, ref)
+    with pytest.raises(ValueError):
+        Alignment(toy_pair[0], toy_pair[1], small_fov_value_min=1e30, **LAGS).align_using_helioprojective()
+
+
+def test_single_lag_and_tiny_images(torch_cuda, tmp_path):
+    """One lag; images too small for the fast kernels (2 x 3 pixels) fall back to the generic kernel."""
+    from euispice_coreg_b200._synth.scene import make_pair, small_spec
+    one = dict(lag_crval1=[24.0], lag_crval2=[6.0], lag_cdelt1=[0], lag_cdelt2=[0], lag_crota=[0])
+    pair = make_pair(str(tmp_path), small_spec(40, 64, true_crval=(-12.0, 8.0)), tag="one")
+    gpu, _ = _gpu_cube(pair, **one)
+    ref, _ = _oracle_cube(pair, **one)
+    assert gpu.shape == (1, 1, 1, 1, 1, 1) and abs(gpu.item() - ref.item()) <= R_TOL
