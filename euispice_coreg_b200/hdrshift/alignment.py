@@ -303,8 +303,47 @@ class Alignment:
         if remove_fov_limits is not None:
             self._set_remove_fov_limits_to_nan(remove_fov_limits)
         if fov_limits is not None:
-            raise NotImplementedError("fov_limits (regular-grid re-sampling of the small image, "
-                                      "alignment.py:1082-1127) is not on the device path yet")
+            self._select_fov_in_small_data(fov_limits)
+
+    def _limits_deg(self, limits):
+        out = []
+        for pair in limits:
+            v, unit = units.strip(pair, "arcsec")
+            out.append(units.convert(np.asarray(v, dtype=np.float64), unit, "deg"))
+        return out
+
+    def _select_fov_in_small_data(self, fov_limits):
+        """`alignment.py:1082-1127`: the small image re-sampled (order `reprojection_order`, NaN fill, float64) onto a
+        regular, unrotated lon / lat grid inside `fov_limits` = [[lonmin, lonmax], [latmin, latmax]] (arcsec numbers
+        or astropy quantities); the search then runs on that image and its new header. Kept as the reference has it,
+        including NAXIS1 / CRPIX1 taken from the grid's ROW count (only matters for non-square selections)."""
+        from .. import _ext
+        torch = _engine._torch()
+        lonlims, latlims = self._limits_deg(fov_limits)
+        lon, lat = Util.AlignEUIUtil.extract_EUI_coordinates(self.hdr_small, dsun=False)
+        long, latg, dlon, dlat = Util.PlotFits.build_regular_grid(lon, lat, lonlims=lonlims, latlims=latlims)
+        if long.size == 0:
+            raise ValueError("fov_limits select no pixel of the small image")
+        mid = [long.shape[0] // 2, long.shape[1] // 2]
+        hdrg = self.hdr_small.copy()
+        hdrg["CRVAL1"] = float(units.convert(long[mid[0], mid[1]], "deg", hdrg["CUNIT1"]))
+        hdrg["CRVAL2"] = float(units.convert(latg[mid[0], mid[1]], "deg", hdrg["CUNIT2"]))
+        hdrg["CRPIX1"] = mid[0] + 1
+        hdrg["CRPIX2"] = mid[1] + 1
+        hdrg["CDELT1"] = float(units.convert(dlon, "deg", hdrg["CUNIT1"]))
+        hdrg["CDELT2"] = float(units.convert(dlat, "deg", hdrg["CUNIT2"]))
+        hdrg["PC1_1"], hdrg["PC2_2"], hdrg["PC1_2"], hdrg["PC2_1"] = 1.0, 1.0, 0.0, 0.0
+        hdrg["CROTA"] = 0.0
+        hdrg["CROTA2"] = 0.0
+        hdrg["NAXIS1"] = long.shape[0]
+        hdrg["NAXIS2"] = long.shape[1]
+        # _extract_coordinates_pixels(hdrg -> hdr_small) + interpol2d, on the device
+        lng_d, lat_d = Util.AlignEUIUtil.extract_EUI_coordinates(hdrg, dsun=False, as_device=True)
+        xg, yg = _ext.tan_world2pix(TanWcs.from_header(self.hdr_small), lng_d, lat_d)
+        img = torch.from_numpy(np.ascontiguousarray(_engine.LagSearchEngine._native_float(self.data_small))).to(xg.device)
+        out = _ext.map_coordinates(img, yg, xg, self.order, float("nan"), torch.float64)
+        self.data_small = out.cpu().numpy()
+        self.hdr_small = hdrg
 
     # ------------------------------------------------------------------------------------------------
     # the seam: lag grid -> correlation cube

@@ -189,6 +189,29 @@ class AlignEUIUtil:
         return lng, lat
 
 
+class PlotFits:
+    """Only the grid helper the pointing search uses (`utils/Util.py:874-904`); plotting lives in `plot/`."""
+
+    @staticmethod
+    def build_regular_grid(longitude, latitude, lonlims=None, latlims=None):
+        """Regular lon / lat grid [deg] spanning the image's footprint at its own sampling. `longitude`, `latitude`:
+        degrees, already wrapped to (-180, 180] (what `extract_EUI_coordinates` returns); limits in degrees.
+        Returns (longitude_grid, latitude_grid, dlon, dlat), all in degrees."""
+        x = np.abs(longitude[0, 1] - longitude[0, 0])
+        y = np.abs(latitude[0, 1] - latitude[0, 0])
+        dlon = np.sqrt(x ** 2 + y ** 2)
+        x = np.abs(longitude[1, 0] - longitude[0, 0])
+        y = np.abs(latitude[1, 0] - latitude[0, 0])
+        dlat = np.sqrt(x ** 2 + y ** 2)
+        longitude1d = np.arange(np.min(longitude), np.max(longitude), dlon)
+        latitude1d = np.arange(np.min(latitude), np.max(latitude), dlat)
+        if (lonlims is not None) or (latlims is not None):
+            longitude1d = longitude1d[(longitude1d > lonlims[0]) & (longitude1d < lonlims[1])]
+            latitude1d = latitude1d[(latitude1d > latlims[0]) & (latitude1d < latlims[1])]
+        longitude_grid, latitude_grid = np.meshgrid(longitude1d, latitude1d)
+        return longitude_grid, latitude_grid, dlon, dlat
+
+
 class AlignSpiceUtil:
 
     @staticmethod

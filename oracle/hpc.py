@@ -164,6 +164,47 @@ def shift_header(hdr, refs: Refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crot
         hdr["PC2_1"] = (1 / lam) * np.sin(rho)
 
 
+def build_regular_grid(longitude, latitude, lonlims=None, latlims=None):
+    """`Util.PlotFits.build_regular_grid` (`utils/Util.py:874-904`) on degree arrays."""
+    x = np.abs(longitude[0, 1] - longitude[0, 0])
+    y = np.abs(latitude[0, 1] - latitude[0, 0])
+    dlon = np.sqrt(x ** 2 + y ** 2)
+    x = np.abs(longitude[1, 0] - longitude[0, 0])
+    y = np.abs(latitude[1, 0] - latitude[0, 0])
+    dlat = np.sqrt(x ** 2 + y ** 2)
+    lon1d = np.arange(np.min(longitude), np.max(longitude), dlon)
+    lat1d = np.arange(np.min(latitude), np.max(latitude), dlat)
+    if (lonlims is not None) or (latlims is not None):
+        lon1d = lon1d[(lon1d > lonlims[0]) & (lon1d < lonlims[1])]
+        lat1d = lat1d[(lat1d > latlims[0]) & (lat1d < latlims[1])]
+    lon_g, lat_g = np.meshgrid(lon1d, lat1d)
+    return lon_g, lat_g, dlon, dlat
+
+
+def select_fov_in_small_data(data_small, hdr_small, fov_limits_arcsec, order):
+    """`Alignment._select_fov_in_small_data` (`hdrshift/alignment.py:1082-1127`): small image on a regular,
+    unrotated lon / lat grid inside the limits; returns (data float64, new header). NAXIS1 / CRPIX1 come from the
+    grid's row count, as in the reference."""
+    lonlims = _convert(fov_limits_arcsec[0], "arcsec", "deg")
+    latlims = _convert(fov_limits_arcsec[1], "arcsec", "deg")
+    lon, lat = wcs_tan.extract_coordinates(hdr_small)
+    long, latg, dlon, dlat = build_regular_grid(lon, lat, lonlims, latlims)
+    mid = [long.shape[0] // 2, long.shape[1] // 2]
+    h = dict(hdr_small)
+    h["CRVAL1"] = float(_convert(long[mid[0], mid[1]], "deg", h["CUNIT1"]))
+    h["CRVAL2"] = float(_convert(latg[mid[0], mid[1]], "deg", h["CUNIT2"]))
+    h["CRPIX1"], h["CRPIX2"] = mid[0] + 1, mid[1] + 1
+    h["CDELT1"] = float(_convert(dlon, "deg", h["CUNIT1"]))
+    h["CDELT2"] = float(_convert(dlat, "deg", h["CUNIT2"]))
+    h["PC1_1"], h["PC2_2"], h["PC1_2"], h["PC2_1"] = 1.0, 1.0, 0.0, 0.0
+    h["CROTA"], h["CROTA2"] = 0.0, 0.0
+    h["NAXIS1"], h["NAXIS2"] = long.shape[0], long.shape[1]
+    xg, yg = wcs_tan.extract_coordinates_pixels(h, hdr_small)
+    out = np.zeros_like(xg)
+    interpol2d(np.array(data_small, dtype=np.float64), x=xg, y=yg, order=order, fill=np.nan, dst=out)
+    return out, h
+
+
 def create_submap_of_large_data(data_large, hdr_large, hdr_small, order):
     x_cut, y_cut = wcs_tan.extract_coordinates_pixels(hdr_small, hdr_large)
     cut = np.zeros_like(x_cut, dtype="float32")
@@ -184,7 +225,7 @@ class HpcSearch:
     def __init__(self, data_large, hdr_large, data_small, hdr_small,
                  lag_crval1, lag_crval2, lag_cdelt1, lag_cdelt2, lag_crota, lag_solar_r=None,
                  small_fov_value_min=None, small_fov_value_max=None, order=2, unit_lag="arcsec",
-                 force_crota_0=False, cdelt_mode="reference"):
+                 force_crota_0=False, cdelt_mode="reference", fov_limits=None):
         self.order = order
         self.cdelt_mode = cdelt_mode
         self.hdr_small = dict(hdr_small)
@@ -195,6 +236,9 @@ class HpcSearch:
             check_and_create_pcij(hdr_large, force_crota_0)
         self.data_small = np.array(data_small, dtype=np.float64)
         threshold_to_nan(self.data_small, small_fov_value_min, small_fov_value_max)
+        if fov_limits is not None:   # alignment.py:859-860, before _set_initial_header_values (:623)
+            self.data_small, self.hdr_small = select_fov_in_small_data(self.data_small, self.hdr_small, fov_limits,
+                                                                       order)
         self.refs = Refs(self.hdr_small, lag_crval1, lag_crval2, lag_cdelt1, lag_cdelt2, lag_crota,
                          lag_solar_r, unit_lag=unit_lag)
         if np.isnan(self.data_small).all():

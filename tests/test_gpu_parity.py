@@ -149,6 +149,25 @@ def test_hpc_cube_parity_ragged_tiles_and_large_shifts(torch_cuda, toy_rect_pair
     assert a.nvalid[4].max() == 0
 
 
+def test_hpc_cube_fov_limits_and_remove_fov_limits(torch_cuda, toy_pair):
+    """fov_limits: the small image is first re-sampled onto a regular, unrotated lon / lat grid inside the limits
+    (alignment.py:1082-1127, non-square selection: the reference's NAXIS1 / CRPIX1 quirk included); the search runs
+    on that image and header."""
+    from euispice_coreg_b200.hdrshift import Alignment
+    from oracle.hpc import HpcSearch
+    fov = [[-80.0, 10.0], [-40.0, 45.0]]
+    a = Alignment(toy_pair[0], toy_pair[1], parallelism=True, **LAGS)
+    gpu = a.align_using_helioprojective(return_type="corr", fov_limits=fov)
+    dl, hl, ds, hs = load_pair(*toy_pair[:2])
+    s = HpcSearch(dl, hl, ds, hs, fov_limits=fov, **LAGS)
+    assert a.hdr_small["NAXIS1"] == s.hdr_small["NAXIS1"] != a.hdr_small["NAXIS2"] and a.hdr_small["CROTA"] == 0.0
+    for k in ("CRVAL1", "CRVAL2", "CDELT1", "CDELT2", "CRPIX1", "CRPIX2"):
+        assert abs(a.hdr_small[k] - s.hdr_small[k]) < 1e-7, k   # device vs numpy trig: ~1e-12 deg
+    _assert_parity(gpu, s.cube())
+    i, j = np.unravel_index(np.nanargmax(gpu), gpu.shape)[:2]
+    assert (LAGS["lag_crval1"][i], LAGS["lag_crval2"][j]) == (24.0, 6.0)
+
+
 def test_hpc_cube_cdelt_semantics(torch_cuda, toy_pair):
     kw = dict(lag_crval1=[22.0, 24.0], lag_crval2=[6.0], lag_cdelt1=[0.0, 0.004], lag_cdelt2=[0.0, -0.003],
               lag_crota=[0.0, 0.3])
