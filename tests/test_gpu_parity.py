@@ -375,3 +375,37 @@ def test_single_lag_and_tiny_images(torch_cuda, tmp_path):
     gpu, _ = _gpu_cube(pair, **one)
     ref, _ = _oracle_cube(pair, **one)
     assert gpu.shape == (1, 1, 1, 1, 1, 1) and abs(gpu.item() - ref.item()) <= R_TOL
+
+
+def test_config1_full_size_properties(torch_cuda):
+    """Size-independent properties at BASELINE's full size (2048^2, 3600 lags), where the oracle is too slow to
+    check every lag: (1) the cube does not depend on how the lag list is sliced or ordered (bitwise); (2) Pearson's
+    r is invariant under a positive affine map of the small image -- scaling by 2 is exact in binary floating
+    point, so the cube must not change by a single bit; a general map moves it only by rounding; (3) every r lies
+    in [-1, 1] and the number of valid pixels decreases away from the zero lag."""
+    import bench
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    from euispice_coreg_b200.hdrshift import Alignment, engine
+    pl, ps = bench.ensure_config1()
+    a = Alignment(pl, ps, parallelism=True, **bench.LAGS)
+    cube = a.align_using_helioprojective(return_type="corr").ravel()
+    eng = a.engine
+    d = engine.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
+    table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
+    # (1) slices and a permutation
+    parts = [eng.search(table[lo:hi]) for lo, hi in ((0, 1), (1, 1237), (1237, 3600))]
+    assert np.array_equal(np.concatenate(parts), cube)
+    perm = np.random.default_rng(0).permutation(table.shape[0])
+    assert np.array_equal(eng.search(table[perm]), cube[perm])
+    # (3)
+    assert np.all(np.abs(cube) <= 1.0)
+    nv = a.nvalid.reshape(60, 60)
+    assert nv[30, 30] == nv.max() and nv[0, 0] < nv[15, 15] < nv[30, 30]
+    # (2)
+    small = eng.small.clone()
+    piv = eng.pivots.clone()
+    eng.set_small((small * 2.0).cpu().numpy())
+    assert np.array_equal(eng.search(table), cube)
+    eng.set_small((small * 3.0 + 100.0).cpu().numpy())
+    assert np.max(np.abs(eng.search(table) - cube)) < 1e-9
+    eng.small, eng.pivots = small, piv
