@@ -206,12 +206,12 @@ class LagSearchEngine:
             arr = arr.astype(np.float64)
         return arr
 
-    def set_small(self, data_small):
+    def set_small(self, data_small, pinned=False):
         """Small image (NaN for masked pixels), float32 or float64 on the host. small_storage="f64" (default): kept
         as float64 on the device (a float32 input is uploaded as float32 and widened there); "auto": kept as float32
         when the input is float32 -- half the gather traffic, same values, but 9 f32->f64 conversions per sample on the
         quarter-rate conversion pipe and no homography kernel: measured slower on B200 (profiles/r1_k1_tuning.md)."""
-        small = self._upload(self._native_float(data_small))
+        small = self._upload(self._native_float(data_small), pinned=pinned)
         if small.dtype == _torch().float32 and self.small_storage == "f64":
             small = _ext.widen_f32(small)
         self.small = small

@@ -21,6 +21,19 @@ from . import engine as _engine
 from .alignment import Alignment, _Refs
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    """One upload / preparation stream per device for the life of the process (the caching allocator keeps a pool per
+    stream: a fresh stream per call would re-allocate every per-frame buffer)."""
+    torch = _engine._torch()
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class SequenceAlignment:
 
     def __init__(self, large_fov_known_pointing: str, list_small_fov_to_correct, lag_crval1, lag_crval2,
@@ -63,7 +76,12 @@ class SequenceAlignment:
         dist, rank, world = _engine._dist_info()
         n_frames = len(self.list_small)
         mine = list(range(rank, n_frames, world))          # frames of this rank (round robin)
-        eng = _engine.LagSearchEngine(order=self.kw["reprojection_order"], strict=self.kw["strict_arithmetic"])
+        # two engines = two sets of per-frame device buffers (small image, cut of the large image, pivots, workspace)
+        # sharing the one resident large image: frame k+1 is uploaded and prepared on a side stream while frame k is
+        # being searched on the main stream
+        engs = [_engine.LagSearchEngine(order=self.kw["reprojection_order"], strict=self.kw["strict_arithmetic"])
+                for _ in range(2)]
+        eng = engs[0]
         self.engine = eng
         # the reference image: read, checked and uploaded once
         a0 = Alignment(self.large_fov_known_pointing, self.list_small[0] if self.list_small else "", **self.kw)
@@ -71,36 +89,53 @@ class SequenceAlignment:
         hdr_large = f_large[a0.large_fov_window].header.copy()
         a0._check_ant_create_pcij_matrix(hdr_large)
         eng.set_large(a0._float_image(f_large[a0.large_fov_window].data), TanWcs.from_header(hdr_large))
+        engs[1].d_large, engs[1].wcs_large = eng.d_large, eng.wcs_large
         shape5 = None
         pending = None                                      # (frame index, device cube, dead mask, Alignment)
         cubes = {}
         aligns = {}
 
         def finish(item):
-            k, out_dev, dead, a = item
-            corr = np.where(dead, 0.0, out_dev.cpu().numpy())
-            cubes[k] = corr
+            # fetch on the side stream, ordered after THIS frame's search only: the main stream may already be busy
+            # with the next frame, and a copy enqueued there would make the host wait for that one too
+            k, out_dev, dead, a, evt = item
+            with torch.cuda.device(out_dev.device), torch.cuda.stream(side):
+                side.wait_event(evt)
+                host = out_dev.cpu()
+            cubes[k] = np.where(dead, 0.0, host.numpy())
             aligns[k] = a
 
+        with torch.cuda.device(eng.device):
+            main = torch.cuda.current_stream()
+            side = _side_stream(eng.device)
+            searched = [None, None]                         # per engine: event after its last search on `main`
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for k in mine:
+        for n, k in enumerate(mine):
+            e = engs[n & 1]
             a = self._host_prepare(self.list_small[k])       # overlaps the device search of the previous frame
             d = _engine.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
             refs = _Refs()
             refs.crval1_ref, refs.crval2_ref, refs.crota_ref = a.crval1_ref, a.crval2_ref, a.crota_ref
             refs.cdelt1_ref, refs.cdelt2_ref = a.cdelt1_ref, a.cdelt2_ref
             shape5 = (len(a.lag_crval1), len(a.lag_crval2), len(a.lag_cdelt1), len(a.lag_cdelt2), len(a.lag_crota))
-            eng.set_small(a.data_small)
-            eng.cut_large(TanWcs.from_header(a.hdr_small))
-            table, dead = eng.hpc_lag_table(a.hdr_small, refs, *d, a.cdelt_semantics)
-            with torch.cuda.device(eng.device):
-                out_dev = torch.empty(table.shape[0], dtype=torch.float64, device=eng.device)
-                eng.evaluate(eng._upload(table), out_dev)     # asynchronous: returns once the kernels are enqueued
+            with torch.cuda.device(e.device), torch.cuda.stream(side):
+                if searched[n & 1] is not None:
+                    side.wait_event(searched[n & 1])         # this engine's buffers are free again
+                e.set_small(a.data_small, pinned=True)
+                e.cut_large(TanWcs.from_header(a.hdr_small))
+                table, dead = e.hpc_lag_table(a.hdr_small, refs, *d, a.cdelt_semantics)
+                tab_dev = e._upload(table, pinned=True)
+                out_dev = torch.empty(table.shape[0], dtype=torch.float64, device=e.device)
+                ready = side.record_event()
+            with torch.cuda.device(e.device):
+                main.wait_event(ready)
+                e.evaluate(tab_dev, out_dev)                  # asynchronous: returns once the kernels are enqueued
+                searched[n & 1] = main.record_event()
             a.data_small = None
             if pending is not None:
                 finish(pending)
-            pending = (k, out_dev, dead, a)
+            pending = (k, out_dev, dead, a, searched[n & 1])
         if pending is not None:
             finish(pending)
         torch.cuda.synchronize()
