@@ -92,8 +92,27 @@ class AlignmentSpice(Alignment):
             for k in ("SOLAR_B0", "RSUN_REF", "DSUN_OBS", "CROTA"):
                 self.hdr_small[k] = hdu.header[k]
             if self.extend_pixel_size:
-                raise NotImplementedError("extend_pixel_size (solar-rotation CDELT1 correction, "
-                                          f"alignment_spice.py:223-248, dt={dt}) is not on the device path")
+                self._correct_solar_rotation(dt)
+
+    def _correct_solar_rotation(self, dt):
+        """`alignment_spice.py:223-248`: the raster steps against solar rotation, so structures are sampled with an
+        effective CDELT1 = CDELT1 - dt * (helioprojective rotation rate) * cos(heliocentric longitude). Host-only
+        header arithmetic, kept as the reference has it (EIT 171 rates for the 174 band; the phi range test of
+        `:241` can never fire)."""
+        b0 = np.deg2rad(self.hdr_small["SOLAR_B0"])
+        band = self.hdr_large["WAVELNTH"]
+        omega_car = np.deg2rad(360 / 25.38 / 86400)
+        if band == 174:
+            band = 171
+        omega = omega_car + Util.diff_rot(b0, f"EIT {band}")
+        rsun, dsun = self.hdr_small["RSUN_REF"], self.hdr_small["DSUN_OBS"]
+        phi_rot = 1.004 * omega * rsun / (dsun - 1.004 * rsun)
+        phi_rot = np.rad2deg(phi_rot) * 3600
+        alpha = float(units.convert(self.hdr_small["CRVAL1"], self.hdr_small["CUNIT1"], "rad"))
+        phi = np.arcsin(((dsun - 1.004 * rsun) / (1.004 * rsun)) * np.sin(alpha))
+        dtx_old = float(units.convert(self.hdr_small["CDELT1"], self.hdr_small["CUNIT1"], "arcsec"))
+        dtx_new = dtx_old - dt * phi_rot * np.cos(phi)
+        self.hdr_small["CDELT1"] = float(units.convert(dtx_new, "arcsec", self.hdr_small["CUNIT1"]))
 
     def _prepare_spice_from_l2(self, hdu):
         """`alignment_spice.py:250-323`: 4-D L2 cube -> 2-D image + 2-D header."""

@@ -189,6 +189,18 @@ class AlignEUIUtil:
         return lng, lat
 
 
+def diff_rot(lat, wvl="default"):
+    """`AlignEUIUtil.diff_rot` (`utils/Util.py:314-345`): omega_diff(lat) - omega_Carrington [rad / s]; lat in
+    radians; A + B sin^2 + C sin^4 in deg / day from Hortin (2003) per EIT band."""
+    p = {"EIT 171": (14.56, -2.65, 0.96), "EIT 195": (14.50, -2.14, 0.66), "EIT 284": (14.60, -0.71, -1.18),
+         "EIT 304": (14.51, -3.12, 0.34)}
+    p["default"] = p["EIT 195"]
+    a, b, c = p[wvl]
+    a_car = 360 / 25.38
+    corr = a - a_car + b * np.sin(lat) ** 2 + c * np.sin(lat) ** 4
+    return np.deg2rad(corr / 86400)
+
+
 class PlotFits:
     """Only the grid helper the pointing search uses (`utils/Util.py:874-904`); plotting lives in `plot/`."""
 
@@ -210,6 +222,9 @@ class PlotFits:
             latitude1d = latitude1d[(latitude1d > latlims[0]) & (latitude1d < latlims[1])]
         longitude_grid, latitude_grid = np.meshgrid(longitude1d, latitude1d)
         return longitude_grid, latitude_grid, dlon, dlat
+
+
+AlignEUIUtil.diff_rot = staticmethod(diff_rot)
 
 
 class AlignSpiceUtil:

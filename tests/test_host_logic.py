@@ -337,3 +337,28 @@ def test_lag_sharding_and_gather_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_spice_solar_rotation_cdelt1_correction():
+    """`extend_pixel_size=True` (alignment_spice.py:223-248): CDELT1 shrinks by dt * helioprojective rotation rate *
+    cos(phi); checked against the formula evaluated by hand for a disc-centre and a near-limb pointing."""
+    from euispice_coreg_b200.hdrshift.alignment_spice import AlignmentSpice
+    from euispice_coreg_b200.utils import Util
+    assert abs(Util.diff_rot(0.0, "EIT 171") - np.deg2rad((14.56 - 360 / 25.38) / 86400)) < 1e-20
+    assert Util.AlignEUIUtil.diff_rot(0.3) == Util.diff_rot(0.3, "EIT 195")
+    for crval1, unit in ((0.0, "arcsec"), (800.0, "arcsec"), (0.2, "deg")):
+        a = AlignmentSpice.__new__(AlignmentSpice)
+        a.hdr_large = {"WAVELNTH": 174}
+        cd = 4.0 if unit == "arcsec" else 4.0 / 3600
+        a.hdr_small = {"SOLAR_B0": -2.0, "RSUN_REF": 6.957e8, "DSUN_OBS": 5.7e10, "CRVAL1": crval1, "CUNIT1": unit,
+                       "CDELT1": cd}
+        dt = 21.3
+        a._correct_solar_rotation(dt)
+        omega = np.deg2rad(360 / 25.38 / 86400) + np.deg2rad(
+            (14.56 - 360 / 25.38 - 2.65 * np.sin(np.deg2rad(-2.0)) ** 2 + 0.96 * np.sin(np.deg2rad(-2.0)) ** 4) / 86400)
+        rate = np.rad2deg(1.004 * omega * 6.957e8 / (5.7e10 - 1.004 * 6.957e8)) * 3600          # arcsec / s
+        alpha = np.deg2rad(crval1 / 3600 if unit == "arcsec" else crval1)
+        phi = np.arcsin((5.7e10 - 1.004 * 6.957e8) / (1.004 * 6.957e8) * np.sin(alpha))
+        want = 4.0 - dt * rate * np.cos(phi)
+        got = a.hdr_small["CDELT1"] * (1.0 if unit == "arcsec" else 3600.0)
+        assert abs(got - want) < 1e-12 and 3.8 < got < 4.0, (got, want)
