@@ -1,10 +1,13 @@
-"""Dependency-free FITS reader/writer for uncompressed image HDUs.
+"""Dependency-free FITS reader/writer for image HDUs, plain or RICE tile-compressed.
 
 Stands in for the `astropy.io.fits` calls of the reference's pointing-search path
 (`hdrshift/alignment.py:299-316`, `utils/Util.py:106-159`, `synras/map_builder.py:106-131,192-203`).
 Scope: primary + IMAGE extension HDUs, BITPIX in {8, 16, 32, 64, -32, -64}, BSCALE/BZERO,
-string/logical/int/float cards, CONTINUE-less headers. Tile-compressed (RICE) HDUs are the
-"next" row of SURVEY.md section 8(f) and raise a clear error here.
+string/logical/int/float cards, CONTINUE-less headers. Tile-compressed images (`ZIMAGE` binary tables with
+`ZCMPTYPE = 'RICE_1'`, the form real Solar Orbiter L2 files come in; `utils/Util.py:144-145`) are read as
+`CompImageHDU`: the header is folded back to an image header on the host, the pixels are decoded ON THE GPU
+(`coreg_rice_decode`, one thread per tile) the first time `.data` is touched, so only the compressed heap crosses
+PCIe. Writing is always uncompressed.
 
 If astropy is importable the caller may still hand astropy headers to the package: everything
 downstream only needs the mapping protocol (`in`, `[]`, `.copy()`, `.keys()`).
@@ -237,6 +240,154 @@ class PrimaryHDU(ImageHDU):
     is_primary = True
 
 
+_TFORM_BYTES = {"L": 1, "X": 1, "B": 1, "I": 2, "J": 4, "K": 8, "A": 1, "E": 4, "D": 8, "C": 8, "M": 16, "P": 8, "Q": 16}
+_Z_DROP = ("ZIMAGE", "ZCMPTYPE", "ZQUANTIZ", "ZDITHER0", "ZBLANK", "ZSCALE", "ZZERO", "TFIELDS", "THEAP", "ZMASKCMP",
+           "ZSIMPLE", "ZEXTEND", "ZBLOCKED", "ZHECKSUM", "ZDATASUM", "CHECKSUM", "DATASUM")
+
+
+def _tform(tform):
+    """'1PB(3241)' -> (repeat, code, element code of a variable-length array or None)."""
+    t = str(tform).strip()
+    i = 0
+    while i < len(t) and t[i].isdigit():
+        i += 1
+    rep = int(t[:i]) if i else 1
+    code = t[i].upper()
+    sub = t[i + 1].upper() if code in "PQ" and len(t) > i + 1 else None
+    return rep, code, sub
+
+
+class CompImageHDU:
+    """A tile-compressed image extension. `header` is the image's own header; `data` decodes on first access."""
+    is_primary = False
+
+    def __init__(self, table_header, body):
+        self._thdr = table_header
+        self._body = body
+        self._data = None
+        self.header = self._image_header(table_header)
+
+    @property
+    def name(self):
+        return self.header.get("EXTNAME", "")
+
+    @staticmethod
+    def _image_header(th):
+        h = Header()
+        naxis = int(th["ZNAXIS"])
+        h["XTENSION"] = "IMAGE"
+        h["BITPIX"] = int(th["ZBITPIX"])
+        h["NAXIS"] = naxis
+        for i in range(1, naxis + 1):
+            h[f"NAXIS{i}"] = int(th[f"ZNAXIS{i}"])
+        h["PCOUNT"] = int(th.get("ZPCOUNT", 0))
+        h["GCOUNT"] = int(th.get("ZGCOUNT", 1))
+        skip = {"XTENSION", "BITPIX", "NAXIS", "NAXIS1", "NAXIS2", "PCOUNT", "GCOUNT", "ZNAXIS", "ZBITPIX", "ZPCOUNT",
+                "ZGCOUNT", "ZTENSION"}
+        for k, (v, c) in th._cards.items():
+            if k in skip or k in _Z_DROP:
+                continue
+            if any(k.startswith(p) and k[len(p):].isdigit() for p in ("ZNAXIS", "ZTILE", "ZNAME", "ZVAL", "TTYPE",
+                                                                          "TFORM", "TUNIT", "TDIM", "TSCAL", "TZERO",
+                                                                          "TNULL", "TDISP")):
+                continue
+            h._cards[k] = (v, c)
+        h._commentary = list(th._commentary)
+        return h
+
+    @property
+    def data(self):
+        if self._data is None:
+            self._data = self._decode(as_device=False)
+            self._body = None
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = None if value is None else np.asarray(value)
+        self._body = None
+
+    def device_data(self, out_dtype=None):
+        """The decoded image as a CUDA tensor, without a round trip through the host (float images only)."""
+        return self._decode(as_device=True, out_dtype=out_dtype)
+
+    def copy(self):
+        return ImageHDU(None if self.data is None else self.data.copy(), self.header.copy())
+
+    def _decode(self, as_device, out_dtype=None):
+        th, body = self._thdr, self._body
+        if body is None:
+            raise OSError("compressed payload already released")
+        cmp = str(th.get("ZCMPTYPE", "")).strip().upper()
+        if cmp not in ("RICE_1", "RICE_ONE"):
+            raise NotImplementedError(f"ZCMPTYPE={cmp!r}: only RICE_1 tiles are decoded here (install astropy for others)")
+        if int(th["ZNAXIS"]) != 2:
+            raise NotImplementedError("only 2-D tile-compressed images are supported")
+        nx, ny = int(th["ZNAXIS1"]), int(th["ZNAXIS2"])
+        tw, tht = int(th.get("ZTILE1", nx)), int(th.get("ZTILE2", 1))
+        row_bytes, n_rows = int(th["NAXIS1"]), int(th["NAXIS2"])
+        params = {str(th[f"ZNAME{i}"]).strip().upper(): th[f"ZVAL{i}"] for i in range(1, 10) if f"ZNAME{i}" in th}
+        blocksize, bytepix = int(params.get("BLOCKSIZE", 32)), int(params.get("BYTEPIX", 4))
+        cols, off = {}, 0
+        for i in range(1, int(th["TFIELDS"]) + 1):
+            rep, code, sub = _tform(th[f"TFORM{i}"])
+            width = _TFORM_BYTES[code] * (1 if code in "PQ" else rep)
+            cols[str(th.get(f"TTYPE{i}", f"COL{i}")).strip().upper()] = (off, code, sub, rep)
+            off += width
+        if off != row_bytes or "COMPRESSED_DATA" not in cols:
+            raise OSError("malformed tile-compressed table")
+        table = np.frombuffer(body, dtype=np.uint8, count=row_bytes * n_rows).reshape(n_rows, row_bytes)
+        theap = int(th.get("THEAP", row_bytes * n_rows))
+        heap = memoryview(body)[theap:theap + int(th.get("PCOUNT", 0))]
+
+        def column(name, dtype):
+            o, code, _, rep = cols[name]
+            w = np.dtype(dtype).itemsize
+            return np.ascontiguousarray(table[:, o:o + w]).view(dtype).ravel()
+
+        o, code, sub, _ = cols["COMPRESSED_DATA"]
+        dsc = np.ascontiguousarray(table[:, o:o + (8 if code == "P" else 16)]).view(">i4" if code == "P" else ">i8")
+        counts, offsets = dsc[:, 0].astype(np.int64), dsc[:, 1].astype(np.int64)
+        if np.any(counts <= 0):
+            raise NotImplementedError("tiles stored uncompressed / gzip-compressed (empty COMPRESSED_DATA rows)")
+        zbitpix = int(th["ZBITPIX"])
+        is_float = zbitpix < 0
+        from .. import _ext   # device decode: the CUDA library is required (no host fallback)
+        torch = _ext._torch()
+        if not torch.cuda.is_available():
+            raise OSError("tile-compressed FITS images are decoded on the GPU: no CUDA device (or install astropy)")
+        if is_float:
+            method = {"NO_DITHER": 0, "NONE": 0, "SUBTRACTIVE_DITHER_1": 1, "SUBTRACTIVE_DITHER_2": 2}.get(
+                str(th.get("ZQUANTIZ", "NO_DITHER")).strip().upper())
+            if method is None:
+                raise NotImplementedError(f"ZQUANTIZ={th.get('ZQUANTIZ')!r}")
+            zscale = column("ZSCALE", ">f8").astype(np.float64) if "ZSCALE" in cols else np.full(n_rows, float(th["ZSCALE"]))
+            zzero = column("ZZERO", ">f8").astype(np.float64) if "ZZERO" in cols else np.full(n_rows, float(th["ZZERO"]))
+            blank = int(th["ZBLANK"]) if "ZBLANK" in th else None
+            if "ZBLANK" in cols:
+                zb = column("ZBLANK", ">i4")
+                if zb.size and np.all(zb == zb[0]):
+                    blank = int(zb[0])
+                else:
+                    raise NotImplementedError("per-tile ZBLANK values")
+            odt = out_dtype or (torch.float32 if zbitpix == -32 else torch.float64)
+            dev = _ext.rice_decode(heap, offsets, counts, tw, tht, nx, ny, blocksize, bytepix, zscale, zzero, method,
+                                   int(th.get("ZDITHER0", 1)), blank, odt)
+            return dev if as_device else dev.cpu().numpy()
+        dev = _ext.rice_decode(heap, offsets, counts, tw, tht, nx, ny, blocksize, bytepix)
+        if as_device:
+            return dev
+        arr = dev.cpu().numpy().astype({8: np.uint8, 16: np.int16, 32: np.int32}[zbitpix])
+        bscale, bzero = float(th.get("BSCALE", 1)), float(th.get("BZERO", 0))
+        if bscale != 1.0 or bzero != 0.0:
+            if bscale == 1.0 and bzero == float(2 ** (zbitpix - 1)) and zbitpix > 8:
+                arr = (arr.astype(np.int64) + int(bzero)).astype(f"u{zbitpix // 8}")
+            else:
+                odt = np.float32 if zbitpix <= 16 else np.float64
+                arr = arr.astype(odt) * odt(bscale) + odt(bzero)
+        return arr
+
+
 class HDUList(list):
     def __getitem__(self, key):
         if isinstance(key, str):
@@ -319,10 +470,11 @@ def open(path, mode="readonly", **_):  # noqa: A001 - mirrors astropy.io.fits.op
             else:
                 arr = arr.astype(dt.newbyteorder("="))
             data = arr
-        elif nbytes and xt == "BINTABLE" and "ZIMAGE" in hdr:
-            raise NotImplementedError(
-                f"{path}: tile-compressed image HDU (ZIMAGE) is not supported by fits_lite; "
-                "decompress it first (e.g. funpack) or install astropy")
+        elif nbytes and xt == "BINTABLE" and hdr.get("ZIMAGE", False):
+            hdus.append(CompImageHDU(hdr, bytes(buf[pos:pos + nbytes])))
+            pos += ((nbytes + BLOCK - 1) // BLOCK) * BLOCK
+            first = False
+            continue
         pos += ((nbytes + BLOCK - 1) // BLOCK) * BLOCK
         hdu = PrimaryHDU(data, hdr) if first else ImageHDU(data, hdr)
         hdus.append(hdu)

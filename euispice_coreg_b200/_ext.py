@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
 
-F32, F64 = 0, 1
+F32, F64, I32 = 0, 1, 2
 FLAG_STRICT = 1
 FLAG_NO_FAST = 4
 
@@ -54,6 +54,8 @@ _SIGNATURES = {
                                         _P, C.c_int, _P]),
     "coreg_tan_trig_planes": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
     "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "coreg_rice_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "coreg_finite_mean": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
     "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
@@ -192,6 +194,55 @@ def tan_trig_planes(lng, lat, alpha_ref_deg):
         _check(lib.coreg_tan_trig_planes(_ptr(lng), _ptr(lat), lng.numel(), float(alpha_ref_deg), _ptr(planes),
                                          _stream()), "coreg_tan_trig_planes")
     return planes
+
+
+_RAND = {}
+
+
+def fits_rand_values():
+    """cfitsio's dither sequence (`fits_init_randoms`): Park-Miller a = 16807, m = 2^31 - 1, seed 1, 10000 numbers
+    stored as float32."""
+    a, m, seed = 16807.0, 2147483647.0, 1.0
+    out = np.empty(10000, dtype=np.float32)
+    for i in range(10000):
+        temp = a * seed
+        seed = temp - m * int(temp / m)
+        out[i] = np.float32(seed / m)
+    return out
+
+
+def rice_decode(heap, offsets, counts, tile_w, tile_h, nx, ny, blocksize, bytepix, zscale=None, zzero=None, method=-1,
+                zdither0=1, blank=None, out_dtype=None, device=None):
+    """Decode a RICE_1 tile-compressed image on the device. `heap`: bytes-like (the table heap); `offsets`, `counts`:
+    per tile. Returns a device tensor [ny, nx] (int32 for integer images, float32 / float64 for quantised ones)."""
+    torch = _torch()
+    lib = load()
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    n_tiles = len(offsets)
+    h = torch.frombuffer(bytearray(heap) if len(heap) else bytearray(1), dtype=torch.uint8).to(dev)
+    o = torch.as_tensor(np.asarray(offsets, dtype=np.int64)).to(dev)
+    c = torch.as_tensor(np.asarray(counts, dtype=np.int32)).to(dev)
+    quant = method >= 0
+    if quant:
+        zs = torch.as_tensor(np.asarray(zscale, dtype=np.float64)).to(dev)
+        zz = torch.as_tensor(np.asarray(zzero, dtype=np.float64)).to(dev)
+        key = str(dev)
+        if key not in _RAND:
+            _RAND[key] = torch.from_numpy(fits_rand_values()).to(dev)
+        rnd = _RAND[key]
+        odt = out_dtype or torch.float32
+        code = F32 if odt == torch.float32 else F64
+    else:
+        zs = zz = rnd = None
+        odt, code = torch.int32, I32
+    out = torch.empty((ny, nx), dtype=odt, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.coreg_rice_decode(_ptr(h), _ptr(o), _ptr(c), n_tiles, int(tile_w), int(tile_h), int(nx), int(ny),
+                                     int(blocksize), int(bytepix), _ptr(zs) if quant else None,
+                                     _ptr(zz) if quant else None, int(method), int(zdither0),
+                                     int(blank is not None), int(blank or 0), _ptr(rnd) if quant else None, _ptr(out),
+                                     code, _stream()), "coreg_rice_decode")
+    return out
 
 
 def widen_f32(img):

@@ -31,6 +31,7 @@ extern "C" {
 
 #define COREG_F32 0
 #define COREG_F64 1
+#define COREG_I32 2
 
 /* flags of the lag-correlation kernels.
  * Default arithmetic: FP64 with fused multiply-add in the spline weights / tap sums (|dr| ~ 1e-15 vs strict).
@@ -112,6 +113,22 @@ int coreg_map_coordinates(const void* img_dev, int img_dtype, int img_ny, int im
  * Hoists the lag-independent half of world_to_pixel out of the per-lag loop (hdrshift/alignment.py:1061-1065). */
 int coreg_tan_trig_planes(const double* lng_dev, const double* lat_dev, int64_t n, double alpha_ref_deg,
                           double* planes_dev, void* stream);
+
+/* ---- FITS tiled-image (RICE_1) decoder ---------------------------------------------------------------------------
+ * Replaces what `astropy.io.fits` does inside `fits.open(path)[window].data` for a tile-compressed image HDU (the
+ * form real Solar Orbiter L2 files come in): hdrshift/alignment.py:299-316, utils/Util.py:144-145. One thread per
+ * tile; only the compressed heap crosses PCIe.
+ *   heap_dev     the binary table's heap (device bytes)        offsets_dev / counts_dev  [n_tiles] start and length of
+ *   each tile's COMPRESSED_DATA in the heap (table-row order = tiles in row-major order)
+ *   tile_w/h     ZTILE1 / ZTILE2; nx, ny = ZNAXIS1 / ZNAXIS2; blocksize, bytepix = the ZVALn of BLOCKSIZE / BYTEPIX
+ *   method       -1: integer image (out = the decoded integers, COREG_I32); 0 NO_DITHER, 1 SUBTRACTIVE_DITHER_1,
+ *                2 SUBTRACTIVE_DITHER_2: floating-point image, out = (q - r + 0.5) * ZSCALE + ZZERO (COREG_F32 / F64)
+ *   zscale_dev, zzero_dev [n_tiles]; zdither0 = ZDITHER0; blank = ZBLANK (-> NaN) when has_blank
+ *   rand_dev     cfitsio's 10000-number dither sequence as float32 (fits_init_randoms) */
+int coreg_rice_decode(const unsigned char* heap_dev, const long long* offsets_dev, const int* counts_dev, int n_tiles,
+                      int tile_w, int tile_h, int nx, int ny, int blocksize, int bytepix, const double* zscale_dev,
+                      const double* zzero_dev, int method, int zdither0, int has_blank, int blank,
+                      const float* rand_dev, void* out_dev, int out_dtype, void* stream);
 
 /* float32 image -> float64 on the device (exact). FITS BITPIX -32 payloads go up as float32 (half the H2D bytes of the
  * reference's host-side np.array(..., dtype=float64), hdrshift/alignment.py:299-316) and are widened once here: the lag

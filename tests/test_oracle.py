@@ -139,3 +139,56 @@ def test_hpc_oracle_reference_cdelt_quirks(toy_pair):
                    lag_crota=[0], cdelt_mode="intended")
     c2 = s2.cube()[0, 0, :, :, 0, 0]
     assert np.all(c2 > 0.5) and c2[0, 0] == c[0, 0] and c2[1, 1] != c2[0, 0]
+
+
+# ----------------------------------------------------------------------------------------------- RICE tiles
+def test_rice_dither_sequence_check_value():
+    """cfitsio documents that the 10 000th seed of `fits_init_randoms` must be 1043618065: the one known-answer
+    vector for the tiled-image codec that is available offline."""
+    from oracle import rice
+    from euispice_coreg_b200 import _ext
+    vals, seed = rice.fits_rand_values()
+    assert seed == 1043618065
+    assert vals.dtype == np.float32 and 0.0 < vals.min() and vals.max() < 1.0
+    assert np.array_equal(_ext.fits_rand_values(), vals)
+
+
+@pytest.mark.parametrize("bytepix", [1, 2, 4])
+def test_rice_codec_round_trip_edge_cases(bytepix):
+    from oracle import rice
+    bits = 8 * bytepix
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    rng = np.random.default_rng(bytepix)
+    cases = [np.array([5]), np.full(64, 7), np.arange(33), rng.integers(lo, hi, 100),        # single, constant, ramp, noise
+             np.clip(np.cumsum(rng.integers(-3, 4, 1000)), lo, hi),                            # low entropy
+             np.array([lo, hi, lo, hi, 0, -1, 1] * 9),                                         # wrap-around differences
+             np.concatenate([np.zeros(32), rng.integers(lo, hi, 32), np.zeros(31)])]           # zero / verbatim / short block
+    for a in cases:
+        a = a.astype(np.int64)
+        buf = rice.rice_encode(a, 32, bytepix)
+        assert np.array_equal(rice.rice_decode(buf, a.size, 32, bytepix), a)
+    # the constant tile costs the first pixel + one FS code (3 / 4 / 5 bits) per block
+    fsbits = {1: 3, 2: 4, 4: 5}[bytepix]
+    assert len(rice.rice_encode(np.full(64, 7), 32, bytepix)) == bytepix + (2 * fsbits + 7) // 8
+
+
+def test_rice_quantisation_round_trip_and_compressed_header(tmp_path):
+    from euispice_coreg_b200._compat import fits_lite
+    from oracle import rice
+    rng = np.random.default_rng(3)
+    tile = 500 + 80 * rng.standard_normal(300)
+    for method in (1, 2):
+        tile[7] = 0.0
+        q = rice.quantize_tile(tile, 0.5, tile.min(), row=17, zdither0=123, method=method)
+        back = rice.unquantize_tile(q, 0.5, tile.min(), row=17, zdither0=123, method=method, out_dtype=np.float64)
+        assert np.max(np.abs(back - tile)) <= 0.25 + 1e-9
+        assert (back[7] == 0.0) == (method == 2)
+    img = (500 + 100 * rng.standard_normal((12, 40))).astype(np.float32)
+    p = str(tmp_path / "c.fits")
+    rice.write_compressed_image(p, img, extra_cards=[("CRVAL1", 12.5), ("CTYPE1", "HPLN-TAN"), ("EXTNAME", "IMG")],
+                                quantize_scale=0.25, zdither0=7)
+    hdus = fits_lite.open(p)
+    assert len(hdus) == 2 and type(hdus[-1]).__name__ == "CompImageHDU" and hdus["IMG"] is hdus[1]
+    h = hdus[1].header
+    assert (h["BITPIX"], h["NAXIS"], h["NAXIS1"], h["NAXIS2"], h["CRVAL1"], h["CTYPE1"]) == (-32, 2, 40, 12, 12.5, "HPLN-TAN")
+    assert not any(k.startswith("Z") or k.startswith("TFORM") for k in h.keys())
