@@ -1702,30 +1702,46 @@ constexpr int kRiceZeroValue = -2147483646;
 struct RiceBits {
   const unsigned char* p;
   const unsigned char* end;
-  unsigned long long acc;
+  unsigned long long acc;   // the low n bits are valid, most significant first
   int n;
-  __device__ __forceinline__ unsigned take(int k) {   // k <= 32
-    while (n < k) {
-      acc = (acc << 8) | (unsigned long long)(p < end ? *p : 0);
-      ++p;
+  // top the accumulator up: single bytes until the pointer is 4-byte aligned, then whole big-endian words
+  __device__ __forceinline__ void refill() {
+    while (n <= 56 && p < end && (reinterpret_cast<uintptr_t>(p) & 3u)) {
+      acc = (acc << 8) | (unsigned long long)*p++;
       n += 8;
+    }
+    if (n <= 32 && p + 4 <= end) {
+      const unsigned w = __byte_perm(*reinterpret_cast<const unsigned*>(p), 0u, 0x0123);
+      acc = (acc << 32) | (unsigned long long)w;
+      n += 32;
+      p += 4;
+    } else {
+      while (n <= 56 && p < end) {
+        acc = (acc << 8) | (unsigned long long)*p++;
+        n += 8;
+      }
+    }
+  }
+  __device__ __forceinline__ unsigned take(int k) {   // k <= 32; bits past the end of the stream read as zero
+    if (n < k) refill();
+    if (n < k) {
+      acc <<= (k - n);
+      n = k;
     }
     n -= k;
     const unsigned v = (unsigned)((acc >> n) & ((1ull << k) - 1ull));
     acc &= (1ull << n) - 1ull;
     return v;
   }
-  __device__ __forceinline__ int zeros_then_one() {   // number of zero bits before the next one bit
+  __device__ __forceinline__ int zeros_then_one() {   // number of zero bits before the next one bit (consumed too)
     int z = 0;
     for (;;) {
-      if (n == 0) {
-        if (p >= end) return z;   // truncated stream: stop (caller sees garbage, never reads out of bounds)
-        acc = *p++;
-        n = 8;
-      }
-      if (acc == 0) {
+      if (n == 0 || acc == 0) {
         z += n;
         n = 0;
+        acc = 0;
+        refill();
+        if (n == 0) return z;   // truncated stream: stop (caller decodes garbage, never reads out of bounds)
         continue;
       }
       const int top = 63 - __clzll((long long)acc);    // position of the highest set bit, < n
