@@ -170,6 +170,77 @@ def run_reference(args):
     return 0
 
 
+CARRINGTON_LAGS = dict(lag_crval1=np.arange(-60, 60, 1.0), lag_crval2=np.arange(-60, 60, 1.0), lag_cdelt1=np.array([0.0]),
+                       lag_cdelt2=np.array([0.0]), lag_crota=np.array([0.0]))
+CARRINGTON_GRID = dict(lonlims=(200.0, 300.0), latlims=(-20.0, 20.0), shape=(2048, 2048))
+
+
+def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0):
+    """BASELINE.json configs[1] (same image pair on a user Carrington grid 2048^2, 120 x 120 CRVAL lags), measured
+    beside the headline: device-timed search with everything resident (lags sharded like the headline) and the wall
+    time of the public call. Returns a dict for the JSON line."""
+    from euispice_coreg_b200.hdrshift import engine as E
+    from euispice_coreg_b200.hdrshift.alignment import Alignment
+    a = Alignment(pl, ps, parallelism=True, **CARRINGTON_LAGS)
+    a.method, a.coordinate_frame, a.method_carrington_reprojection = "correlation", "final_carrington", "fa"
+    a._load_pair()
+    a._set_initial_header_values(True)
+    a.lonlims, a.latlims, a.shape = (CARRINGTON_GRID[k] for k in ("lonlims", "latlims", "shape"))
+    d1, d2, _, _, _ = E.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
+    eng = E.LagSearchEngine(order=2, small_storage="auto", variant=variant)   # float32 storage, as Alignment does here
+    eng.set_small(a.data_small)
+    r_sun = float(a.lag_solar_r[0])
+    eng.prepare_carrington_large(a.data_large, a.hdr_large, r_sun, a.lonlims, a.latlims, a.shape)
+    planes = eng.carrington_planes(a.hdr_small, r_sun, a.lonlims, a.latlims, a.shape)
+    roll = a.hdr_small["CROTA"] if "CROTA" in a.hdr_small else a.hdr_small["CROTA2"]
+    x0, y0 = eng.carrington_offset(a.hdr_small, a.crval1_ref + d1, a.crval2_ref + d2, roll)
+    table = np.stack([x0, y0], axis=1).astype(np.float64)
+    n = table.shape[0]
+    rank = dist.get_rank() if world > 1 else 0
+    chunk, bounds = E.shard_bounds(n, world)
+    lo, hi = bounds[rank]
+    tab_dev = eng._upload(table[lo:hi])
+    out = torch.full((chunk,), float("nan"), dtype=torch.float64, device=eng.device)
+    nv = torch.zeros(chunk, dtype=torch.int64, device=eng.device)
+    full = torch.empty(chunk * world, dtype=torch.float64, device=eng.device)
+
+    def step():
+        eng.evaluate(tab_dev, out[:hi - lo], nv[:hi - lo], planes)
+        if world > 1:
+            dist.all_gather_into_tensor(full, out)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=eng.device)
+    eff = nv[:hi - lo].sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(eff, op=dist.ReduceOp.SUM)
+    ms = float(t.item()) / steps
+    barrier()
+    t0 = time.perf_counter()
+    res = Alignment(pl, ps, parallelism=True, **CARRINGTON_LAGS).align_using_carrington(method="correlation",
+                                                                                      **CARRINGTON_GRID)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    am = tuple(int(v) for v in res.max_index[:2])
+    return {"workload": "configs[1]: same pair on a Carrington grid 2048x2048 (lon 200-300 deg, lat +-20 deg), 120x120 "
+                        "CRVAL lags @1arcsec", "lags": n, "ms_per_search": ms, "lag_evals_per_s": n / (ms * 1e-3),
+            "effective_pixel_samples_per_s": float(eff.item()) / (ms * 1e-3),
+            "effective_fraction_of_grid": float(eff.item()) / (n * 2048.0 * 2048.0),
+            "align_wall_s": wall,
+            "argmax_lag_arcsec": [float(CARRINGTON_LAGS["lag_crval1"][am[0]]), float(CARRINGTON_LAGS["lag_crval2"][am[1]])]}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
@@ -292,6 +363,8 @@ def run_gpu(args):
     res = Alignment(pl, ps, parallelism=True, **LAGS).align_using_helioprojective()
     torch.cuda.synchronize()
     align_wall = time.perf_counter() - t0
+    carr = None if args.no_carrington else carrington_secondary(pl, ps, args.steps, world, barrier, torch, dist,
+                                                                 args.carrington_variant)
     if rank == 0:
         am = tuple(int(v) for v in res.max_index[:2])
         best = (float(LAGS["lag_crval1"][am[0]]), float(LAGS["lag_crval2"][am[1]]))
@@ -329,6 +402,7 @@ def run_gpu(args):
                             "the FITS files hold them): H2D images + lag table, one-time resampling, search, "
                             "all-gather, D2H cube"},
             "align_wall_s": align_wall, "argmax_lag_arcsec": best,
+            "carrington": carr,
             # own kernels inside the timed region: per lag-kernel launch the homography table (fast path), the fused
             # lag kernel and the finalize kernel (the L2 flush memset and the NCCL all-gather are not ours)
             "gpu_launches": int(k1_launches * (3 if fast else 2)),
@@ -379,6 +453,8 @@ def main():
     ap.add_argument("--no-fast", action="store_true", help="force the generic fused kernel")
     ap.add_argument("--small-storage", default="f64", choices=["auto", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-carrington", action="store_true", help="skip the secondary configs[1] measurement")
+    ap.add_argument("--carrington-variant", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -367,7 +367,11 @@ class Alignment:
         refs.crval1_ref, refs.crval2_ref, refs.crota_ref = self.crval1_ref, self.crval2_ref, self.crota_ref
         refs.cdelt1_ref, refs.cdelt2_ref = self.cdelt1_ref, self.cdelt2_ref
 
-        eng = _engine.LagSearchEngine(order=self.order, strict=self.strict_arithmetic)
+        # small-image storage on the device: float64 for the helioprojective kernels (FP64-issue bound: no per-tap
+        # conversion); float32, when the file holds float32, for the Carrington kernel, whose gather is sparse in the
+        # small image (several detector pixels per Carrington pixel) and therefore bound by L1 wavefronts, not FP64
+        storage = "auto" if self.coordinate_frame == "final_carrington" else "f64"
+        eng = _engine.LagSearchEngine(order=self.order, strict=self.strict_arithmetic, small_storage=storage)
         self.engine = eng
         eng.set_small(self.data_small)
         n_r = len(self.lag_solar_r)
