@@ -42,7 +42,8 @@ class Alignment:
                  small_fov_value_max: object = None, counts_cpu_max: int = 40, large_fov_window: object = -1,
                  small_fov_window: object = -1,
                  path_save_figure: str = None, reprojection_order=2, force_crota_0=False,
-                 unit_lag="arcsec", cdelt_semantics="reference", strict_arithmetic=False):
+                 unit_lag="arcsec", cdelt_semantics="reference", strict_arithmetic=False, lag_search="dense",
+                 coarse_stride=None):
         """Same parameters as the reference (`hdrshift/alignment.py:47-83`). Two additions:
 
         cdelt_semantics: "reference" reproduces the reference's handling of CDELT lags (a CDELT1 lag only
@@ -50,6 +51,12 @@ class Alignment:
             SURVEY App. B1); "intended" applies CDELTi = ref + lag before the PCi_j rebuild.
         strict_arithmetic: evaluate the spline weights / tap sums in scipy's exact operation order (separate
             multiply and add) instead of fused multiply-add; per-sample bit-faithful, ~1e-15 in r, slower.
+        lag_search: "dense" (default) evaluates every lag like the reference. "coarse_to_fine" (helioprojective frame)
+            evaluates the CRVAL1 x CRVAL2 plane on a sub-lattice of stride `coarse_stride` first (all CDELT / CROTA
+            lags), then densely in a window around the best coarse lag, re-centring while the maximum sits on the
+            window's edge; lags that were not evaluated are NaN in the cube. Every evaluated entry is bit-identical
+            to the dense cube's; the arg-max is the dense one whenever the correlation peak is wider than the
+            stride (default stride: the large image's pixel size in lag steps, at least 2).
         """
         self.large_fov_known_pointing = large_fov_known_pointing
         self.small_fov_to_correct = small_fov_to_correct
@@ -94,6 +101,11 @@ class Alignment:
         self.use_sunpy = False
         self.cdelt_semantics = cdelt_semantics
         self.strict_arithmetic = strict_arithmetic
+        if lag_search not in ("dense", "coarse_to_fine"):
+            raise ValueError("lag_search must be 'dense' or 'coarse_to_fine'")
+        self.lag_search = lag_search
+        self.coarse_stride = coarse_stride
+        self.lags_evaluated = None
         self.engine = None
         self.nvalid = None
         for lag_name in ("lag_crval1", "lag_crval2", "lag_crota", "lag_cdelt1", "lag_cdelt2"):
@@ -382,7 +394,11 @@ class Alignment:
             eng.prepare_hpc(self.data_large, w_large, w_small)
             self.hdr_large = self.hdr_small.copy()   # alignment.py:1000
             table, dead = eng.hpc_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, self.cdelt_semantics)
-            corr, nvalid = eng.search(table, return_nvalid=True)
+            if self.lag_search == "coarse_to_fine":
+                corr, nvalid = self._coarse_to_fine(eng, table, shape5, w_large)
+            else:
+                corr, nvalid = eng.search(table, return_nvalid=True)
+                self.lags_evaluated = int(table.shape[0])
             corr = np.where(dead, 0.0, corr)
             for kk in range(n_r):
                 cube[..., kk] = corr.reshape(shape5)
@@ -398,6 +414,49 @@ class Alignment:
             raise NotImplementedError(self.coordinate_frame)
         self.data_large = None
         return cube
+
+    def _coarse_to_fine(self, eng, table, shape5, w_large):
+        """Sub-lattice pass over the CRVAL1 x CRVAL2 plane, then dense windows around the running maximum (SURVEY.md
+        section 8f-3). Returns (corr, nvalid) over the full flat lag list, NaN / 0 where nothing was evaluated."""
+        n1, n2 = shape5[0], shape5[1]
+        rest = int(np.prod(shape5[2:]))
+        stride = self.coarse_stride
+        if stride is None:
+            step = min(abs(float(np.diff(np.asarray(lag, dtype=np.float64)).mean())) if len(lag) > 1 else np.inf
+                       for lag in (self.lag_crval1, self.lag_crval2))
+            pix = abs(w_large.cdelt1) / TanWcs.from_header(self.hdr_small).unit_scale1     # large pixel, header units
+            stride = int(max(2, np.floor(pix / step))) if np.isfinite(step) and step > 0 else 2
+        stride = int(max(1, stride))
+        corr = np.full(table.shape[0], np.nan)
+        nvalid = np.zeros(table.shape[0], dtype=np.int64)
+        done = np.zeros((n1, n2), dtype=bool)
+
+        def evaluate(mask2d):
+            todo = mask2d & ~done
+            if not todo.any():
+                return
+            idx = np.nonzero(np.repeat(todo.ravel(), rest))[0]      # C order: (crval1, crval2) slowest
+            c, nv = eng.search(table[idx], return_nvalid=True)
+            corr[idx], nvalid[idx] = c, nv
+            done[todo] = True
+
+        coarse = np.zeros((n1, n2), dtype=bool)
+        i1 = np.unique(np.r_[np.arange(0, n1, stride), n1 - 1])
+        i2 = np.unique(np.r_[np.arange(0, n2, stride), n2 - 1])
+        coarse[np.ix_(i1, i2)] = True
+        evaluate(coarse)
+        half = stride + 2
+        for _ in range(8):
+            best = np.unravel_index(np.nanargmax(corr), (n1, n2, rest))[:2]
+            lo1, hi1 = max(0, best[0] - half), min(n1, best[0] + half + 1)
+            lo2, hi2 = max(0, best[1] - half), min(n2, best[1] + half + 1)
+            win = np.zeros((n1, n2), dtype=bool)
+            win[lo1:hi1, lo2:hi2] = True
+            if not (win & ~done).any():
+                break
+            evaluate(win)
+        self.lags_evaluated = int(done.sum()) * rest
+        return corr, nvalid
 
     def _carrington_search(self, eng, refs, d1, d2, d3, d4, d5, d_solar_r):
         """Per CROTA-lag value one pair of detector planes; CRVAL lags are pure offsets on them

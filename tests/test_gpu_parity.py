@@ -409,3 +409,21 @@ def test_config1_full_size_properties(torch_cuda):
     eng.set_small((small * 3.0 + 100.0).cpu().numpy())
     assert np.max(np.abs(eng.search(table) - cube)) < 1e-9
     eng.small, eng.pivots = small, piv
+
+
+def test_coarse_to_fine_search_equals_dense_where_evaluated(torch_cuda, toy_pair):
+    """lag_search="coarse_to_fine" (SURVEY 8f-3): same arg-max and same fitted shift as the dense search from a
+    fraction of the lags; every evaluated entry has the dense cube's bits, the rest is NaN."""
+    from euispice_coreg_b200.hdrshift import Alignment
+    lags = dict(lag_crval1=np.arange(4, 45, 1.0), lag_crval2=np.arange(-14, 27, 1.0), lag_cdelt1=[0], lag_cdelt2=[0],
+                lag_crota=[0.0, 0.5])
+    dense = Alignment(toy_pair[0], toy_pair[1], parallelism=True, **lags)
+    rd = dense.align_using_helioprojective()
+    c2f = Alignment(toy_pair[0], toy_pair[1], parallelism=True, lag_search="coarse_to_fine", **lags)
+    rc = c2f.align_using_helioprojective()
+    ev = ~np.isnan(rc.corr)
+    assert c2f.lags_evaluated == ev.sum() < 0.35 * rd.corr.size and dense.lags_evaluated == rd.corr.size
+    assert np.array_equal(rc.corr[ev], rd.corr[ev])
+    assert rc.max_index == rd.max_index and rc.shift_arcsec == rd.shift_arcsec
+    with pytest.raises(ValueError):
+        Alignment(toy_pair[0], toy_pair[1], lag_search="pyramid", **lags)
