@@ -1178,9 +1178,8 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
     const double t = fma(q2, wy2, fma(q1, wy1, q0 * wy0));
     double b;
     if (ROUND32) {
-      const float bf = __double2float_rn(t);
-      bmax = max(bmax, (unsigned)__float_as_int(bf) & 0x7FFFFFFFu);
-      b = (double)bf;
+      // a non-finite float32 sample makes Sbb non-finite: the caller tests that once per segment
+      b = (double)__double2float_rn(t);
     } else {
       // finite and not the -32762 fill: fold both into the same flag (the fill marks the sample as missing)
       const unsigned hi = (unsigned)__double2hiint(t) & 0x7FFFFFFFu;
@@ -1349,7 +1348,10 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
         else
           roll_segment<1, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
                                       a_c, sb, sbb, sab, vmax, bmax);
-        fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u);
+        // all fractional parts in [0, 1), every sample finite (|bc| < 2^129 keeps bc^2 finite, so Sbb is finite
+        // exactly when all samples are)
+        fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u) &&
+               (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
       }
       unsigned miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
       if (!fast && a_ok) {
