@@ -31,9 +31,9 @@ if ROOT not in sys.path:
 WORKLOAD = "config1: HRIEUV-like 2048x2048 vs FSI174-like 3072x3072, helioprojective, 60x60 CRVAL lags @1arcsec"
 FP64_INSTR_PER_SAMPLE = 69.0   # algorithmic FP64 instructions per pixel-sample (HPC), counted
 #                                on the reference's formulation (pixel -> world -> pixel per lag)
-K1_DRAM_BYTES_PER_LAUNCH = 613.9e6  # dram__bytes_read.sum + dram__bytes_write.sum of one config-1 launch of the rolling
-#                                     kernel (ncu --set full, profiles/r1_ncu_roll_v5_raw.csv): 309.4 MB + 304.5 MB
-FP64_EXECUTED_PER_SAMPLE = 36.7  # FP64 thread-instructions the column-rolling kernel executes per pixel-sample = the
+K1_DRAM_BYTES_PER_LAUNCH = 609.1e6  # dram__bytes_read.sum + dram__bytes_write.sum of one config-1 launch of the rolling
+#                                     kernel (ncu --set full, profiles/r1_ncu_roll_v6_raw.csv): 305.3 MB + 303.9 MB
+FP64_EXECUTED_PER_SAMPLE = 31.7  # FP64 thread-instructions the column-rolling kernel executes per pixel-sample = the
 #                                  algorithmic count of ITS formulation (ncu: DADD + DMUL + DFMA of
 #                                  one launch / pixel-samples, profiles/r1_roll_kernel.md)
 BYTES_PER_SAMPLE = 8.0         # un-amortised: one f32 sample of each image per pixel-sample
