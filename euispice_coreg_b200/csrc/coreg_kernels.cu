@@ -389,9 +389,24 @@ constexpr int kLagSub = 64;   // lags staged in shared memory at a time
 constexpr int kMom = 8;       // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
 constexpr int kMinTileH = 16; // smallest tile height of any variant (workspace sizing)
 
+constexpr int kRollWRows = 12;  // rows per thread of the warp-record kernel (tile height 48)
+struct RollWLayout {
+  size_t rows, rec, corr, cst, mask, total;   // byte offsets into the workspace
+};
+inline RollWLayout rollw_layout(int gnx, int gny, int64_t n_lags) {
+  RollWLayout L;
+  const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + 4 * kRollWRows - 1) / (4 * kRollWRows));
+  L.rows = tiles * (kThreads / 32);
+  L.rec = 0;
+  L.corr = L.rec + L.rows * (size_t)n_lags * 3 * sizeof(double);
+  L.cst = L.corr + L.rows * (size_t)n_lags * 3 * sizeof(double);
+  L.mask = L.cst + L.rows * 3 * sizeof(double);
+  L.total = L.mask + ((tiles * (size_t)n_lags * sizeof(unsigned) + 15) / 16) * 16;
+  return L;
+}
 inline size_t partials_bytes(int gnx, int gny, int64_t n_lags) {
   const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kMinTileH - 1) / kMinTileH);
-  return tiles * (size_t)n_lags * kMom * sizeof(double);
+  return std::max(tiles * (size_t)n_lags * kMom * sizeof(double), rollw_layout(gnx, gny, n_lags).total);
 }
 
 struct TanCoord {
@@ -1230,6 +1245,74 @@ __device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ sma
   return isfinite(t) && (t != -32762.0);
 }
 
+// One lag for one thread's column segment: first-pixel coordinates, shared floors, window test, the regular rolling
+// segment or -- image borders, irregular columns (rotated lags), missing pixels, division-mode lags -- the segment
+// pixel by pixel. Out: the thread's Sb, Sbb, Sab over its valid samples and the mask of pixels that have a finite
+// reference value but no valid sample.
+template <bool ROUND32, int P>
+__device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small, int snx, int sny,
+                                         unsigned row_elems, double di, double dj0, const double (&a_c)[P],
+                                         unsigned a_ok, bool all_ref, double pivot_b, double& sb, double& sbb,
+                                         double& sab, unsigned& miss) {
+  const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
+  const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
+  // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
+  const double bnx = fma(hx1, dj0, fma(C.hx0, di, C.hx2));
+  const double bny = fma(hy1, dj0, fma(C.hy0, di, C.hy2));
+  const double be = fma(he1, dj0, fma(C.he0, di, C.he2));
+  const double inv0 = (mode == 0) ? recip_1me_tiny(be) : ((mode == 1) ? recip_1me_small(be) : recip_1me_div(be));
+  const double sx0 = fma(bnx, inv0, x0h), sy0 = fma(bny, inv0, y0h);  // coordinates + 0.5
+  // floors shared by the segment
+  const double mx0 = __dadd_rd(sx0, kMagic), my0 = __dadd_rd(sy0, kMagic);
+  const int ix0 = __double2loint(mx0), iy0 = __double2loint(my0);
+  const double xoff = x0h - (mx0 - kMagic), yoff = y0h - (my0 - kMagic);
+  sb = sbb = sab = 0.0;
+  // whole window inside the image: columns ix0-1 .. ix0+1, rows iy0-1 .. iy0+P; |coordinate| < 2^30 keeps the
+  // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
+  bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
+              ((unsigned)(ix0 - 1) < (unsigned)(snx - 2)) && (iy0 >= 1) && (iy0 + P <= sny - 1);
+  if (fast) {
+    const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
+    unsigned vmax = 0, bmax = 0;
+    if (mode == 0)
+      roll_segment<0, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
+                                  a_c, sb, sbb, sab, vmax, bmax);
+    else
+      roll_segment<1, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
+                                  a_c, sb, sbb, sab, vmax, bmax);
+    // all fractional parts in [0, 1), every sample finite (|bc| < 2^129 keeps bc^2 finite, so Sbb is finite
+    // exactly when all samples are)
+    fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u) &&
+           (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
+  }
+  miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
+  if (!fast && a_ok) {
+    // image borders, irregular columns (rotated lags), missing pixels: the segment pixel by pixel
+    sb = sbb = sab = 0.0;
+#pragma unroll 1
+    for (int p = 0; p < P; ++p) {
+      if (!(a_ok & (1u << p))) continue;
+      const double e = fma(he1, (double)p, be);
+      const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
+      const double sx = fma(fma(hx1, (double)p, bnx), inv, x0h);
+      const double sy = fma(fma(hy1, (double)p, bny), inv, y0h);
+      double ac = a_c[0];
+#pragma unroll
+      for (int q = 1; q < P; ++q)
+        if (q == p) ac = a_c[q];
+      double b;
+      if (sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, &b)) {
+        const double bc = b - pivot_b;
+        sb += bc;
+        sbb = fma(bc, bc, sbb);
+        sab = fma(ac, bc, sab);
+      } else {
+        miss |= 1u << p;
+      }
+    }
+  }
+}
+
 #ifndef COREG_ROLL_CHUNK
 #define COREG_ROLL_CHUNK 8
 #endif
@@ -1322,64 +1405,10 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
     }
     __syncthreads();
     for (int l = 0; l < cnt; ++l) {
-      const HomLag& C = S.lag[l];
-      const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
-      const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
-      // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
-      const double bnx = fma(hx1, dj0, fma(C.hx0, di, C.hx2));
-      const double bny = fma(hy1, dj0, fma(C.hy0, di, C.hy2));
-      const double be = fma(he1, dj0, fma(C.he0, di, C.he2));
-      const double inv0 = (mode == 0) ? recip_1me_tiny(be) : ((mode == 1) ? recip_1me_small(be) : recip_1me_div(be));
-      const double sx0 = fma(bnx, inv0, x0h), sy0 = fma(bny, inv0, y0h);  // coordinates + 0.5
-      // floors shared by the segment
-      const double mx0 = __dadd_rd(sx0, kMagic), my0 = __dadd_rd(sy0, kMagic);
-      const int ix0 = __double2loint(mx0), iy0 = __double2loint(my0);
-      const double xoff = x0h - (mx0 - kMagic), yoff = y0h - (my0 - kMagic);
-      double sb = 0.0, sbb = 0.0, sab = 0.0;
-      // whole window inside the image: columns ix0-1 .. ix0+1, rows iy0-1 .. iy0+P; |coordinate| < 2^30 keeps the
-      // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
-      bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
-                  ((unsigned)(ix0 - 1) < (unsigned)(snx - 2)) && (iy0 >= 1) && (iy0 + P <= sny - 1);
-      if (fast) {
-        const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
-        unsigned vmax = 0, bmax = 0;
-        if (mode == 0)
-          roll_segment<0, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
-                                      a_c, sb, sbb, sab, vmax, bmax);
-        else
-          roll_segment<1, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
-                                      a_c, sb, sbb, sab, vmax, bmax);
-        // all fractional parts in [0, 1), every sample finite (|bc| < 2^129 keeps bc^2 finite, so Sbb is finite
-        // exactly when all samples are)
-        fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u) &&
-               (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
-      }
-      unsigned miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
-      if (!fast && a_ok) {
-        // image borders, irregular columns (rotated lags), missing pixels: the segment pixel by pixel
-        sb = sbb = sab = 0.0;
-#pragma unroll 1
-        for (int p = 0; p < P; ++p) {
-          if (!(a_ok & (1u << p))) continue;
-          const double e = fma(he1, (double)p, be);
-          const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
-          const double sx = fma(fma(hx1, (double)p, bnx), inv, x0h);
-          const double sy = fma(fma(hy1, (double)p, bny), inv, y0h);
-          double ac = a_c[0];
-#pragma unroll
-          for (int q = 1; q < P; ++q)
-            if (q == p) ac = a_c[q];
-          double b;
-          if (sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, &b)) {
-            const double bc = b - pivot_b;
-            sb += bc;
-            sbb = fma(bc, bc, sbb);
-            sab = fma(ac, bc, sab);
-          } else {
-            miss |= 1u << p;
-          }
-        }
-      }
+      double sb, sbb, sab;
+      unsigned miss;
+      roll_lag<ROUND32, P>(S.lag[l], small, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb, sbb, sab,
+                           miss);
       S.acc[l][0][tid] = sb;
       S.acc[l][1][tid] = sbb;
       S.acc[l][2][tid] = sab;
@@ -1416,6 +1445,170 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
         dst[v == 0 ? 0 : (v == 1 ? 1 : 3)] = S.tile_const[v] - c;
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-independent form of the rolling kernel: no block barrier inside the lag walk. Every warp keeps its own
+// shared-memory slice (its lanes' Sb, Sbb, Sab for kRollChunk lags, and its own copy of the chunk's 3x3 matrices),
+// folds it with __syncwarp only, and writes one 24-byte record per (warp, lag) straight to the workspace; the
+// finalize kernel sums 8 records per tile instead of one. Corrections for missing samples (rare) go to a second
+// array that is only read where a bit of the per-(tile, lag) mask is set, so it needs no initialisation; the
+// mask itself (4 B per tile and lag) is cleared by the launcher.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAccPad = 33;   // lane stride of the per-warp accumulators (bank-conflict-free transposed reads)
+
+struct RollWShared {
+  double acc[kWarps][kRollChunk][3][kAccPad];
+  HomLag lag[kWarps][kRollChunk];
+};
+
+template <typename RefT, bool ROUND32, int P, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+lag_corr_rollw_kernel(const RefT* __restrict__ ref, const double* __restrict__ small, int snx, int sny, int gnx,
+                      int gny, const HomLag* __restrict__ lags, int n_lags, int lags_per_block,
+                      const double* __restrict__ pivots, double* __restrict__ wrec, double* __restrict__ wcorr,
+                      double* __restrict__ wconst, unsigned* __restrict__ wmask) {
+  constexpr int TILE_H = kRowsPerPass * P;
+  extern __shared__ __align__(16) unsigned char roll_smem[];
+  RollWShared& S = *reinterpret_cast<RollWShared*>(roll_smem);
+
+  const int tiles_x = (gnx + kTileW - 1) / kTileW;
+  const int tile = blockIdx.x;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & (kTileW - 1), rg = tid / kTileW;
+  const int gx = tile_x * kTileW + tx;
+  const int gy0 = tile_y * TILE_H + rg * P;
+  const double pivot_a = pivots[0], pivot_b = pivots[1];
+  const unsigned row_elems = (unsigned)snx;
+  const double di = (double)gx, dj0 = (double)gy0;
+  const size_t wid = (size_t)tile * kWarps + warp;   // this warp's record row
+
+  double a_c[P];
+  unsigned a_ok = 0;
+  double sa_all = 0.0, saa_all = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int gy = gy0 + p;
+    a_c[p] = 0.0;
+    if (gx < gnx && gy < gny) {
+      const double a = (double)ref[(int64_t)gy * gnx + gx];
+      if (isfinite(a)) {
+        a_c[p] = a - pivot_a;
+        a_ok |= 1u << p;
+        sa_all += a_c[p];
+        saa_all = fma(a_c[p], a_c[p], saa_all);
+      }
+    }
+  }
+  const bool all_ref = a_ok == ((1u << P) - 1u);
+  if (blockIdx.y == 0) {
+    // lag-independent reference moments of this warp's pixels (n, Sa, Saa): one record per warp, written once
+    double wsa = sa_all, wsaa = saa_all;
+    int wn = __popc(a_ok);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
+      wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
+      wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    }
+    if (lane == 0) {
+      wconst[wid * 3 + 0] = (double)wn;
+      wconst[wid * 3 + 1] = wsa;
+      wconst[wid * 3 + 2] = wsaa;
+    }
+  }
+
+  const int lag_begin = blockIdx.y * lags_per_block;
+  const int lag_end = min(n_lags, lag_begin + lags_per_block);
+  for (int l0 = lag_begin; l0 < lag_end; l0 += kRollChunk) {
+    const int cnt = min(kRollChunk, lag_end - l0);
+    __syncwarp();   // previous chunk folded
+    {
+      const double* src = reinterpret_cast<const double*>(lags + l0);
+      double* dst = reinterpret_cast<double*>(&S.lag[warp][0]);
+      const int nd = cnt * (int)(sizeof(HomLag) / sizeof(double));
+      for (int i = lane; i < nd; i += 32) dst[i] = __ldg(src + i);
+    }
+    __syncwarp();
+    for (int l = 0; l < cnt; ++l) {
+      double sb, sbb, sab;
+      unsigned miss;
+      roll_lag<ROUND32, P>(S.lag[warp][l], small, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb, sbb,
+                           sab, miss);
+      S.acc[warp][l][0][lane] = sb;
+      S.acc[warp][l][1][lane] = sbb;
+      S.acc[warp][l][2][lane] = sab;
+      if (__any_sync(0xffffffffu, miss != 0)) {
+        double m[4] = {(double)__popc(miss), 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (miss & (1u << p)) {
+            m[1] += a_c[p];
+            m[2] = fma(a_c[p], a_c[p], m[2]);
+          }
+        const double tot = warp_transpose_reduce4(m, lane);  // lanes 0, 8, 16: n, Sa, Saa of the missing pixels
+        if ((lane & 7) == 0 && lane < 24) wcorr[(wid * n_lags + (l0 + l)) * 3 + (lane >> 3)] = tot;
+        if (lane == 0) atomicOr(wmask + ((size_t)tile * n_lags + (l0 + l)), 1u << warp);
+      }
+    }
+    __syncwarp();
+    if (lane < cnt * 3) {
+      const int l = lane / 3, v = lane - 3 * l;
+      const double* src = &S.acc[warp][l][v][0];
+      double t = src[0];
+#pragma unroll
+      for (int k = 1; k < 32; ++k) t += src[k];
+      wrec[(wid * n_lags + (l0 + l)) * 3 + v] = t;
+    }
+  }
+}
+
+// one block per lag: sum the warp records in a fixed order, moments -> Pearson r
+__global__ void __launch_bounds__(128)
+lag_corr_finalize_w_kernel(const double* __restrict__ wrec, const double* __restrict__ wcorr,
+                           const double* __restrict__ wconst, const unsigned* __restrict__ wmask, int n_rows,
+                           int n_lags, double* __restrict__ corr, int64_t* __restrict__ nvalid) {
+  __shared__ double s[128][6];
+  const int lag = blockIdx.x;
+  double m[6] = {0, 0, 0, 0, 0, 0};   // n, Sa, Sb, Saa, Sbb, Sab
+  for (int r = threadIdx.x; r < n_rows; r += 128) {
+    const double* p = wrec + ((size_t)r * n_lags + lag) * 3;
+    m[2] += p[0];
+    m[4] += p[1];
+    m[5] += p[2];
+    m[0] += wconst[(size_t)r * 3 + 0];
+    m[1] += wconst[(size_t)r * 3 + 1];
+    m[3] += wconst[(size_t)r * 3 + 2];
+    if ((wmask[(size_t)(r / kWarps) * n_lags + lag] >> (r % kWarps)) & 1u) {
+      const double* c = wcorr + ((size_t)r * n_lags + lag) * 3;
+      m[0] -= c[0];
+      m[1] -= c[1];
+      m[3] -= c[2];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s[threadIdx.x][q] = m[q];
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s[threadIdx.x][q] += s[threadIdx.x + o][q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = s[0][0], sa = s[0][1], sb = s[0][2], saa = s[0][3], sbb = s[0][4], sab = s[0][5];
+    double r = CUDART_NAN;
+    if (n > 0.0) {
+      const double cov = sab - sa * sb / n;
+      const double va = saa - sa * sa / n;
+      const double vb = sbb - sb * sb / n;
+      r = cov / sqrt(va * vb);
+    }
+    corr[lag] = r;
+    if (nvalid) nvalid[lag] = (int64_t)n;
   }
 }
 
@@ -1531,6 +1724,38 @@ int launch_lag_roll(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
   }
 #undef X
   return done ? COREG_OK : fail(COREG_EINVAL, "no such kernel variant");
+}
+
+// warp-record form (12 rows per thread): kernel + its own finalize
+template <typename RefT, bool ROUND32>
+int launch_lag_rollw(int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref, const double* small,
+                     int snx, int sny, const HomLag* ft, const double* pivots, void* work, double* corr,
+                     int64_t* nvalid, bool prof) {
+  const RollWLayout L = rollw_layout(gnx, gny, n_lags);
+  char* base = static_cast<char*>(work);
+  double* wrec = reinterpret_cast<double*>(base + L.rec);
+  double* wcorr = reinterpret_cast<double*>(base + L.corr);
+  double* wconst = reinterpret_cast<double*>(base + L.cst);
+  unsigned* wmask = reinterpret_cast<unsigned*>(base + L.mask);
+  dim3 grid;
+  int lpb, tiles;
+  if (!lag_grid(4 * kRollWRows, 2, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk))
+    return fail(COREG_EINVAL, "lag grid too large for one launch");
+  CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
+  if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
+  auto kern = lag_corr_rollw_kernel<RefT, ROUND32, kRollWRows, 2>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));
+  kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, snx, sny, gnx, gny, ft, (int)n_lags, lpb, pivots, wrec,
+                                                   wcorr, wconst, wmask);
+  CK_LAUNCH("lag_corr_rollw_kernel");
+  if (prof) {
+    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+    ++g_prof_n;
+  }
+  lag_corr_finalize_w_kernel<<<(unsigned)n_lags, 128, 0, s>>>(wrec, wcorr, wconst, wmask, (int)L.rows, (int)n_lags, corr,
+                                                              nvalid);
+  CK_LAUNCH("lag_corr_finalize_w_kernel");
+  return COREG_OK;
 }
 
 template <typename SmallT, typename RefT, bool ROUND32>
@@ -1855,8 +2080,11 @@ int hpc_lag_corr_wcs_impl(const float* ref, const double* small, int snx, int sn
   if (prof) {
     CK(cudaEventCreate(&g_prof[g_prof_n].a));
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
-    CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
+  if (((flags >> 8) & 15) >= 8)
+    return launch_lag_rollw<float, true>(gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, work, corr, nvalid,
+                                         prof);
+  if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   int tiles = 0;
   rc = launch_lag_roll<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, w,
                                     &tiles);
