@@ -389,7 +389,7 @@ constexpr int kLagSub = 64;   // lags staged in shared memory at a time
 constexpr int kMom = 8;       // n, Sa, Sb, Saa, Sbb, Sab, pad, pad  (64 B per (tile, lag) partial)
 constexpr int kMinTileH = 16; // smallest tile height of any variant (workspace sizing)
 
-constexpr int kRollWRows = 12;  // rows per thread of the warp-record kernel (tile height 48)
+constexpr int kRollWRows = 12;  // smallest rows-per-thread of the rolling kernel (tile height 48): sizes the workspace
 struct RollWLayout {
   size_t rows, rec, corr, cst, mask, total;   // byte offsets into the workspace
 };
@@ -1316,140 +1316,10 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
 #ifndef COREG_ROLL_CHUNK
 #define COREG_ROLL_CHUNK 8
 #endif
-constexpr int kRollChunk = COREG_ROLL_CHUNK;  // lags whose per-thread sums wait in shared memory for one block-wide reduction
-
-// Shared memory of the rolling kernel, per block: per-thread (Sb, Sbb, Sab) of kRollChunk lags, transposed so that
-// both the stores and the reduction reads are conflict-free; per-warp corrections (n, Sa, Saa of the pixels that
-// have a reference value but no sample) for the rare lags that have any.
-struct RollShared {
-  double acc[kRollChunk][3][kThreads];
-  double corr[kRollChunk][kWarps][3];
-  HomLag lag[kRollChunk];
-  double tile_const[3];  // n, Sa, Saa over the tile's finite reference pixels
-  double warp_const[kWarps][3];
-};
-
-template <typename RefT, bool ROUND32, int P, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small, int snx, int sny, int gnx,
-                     int gny, const HomLag* __restrict__ lags, int n_lags, int lags_per_block,
-                     const double* __restrict__ pivots, double* __restrict__ work) {
-  constexpr int TILE_H = kRowsPerPass * P;  // 4 row groups of P consecutive rows
-  extern __shared__ __align__(16) unsigned char roll_smem[];
-  RollShared& S = *reinterpret_cast<RollShared*>(roll_smem);
-
-  const int tiles_x = (gnx + kTileW - 1) / kTileW;
-  const int tile = blockIdx.x;
-  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & (kTileW - 1), rg = tid / kTileW;
-  const int gx = tile_x * kTileW + tx;
-  const int gy0 = tile_y * TILE_H + rg * P;
-  const double pivot_a = pivots[0], pivot_b = pivots[1];
-  const unsigned row_elems = (unsigned)snx;
-  const double di = (double)gx, dj0 = (double)gy0;
-
-  double a_c[P];
-  unsigned a_ok = 0;
-  double sa_all = 0.0, saa_all = 0.0;
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    const int gy = gy0 + p;
-    a_c[p] = 0.0;
-    if (gx < gnx && gy < gny) {
-      const double a = (double)ref[(int64_t)gy * gnx + gx];
-      if (isfinite(a)) {
-        a_c[p] = a - pivot_a;
-        a_ok |= 1u << p;
-        sa_all += a_c[p];
-        saa_all = fma(a_c[p], a_c[p], saa_all);
-      }
-    }
-  }
-  const bool all_ref = a_ok == ((1u << P) - 1u);
-  {
-    // lag-independent reference moments of the tile: warp butterflies, then a fixed-order fold over the warps
-    double wsa = sa_all, wsaa = saa_all;
-    int wn = __popc(a_ok);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
-      wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
-      wn += __shfl_xor_sync(0xffffffffu, wn, o);
-    }
-    if (lane == 0) {
-      S.warp_const[warp][0] = (double)wn;
-      S.warp_const[warp][1] = wsa;
-      S.warp_const[warp][2] = wsaa;
-    }
-    __syncthreads();
-    if (tid < 3) {
-      double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) t += S.warp_const[w][tid];
-      S.tile_const[tid] = t;
-    }
-  }
-
-  const int lag_begin = blockIdx.y * lags_per_block;
-  const int lag_end = min(n_lags, lag_begin + lags_per_block);
-  for (int l0 = lag_begin; l0 < lag_end; l0 += kRollChunk) {
-    const int cnt = min(kRollChunk, lag_end - l0);
-    __syncthreads();  // previous chunk fully reduced
-    {
-      const double* src = reinterpret_cast<const double*>(lags + l0);
-      double* dst = reinterpret_cast<double*>(S.lag);
-      const int nd = cnt * (int)(sizeof(HomLag) / sizeof(double));
-      for (int i = tid; i < nd; i += kThreads) dst[i] = src[i];
-      for (int i = tid; i < kRollChunk * kWarps * 3; i += kThreads) (&S.corr[0][0][0])[i] = 0.0;
-    }
-    __syncthreads();
-    for (int l = 0; l < cnt; ++l) {
-      double sb, sbb, sab;
-      unsigned miss;
-      roll_lag<ROUND32, P>(S.lag[l], small, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb, sbb, sab,
-                           miss);
-      S.acc[l][0][tid] = sb;
-      S.acc[l][1][tid] = sbb;
-      S.acc[l][2][tid] = sab;
-      if (__any_sync(0xffffffffu, miss != 0)) {
-        double m[4] = {(double)__popc(miss), 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-          if (miss & (1u << p)) {
-            m[1] += a_c[p];
-            m[2] = fma(a_c[p], a_c[p], m[2]);
-          }
-        const double tot = warp_transpose_reduce4(m, lane);  // lanes 0, 8, 16: n, Sa, Saa of the missing pixels
-        if ((lane & 7) == 0 && lane < 24) S.corr[l][warp][lane >> 3] = tot;
-      }
-    }
-    __syncthreads();
-    // block-wide reduction of the chunk in a fixed order: warp w takes (lag, moment) pairs w, w + 8, ...;
-    // every lane folds its 8 strided values, then one butterfly
-    for (int pair = warp; pair < cnt * 3; pair += kWarps) {
-      const int l = pair / 3, v = pair % 3;
-      const double* src = &S.acc[l][v][0];
-      double t = src[lane];
-#pragma unroll
-      for (int k = 1; k < kThreads / 32; ++k) t += src[lane + 32 * k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) {
-        double c = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) c += S.corr[l][w][v];
-        double* dst = work + ((size_t)tile * n_lags + (l0 + l)) * kMom;
-        // slots: n, Sa, Sb, Saa, Sbb, Sab
-        dst[v == 0 ? 2 : (v == 1 ? 4 : 5)] = t;
-        dst[v == 0 ? 0 : (v == 1 ? 1 : 3)] = S.tile_const[v] - c;
-      }
-    }
-  }
-}
+constexpr int kRollChunk = COREG_ROLL_CHUNK;  // lags whose per-lane sums wait in a warp's shared-memory slice for one fold
 
 // ---------------------------------------------------------------------------------------------------------
-// Warp-independent form of the rolling kernel: no block barrier inside the lag walk. Every warp keeps its own
+// The rolling kernel proper. Warps are independent: no block barrier inside the lag walk. Every warp keeps its own
 // shared-memory slice (its lanes' Sb, Sbb, Sab for kRollChunk lags, and its own copy of the chunk's 3x3 matrices),
 // folds it with __syncwarp only, and writes one 24-byte record per (warp, lag) straight to the workspace; the
 // finalize kernel sums 8 records per tile instead of one. Corrections for missing samples (rare) go to a second
@@ -1465,7 +1335,7 @@ struct RollWShared {
 
 template <typename RefT, bool ROUND32, int P, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
-lag_corr_rollw_kernel(const RefT* __restrict__ ref, const double* __restrict__ small, int snx, int sny, int gnx,
+lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small, int snx, int sny, int gnx,
                       int gny, const HomLag* __restrict__ lags, int n_lags, int lags_per_block,
                       const double* __restrict__ pivots, double* __restrict__ wrec, double* __restrict__ wcorr,
                       double* __restrict__ wconst, unsigned* __restrict__ wmask) {
@@ -1696,41 +1566,13 @@ int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
   return COREG_OK;
 }
 
-// tuning variants of the column-rolling kernel: (consecutive rows per thread, resident CTAs per SM)
-#ifndef COREG_ROLL_VARIANTS
-#define COREG_ROLL_VARIANTS X(0, 12, 2) X(1, 8, 2) X(2, 16, 2) X(3, 6, 3) X(4, 14, 2)
-#endif
+// rolling kernel + its finalize. Tuning variants (flags bits 8..11): rows per thread 12 (default), 16, 14; the
+// workspace layout is sized for 12 (fewer rows per thread would need more record rows)
 template <typename RefT, bool ROUND32>
-int launch_lag_roll(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
-                    const double* small, int snx, int sny, const HomLag* ft, const double* pivots, double* w,
-                    int* tiles_out) {
-  dim3 grid;
-  int lpb;
-  bool done = false;
-#define X(V_, P_, MINB_)                                                                                        \
-  if (!done && variant == V_) {                                                                                 \
-    if (!lag_grid(kRowsPerPass * P_, MINB_, gnx, gny, n_lags, sms, &grid, &lpb, tiles_out, kRollChunk))        \
-      return fail(COREG_EINVAL, "lag grid too large for one launch");                                           \
-    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, MINB_>;                                                 \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollShared));           \
-    kern<<<grid, kThreads, sizeof(RollShared), s>>>(ref, small, snx, sny, gnx, gny, ft, (int)n_lags, lpb,       \
-                                                    pivots, w);                                                 \
-    done = true;                                                                                                \
-  }
-  COREG_ROLL_VARIANTS
-  if (!done) {
-    variant = 0;
-    COREG_ROLL_VARIANTS
-  }
-#undef X
-  return done ? COREG_OK : fail(COREG_EINVAL, "no such kernel variant");
-}
-
-// warp-record form (12 rows per thread): kernel + its own finalize
-template <typename RefT, bool ROUND32>
-int launch_lag_rollw(int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref, const double* small,
-                     int snx, int sny, const HomLag* ft, const double* pivots, void* work, double* corr,
-                     int64_t* nvalid, bool prof) {
+int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
+                     const double* small, int snx, int sny, const HomLag* ft, const double* pivots, void* work,
+                     double* corr, int64_t* nvalid, bool prof) {
+  const int rows_per_thread = (variant == 1) ? 16 : ((variant == 2) ? 14 : kRollWRows);
   const RollWLayout L = rollw_layout(gnx, gny, n_lags);
   char* base = static_cast<char*>(work);
   double* wrec = reinterpret_cast<double*>(base + L.rec);
@@ -1739,21 +1581,27 @@ int launch_lag_rollw(int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, 
   unsigned* wmask = reinterpret_cast<unsigned*>(base + L.mask);
   dim3 grid;
   int lpb, tiles;
-  if (!lag_grid(4 * kRollWRows, 2, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk))
+  if (!lag_grid(kRowsPerPass * rows_per_thread, 2, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk))
     return fail(COREG_EINVAL, "lag grid too large for one launch");
   CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
   if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
-  auto kern = lag_corr_rollw_kernel<RefT, ROUND32, kRollWRows, 2>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));
-  kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, snx, sny, gnx, gny, ft, (int)n_lags, lpb, pivots, wrec,
-                                                   wcorr, wconst, wmask);
-  CK_LAUNCH("lag_corr_rollw_kernel");
+#define RW(P_)                                                                                                       \
+  {                                                                                                                  \
+    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2>;                                                          \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));               \
+    kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, snx, sny, gnx, gny, ft, (int)n_lags, lpb, pivots,   \
+                                                     wrec, wcorr, wconst, wmask);                                    \
+  }
+  if (rows_per_thread == 16) RW(16) else if (rows_per_thread == 14) RW(14) else RW(kRollWRows)
+#undef RW
+  CK_LAUNCH("lag_corr_roll_kernel");
   if (prof) {
     CK(cudaEventRecord(g_prof[g_prof_n].b, s));
     ++g_prof_n;
   }
-  lag_corr_finalize_w_kernel<<<(unsigned)n_lags, 128, 0, s>>>(wrec, wcorr, wconst, wmask, (int)L.rows, (int)n_lags, corr,
-                                                              nvalid);
+  // record rows actually written: 8 warps per tile of this variant (<= L.rows)
+  lag_corr_finalize_w_kernel<<<(unsigned)n_lags, 128, 0, s>>>(wrec, wcorr, wconst, wmask, tiles * kWarps, (int)n_lags,
+                                                              corr, nvalid);
   CK_LAUNCH("lag_corr_finalize_w_kernel");
   return COREG_OK;
 }
@@ -2072,7 +1920,6 @@ int hpc_lag_corr_wcs_impl(const float* ref, const double* small, int snx, int sn
   if (rc) return rc;
   int sms = coreg_device_sm_count();
   if (sms <= 0) sms = 148;
-  double* w = static_cast<double*>(work);
   HomLag* ft = reinterpret_cast<HomLag*>(static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags));
   tan_homography_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(g, lag_wcs, (int)n_lags, ft);
   CK_LAUNCH("tan_homography_kernel");
@@ -2081,22 +1928,8 @@ int hpc_lag_corr_wcs_impl(const float* ref, const double* small, int snx, int sn
     CK(cudaEventCreate(&g_prof[g_prof_n].a));
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
   }
-  if (((flags >> 8) & 15) >= 8)
-    return launch_lag_rollw<float, true>(gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, work, corr, nvalid,
-                                         prof);
-  if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
-  int tiles = 0;
-  rc = launch_lag_roll<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, w,
-                                    &tiles);
-  if (rc) return rc;
-  CK_LAUNCH("lag_corr_roll_kernel");
-  if (prof) {
-    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
-    ++g_prof_n;
-  }
-  lag_corr_finalize_kernel<<<(unsigned)n_lags, 128, 0, s>>>(w, tiles, (int)n_lags, corr, nvalid);
-  CK_LAUNCH("lag_corr_finalize_kernel");
-  return COREG_OK;
+  return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, work,
+                                       corr, nvalid, prof);
 }
 
 }  // namespace

@@ -167,7 +167,7 @@ def gather_slices(local, n_total, chunk):
 class LagSearchEngine:
     """Resident images + workspaces for one (large, small) pair on the current CUDA device."""
 
-    max_workspace_bytes = 1 << 30
+    max_workspace_bytes = 2 << 30   # 3968 lags of a 2048^2 grid per launch (535 KB of warp records per lag)
 
     def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64", no_fast=False):
         torch = _torch()
@@ -330,8 +330,10 @@ class LagSearchEngine:
         return self._work
 
     def lags_per_launch(self, gnx, gny):
-        per_lag = max(1, _ext.lag_corr_workspace_bytes(gnx, gny, 1))
-        return max(64, (self.max_workspace_bytes // per_lag) // 64 * 64)
+        """Largest multiple of 64 lags whose workspace fits `max_workspace_bytes` (the size is affine in the lags)."""
+        fixed = _ext.lag_corr_workspace_bytes(gnx, gny, 1)
+        per_lag = max(1, (_ext.lag_corr_workspace_bytes(gnx, gny, 1025) - fixed) // 1024)
+        return max(64, ((self.max_workspace_bytes - fixed) // per_lag) // 64 * 64)
 
     def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None):
         """Run the fused kernel over a device lag table [n, k]; results into out_dev[n]. Helioprojective frame:

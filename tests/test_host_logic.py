@@ -303,8 +303,11 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert lib.coreg_version() >= 100
     lib.coreg_lag_corr_workspace_bytes.restype = ctypes.c_size_t
     lib.coreg_lag_corr_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64]
-    # [tiles of 64x16][lags][8 doubles] partials + one 96-byte fast-path row per lag
-    assert lib.coreg_lag_corr_workspace_bytes(2048, 2048, 3600) == 32 * 128 * 3600 * 64 + 3600 * 96
+    # rolling kernel: [32 x 43 tiles of 64x48][8 warps] record rows x (3 + 3 doubles per lag) + 3 constants per row
+    # + a 4-byte mask per (tile, lag), then one 96-byte homography row per lag
+    rows = 32 * 43 * 8
+    assert lib.coreg_lag_corr_workspace_bytes(2048, 2048, 3600) == (rows * 3600 * 48 + rows * 24 + 32 * 43 * 3600 * 4
+                                                                    + 3600 * 96)
     assert lib.coreg_lag_corr_workspace_bytes(0, 5, 5) == 0
 
 
