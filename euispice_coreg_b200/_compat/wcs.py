@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, replace
+from typing import ClassVar
 
 import numpy as np
 
@@ -71,6 +72,13 @@ class TanWcs:
     unit_scale1: float = 1.0  # CUNIT1 -> deg factor that was applied
     unit_scale2: float = 1.0
 
+    _PROJ: ClassVar[str] = "TAN"
+
+    @staticmethod
+    def _default_lonpole(crval2):
+        """wcslib celset: LONPOLE defaults to 0 when CRVAL2 >= theta0 (90 deg for zenithal projections), else 180."""
+        return 0.0 if crval2 >= 90.0 else 180.0
+
     # -- construction ----------------------------------------------------
     @classmethod
     def from_header(cls, hdr, ilon: int | None = None, ilat: int | None = None):
@@ -78,9 +86,10 @@ class TanWcs:
             ilon, ilat = celestial_axes(hdr)
         for i in (ilon, ilat):
             ct = str(hdr["CTYPE%d" % i]).upper()
-            if not ct.endswith("TAN"):
+            if not ct.endswith(cls._PROJ):
                 raise NotImplementedError(
-                    f"CTYPE{i}={ct!r}: only the gnomonic -TAN projection is on the device path")
+                    f"CTYPE{i}={ct!r}: a -{cls._PROJ} projection is expected here (the device path handles -TAN and, "
+                    "for align_using_initial_carrington, -CAR)")
         s1 = units.factor(_axis_unit(hdr, ilon), "deg")
         s2 = units.factor(_axis_unit(hdr, ilat), "deg")
         cdelt1 = float(hdr.get("CDELT%d" % ilon, 1.0))
@@ -118,7 +127,7 @@ class TanWcs:
         if "LONPOLE" in hdr:
             lonpole = float(hdr["LONPOLE"])
         else:
-            lonpole = 0.0 if crval2 >= 90.0 else 180.0
+            lonpole = cls._default_lonpole(crval2)
         nax1 = hdr.get("ZNAXIS%d" % ilon, hdr.get("NAXIS%d" % ilon, 0))
         nax2 = hdr.get("ZNAXIS%d" % ilat, hdr.get("NAXIS%d" % ilat, 0))
         return cls(crpix1=float(hdr.get("CRPIX%d" % ilon, 0.0)), crpix2=float(hdr.get("CRPIX%d" % ilat, 0.0)),
@@ -198,6 +207,159 @@ class TanWcs:
         y = mi[1, 0] * px + mi[1, 1] * py + (self.crpix2 - 1.0)
         bad = den <= 0.0
         return np.where(bad, np.nan, x), np.where(bad, np.nan, y)
+
+
+# ------------------------------------------------------------------------------------------------------
+# plate-carree (-CAR) headers: Carrington maps as inputs (`Alignment.align_using_initial_carrington`)
+# ------------------------------------------------------------------------------------------------------
+def _sind(a):
+    a = np.asarray(a, dtype=np.float64)
+    q = a / 90.0
+    exact = np.array([0.0, 1.0, 0.0, -1.0])[np.mod(np.round(q), 4).astype(np.int64)]
+    return np.where(q == np.round(q), exact, np.sin(a * D2R))
+
+
+def _cosd(a):
+    return _sind(np.asarray(a, dtype=np.float64) + 90.0)
+
+
+def car_celestial_pole(lng0, lat0, lonpole, latpole=90.0, tol=1.0e-10):
+    """Celestial coordinates (lng_p, lat_p) of the native pole and the native longitude phi_p of the celestial pole
+    for a cylindrical projection (fiducial point (phi0, theta0) = (0, 0)) whose reference point is (lng0, lat0), as
+    wcslib's `celset` derives them (FITS-WCS Paper II, eqs. 8-10). Degrees, vectorised over candidate headers.
+    `lonpole` NaN = keyword absent: 0 when lat0 >= 0, else 180. Returns (lng_p, lat_p, phi_p, valid); `valid` is False
+    where wcslib rejects the header (no native pole within [-90, 90])."""
+    lng0, lat0, lonpole, latpole = np.broadcast_arrays(*(np.asarray(v, dtype=np.float64)
+                                                         for v in (lng0, lat0, lonpole, latpole)))
+    phip = np.where(np.isnan(lonpole), np.where(lat0 < 0.0, 180.0, 0.0), lonpole)
+    slat0, clat0 = _sind(lat0), _cosd(lat0)
+    sphip, cphip = _sind(phip), _cosd(phip)
+    # theta0 = 0: x = cos(theta0) cos(phi_p - phi0) = cphip, y = sin(theta0) = 0
+    z = np.abs(cphip)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        slz = slat0 / z
+    valid = np.ones(lat0.shape, dtype=bool)
+    over = np.abs(slz) > 1.0
+    valid &= ~(over & (np.abs(slz) - 1.0 >= tol))
+    slz = np.clip(slz, -1.0, 1.0)
+    u = np.where(cphip < 0.0, 180.0, 0.0)                        # atan2d(0, cphip)
+    v = np.arccos(slz) * R2D
+    norm = lambda a: np.where(a > 180.0, a - 360.0, np.where(a < -180.0, a + 360.0, a))   # noqa: E731
+    latp1, latp2 = norm(u + v), norm(u - v)
+    ok1, ok2 = np.abs(latp1) < 90.0 + tol, np.abs(latp2) < 90.0 + tol
+    closer1 = np.abs(latpole - latp1) < np.abs(latpole - latp2)
+    latp = np.where(ok1 & ok2, np.where(closer1, latp1, latp2), np.where(ok1, latp1, latp2))
+    valid &= ok1 | ok2
+    flat = z == 0.0                                              # phi_p = +-90: any pole latitude serves
+    latp = np.where(flat, latpole, latp)
+    valid = np.where(flat, slat0 == 0.0, valid)
+    latp = np.where(np.abs(latp) > 90.0, np.sign(latp) * 90.0, latp)
+    zz = _cosd(latp) * clat0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x = (0.0 - _sind(latp) * slat0) / zz
+        y = sphip / clat0
+        general = lng0 - np.arctan2(y, x) * R2D
+    lngp = np.where(np.abs(zz) < tol,
+                    np.where(np.abs(clat0) < tol, lng0, np.where(latp > 0.0, lng0 + phip - 180.0, lng0 - phip)),
+                    general)
+    lngp = np.where(lng0 >= 0.0,
+                    np.where(lngp < 0.0, lngp + 360.0, np.where(lngp > 360.0, lngp - 360.0, lngp)),
+                    np.where(lngp > 0.0, lngp - 360.0, np.where(lngp < -360.0, lngp + 360.0, lngp)))
+    return lngp, latp, phip, valid
+
+
+def car_rotation(lngp, latp, phip):
+    """[n, 3, 3] rotations taking celestial unit vectors to native ones: R = Rz(phi_p) . A(lat_p) . Rz(-lng_p) with
+    A = [[-sin lat_p, 0, cos lat_p], [0, -1, 0], [cos lat_p, 0, sin lat_p]] (wcslib's sphs2x written as a matrix)."""
+    lngp, latp, phip = (np.atleast_1d(np.asarray(v, dtype=np.float64)) for v in (lngp, latp, phip))
+    n = lngp.size
+
+    def rz(a):
+        m = np.zeros((n, 3, 3))
+        m[:, 0, 0], m[:, 0, 1] = _cosd(a), -_sind(a)
+        m[:, 1, 0], m[:, 1, 1] = _sind(a), _cosd(a)
+        m[:, 2, 2] = 1.0
+        return m
+
+    a = np.zeros((n, 3, 3))
+    a[:, 0, 0], a[:, 0, 2] = -_sind(latp), _cosd(latp)
+    a[:, 1, 1] = -1.0
+    a[:, 2, 0], a[:, 2, 2] = _cosd(latp), _sind(latp)
+    return rz(phip) @ a @ rz(-lngp)
+
+
+@dataclass(frozen=True)
+class CarWcs(TanWcs):
+    """Constants of a 2-D plate-carree WCS (CRLN-CAR / CRLT-CAR), degrees. `lonpole` is NaN when the header has no
+    LONPOLE keyword (wcslib then picks 0 or 180 from the sign of CRVAL2, i.e. per candidate header)."""
+    latpole: float = 90.0
+
+    _PROJ: ClassVar[str] = "CAR"
+
+    @staticmethod
+    def _default_lonpole(crval2):
+        return float("nan")
+
+    @classmethod
+    def from_header(cls, hdr, ilon: int | None = None, ilat: int | None = None):
+        w = super().from_header(hdr, ilon, ilat)
+        if "LATPOLE" in hdr:
+            w = replace(w, latpole=float(hdr["LATPOLE"]))
+        return w
+
+    @staticmethod
+    def lag_rows(crval1, crval2, cdelt1, cdelt2, pc11, pc12, pc21, pc22, crpix1, crpix2, lonpole, latpole=90.0):
+        """[n, 16] float64 `CoregLagCar` rows (include/coreg_b200.h) of candidate headers given in degrees, and the
+        mask of headers wcslib would reject (their rows are NaN)."""
+        crval1 = np.atleast_1d(np.asarray(crval1, dtype=np.float64))
+        n = crval1.size
+        b = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), (n,))   # noqa: E731
+        lngp, latp, phip, valid = car_celestial_pole(crval1, b(crval2), b(lonpole), b(latpole))
+        rot = car_rotation(lngp, latp, phip)
+        f11, f12 = b(cdelt1) * b(pc11), b(cdelt1) * b(pc12)
+        f21, f22 = b(cdelt2) * b(pc21), b(cdelt2) * b(pc22)
+        det = f11 * f22 - f12 * f21
+        tab = np.empty((n, 16), dtype=np.float64)
+        tab[:, :9] = rot.reshape(n, 9)
+        tab[:, 9], tab[:, 10], tab[:, 11], tab[:, 12] = f22 / det, -f12 / det, -f21 / det, f11 / det
+        tab[:, 13], tab[:, 14] = b(crpix1) - 1.0, b(crpix2) - 1.0
+        tab[:, 15] = lngp
+        tab[~valid] = np.nan
+        return tab, ~valid
+
+    # -- small-N host evaluation (numpy; the per-pixel work is on the device) ------------------------------------
+    def pixel_to_world(self, x, y):
+        """0-based pixel -> (lon, lat) degrees, lon in wcslib's range (sign of the native pole's longitude)."""
+        row = self.lag_row()
+        r = row[:9].reshape(3, 3)
+        f = np.linalg.inv(np.array([[row[9], row[10]], [row[11], row[12]]]))
+        u1 = np.asarray(x, dtype=np.float64) - row[13]
+        u2 = np.asarray(y, dtype=np.float64) - row[14]
+        phi, theta = (f[0, 0] * u1 + f[0, 1] * u2) * D2R, (f[1, 0] * u1 + f[1, 1] * u2) * D2R
+        nat = np.stack([np.cos(theta) * np.cos(phi), np.cos(theta) * np.sin(phi), np.sin(theta)])
+        c = np.tensordot(r.T, nat, 1)
+        lon = np.arctan2(c[1], c[0]) * R2D
+        lon = np.where(lon < 0.0, lon + 360.0, lon) if row[15] >= 0.0 else np.where(lon > 0.0, lon - 360.0, lon)
+        return lon, np.arctan2(c[2], np.hypot(c[0], c[1])) * R2D
+
+    def world_to_pixel(self, lon, lat):
+        row = self.lag_row()
+        r = row[:9].reshape(3, 3)
+        lon = np.asarray(lon, dtype=np.float64) * D2R
+        lat = np.asarray(lat, dtype=np.float64) * D2R
+        c = np.stack([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+        v = np.tensordot(r, c, 1)
+        phi = np.arctan2(v[1], v[0]) * R2D
+        theta = np.arctan2(v[2], np.hypot(v[0], v[1])) * R2D
+        return row[9] * phi + row[10] * theta + row[13], row[11] * phi + row[12] * theta + row[14]
+
+    def lag_row(self):
+        """This header's own `CoregLagCar` row."""
+        tab, bad = self.lag_rows(self.crval1, self.crval2, self.cdelt1, self.cdelt2, self.pc11, self.pc12, self.pc21,
+                                 self.pc22, self.crpix1, self.crpix2, self.lonpole, self.latpole)
+        if bad[0]:
+            raise ValueError("invalid -CAR header: no native pole within [-90, 90] deg (CRVAL2 / LONPOLE / LATPOLE)")
+        return tab[0]
 
 
 # ------------------------------------------------------------------------------------------------------

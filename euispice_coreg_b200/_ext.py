@@ -42,6 +42,7 @@ class CoregCarrington(C.Structure):
 LAG_TAN_DOUBLES = 10    # sizeof(CoregLagTan) / 8
 TAN_WCS_DOUBLES = 11    # sizeof(CoregTanWcs) / 8
 LAG_OFFSET_DOUBLES = 2  # sizeof(CoregLagOffset) / 8
+LAG_CAR_DOUBLES = 16    # sizeof(CoregLagCar) / 8
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -66,6 +67,10 @@ _SIGNATURES = {
     "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
                                         C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_car_pix2world": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "coreg_car_world2pix": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
+    "coreg_car_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
+                                     C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_synras_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                      C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
@@ -350,6 +355,58 @@ def offset_lag_corr(ref, small, tx, ty, lags, order, pivots, work, corr_out, nva
                                          _ptr(work), work.numel() * work.element_size(), _ptr(corr_out),
                                          _ptr(nvalid_out) if nvalid_out is not None else None,
                                          int(flags), _stream()), "coreg_offset_lag_corr")
+
+
+def _car_row(row):
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    if row.shape != (LAG_CAR_DOUBLES,):
+        raise ValueError("one CoregLagCar row (16 float64) expected")
+    return row
+
+
+def car_pix2world(car_row, nx, ny, device=None):
+    """(lng, lat) float64 device tensors [ny, nx], degrees, of a plate-carree image; `car_row`: one `CoregLagCar`
+    row (`_compat.wcs.CarWcs.lag_rows`)."""
+    torch = _torch()
+    lib = load()
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    lng = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+    lat = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+    row = _car_row(car_row)
+    with torch.cuda.device(dev):
+        _check(lib.coreg_car_pix2world(row.ctypes.data_as(_P), int(nx), int(ny), _ptr(lng), _ptr(lat), _stream()),
+               "coreg_car_pix2world")
+    return lng, lat
+
+
+def car_world2pix(car_row, lng, lat):
+    torch = _torch()
+    lib = load()
+    _require_cuda(lng, lat)
+    x = torch.empty_like(lng)
+    y = torch.empty_like(lat)
+    row = _car_row(car_row)
+    with torch.cuda.device(lng.device):
+        _check(lib.coreg_car_world2pix(row.ctypes.data_as(_P), _ptr(lng), _ptr(lat), lng.numel(), _ptr(x), _ptr(y),
+                                       _stream()), "coreg_car_world2pix")
+    return x, y
+
+
+def car_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid_out=None, flags=0):
+    """Lag search on plate-carree images. `planes`: unit-vector planes of the common grid (`tan_trig_planes(lng, lat,
+    0.0)`); `lags`: device float64 [n_lags, 16] (`CoregLagCar` rows)."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(ref, small, planes, lags, pivots, work, corr_out)
+    if ref.dtype != torch.float32:
+        raise TypeError("ref must be float32 (the reference keeps the cut large image in float32)")
+    gny, gnx = ref.shape
+    with torch.cuda.device(ref.device):
+        _check(lib.coreg_car_lag_corr(_ptr(ref), _ptr(small), _dt(small), small.shape[1], small.shape[0], gnx, gny,
+                                      _ptr(planes), _ptr(lags), lags.shape[0], int(order), _ptr(pivots), _ptr(work),
+                                      work.numel() * work.element_size(), _ptr(corr_out),
+                                      _ptr(nvalid_out) if nvalid_out is not None else None,
+                                      int(flags), _stream()), "coreg_car_lag_corr")
 
 
 def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):

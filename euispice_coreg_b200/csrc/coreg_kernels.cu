@@ -379,6 +379,60 @@ __global__ void finite_mean_kernel(const T* __restrict__ img, int64_t n, double*
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// plate-carree (-CAR) device math: a sphere rotation followed by (phi, theta) -> pixel, see CoregLagCar
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void car_map_unit(const CoregLagCar& L, double cx, double cy, double cz, double& x,
+                                             double& y) {
+  const double vx = fma(L.r[0], cx, fma(L.r[1], cy, L.r[2] * cz));
+  const double vy = fma(L.r[3], cx, fma(L.r[4], cy, L.r[5] * cz));
+  const double vz = fma(L.r[6], cx, fma(L.r[7], cy, L.r[8] * cz));
+  const double phi = atan2(vy, vx) * kR2D;
+  const double theta = atan2(vz, sqrt(fma(vx, vx, vy * vy))) * kR2D;
+  x = fma(L.m11, phi, fma(L.m12, theta, L.x0));
+  y = fma(L.m21, phi, fma(L.m22, theta, L.y0));
+}
+
+__global__ void car_pix2world_kernel(CoregLagCar L, double f11, double f12, double f21, double f22, int nx, int ny,
+                                     double* __restrict__ lng, double* __restrict__ lat) {
+  const int64_t n = (int64_t)nx * ny;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % nx), j = (int)(idx / nx);
+    const double u1 = (double)i - L.x0, u2 = (double)j - L.y0;
+    const double phi = (f11 * u1 + f12 * u2) * kD2R, theta = (f21 * u1 + f22 * u2) * kD2R;
+    double sp, cp, st, ct;
+    sincos(phi, &sp, &cp);
+    sincos(theta, &st, &ct);
+    const double nx_ = ct * cp, ny_ = ct * sp, nz_ = st;
+    // celestial = R^T native
+    const double cx = L.r[0] * nx_ + L.r[3] * ny_ + L.r[6] * nz_;
+    const double cy = L.r[1] * nx_ + L.r[4] * ny_ + L.r[7] * nz_;
+    const double cz = L.r[2] * nx_ + L.r[5] * ny_ + L.r[8] * nz_;
+    double lo = atan2(cy, cx) * kR2D;
+    if (L.lng_ref >= 0.0) {
+      if (lo < 0.0) lo += 360.0;
+    } else {
+      if (lo > 0.0) lo -= 360.0;
+    }
+    lng[idx] = lo;
+    lat[idx] = atan2(cz, sqrt(cx * cx + cy * cy)) * kR2D;
+  }
+}
+
+__global__ void car_world2pix_kernel(CoregLagCar L, const double* __restrict__ lng, const double* __restrict__ lat,
+                                     int64_t n, double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double sl, cl, sa, ca, xx, yy;
+    sincos(lat[idx] * kD2R, &sl, &cl);
+    sincos(lng[idx] * kD2R, &sa, &ca);
+    car_map_unit(L, cl * ca, cl * sa, sl, xx, yy);
+    x[idx] = xx;
+    y[idx] = yy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // fused lag search
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTileW = 64;
@@ -467,6 +521,19 @@ struct OffsetCoord {
   __device__ static __forceinline__ void map(const Pix& q, const Lag& L, double& x, double& y) {
     x = __dadd_rn(L.x0, q.tx);
     y = __dadd_rn(L.y0, q.ty);
+  }
+};
+
+// plate-carree candidate headers: planes = (sin lat, cos lat sin lng, cos lat cos lng) of the common grid's pixels
+// (coreg_tan_trig_planes with alpha_ref = 0), per lag one sphere rotation + two atan2
+struct CarCoord {
+  typedef CoregLagCar Lag;
+  typedef TanCoord::Planes Planes;
+  typedef TanCoord::Pix Pix;
+  __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx) { return TanCoord::load(pl, idx); }
+  __device__ static __forceinline__ Pix dead() { return TanCoord::dead(); }
+  __device__ static __forceinline__ void map(const Pix& q, const Lag& L, double& x, double& y) {
+    car_map_unit(L, q.p2, q.p1, q.p0, x, y);
   }
 };
 
@@ -1624,6 +1691,12 @@ int launch_offset_fast(int, int, int, int64_t, int, cudaStream_t, const RefT*, c
   return fail(COREG_EINVAL, "internal: offset fast path requested for the TAN functor");
 }
 
+template <typename SmallT, typename RefT, bool ROUND32>
+int launch_offset_fast(int, int, int, int64_t, int, cudaStream_t, const RefT*, const SmallT*, int, int,
+                       TanCoord::Planes, const CoregLagCar*, const double*, double*, void*, int*) {
+  return fail(COREG_EINVAL, "internal: offset fast path requested for the CAR functor");
+}
+
 // generic kernel: variant 1 = 8 pixels per thread, 2 CTAs / SM; anything else 4 pixels per thread, 4 CTAs / SM
 template <class Coord, int ORDER, bool STRICT, typename SmallT, typename RefT, bool ROUND32>
 int launch_lag_variant(int variant, dim3 grid_tiles_of, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s,
@@ -2135,6 +2208,57 @@ int coreg_offset_lag_corr(const double* ref, const void* small, int small_dtype,
     return launch_lag_corr<OffsetCoord, float, double, false>(ref, (const float*)small, snx, sny, gnx, gny, pl, lags,
                                                               n_lags, order, pivots, work, work_bytes, corr, nvalid,
                                                               flags, s);
+  return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
+}
+
+static int car_forward(const CoregLagCar* m, double* f) {
+  if (!m) return fail(COREG_EINVAL, "null CoregLagCar");
+  const double det = m->m11 * m->m22 - m->m12 * m->m21;
+  if (!(det != 0.0) || det != det) return fail(COREG_EINVAL, "singular CDELT*PC matrix");
+  f[0] = m->m22 / det;
+  f[1] = -m->m12 / det;
+  f[2] = -m->m21 / det;
+  f[3] = m->m11 / det;
+  return COREG_OK;
+}
+
+int coreg_car_pix2world(const CoregLagCar* map, int nx, int ny, double* lng, double* lat, void* stream) {
+  double f[4];
+  int rc = car_forward(map, f);
+  if (rc) return rc;
+  if (nx <= 0 || ny <= 0) return COREG_OK;
+  if (!lng || !lat) return fail(COREG_EINVAL, "null output plane");
+  const int64_t n = (int64_t)nx * ny;
+  car_pix2world_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*map, f[0], f[1], f[2], f[3], nx, ny, lng, lat);
+  CK_LAUNCH("car_pix2world_kernel");
+  return COREG_OK;
+}
+
+int coreg_car_world2pix(const CoregLagCar* map, const double* lng, const double* lat, int64_t n, double* x, double* y,
+                        void* stream) {
+  if (!map) return fail(COREG_EINVAL, "null CoregLagCar");
+  if (n <= 0) return COREG_OK;
+  if (!lng || !lat || !x || !y) return fail(COREG_EINVAL, "null pointer");
+  car_world2pix_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*map, lng, lat, n, x, y);
+  CK_LAUNCH("car_world2pix_kernel");
+  return COREG_OK;
+}
+
+int coreg_car_lag_corr(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
+                       const double* planes, const CoregLagCar* lags, int64_t n_lags, int order, const double* pivots,
+                       void* work, size_t work_bytes, double* corr, int64_t* nvalid, int flags, void* stream) {
+  if (!ref || !small || !planes || !lags || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_car_lag_corr: null pointer");
+  CarCoord::Planes pl{planes, (int64_t)gnx * gny};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (small_dtype == COREG_F64)
+    return launch_lag_corr<CarCoord, double, float, true>(ref, (const double*)small, snx, sny, gnx, gny, pl, lags,
+                                                          n_lags, order, pivots, work, work_bytes, corr, nvalid,
+                                                          flags, s);
+  if (small_dtype == COREG_F32)
+    return launch_lag_corr<CarCoord, float, float, true>(ref, (const float*)small, snx, sny, gnx, gny, pl, lags,
+                                                         n_lags, order, pivots, work, work_bytes, corr, nvalid, flags,
+                                                         s);
   return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
 }
 

@@ -18,7 +18,7 @@ import warnings
 import numpy as np
 
 from .._compat import fits_lite, units
-from .._compat.wcs import TanWcs
+from .._compat.wcs import CarWcs, TanWcs
 from ..utils import Util
 from . import engine as _engine
 from .AlignmentResults import AlignmentResults
@@ -171,7 +171,41 @@ class Alignment:
         return self._wrap_results(results, return_type)
 
     def align_using_initial_carrington(self, method='correlation', return_type='AlignmentResults'):
-        raise NotImplementedError("CRLN-CAR inputs (alignment.py:344-399) are outside the device path (SURVEY 8f-4)")
+        """Co-alignment of two images that already are Carrington maps, CTYPE CRLN-CAR / CRLT-CAR
+        (`hdrshift/alignment.py:344-399`): the helioprojective search with the plate-carree projection, both images
+        rounded to float32 when read (`:373, 387`), lags converted to header units without longitude wrapping
+        (`:388, 831-837`), and -- unlike the other two entry points -- the lag arrays handed to `AlignmentResults`
+        as they are (`:392-399`)."""
+        self.lonlims = None
+        self.latlims = None
+        self.shape = None
+        self.reference_date = None
+        self.method = method
+        self.coordinate_frame = "initial_carrington"
+        self.lon_ctype = "CRLN-CAR"
+        self.lat_ctype = "CRLT-CAR"
+        self.ang2pipi = False
+        f_large = self._open_large()
+        f_small = self._open_small()
+        self.data_large = np.array(f_large[self.large_fov_window].data, dtype="float32")
+        self.hdr_large = f_large[self.large_fov_window].header.copy()
+        self.hdr_small = f_small[self.small_fov_window].header.copy()
+        self._check_ant_create_pcij_matrix(self.hdr_small)
+        self._check_ant_create_pcij_matrix(self.hdr_large)
+        self.data_small = np.array(f_small[self.small_fov_window].data, dtype="float32")
+        f_large.close()
+        f_small.close()
+        results = self._find_best_header_parameters(ang2pipi=False)
+        if return_type == "corr":
+            return results
+        if return_type == "AlignmentResults":
+            return AlignmentResults(corr=results, lag_crval1=self.lag_crval1, lag_crval2=self.lag_crval2,
+                                    lag_cdelt1=self.lag_cdelt1, lag_cdelt2=self.lag_cdelt2, lag_crota=self.lag_crota,
+                                    unit_lag=self.unit_lag, image_to_align_path=self.small_fov_to_correct,
+                                    image_to_align_window=self.small_fov_window,
+                                    reference_image_path=self.large_fov_known_pointing,
+                                    reference_image_window=self.large_fov_window)
+        return results
 
     # ------------------------------------------------------------------------------------------------
     # host preparation (mirrors alignment.py:299-316, 580-611, 799-887)
@@ -399,6 +433,22 @@ class Alignment:
             else:
                 corr, nvalid = eng.search(table, return_nvalid=True)
                 self.lags_evaluated = int(table.shape[0])
+            corr = np.where(dead, 0.0, corr)
+            for kk in range(n_r):
+                cube[..., kk] = corr.reshape(shape5)
+            self.nvalid = nvalid.reshape(shape5)
+        elif self.coordinate_frame == "initial_carrington":
+            if fov_limits is not None or remove_fov_limits is not None:
+                raise ValueError("fov_limits / remove_fov_limits need HPLN-TAN headers (utils/Util.py:283-286)")
+            if self.lag_search != "dense":
+                raise ValueError("lag_search='coarse_to_fine' is implemented for the helioprojective frame only")
+            w_small = CarWcs.from_header(self.hdr_small)
+            w_large = CarWcs.from_header(self.hdr_large)
+            eng.prepare_car(self.data_large, w_large, w_small)
+            self.hdr_large = self.hdr_small.copy()   # alignment.py:1000
+            table, dead = _engine.car_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, self.cdelt_semantics)
+            corr, nvalid = eng.search(table, return_nvalid=True)
+            self.lags_evaluated = int(table.shape[0])
             corr = np.where(dead, 0.0, corr)
             for kk in range(n_r):
                 cube[..., kk] = corr.reshape(shape5)

@@ -16,7 +16,7 @@ import numpy as np
 
 from .. import _ext
 from .._compat import units
-from .._compat.wcs import TanWcs
+from .._compat.wcs import CarWcs, TanWcs
 
 R2D = 180.0 / math.pi
 D2R = math.pi / 180.0
@@ -42,14 +42,14 @@ def shard_bounds(n_lags: int, world: int):
     return c, [(min(r * c, n_lags), min((r + 1) * c, n_lags)) for r in range(world)]
 
 
-def shifted_pc(hdr, crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1, cdelt2):
+def shifted_pc(hdr, crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1, cdelt2, wcs_cls=TanWcs):
     """PCi_j of the shifted header, vectorised over lags (`_shift_header`, `alignment.py:401-468`).
     Lags that touch none of CDELT/CROTA keep the header's own PC."""
     change = (d_cdelt1 != 0.0) | (d_cdelt2 != 0.0) | (d_crota != 0.0)
     crot = np.where(d_crota != 0.0, crota_ref + d_crota, crota_ref)
     rho = np.deg2rad(crot)
     lam = cdelt2 / cdelt1
-    own = TanWcs.from_header(hdr)   # PCi_j as wcslib would read them (identity when absent)
+    own = wcs_cls.from_header(hdr)   # PCi_j as wcslib would read them (identity when absent)
     pc11 = np.where(change, np.cos(rho), own.pc11)
     pc22 = np.where(change, np.cos(rho), own.pc22)
     pc12 = np.where(change, -lam * np.sin(rho), own.pc12)
@@ -57,9 +57,10 @@ def shifted_pc(hdr, crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1, cdelt2):
     return pc11, pc12, pc21, pc22
 
 
-def _shifted_header_constants(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics):
+def _shifted_header_constants(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics,
+                              wcs_cls=TanWcs):
     """Per-lag constants of `_shift_header` (`alignment.py:401-468`) in degrees, vectorised over lags."""
-    w0 = TanWcs.from_header(hdr_small)
+    w0 = wcs_cls.from_header(hdr_small)
     s1, s2 = w0.unit_scale1, w0.unit_scale2
     n = d_crval1.size
     crval1 = (refs.crval1_ref + d_crval1) * s1
@@ -74,7 +75,7 @@ def _shifted_header_constants(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_c
         dead = d_cdelt2 != 0.0
     else:
         raise ValueError("cdelt_semantics must be 'reference' or 'intended'")
-    pc = shifted_pc(hdr_small, refs.crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1_h, cdelt2_h)
+    pc = shifted_pc(hdr_small, refs.crota_ref, d_cdelt1, d_cdelt2, d_crota, cdelt1_h, cdelt2_h, wcs_cls)
     return w0, crval1, crval2, cdelt1_h * s1, cdelt2_h * s2, pc, dead
 
 
@@ -129,6 +130,18 @@ def tan_wcs_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_cro
     tab[:, 8], tab[:, 9] = crval1, crval2
     tab[:, 10] = w0.lonpole
     return tab, dead
+
+
+def car_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics="reference"):
+    """[n_lags, 16] float64 rows of `CoregLagCar` for candidate headers of a Carrington map (CRLN-CAR / CRLT-CAR):
+    `_shift_header` (`alignment.py:401-468`) followed by what `WCS(hdr_shifted)` derives in wcslib's celset -- the
+    native pole of every candidate, as a sphere rotation. The returned mask also flags candidates wcslib rejects
+    (an explicit LONPOLE that admits no native pole once CRVAL2 changes sign): the reference's worker dies on them."""
+    w0, crval1, crval2, cd1, cd2, (pc11, pc12, pc21, pc22), dead = _shifted_header_constants(
+        hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, cdelt_semantics, wcs_cls=CarWcs)
+    tab, bad = CarWcs.lag_rows(crval1, crval2, cd1, cd2, pc11, pc12, pc21, pc22, w0.crpix1, w0.crpix2, w0.lonpole,
+                               w0.latpole)
+    return tab, dead | bad
 
 
 def _dist_info():
@@ -248,6 +261,23 @@ class LagSearchEngine:
         self.cut_large(wcs_small)
         self.d_large = None
 
+    # ---- Carrington maps as inputs (CRLN-CAR / CRLT-CAR) -----------------------------------------------------
+    def prepare_car(self, data_large, wcs_large: CarWcs, wcs_small: CarWcs):
+        """One-time part of `align_using_initial_carrington` (`alignment.py:344-399, 987-1016`): Carrington
+        coordinates of the unshifted small grid, the large map resampled onto it as float32, the grid's unit-vector
+        planes and the ref pivot."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            d_large = self._upload(self._native_float(data_large))
+            lng, lat = _ext.car_pix2world(wcs_small.lag_row(), wcs_small.naxis1, wcs_small.naxis2, self.device)
+            x, y = _ext.car_world2pix(wcs_large.lag_row(), lng, lat)
+            self.ref = _ext.map_coordinates(d_large, y, x, self.order, float("nan"), torch.float32)
+            self.planes = _ext.tan_trig_planes(lng, lat, 0.0)
+            del x, y, lng, lat, d_large
+            self.grid_wcs = wcs_small
+            _ext.finite_mean(self.ref, self.pivots[0:1])
+        self.frame = "car"
+
     def _hpc_planes(self):
         """Lag-independent trig planes of the generic helioprojective kernel (101 MB at 2048^2), built lazily:
         the homography kernel does not need them."""
@@ -352,6 +382,9 @@ class LagSearchEngine:
                 if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
                     _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
                                           self.pivots, work, out_dev[lo:hi], nv, self.flags)
+                elif self.frame == "car":
+                    _ext.car_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order,
+                                      self.pivots, work, out_dev[lo:hi], nv, self.flags)
                 elif self.frame == "hpc":
                     _ext.hpc_lag_corr(self.ref, self.small, self._hpc_planes(), table_dev[lo:hi], self.order,
                                       self.pivots, work, out_dev[lo:hi], nv, self.flags)

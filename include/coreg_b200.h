@@ -74,6 +74,22 @@ typedef struct CoregLagOffset {
   double x0, y0;
 } CoregLagOffset;
 
+/* One plate-carree (-CAR) header reduced on the host to the constants of its world<->pixel maps: the common grid,
+ * the large image, or one candidate ("lag") header of a search on images that already are Carrington maps
+ * (CTYPE CRLN-CAR / CRLT-CAR). Replaces `_shift_header` + `WCS(hdr_shifted)` + wcslib's celset / sphs2x / cars2x:
+ * hdrshift/alignment.py:344-399, 401-468, 1038-1069.  With c the unit vector of a world point
+ * (cos lat cos lng, cos lat sin lng, sin lat):
+ *   v = R c;  phi = atan2(v.y, v.x), theta = atan2(v.z, hypot(v.x, v.y))     [deg, native longitude / latitude]
+ *   x = m11 phi + m12 theta + x0;  y = m21 phi + m22 theta + y0              [0-based pixel]
+ * R = Rz(phi_p) . A(delta_p) . Rz(-alpha_p) from the header's Euler angles (celset). */
+typedef struct CoregLagCar {
+  double r[9];               /* row-major rotation, celestial -> native */
+  double m11, m12, m21, m22; /* (diag(CDELT) PC)^-1, deg -> pixel */
+  double x0, y0;             /* CRPIX - 1 */
+  double lng_ref;            /* celestial longitude of the native pole [deg]: its sign picks the longitude range of
+                                coreg_car_pix2world ([0, 360) when >= 0, (-360, 0] otherwise), as wcslib's sphx2s does */
+} CoregLagCar;
+
 /* Per-image constants of the Carrington ("fa") transform. Replaces rectify.CarringtonTransform.__init__ /
  * SphericalTransform.__init__: utils/rectify.py:314-338, 377-423. Angles in RADIANS (already converted on the
  * host exactly as the reference does with np.radians), cdelt in arcsec/pixel. */
@@ -202,6 +218,21 @@ int coreg_offset_lag_corr(const double* ref_dev, const void* small_dev, int smal
                           int gny, const double* tx_dev, const double* ty_dev, const CoregLagOffset* lags_dev,
                           int64_t n_lags, int order, const double* pivots_dev, void* work_dev, size_t work_bytes,
                           double* corr_dev, int64_t* nvalid_dev, int flags, void* stream);
+
+/* ---- plate-carree (-CAR) images: the frame of Alignment.align_using_initial_carrington ------------------------------
+ * hdrshift/alignment.py:344-399: both images already are Carrington maps; the search is the helioprojective one with
+ * the CAR projection in place of TAN and no longitude wrapping (utils/Util.py:295-305).
+ * coreg_car_pix2world: lng / lat [deg] of every pixel of an nx x ny image (extract_EUI_coordinates, utils/Util.py:283-
+ *   305, for lon_ctype = "CRLN-CAR").  coreg_car_world2pix: WCS(hdr).world_to_pixel (hdrshift/alignment.py:1065).
+ * coreg_car_lag_corr: same computation, outputs and workspace as coreg_hpc_lag_corr with planes_dev = the unit-vector
+ *   planes of the common grid (coreg_tan_trig_planes with alpha_ref = 0) and one CoregLagCar per candidate header. */
+int coreg_car_pix2world(const CoregLagCar* map_host, int nx, int ny, double* lng_dev, double* lat_dev, void* stream);
+int coreg_car_world2pix(const CoregLagCar* map_host, const double* lng_dev, const double* lat_dev, int64_t n,
+                        double* x_dev, double* y_dev, void* stream);
+int coreg_car_lag_corr(const float* ref_dev, const void* small_dev, int small_dtype, int snx, int sny, int gnx,
+                       int gny, const double* planes_dev, const CoregLagCar* lags_dev, int64_t n_lags, int order,
+                       const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
+                       int64_t* nvalid_dev, int flags, void* stream);
 
 /* ---- K6: synthetic raster ----------------------------------------------------------------------------------------
  * Replaces the column loop of SPICEComposedMapBuilder._create_map_from_hdu (synras/map_builder.py:95-131):

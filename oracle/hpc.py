@@ -205,27 +205,41 @@ def select_fov_in_small_data(data_small, hdr_small, fov_limits_arcsec, order):
     return out, h
 
 
-def create_submap_of_large_data(data_large, hdr_large, hdr_small, order):
-    x_cut, y_cut = wcs_tan.extract_coordinates_pixels(hdr_small, hdr_large)
+def create_submap_of_large_data(data_large, hdr_large, hdr_small, order, coords=wcs_tan):
+    x_cut, y_cut = coords.extract_coordinates_pixels(hdr_small, hdr_large)
     cut = np.zeros_like(x_cut, dtype="float32")
     interpol2d(data_large.copy(), x=x_cut, y=y_cut, dst=cut, order=order, fill=np.nan)
     return np.array(cut)
 
 
-def interpolate_on_large_data_grid(data_small, hdr_grid, hdr_shifted, order, world=None):
-    x, y = wcs_tan.extract_coordinates_pixels(hdr_grid, hdr_shifted, world=world)
+def interpolate_on_large_data_grid(data_small, hdr_grid, hdr_shifted, order, world=None, coords=wcs_tan):
+    x, y = coords.extract_coordinates_pixels(hdr_grid, hdr_shifted, world=world)
     out = np.zeros_like(x, dtype="float32")
     interpol2d(data_small.copy(), x=x, y=y, order=order, fill=np.nan, dst=out)
     return out
 
 
 class HpcSearch:
-    """State of one helioprojective search after the one-time preparation."""
+    """State of one helioprojective search after the one-time preparation. frame="car" is the same search on two
+    Carrington maps (`align_using_initial_carrington`, `hdrshift/alignment.py:344-399`): -CAR headers, no longitude
+    wrapping of lags or world coordinates, both images rounded to float32 when read (`:373, 387`)."""
 
     def __init__(self, data_large, hdr_large, data_small, hdr_small,
                  lag_crval1, lag_crval2, lag_cdelt1, lag_cdelt2, lag_crota, lag_solar_r=None,
                  small_fov_value_min=None, small_fov_value_max=None, order=2, unit_lag="arcsec",
-                 force_crota_0=False, cdelt_mode="reference", fov_limits=None):
+                 force_crota_0=False, cdelt_mode="reference", fov_limits=None, frame="hpc"):
+        if frame not in ("hpc", "car"):
+            raise ValueError("frame must be 'hpc' or 'car'")
+        self.frame = frame
+        if frame == "car":
+            from . import wcs_car
+            self.coords = wcs_car
+            data_large = np.array(data_large, dtype="float32")
+            data_small = np.array(data_small, dtype="float32")
+            if fov_limits is not None:
+                raise NotImplementedError("fov_limits on -CAR inputs (the reference's helper is TAN-only)")
+        else:
+            self.coords = wcs_tan
         self.order = order
         self.cdelt_mode = cdelt_mode
         self.hdr_small = dict(hdr_small)
@@ -240,12 +254,12 @@ class HpcSearch:
             self.data_small, self.hdr_small = select_fov_in_small_data(self.data_small, self.hdr_small, fov_limits,
                                                                        order)
         self.refs = Refs(self.hdr_small, lag_crval1, lag_crval2, lag_cdelt1, lag_cdelt2, lag_crota,
-                         lag_solar_r, unit_lag=unit_lag)
+                         lag_solar_r, unit_lag=unit_lag, ang2pipi=(frame == "hpc"))
         if np.isnan(self.data_small).all():
             raise ValueError("minimum or maximum value have set all small FOV to nan")
         # one-time: large image onto the unshifted small grid, float32 (alignment.py:649-651, 987-1016)
         self.data_large = create_submap_of_large_data(np.array(data_large, dtype=np.float64), hdr_large,
-                                                      self.hdr_small, order)
+                                                      self.hdr_small, order, coords=self.coords)
         self.hdr_grid = dict(self.hdr_small)  # self.hdr_large = hdr_cut.copy()  (:1000)
         self._world = None
 
@@ -259,14 +273,20 @@ class HpcSearch:
         """Lag-independent world grid of the common grid. The reference recomputes it for every lag
         (`alignment.py:1061`); the values are identical, so the oracle may cache them."""
         if self._world is None:
-            self._world = wcs_tan.extract_coordinates(self.hdr_grid)
+            self._world = self.coords.extract_coordinates(self.hdr_grid)
         return self._world
 
     def reprojected(self, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, reuse_world=True):
         hdr = dict(self.hdr_small)
         shift_header(hdr, self.refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, self.cdelt_mode)
         world = self.world() if reuse_world else None
-        return interpolate_on_large_data_grid(self.data_small, self.hdr_grid, hdr, self.order, world=world)
+        try:
+            return interpolate_on_large_data_grid(self.data_small, self.hdr_grid, hdr, self.order, world=world,
+                                                  coords=self.coords)
+        except ValueError as exc:    # WCS(hdr_shifted) rejected by wcslib's celset: the reference's worker dies
+            if "Invalid coordinate transformation" in str(exc):
+                raise LagKillsWorker(str(exc))
+            raise
 
     def step(self, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_crota, reuse_world=True):
         """One lag -> Pearson r (`_step`, `alignment.py:509-542`)."""
