@@ -71,6 +71,10 @@ _SIGNATURES = {
     "coreg_car_world2pix": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "coreg_car_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_pixel_shift_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "coreg_pixel_shift_corr": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int, _P, _P, C.c_size_t,
+                                         _P, _P, _P]),
     "coreg_synras_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                      C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
@@ -407,6 +411,32 @@ def car_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
                                       work.numel() * work.element_size(), _ptr(corr_out),
                                       _ptr(nvalid_out) if nvalid_out is not None else None,
                                       int(flags), _stream()), "coreg_car_lag_corr")
+
+
+def pixel_shift_corr(large, smalls, x0, y0, lag_dx, lag_dy, pivots, return_nvalid=False):
+    """Pixel-shift lag search. large: device float64 [lny, lnx]; smalls: device float64 [n_rot, sny, snx]; lag_dx /
+    lag_dy: integer sequences. Returns device corr [n_dx, n_dy, n_rot] (and nvalid)."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(large, smalls, pivots)
+    if large.dtype != torch.float64 or smalls.dtype != torch.float64:
+        raise TypeError("float64 images expected (the reference reads both as float64)")
+    n_rot, sny, snx = smalls.shape
+    lny, lnx = large.shape
+    n_dx, n_dy = len(lag_dx), len(lag_dy)
+    dx = (C.c_int * n_dx)(*[int(v) for v in lag_dx])
+    dy = (C.c_int * n_dy)(*[int(v) for v in lag_dy])
+    need = int(lib.coreg_pixel_shift_workspace_bytes(snx, sny, n_dx, n_dy, n_rot))
+    work = torch.empty((need + 7) // 8, dtype=torch.float64, device=large.device)
+    corr = torch.empty((n_dx, n_dy, n_rot), dtype=torch.float64, device=large.device)
+    nvalid = torch.empty((n_dx, n_dy, n_rot), dtype=torch.int64, device=large.device) if return_nvalid else None
+    with torch.cuda.device(large.device):
+        _check(lib.coreg_pixel_shift_corr(_ptr(large), lnx, lny, _ptr(smalls), n_rot, snx, sny, int(x0), int(y0),
+                                          dx, n_dx, dy, n_dy, _ptr(pivots), _ptr(work), work.numel() * 8, _ptr(corr),
+                                          _ptr(nvalid) if nvalid is not None else None, _stream()),
+               "coreg_pixel_shift_corr")
+        torch.cuda.current_stream().synchronize()   # `dx` / `dy` are host temporaries, `work` is freed on return
+    return (corr, nvalid) if return_nvalid else corr
 
 
 def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):

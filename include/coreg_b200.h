@@ -234,6 +234,24 @@ int coreg_car_lag_corr(const float* ref_dev, const void* small_dev, int small_dt
                        const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
                        int64_t* nvalid_dev, int flags, void* stream);
 
+/* ---- pixel-shift lag search --------------------------------------------------------------------------------------
+ * Replaces the lag loops of pxlshift.AlignmentPixels.find_best_parameters / _iteration_along_dy / _step and the numba
+ * c_correlate they call: pxlshift/alignment_pixels.py:35-84, pxlshift/c_correlate.py:41-62. For every rotation k,
+ * every dx[i] and every dy[j]: Pearson r of smalls[k] against large[y0 + dy : y0 + dy + sny, x0 + dx : x0 + dx + snx]
+ * over the pixels where neither is NaN; the centred cross sum is rounded to float32 before the division, as the
+ * reference stores it. (x0, y0) = the centred slice of `_initialise_slice_corresponding_to_small` (:145-148).
+ *   large_dev   [lny*lnx] float64: the large image already at the small image's pixel size (coreg_map_coordinates)
+ *   smalls_dev  [n_rot][sny*snx] float64: the small image rotated by each rotation lag (coreg_map_coordinates)
+ *   lag_dx_host / lag_dy_host   integer displacements (host); a displacement that leaves the large image returns
+ *                               COREG_EINVAL "too large shift : outside FSI" (`_check_boundaries`, :150-156)
+ *   pivots_dev  [2]: pivot of large, pivot of smalls (coreg_finite_mean)
+ *   corr_dev    [n_dx][n_dy][n_rot] float64 out; nvalid_dev same shape int64 (may be NULL) */
+size_t coreg_pixel_shift_workspace_bytes(int snx, int sny, int n_dx, int n_dy, int n_rot);
+int coreg_pixel_shift_corr(const double* large_dev, int lnx, int lny, const double* smalls_dev, int n_rot, int snx,
+                           int sny, int x0, int y0, const int* lag_dx_host, int n_dx, const int* lag_dy_host, int n_dy,
+                           const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
+                           int64_t* nvalid_dev, void* stream);
+
 /* ---- K6: synthetic raster ----------------------------------------------------------------------------------------
  * Replaces the column loop of SPICEComposedMapBuilder._create_map_from_hdu (synras/map_builder.py:95-131):
  * output pixel (row j, column i) = order-k sample of imager frame frame_of_col[i] at the pixel position of the sky
