@@ -198,7 +198,9 @@ def test_gpu_initial_carrington_rotation_lags_results_and_dead_lags(torch_cuda, 
     assert np.nanmax(np.abs(res.corr - ref)) < R_TOL
     assert tuple(res.max_index[:2]) == (1, 1) and res.max_index[4] == 1
     assert res.unit_lag == "deg"
-    assert np.allclose(res.parameters_alignment["lag_crval1"], lag1 / 3600.0, rtol=0, atol=1e-15)
+    vals, unit = res.parameters_alignment["lag_crval1"]
+    assert unit == "deg" and np.allclose(vals, lag1 / 3600.0, rtol=0, atol=1e-15)
+    assert np.allclose(res.parameters_alignment_arcsec["lag_crval1"], lag1, rtol=0, atol=1e-9)
     # explicit LONPOLE = 0 on a small map whose header latitude is +0.02 deg: candidates below the equator are invalid
     hd = fits_lite.open(p_small)[0]
     h = hd.header.copy()
