@@ -86,7 +86,11 @@ class AlignmentSpice(Alignment):
             if level == 2:
                 self._prepare_spice_from_l2(hdu)
             elif level == 3:
-                raise NotImplementedError("level 3 (fitted) SPICE files are outside the device path")
+                # the reference's own level-3 branch cannot run: `_prepare_spice_from_l3` indexes the [y, x, parameter]
+                # data as `data[coeff, ...]` and leaves hdr_small without NAXIS1 / NAXIS2, which the search then needs
+                # (`alignment_spice.py:341-356`, `utils/Util.py:287`); `pxlshift.AlignmentSpicePixel` handles L3 files
+                raise NotImplementedError("level 3 (fitted) SPICE files: the reference's AlignmentSpice branch for "
+                                          "them does not run either; use pxlshift.AlignmentSpicePixel")
             else:
                 raise ValueError("level must be 2 or 3")
             for k in ("SOLAR_B0", "RSUN_REF", "DSUN_OBS", "CROTA"):

@@ -167,6 +167,26 @@ class ComposedMapBuilder(MapBuilder):
             detector = self.hdr_composed["INSTRUME"]
         else:
             raise ValueError("No info on reference instrument")
+        if keep_original_imager_pixel_size:
+            # `synras/map_builder.py:165-192`: the composed header gets the imager's pixel size, a PCi_j rebuilt for the
+            # new CDELT ratio, and its reference pixel at the centre of the new grid (KeyError, like the reference, when
+            # the raster's PCi_j is the identity and `to_header()` left it out)
+            w_xy = spice_wcs.celestial()
+            x_mid = (naxis1 - 1) / 2
+            y_mid = (naxis2 - 1) / 2
+            lon_mid, lat_mid = w_xy.pixel_to_world(np.array([x_mid]), np.array([y_mid]))
+            h = self.hdr_composed
+            h["CDELT1"] = float(units.convert(hdr_im["CDELT1"], hdr_im["CUNIT1"], h["CUNIT1"]))
+            h["CDELT2"] = float(units.convert(hdr_im["CDELT2"], hdr_im["CUNIT2"], h["CUNIT2"]))
+            lam = h["CDELT2"] / h["CDELT1"]
+            rho = np.arccos(h["PC1_1"])
+            rho = rho * (-np.sign(h["PC1_2"]))
+            h["PC1_2"] = float(-lam * np.sin(rho))
+            h["PC2_1"] = float((1 / lam) * np.sin(rho))
+            h["CRPIX1"] = (self.data_composed.shape[1] + 1) / 2
+            h["CRPIX2"] = (self.data_composed.shape[0] + 1) / 2
+            h["CRVAL1"] = float(units.convert(lon_mid[0], "deg", h["CUNIT1"]))
+            h["CRVAL2"] = float(units.convert(lat_mid[0], "deg", h["CUNIT2"]))
         if basename_output is None:
             date = timeutil.from_seconds(utc_composed)[:19].replace(":", "_")
             basename_new = f"solo_L3_{detector}{wave}-image-composed-{date}_{random.randint(1, 99999):05d}.fits"
@@ -193,21 +213,36 @@ class SPICEComposedMapBuilder(ComposedMapBuilder):
                          threshold_time=threshold_time, window_imager=window_imager, window_spectro=window_spectro)
 
     def _prepare_spectro_data(self, hdr_spice, keep_original_imager_pixel_size, level):
-        """`synras/map_builder.py:249-294` for level 2 on the raster's own pixel grid: sky coordinates of every
-        (y, x) at the first time index (device, K3) and the exposure time of every column (host)."""
-        if level != 2:
-            raise NotImplementedError("level 3 (fitted) SPICE files are outside the device path")
-        if keep_original_imager_pixel_size:
-            raise NotImplementedError("keep_original_imager_pixel_size=True is not on the device path yet")
+        """`synras/map_builder.py:249-344`: sky coordinates of the output grid at the first time index (device, K3) and
+        the exposure time of every column (host). Level 2: the raster's (x, y) = FITS axes (1, 2); level 3 (fitted
+        files, axes: parameter, x, y, time): axes (2, 3). `keep_original_imager_pixel_size`: the grid steps through
+        the raster in units of the imager's pixel, `np.arange(0, NAXIS, CDELT_imager / CDELT_raster)` -- a plain ratio
+        of header values, no unit conversion, as in the reference (`:262-263, 314-315`)."""
+        if level == 2:
+            ax1, ax2 = 1, 2
+        elif level == 3:
+            ax1, ax2 = 2, 3
+        else:
+            raise ValueError("level must be 2 or 3")
         sw = SpiceWcs(hdr_spice)
-        naxis1, naxis2 = int(hdr_spice["NAXIS1"]), int(hdr_spice["NAXIS2"])
-        w = sw.celestial()
-        lng, lat = _ext.tan_pix2world(w, naxis1, naxis2, wrap_pipi=False)
-        t_ref = timeutil.to_seconds(hdr_spice.get("DATEREF", hdr_spice.get("DATE-BEG", hdr_spice["DATE-OBS"])))
-        x = np.arange(naxis1, dtype=np.float64)
-        y = np.arange(naxis2, dtype=np.float64)
-        utc_cols = t_ref + sw.time_seconds(x[None, :], 0.0, y[:, None])      # [naxis2, naxis1]
+        naxis1, naxis2 = int(hdr_spice["NAXIS%d" % ax1]), int(hdr_spice["NAXIS%d" % ax2])
         with _fits().open(self.list_imager_paths[0]) as hdul_im:
             hdr_im = hdul_im[self.window_imager].header.copy()
+        w = sw.celestial()
+        if keep_original_imager_pixel_size:
+            r1 = hdr_im["CDELT1"] / hdr_spice["CDELT%d" % ax1]
+            r2 = hdr_im["CDELT2"] / hdr_spice["CDELT%d" % ax2]
+            x = np.arange(0, naxis1, r1, dtype=np.float64)
+            y = np.arange(0, naxis2, r2, dtype=np.float64)
+            # pixel k * r of the raster == pixel k of a grid with PCi_j scaled column-wise and CRPIX moved
+            w_grid = w.replace(crpix1=1.0 + (w.crpix1 - 1.0) / r1, crpix2=1.0 + (w.crpix2 - 1.0) / r2,
+                               pc11=w.pc11 * r1, pc21=w.pc21 * r1, pc12=w.pc12 * r2, pc22=w.pc22 * r2)
+        else:
+            x = np.arange(naxis1, dtype=np.float64)
+            y = np.arange(naxis2, dtype=np.float64)
+            w_grid = w
+        lng, lat = _ext.tan_pix2world(w_grid, len(x), len(y), wrap_pipi=False)
+        t_ref = timeutil.to_seconds(hdr_spice.get("DATEREF", hdr_spice.get("DATE-BEG", hdr_spice["DATE-OBS"])))
+        utc_cols = t_ref + sw.time_seconds(x[None, :], 0.0, y[:, None])      # [len(y), len(x)]
         self.hdr_spice_ = sw.xy_header()
-        return hdr_im, lng, lat, naxis1, naxis2, naxis1, utc_cols, sw
+        return hdr_im, lng, lat, naxis1, naxis2, len(x), utc_cols, sw

@@ -72,12 +72,18 @@ def spice_l2_image(data4, h4, wave_interval="all"):
     return img, hdr
 
 
-def build_synras(h4, imager_frames, imager_headers, threshold_s, order=2):
-    """-> (data_composed float64 [NAXIS2, NAXIS1], frame index per column)."""
+def build_synras(h4, imager_frames, imager_headers, threshold_s, order=2, keep_original_imager_pixel_size=False):
+    """-> (data_composed float64 [rows, columns], frame index per column). With `keep_original_imager_pixel_size` the
+    grid is `np.arange(0, NAXIS, CDELT_imager / CDELT_raster)` along each axis (`map_builder.py:259-275`)."""
     nx, ny = int(h4["NAXIS1"]), int(h4["NAXIS2"])
     hxy = dict(xy_header(h4), NAXIS1=nx, NAXIS2=ny)
     w = wcs_tan.WcsTan(hxy)
-    x, y = np.meshgrid(np.arange(nx), np.arange(ny))
+    if keep_original_imager_pixel_size:
+        h_im = imager_headers[0]
+        x, y = np.meshgrid(np.arange(0, nx, h_im["CDELT1"] / h4["CDELT1"]), np.arange(0, ny, h_im["CDELT2"] / h4["CDELT2"]))
+        ny, nx = x.shape
+    else:
+        x, y = np.meshgrid(np.arange(nx), np.arange(ny))
     lng, lat = w.pixel_to_world(x, y)          # no ang2pipi here (map_builder.py:294)
     t_ref = _to_s(h4["DATEREF"] if "DATEREF" in h4 else h4["DATE-BEG"])
     pc41 = h4["PC4_1"] if "PC4_1" in h4 else 0.0

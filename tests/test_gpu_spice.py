@@ -51,6 +51,78 @@ def test_synras_matches_oracle(spice_case):
         SPICEComposedMapBuilder(p_spice, imagers, threshold_time=1.0).process(print_filename=False)
 
 
+def test_synras_keep_original_imager_pixel_size(spice_case):
+    """`keep_original_imager_pixel_size=True` (`map_builder.py:259-275, 165-192`): the raster is stepped in units of
+    the imager's pixel along both axes (fractional raster pixels), and the composed header is rebuilt around the centre
+    of the new grid with the imager's CDELT."""
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    from euispice_coreg_b200.synras import SPICEComposedMapBuilder
+    from oracle.synras import build_synras, xy_header
+    p_spice, imagers, spec, d = spice_case
+    _, h4 = _load(p_spice)
+    frames, hdrs = zip(*[_load(p) for p in imagers])
+    b = SPICEComposedMapBuilder(p_spice, imagers, threshold_time=100.0)
+    b.process(print_filename=False, keep_original_imager_pixel_size=True)
+    ref, chosen = build_synras(h4, frames, hdrs, 100.0, keep_original_imager_pixel_size=True)
+    r1, r2 = hdrs[0]["CDELT1"] / h4["CDELT1"], hdrs[0]["CDELT2"] / h4["CDELT2"]
+    assert b.data_composed.shape == ref.shape == (len(np.arange(0, spec.n_y, r2)), len(np.arange(0, spec.n_x, r1)))
+    assert ref.shape != (spec.n_y, spec.n_x)
+    assert np.array_equal(np.isnan(b.data_composed), np.isnan(ref))
+    assert np.nanmax(np.abs(b.data_composed - ref) / np.abs(ref)) < 2e-7
+    h = b.hdr_composed
+    s_im = 1.0 / 3600.0 if hdrs[0]["CUNIT1"].strip() == "arcsec" else 1.0
+    assert h["CDELT1"] == hdrs[0]["CDELT1"] * s_im and h["CDELT2"] == hdrs[0]["CDELT2"] * s_im
+    assert h["CRPIX1"] == (ref.shape[1] + 1) / 2 and h["CRPIX2"] == (ref.shape[0] + 1) / 2
+    assert h["NAXIS1"] == ref.shape[1] and h["NAXIS2"] == ref.shape[0]
+    from oracle import wcs_tan
+    lon_mid, lat_mid = wcs_tan.WcsTan(dict(xy_header(h4), NAXIS1=spec.n_x, NAXIS2=spec.n_y)).pixel_to_world(
+        np.array([(spec.n_x - 1) / 2]), np.array([(spec.n_y - 1) / 2]))
+    assert abs((h["CRVAL1"] - lon_mid[0] + 180.0) % 360.0 - 180.0) < 1e-11 and abs(h["CRVAL2"] - lat_mid[0]) < 1e-11
+    lam = h["CDELT2"] / h["CDELT1"]
+    rho = np.arccos(h["PC1_1"]) * (-np.sign(h4["PC1_2"]))
+    assert abs(h["PC1_2"] + lam * np.sin(rho)) < 1e-15 and abs(h["PC2_1"] - np.sin(rho) / lam) < 1e-15
+    assert TanWcs.from_header(h).cdelt1 == h["CDELT1"]
+
+
+def test_synras_level3_header_gives_the_level2_raster(spice_case, tmp_path):
+    """Level-3 (fitted) SPICE files carry the axes (parameter, x, y, time): `map_builder.py:297-344` builds the same
+    raster from axes (2, 3) and the time dependence PC4_2. The same geometry written both ways must give the same
+    synthetic raster bit for bit; without an output folder the reference raises NotImplementedError for level 3."""
+    from euispice_coreg_b200._compat import fits_lite
+    from euispice_coreg_b200.synras import SPICEComposedMapBuilder
+    p_spice, imagers, spec, d = spice_case
+    hdu = fits_lite.open(p_spice)[0]
+    h2 = hdu.header
+    h3 = fits_lite.Header()
+    for k, v in h2.items():
+        if k in ("SIMPLE", "BITPIX", "EXTEND") or k.startswith("NAXIS"):
+            continue
+        if k[:5] in ("CTYPE", "CUNIT", "CRPIX", "CRVAL", "CDELT") or k[:2] == "PC" and "_" in k:
+            continue
+        h3[k] = v
+    old_to_new = {1: 2, 2: 3, 4: 4}          # x, y, time; the dispersion axis is gone, axis 1 = fit parameter
+    h3["WCSAXES"] = 4
+    h3["CTYPE1"], h3["CUNIT1"], h3["CRPIX1"], h3["CRVAL1"], h3["CDELT1"] = "PARAMETER", "", 1.0, 1.0, 1.0
+    for o, n in old_to_new.items():
+        for key in ("CTYPE", "CUNIT", "CRPIX", "CRVAL", "CDELT"):
+            h3[f"{key}{n}"] = h2[f"{key}{o}"]
+        for o2, n2 in old_to_new.items():
+            if f"PC{o}_{o2}" in h2:
+                h3[f"PC{n}_{n2}"] = h2[f"PC{o}_{o2}"]
+    data3 = np.zeros((spec.n_y, spec.n_x, 3), dtype=np.float32)
+    p3 = str(tmp_path / "solo_L3_spice_toy.fits")
+    fits_lite.writeto(p3, [fits_lite.PrimaryHDU(data3, h3)], overwrite=True)
+    b2 = SPICEComposedMapBuilder(p_spice, imagers, threshold_time=100.0)
+    b2.process(print_filename=False)
+    b3 = SPICEComposedMapBuilder(p3, imagers, threshold_time=100.0)
+    b3.process(folder_path_output=str(tmp_path), basename_output="synras_l3.fits", print_filename=False, level=3)
+    assert np.array_equal(b2.data_composed, b3.data_composed, equal_nan=True)
+    for k in ("CRVAL1", "CRVAL2", "CDELT1", "CDELT2", "PC1_2", "PC2_1", "CRPIX1", "CRPIX2"):
+        assert b2.hdr_composed[k] == b3.hdr_composed[k], k
+    with pytest.raises(NotImplementedError):
+        SPICEComposedMapBuilder(p3, imagers, threshold_time=100.0).process(print_filename=False, level=3)
+
+
 def test_alignment_spice_parity_and_recovers_shift(spice_case, tmp_path):
     """SPICE-style inputs: 4-axis L2 cube, degrees after the 2-D header extraction, anisotropic pixels, NaN slit
     edges. A synthetic raster has the SPICE header by construction, so the one-time cut of the large image maps
