@@ -31,8 +31,9 @@ if ROOT not in sys.path:
 WORKLOAD = "config1: HRIEUV-like 2048x2048 vs FSI174-like 3072x3072, helioprojective, 60x60 CRVAL lags @1arcsec"
 FP64_INSTR_PER_SAMPLE = 69.0   # algorithmic FP64 instructions per pixel-sample (HPC), counted
 #                                on the reference's formulation (pixel -> world -> pixel per lag)
-K1_DRAM_BYTES_PER_LAUNCH = 609.1e6  # dram__bytes_read.sum + dram__bytes_write.sum of one config-1 launch of the rolling
-#                                     kernel (ncu --set full, profiles/r1_ncu_roll_v6_raw.csv): 305.3 MB + 303.9 MB
+K1_DRAM_BYTES_PER_LAUNCH = 1708.3e6  # dram__bytes_read.sum + dram__bytes_write.sum of one config-1 launch of the rolling
+#                                      kernel (ncu --set full, profiles/r1_ncu_roll_v7_raw.csv): 733.6 MB + 974.6 MB (the
+#                                      per-warp records of the barrier-free variant are written and read back once)
 FP64_EXECUTED_PER_SAMPLE = 31.7  # FP64 thread-instructions the column-rolling kernel executes per pixel-sample = the
 #                                  algorithmic count of ITS formulation (ncu: DADD + DMUL + DFMA of
 #                                  one launch / pixel-samples, profiles/r1_roll_kernel.md)
@@ -365,6 +366,14 @@ def run_gpu(args):
     align_wall = time.perf_counter() - t0
     carr = None if args.no_carrington else carrington_secondary(pl, ps, args.steps, world, barrier, torch, dist,
                                                                  args.carrington_variant)
+    widened = None
+    if world == 1 and not args.no_carrington:
+        # the SURVEY 8f-4 paths, timed for the record (single GPU only: not part of `value`)
+        try:
+            from tools import car_bench, pxl_bench
+            widened = {"initial_carrington": car_bench.run(2048, 1024, 60), "pixel_shift": pxl_bench.run()}
+        except Exception as exc:   # never lose the headline line over a secondary measurement
+            widened = {"error": repr(exc)}
     if rank == 0:
         am = tuple(int(v) for v in res.max_index[:2])
         best = (float(LAGS["lag_crval1"][am[0]]), float(LAGS["lag_crval2"][am[1]]))
@@ -403,6 +412,7 @@ def run_gpu(args):
                             "all-gather, D2H cube"},
             "align_wall_s": align_wall, "argmax_lag_arcsec": best,
             "carrington": carr,
+            "widened": widened,
             # own kernels inside the timed region: per lag-kernel launch the homography table (fast path), the fused
             # lag kernel and the finalize kernel (the L2 flush memset and the NCCL all-gather are not ours)
             "gpu_launches": int(k1_launches * (3 if fast else 2)),

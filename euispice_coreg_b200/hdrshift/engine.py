@@ -11,6 +11,7 @@ all-gather assembles the cube.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -277,6 +278,9 @@ class LagSearchEngine:
             self.grid_wcs = wcs_small
             _ext.finite_mean(self.ref, self.pivots[0:1])
         self.frame = "car"
+        # the two inlined atan2 need registers: 8 pixels per thread x 2 CTAs / SM (128 registers) instead of the generic
+        # kernel's default 4 x 4 (64 registers: 9e8 local-memory loads per search, profiles/r1_ncu_car_v0.txt)
+        self.flags = _ext.make_flags(self.strict, int(os.environ.get("COREG_CAR_VARIANT", "1")), no_fast=self.no_fast)
 
     def _hpc_planes(self):
         """Lag-independent trig planes of the generic helioprojective kernel (101 MB at 2048^2), built lazily:

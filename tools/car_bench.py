@@ -13,11 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run(snx=2048, sny=1024, nl=60):
     import torch
     from euispice_coreg_b200._synth.carmaps import CarPairSpec, make_car_pair
     from euispice_coreg_b200.hdrshift import Alignment
-    snx, sny, nl = (int(v) for v in (sys.argv[1:4] or (2048, 1024, 60)))
     spec = CarPairSpec(small_n=(snx, sny), large_n=(snx * 3 // 4, sny * 3 // 4), small_cdelt=0.02 * 96 / snx * 8,
                        large_cdelt=0.02 * 96 / snx * 8 * 2.5, master_n=4096, master_cdelt=0.02 * 96 / snx * 8 * snx * 1.7 / 4096)
     d = tempfile.mkdtemp()
@@ -48,13 +47,13 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     i = np.unravel_index(np.nanargmax(cube), cube.shape)
-    print(json.dumps({"workload": f"initial_carrington: CAR maps {snx}x{sny} vs {spec.large_n[0]}x{spec.large_n[1]}, "
+    return ({"workload": f"initial_carrington: CAR maps {snx}x{sny} vs {spec.large_n[0]}x{spec.large_n[1]}, "
                                   f"{nl}x{nl} CRVAL lags", "lags": int(table.shape[0]), "ms_per_search": ms,
                       "lag_evals_per_s": table.shape[0] / ms * 1e3,
                       "pixel_samples_per_s": table.shape[0] * snx * sny / ms * 1e3, "align_wall_first_s": wall_first,
                       "argmax_lag_deg": [float(a.lag_crval1[i[0]]), float(a.lag_crval2[i[1]])],
-                      "true_shift_deg": list(spec.true_shift), "max_r": float(np.nanmax(cube))}))
+                      "true_shift_deg": list(spec.true_shift), "max_r": float(np.nanmax(cube))})
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(*(int(v) for v in sys.argv[1:4]))))

@@ -10,10 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run(ln=2048, sn=1024, nl=61, nr=3):
     import torch
     from euispice_coreg_b200 import _ext
-    ln, sn, nl, nr = (int(v) for v in (sys.argv[1:5] or (2048, 1024, 61, 3)))
     rng = np.random.default_rng(5)
     large = torch.from_numpy(rng.lognormal(5, 1, (ln, ln))).cuda()
     y0 = x0 = (ln - sn - 1) // 2
@@ -33,12 +32,12 @@ def main():
     c = corr.cpu().numpy()
     i = np.unravel_index(np.argmax(c), c.shape)
     samples = float(nl * nl * nr) * sn * sn
-    print(json.dumps({"workload": f"pixel shift: small {sn}x{sn} in large {ln}x{ln}, {nl}x{nl}x{nr} lags",
+    return ({"workload": f"pixel shift: small {sn}x{sn} in large {ln}x{ln}, {nl}x{nl}x{nr} lags",
                       "lags": nl * nl * nr, "kernel_ms": ms, "lag_evals_per_s": nl * nl * nr / ms * 1e3,
                       "pixel_samples_per_s": samples / ms * 1e3,
                       "unamortised_GBps": samples * 16 / ms * 1e3 / 1e9,
-                      "argmax": [int(lag[i[0]]), int(lag[i[1]]), int(i[2])], "max_r": float(c.max())}))
+                      "argmax": [int(lag[i[0]]), int(lag[i[1]]), int(i[2])], "max_r": float(c.max())})
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(*(int(v) for v in sys.argv[1:5]))))
