@@ -1782,8 +1782,9 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
 // One block = one 64 x 32 tile of the small image (8 pixels per thread, in registers, pivot-subtracted) x one chunk
 // of up to 8 x 8 (dx, dy) lags x one rotation. The part of the large image the chunk can reach -- the tile grown by
 // the chunk's dx / dy spans -- is staged once in shared memory; every lag then reads it at its own offset (LDS.64,
-// conflict-free along x). Six moments per lag (the mask is pairwise, so all of them are lag-dependent), reduced with
-// the warp butterfly, folded over the warps in a fixed order, one 64 B partial per (tile, lag).
+// conflict-free along x). The mask is pairwise, so in general all six moments depend on the lag; when the staged window
+// holds no missing pixel (the common case) only Sa, Saa, Sab do and the loop is select-free. Warp butterfly, warps
+// folded in a fixed order, one 64 B partial per (tile, lag).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPxTileH = 32;
 constexpr int kPxPPT = kPxTileH / kRowsPerPass;   // 8
@@ -1808,26 +1809,81 @@ pixel_shift_corr_kernel(const double* __restrict__ large, int lnx, int lny, cons
   int dxmin = lag_dx[i0], dxmax = dxmin, dymin = lag_dy[j0], dymax = dymin;
   for (int i = i0 + 1; i < i1; ++i) { dxmin = min(dxmin, lag_dx[i]); dxmax = max(dxmax, lag_dx[i]); }
   for (int j = j0 + 1; j < j1; ++j) { dymin = min(dymin, lag_dy[j]); dymax = max(dymax, lag_dy[j]); }
-  // stage the reachable window of the large image (pivot-subtracted; outside the image: NaN, only dead pixels see it)
+  // stage the reachable window of the large image (pivot-subtracted). Positions outside the image are only ever read
+  // by dead pixels (the host checked every lag's slice against the image), they hold 0.
   const int need_w = kTileW + (dxmax - dxmin), need_h = kPxTileH + (dymax - dymin);
   const int gx0 = x0 + tile_x * kTileW + dxmin, gy0 = y0 + tile_y * kPxTileH + dymin;
+  int saw_nan = 0;
   for (int idx = tid; idx < need_w * need_h; idx += kThreads) {
     const int wy = idx / need_w, wx = idx - wy * need_w;
     const int gy = gy0 + wy, gx = gx0 + wx;
-    double v = CUDART_NAN;
-    if (gx >= 0 && gx < lnx && gy >= 0 && gy < lny) v = __ldg(large + (size_t)gy * lnx + gx) - pivot_a;
+    double v = 0.0;
+    if (gx >= 0 && gx < lnx && gy >= 0 && gy < lny) {
+      v = __ldg(large + (size_t)gy * lnx + gx) - pivot_a;
+      saw_nan |= !(fabs(v) <= 1.7976931348623157e308);   // NaN or Inf: the general path keeps the reference's semantics
+    }
     s_win[wy * win_w + wx] = v;
   }
-  double b[kPxPPT];
+  // the small tile: value (0 where missing) and 0 / 1 weight per pixel, lag-independent
+  double bz[kPxPPT], wb[kPxPPT];
   const double* sm = smalls + (size_t)rot * snx * sny;
+  double inv[4] = {0.0, 0.0, 0.0, 0.0};   // n, Sb, Sbb over the live pixels of this thread
 #pragma unroll
   for (int k = 0; k < kPxPPT; ++k) {
     const int sx = tile_x * kTileW + tx, sy = tile_y * kPxTileH + ty + k * kRowsPerPass;
-    b[k] = (sx < snx && sy < sny) ? __ldg(sm + (size_t)sy * snx + sx) - pivot_b : CUDART_NAN;
+    const double b = (sx < snx && sy < sny) ? __ldg(sm + (size_t)sy * snx + sx) - pivot_b : CUDART_NAN;
+    const bool live = (b == b);
+    bz[k] = live ? b : 0.0;
+    wb[k] = live ? 1.0 : 0.0;
+    inv[0] += wb[k];
+    inv[1] += bz[k];
+    inv[2] = fma(bz[k], bz[k], inv[2]);
   }
-  __syncthreads();
+  const int window_has_nan = __syncthreads_or(saw_nan);   // also the barrier behind the staging
   const int n_lags = n_dx * n_dy * n_rot;
   const int cj = j1 - j0;
+  if (!window_has_nan) {
+    // no missing pixel of the large image in reach: the mask is the small image's alone, so n, Sb, Sbb do not depend on
+    // the lag and the loop carries three sums, without a compare or a select: 1 LDS.64 + 1 DMUL + 3 DFMA per pixel-sample
+    for (int i = i0; i < i1; ++i) {
+      const int ox = lag_dx[i] - dxmin + tx;
+      for (int j = j0; j < j1; ++j) {
+        const int oy = lag_dy[j] - dymin + ty;
+        double m[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < kPxPPT; ++k) {
+          const double a = s_win[(oy + k * kRowsPerPass) * win_w + ox];
+          const double aw = a * wb[k];
+          m[0] += aw;
+          m[1] = fma(a, aw, m[1]);
+          m[2] = fma(a, bz[k], m[2]);
+        }
+        const double tot = warp_transpose_reduce4(m, lane);
+        if ((lane & 7) == 0) s_part[warp][(i - i0) * cj + (j - j0)][lane >> 3] = tot;
+      }
+    }
+    const double itot = warp_transpose_reduce4(inv, lane);
+    if ((lane & 7) == 0) s_part[warp][kPxChunk * kPxChunk - 1][4 + (lane >> 3)] = itot;   // slots 4..7 of the last row
+    __syncthreads();
+    const int cnt = (i1 - i0) * cj;
+    for (int e = tid; e < cnt * kMom; e += kThreads) {
+      const int l = e / kMom, q = e % kMom;
+      // q: n, Sa, Sb, Saa, Sbb, Sab, pad, pad  <-  invariant 0, varying 0, invariant 1, varying 1, invariant 2, varying 2
+      const bool varying = (q == 1 || q == 3 || q == 5);
+      const int src = (q == 1) ? 0 : (q == 3) ? 1 : (q == 5) ? 2 : (q == 0) ? 4 : (q == 2) ? 5 : (q == 4) ? 6 : 7;
+      const int row = varying ? l : kPxChunk * kPxChunk - 1;
+      double acc = 0.0;
+      if (q < 6) {
+        acc = s_part[0][row][src];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) acc += s_part[w][row][src];
+      }
+      const int i = i0 + l / cj, j = j0 + l % cj;
+      const size_t lag = ((size_t)i * n_dy + j) * n_rot + rot;
+      work[((size_t)tile * n_lags + lag) * kMom + q] = acc;
+    }
+    return;
+  }
   for (int i = i0; i < i1; ++i) {
     const int ox = lag_dx[i] - dxmin + tx;
     for (int j = j0; j < j1; ++j) {
@@ -1836,8 +1892,8 @@ pixel_shift_corr_kernel(const double* __restrict__ large, int lnx, int lny, cons
 #pragma unroll
       for (int k = 0; k < kPxPPT; ++k) {
         const double a = s_win[(oy + k * kRowsPerPass) * win_w + ox];
-        const bool ok = (a == a) && (b[k] == b[k]);          // np.isnan on either side masks the pair
-        const double av = ok ? a : 0.0, bv = ok ? b[k] : 0.0;
+        const bool ok = (a == a) && (wb[k] != 0.0);          // np.isnan on either side masks the pair
+        const double av = ok ? a : 0.0, bv = ok ? bz[k] : 0.0;
         m[0] += ok ? 1.0 : 0.0;
         m[1] += av;
         m[2] += bv;

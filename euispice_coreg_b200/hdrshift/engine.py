@@ -278,9 +278,10 @@ class LagSearchEngine:
             self.grid_wcs = wcs_small
             _ext.finite_mean(self.ref, self.pivots[0:1])
         self.frame = "car"
-        # the two inlined atan2 need registers: 8 pixels per thread x 2 CTAs / SM (128 registers) instead of the generic
-        # kernel's default 4 x 4 (64 registers: 9e8 local-memory loads per search, profiles/r1_ncu_car_v0.txt)
-        self.flags = _ext.make_flags(self.strict, int(os.environ.get("COREG_CAR_VARIANT", "1")), no_fast=self.no_fast)
+        # launch shape of the generic kernel: the default 4 pixels x 4 CTAs / SM (64 registers, the atan2 temporaries
+        # spill to L1-resident local memory) measured faster than 8 x 2 with 128 registers: 101.9 vs 115.7 ms on
+        # 2048 x 1024 maps, 3600 lags (profiles/r1_widened_kernels.md)
+        self.flags = _ext.make_flags(self.strict, int(os.environ.get("COREG_CAR_VARIANT", "0")), no_fast=self.no_fast)
 
     def _hpc_planes(self):
         """Lag-independent trig planes of the generic helioprojective kernel (101 MB at 2048^2), built lazily:
