@@ -50,8 +50,9 @@ def slit_limits(h):
     return beg, end
 
 
-def spice_l2_image(data4, h4, wave_interval="all"):
-    """2-D image + 2-D header of an L2 cube [1, n_lambda, ny, nx]."""
+def spice_l2_image(data4, h4, wave_interval="all", sub_fov_arcsec=None):
+    """2-D image + 2-D header of an L2 cube [1, n_lambda, ny, nx]. `sub_fov_arcsec` = (lon_min, lon_max, lat_min,
+    lat_max): pixels outside are set to NaN (`alignment_spice.py:289-312`; longitudes as wcslib reports them)."""
     data = np.array(data4, dtype=np.float64)
     ymin, ymax = slit_limits(h4)
     data[:, :, :ymin, :] = np.nan
@@ -65,6 +66,13 @@ def spice_l2_image(data4, h4, wave_interval="all"):
         img = np.nansum(data[0, sel, :, :], axis=0)
     img[:ymin, :] = np.nan
     img[ymax:, :] = np.nan
+    if sub_fov_arcsec is not None:
+        ny, nx = img.shape
+        w = wcs_tan.WcsTan(dict(xy_header(h4), NAXIS1=nx, NAXIS2=ny))
+        lon, lat = w.pixel_to_world(*np.meshgrid(np.arange(nx), np.arange(ny)))
+        lims = [v * (1.0 / 3600.0) for v in sub_fov_arcsec]
+        sel = (lon >= lims[0]) & (lon <= lims[1]) & (lat >= lims[2]) & (lat <= lims[3])
+        img[~sel] = np.nan
     hdr = xy_header(h4)
     for k in ("SOLAR_B0", "RSUN_REF", "DSUN_OBS", "CROTA"):
         hdr[k] = h4[k]

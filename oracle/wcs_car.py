@@ -233,6 +233,8 @@ class WcsCar:
         self.eul = celset_cylindrical(self.crval[0], self.crval[1],
                                       float(hdr["LONPOLE"]) if "LONPOLE" in hdr else None,
                                       float(hdr["LATPOLE"]) if "LATPOLE" in hdr else None)
+        self.pc = pc
+        self.lonpole = float(self.eul[2])
         self.pixel_shape = (int(hdr["ZNAXIS1"] if "ZNAXIS1" in hdr else hdr["NAXIS1"]),
                             int(hdr["ZNAXIS2"] if "ZNAXIS2" in hdr else hdr["NAXIS2"]))
 

@@ -105,12 +105,55 @@ class _TimeDelta:
         return Quantity(self.seconds, "s")
 
 
+_EPOCH = datetime.datetime(2000, 1, 1, 12, 0, 0)
+
+
+def _iso_to_seconds(iso):
+    d = datetime.datetime.fromisoformat(str(iso).replace("Z", ""))
+    whole = d.replace(microsecond=0) - _EPOCH
+    return whole.days * 86400.0 + whole.seconds + d.microsecond * 1e-6
+
+
 class Time:
-    def __init__(self, iso):
-        self.t = iso.t if isinstance(iso, Time) else datetime.datetime.fromisoformat(str(iso))
+    """Scalar or array of UTC instants held as float seconds since J2000 (what the product and the oracle use; astropy
+    keeps two doubles, the 1e-7 s difference only shows in which imager frame is 'closest' at exact ties)."""
+
+    def __init__(self, value):
+        if isinstance(value, Time):
+            self.s = value.s
+        elif isinstance(value, (float, np.floating, np.ndarray)):
+            self.s = value
+        else:
+            self.s = _iso_to_seconds(value)
 
     def __sub__(self, other):
-        return _TimeDelta((self.t - other.t).total_seconds())
+        if isinstance(other, Time):
+            return _TimeDelta(self.s - other.s)
+        if isinstance(other, Quantity):
+            assert other.unit == "s"
+            return Time(self.s - other.value)
+        return NotImplemented
+
+    def __getitem__(self, i):
+        return Time(self.s[i])
+
+    def __len__(self):
+        return len(self.s)
+
+    def __iter__(self):
+        return (Time(v) for v in self.s)
+
+    @property
+    def shape(self):
+        return np.shape(self.s)
+
+    @property
+    def fits(self):
+        whole = int(np.floor(self.s))
+        ms = int(round((self.s - whole) * 1000.0))
+        if ms == 1000:
+            whole, ms = whole + 1, 0
+        return (_EPOCH + datetime.timedelta(seconds=whole)).strftime("%Y-%m-%dT%H:%M:%S") + ".%03d" % ms
 
 
 class FITSFixedWarning(Warning):
@@ -122,29 +165,141 @@ class SkyCoord:
 
 
 class _WcsPrm:
-    def __init__(self, ctype):
-        self.ctype = ctype
+    def __init__(self, ctype, pc=None, crpix=None, cdelt=None, crval=None, cunit=None):
+        self.ctype, self.pc, self.crpix, self.cdelt, self.crval, self.cunit = ctype, pc, crpix, cdelt, crval, cunit
+
+
+_TIME_SCALE = {"s": 1.0, "min": 60.0, "h": 3600.0, "d": 86400.0}
 
 
 class WCS:
-    """`astropy.wcs.WCS(header)` for 2-axis -TAN / -CAR headers, arithmetic from the oracle restatements."""
+    """`astropy.wcs.WCS(header)`: a celestial -TAN / -CAR pair (arithmetic from the oracle restatements) plus linear
+    spectral / time axes, with the handful of methods the reference calls: `dropaxis`, `deepcopy`, `sub(['spectral'])`,
+    `pixel_to_world`, `world_to_pixel`, `to_header`, `.wcs.ctype`, `.wcs.pc`, `.pixel_shape`."""
 
     def __init__(self, hdr):
-        from oracle import wcs_car, wcs_tan
+        import copy
         h = dict(hdr.items()) if hasattr(hdr, "items") else dict(hdr)
-        impl = wcs_car.WcsCar if str(h["CTYPE1"]).endswith("CAR") else wcs_tan.WcsTan
-        self._w = impl(h)
-        self.wcs = _WcsPrm([str(h["CTYPE1"]), str(h["CTYPE2"])])
-        self.pixel_shape = self._w.pixel_shape
+        n = int(h.get("WCSAXES", h.get("NAXIS", 2)))
+        rng = range(1, n + 1)
+        pc = np.eye(n)
+        for i in rng:
+            for j in rng:
+                if f"PC{i}_{j}" in h:
+                    pc[i - 1, j - 1] = float(h[f"PC{i}_{j}"])
+        self.wcs = _WcsPrm([str(h.get(f"CTYPE{i}", "")) for i in rng], pc,
+                           [float(h.get(f"CRPIX{i}", 0.0)) for i in rng], [float(h.get(f"CDELT{i}", 1.0)) for i in rng],
+                           [float(h.get(f"CRVAL{i}", 0.0)) for i in rng], [str(h.get(f"CUNIT{i}", "")).strip() for i in rng])
+        shape = [h.get(f"ZNAXIS{i}", h.get(f"NAXIS{i}")) for i in rng]
+        self._shape = [None if v is None else int(v) for v in shape]
+        self._has_pc = any(f"PC{i}_{j}" in h for i in rng for j in rng)
+        self._rota = h.get("CROTA2", h.get("CROTA")) if not self._has_pc else None
+        self._extra = {k: copy.copy(h[k]) for k in ("LONPOLE", "LATPOLE", "DATEREF", "DATE-BEG", "DATE-OBS", "DATE-AVG",
+                                                    "DATE-END", "RSUN_REF", "DSUN_OBS") if k in h}
 
-    def pixel_to_world(self, x, y):
-        lng, lat = self._w.pixel_to_world(x, y)
-        return [Quantity(lng, "deg"), Quantity(lat, "deg")]
+    @property
+    def naxis(self):
+        return len(self.wcs.ctype)
+
+    @property
+    def pixel_shape(self):
+        return None if any(v is None for v in self._shape) else tuple(self._shape)
+
+    def deepcopy(self):
+        import copy
+        return copy.deepcopy(self)
+
+    def _keep(self, keep):
+        w = self.deepcopy()
+        w.wcs = _WcsPrm([self.wcs.ctype[i] for i in keep], self.wcs.pc[np.ix_(keep, keep)].copy(),
+                        [self.wcs.crpix[i] for i in keep], [self.wcs.cdelt[i] for i in keep],
+                        [self.wcs.crval[i] for i in keep], [self.wcs.cunit[i] for i in keep])
+        w._shape = [self._shape[i] for i in keep]
+        return w
+
+    def dropaxis(self, axis):
+        return self._keep([i for i in range(self.naxis) if i != axis])
+
+    def sub(self, axes):
+        assert list(axes) == ["spectral"]
+        return self._keep([i for i, c in enumerate(self.wcs.ctype) if c[:4] in ("WAVE", "AWAV", "FREQ")])
+
+    def _celestial(self):
+        idx = [i for i, c in enumerate(self.wcs.ctype) if c[:4] in ("HPLN", "HPLT", "CRLN", "CRLT")]
+        return idx if len(idx) == 2 else None
+
+    def _celestial_header(self):
+        a, b = self._celestial()
+        w = self.wcs
+        for i in (a, b):
+            for j in range(self.naxis):
+                assert j in (a, b) or w.pc[i, j] == 0.0, "celestial axis coupled to a non-celestial one"
+        h = {"CTYPE1": w.ctype[a], "CTYPE2": w.ctype[b], "CUNIT1": w.cunit[a] or "deg", "CUNIT2": w.cunit[b] or "deg",
+             "CRPIX1": w.crpix[a], "CRPIX2": w.crpix[b], "CDELT1": w.cdelt[a], "CDELT2": w.cdelt[b],
+             "CRVAL1": w.crval[a], "CRVAL2": w.crval[b], "NAXIS1": self._shape[a] or 0, "NAXIS2": self._shape[b] or 0}
+        if self._has_pc:
+            h.update(PC1_1=w.pc[a, a], PC1_2=w.pc[a, b], PC2_1=w.pc[b, a], PC2_2=w.pc[b, b])
+        elif self._rota is not None:
+            h["CROTA2"] = self._rota
+        for k in ("LONPOLE", "LATPOLE"):
+            if k in self._extra:
+                h[k] = self._extra[k]
+        return h
+
+    def _impl(self):
+        from oracle import wcs_car, wcs_tan
+        h = self._celestial_header()
+        return (wcs_car.WcsCar if str(h["CTYPE1"]).endswith("CAR") else wcs_tan.WcsTan)(h)
+
+    def pixel_to_world(self, *pix):
+        pix = [np.asarray(p, dtype=np.float64) for p in pix]
+        assert len(pix) == self.naxis
+        cel = self._celestial()
+        out = [None] * self.naxis
+        if cel is not None:
+            lng, lat = self._impl().pixel_to_world(pix[cel[0]], pix[cel[1]])
+            out[cel[0]], out[cel[1]] = Quantity(lng, "deg"), Quantity(lat, "deg")
+        w = self.wcs
+        for k in range(self.naxis):
+            if out[k] is not None:
+                continue
+            lin = sum(w.pc[k, j] * (pix[j] + 1.0 - w.crpix[j]) for j in range(self.naxis))
+            world = w.crval[k] + w.cdelt[k] * lin
+            if w.ctype[k] in ("UTC", "TIME", "TAI", "TT"):
+                ref = self._extra.get("DATEREF", self._extra.get("DATE-BEG", self._extra.get("DATE-OBS")))
+                out[k] = Time(_iso_to_seconds(ref) + world * _TIME_SCALE.get(w.cunit[k], 1.0))
+            else:
+                out[k] = Quantity(world, w.cunit[k] or "")
+        return out if self.naxis > 1 else out[0]
 
     def world_to_pixel(self, lng, lat):
+        assert self.naxis == 2
         lng = lng.to("deg").value if isinstance(lng, Quantity) else lng
         lat = lat.to("deg").value if isinstance(lat, Quantity) else lat
-        return self._w.world_to_pixel(lng, lat)
+        return self._impl().world_to_pixel(lng, lat)
+
+    def to_header(self):
+        """Two celestial axes: degrees, PCi_j only where they differ from the identity (what wcslib's wcshdo writes)."""
+        from euispice_coreg_b200._compat import fits_lite
+        assert self.naxis == 2
+        impl = self._impl()
+        h = fits_lite.Header()
+        h["WCSAXES"] = 2
+        h["CRPIX1"], h["CRPIX2"] = impl.crpix
+        for key, val, default in (("PC1_1", impl.pc[0][0], 1.0), ("PC1_2", impl.pc[0][1], 0.0),
+                                  ("PC2_1", impl.pc[1][0], 0.0), ("PC2_2", impl.pc[1][1], 1.0)):
+            if val != default:
+                h[key] = float(val)
+        h["CDELT1"], h["CDELT2"] = impl.cdelt
+        h["CUNIT1"], h["CUNIT2"] = "deg", "deg"
+        h["CTYPE1"], h["CTYPE2"] = self.wcs.ctype
+        h["CRVAL1"], h["CRVAL2"] = impl.crval
+        h["LONPOLE"] = float(impl.lonpole)
+        h["LATPOLE"] = float(self._extra.get("LATPOLE", impl.crval[1]))
+        for k in ("DATE-OBS", "DATE-BEG", "DATE-AVG", "DATE-END", "RSUN_REF", "DSUN_OBS"):
+            if k in self._extra:
+                h[k] = self._extra[k]
+        return h
 
 
 class _HeaderDiff:
