@@ -36,6 +36,10 @@ standard library's shared memory as `multiprocess.shared_memory`, and `astropy.w
             helioprojective x4, Carrington "fa", initial Carrington -- bit for bit
             (`tests/golden/make_alignment_golden.py` -> `alignment_golden.npz`, `tests/test_reference_golden.py`).
             The Carrington "fa" chain (`utils/rectify.py`, NumPy dtype trail included) involves no WCS: fully pinned.
+            `oracle.synras` (+ the SPICE search through `oracle.hpc`) against the reference's own
+            `SPICEComposedMapBuilder.process` and `AlignmentSpice.align_using_helioprojective`: synthetic raster, composed
+            header and three cubes bit for bit (`make_spice_golden.py` -> `spice_golden.npz`,
+            `tests/test_reference_golden_spice.py`).
             `oracle.pxlshift` against the reference's own `AlignmentPixels.find_best_parameters`, bit for bit
             (`make_pxlshift_golden.py` -> `pxlshift_golden.npz`, `tests/test_pxlshift.py`).
             `oracle.pearson` against the reference's numba `c_correlate` (`make_pearson_golden.py`);
