@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--out", default="gpurun_out/config_runs.json")
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--skip", default="")
+    ap.add_argument("--grid5d-full", action="store_true",
+                    help="configs[3] at BASELINE size: 20 x 20 x 10 x 16 x 16 = 1.024e6 lags (crota step 0.1 deg, "
+                         "cdelt step 0.001 arcsec; SURVEY 8d)")
     args = ap.parse_args()
     skip = set(args.skip.split(","))
     pl, ps = bench.ensure_config1()
@@ -97,6 +100,10 @@ def main():
         lags = dict(lag_crval1=np.arange(12, 36, 1.0), lag_crval2=np.arange(-6, 18, 1.0),
                     lag_cdelt1=np.arange(-0.002, 0.0021, 0.001), lag_cdelt2=np.arange(-0.002, 0.0021, 0.001),
                     lag_crota=np.arange(-0.25, 0.3, 0.1))
+        if args.grid5d_full:
+            lags = dict(lag_crval1=np.arange(14, 34, 1.0), lag_crval2=np.arange(-4, 16, 1.0),
+                        lag_cdelt1=(np.arange(16) - 8) * 0.001, lag_cdelt2=(np.arange(16) - 8) * 0.001,
+                        lag_crota=(np.arange(10) - 5) * 0.1)
         n = int(np.prod([len(v) for v in lags.values()]))
         run = lambda: Alignment(pl, ps, parallelism=True, cdelt_semantics="intended", **lags)\
             .align_using_helioprojective(return_type="corr")  # noqa: E731
