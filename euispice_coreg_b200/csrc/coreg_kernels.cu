@@ -834,12 +834,6 @@ __device__ __forceinline__ double recip_1me_div(double e) {
   return (den > 0.0) ? 1.0 / den : CUDART_NAN;
 }
 
-// v in [0, 1)  <=>  sign bit clear and biased exponent < 1023: one unsigned compare on the high word
-// (false for negatives, -0.0, NaN and Inf)
-__device__ __forceinline__ bool in_unit_interval(double v) {
-  return (unsigned)__double2hiint(v) < 0x3FF00000u;
-}
-
 // |v| < 2^30 (false for NaN / Inf): the range in which the magic-number floor of the fast kernels is exact
 __device__ __forceinline__ bool small_magnitude(double v) {
   return (unsigned)(__double2hiint(v) & 0x7FFFFFFF) < 0x41D00000u;
@@ -2568,7 +2562,7 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   if ((large_dtype != COREG_F32 && large_dtype != COREG_F64) || (small_dtype != COREG_F32 && small_dtype != COREG_F64))
     return fail(COREG_EINVAL, "coreg_hpc_search_host: dtype must be COREG_F32 or COREG_F64");
   const int64_t ns = (int64_t)snx * sny, nl = (int64_t)lnx * lny;
-  const size_t lsz = large_dtype == COREG_F32 ? 4 : 8, ssz = small_dtype == COREG_F32 ? 4 : 8;
+  const size_t lsz = large_dtype == COREG_F32 ? 4 : 8;
   const size_t work_bytes = coreg_lag_corr_workspace_bytes(snx, sny, n_lags);
   const bool fast = (order == 2) && !(flags & (COREG_FLAG_STRICT | COREG_FLAG_NO_FAST)) && snx >= 3 && sny >= 3;
   void *d_large = nullptr, *d_small_in = nullptr;
