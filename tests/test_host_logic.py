@@ -313,6 +313,45 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert lib.coreg_lag_corr_workspace_bytes(0, 5, 5) == 0
 
 
+def test_c_abi_argument_validation_needs_no_device():
+    """Error behaviour at the boundary: bad arguments come back as negative COREG_E* codes with a message, before any
+    CUDA call (these calls touch no device memory, so they run on the CPU box)."""
+    from euispice_coreg_b200 import _ext
+    lib = _ext.load()
+    null, fake = None, ctypes.c_void_p(0x1000)          # never dereferenced: validation fails first
+    EINVAL, ENOMEM = -1, -3
+    assert ctypes.sizeof(ctypes.c_double) * _ext.LAG_CAR_DOUBLES == 128
+
+    def msg():
+        return lib.coreg_last_error().decode()
+
+    rc = lib.coreg_hpc_lag_corr(null, null, 0, 8, 8, 8, 8, null, null, 4, 2, null, null, 0, null, null, 0, null)
+    assert rc == EINVAL and "null pointer" in msg()
+    rc = lib.coreg_car_lag_corr(fake, fake, 7, 8, 8, 8, 8, fake, fake, 4, 2, fake, fake, 1 << 30, fake, null, 0, null)
+    assert rc == EINVAL and "small_dtype" in msg()
+    rc = lib.coreg_hpc_lag_corr(fake, fake, _ext.F64, 8, 8, 8, 8, fake, fake, 4, 2, fake, fake, 16, fake, null, 0, null)
+    assert rc == ENOMEM and "workspace" in msg()
+    rc = lib.coreg_car_pix2world(null, 8, 8, fake, fake, null)
+    assert rc == EINVAL and "CoregLagCar" in msg()
+    singular = np.zeros(_ext.LAG_CAR_DOUBLES)
+    rc = lib.coreg_car_pix2world(singular.ctypes.data_as(ctypes.c_void_p), 8, 8, fake, fake, null)
+    assert rc == EINVAL and "singular" in msg()
+    tan = _ext.CoregTanWcs(1, 1, 0.0, 1.0, 1, 0, 0, 1, 0, 0, 180)     # CDELT1 = 0
+    rc = lib.coreg_tan_pix2world(ctypes.byref(tan), 8, 8, 0, fake, fake, null)
+    assert rc == EINVAL and "singular" in msg()
+    # pixel shift: `_check_boundaries` (pxlshift/alignment_pixels.py:150-156) on the host lag arrays
+    dx, dy = (ctypes.c_int * 2)(0, 9), (ctypes.c_int * 1)(0)
+    need = lib.coreg_pixel_shift_workspace_bytes(10, 10, 2, 1, 1)
+    assert need == 1 * 2 * 64 + (2 + 1 + 2) * 4
+    rc = lib.coreg_pixel_shift_corr(fake, 20, 20, fake, 1, 10, 10, 5, 5, dx, 2, dy, 1, fake, fake, need, fake, null, null)
+    assert rc == EINVAL and msg() == "too large shift : outside FSI"
+    rc = lib.coreg_pixel_shift_corr(fake, 20, 20, fake, 1, 10, 10, 5, 5, dx, 2, dy, 1, fake, fake, need - 1, fake, null,
+                                    null)
+    assert rc == ENOMEM
+    rc = lib.coreg_map_coordinates(fake, 5, 4, 4, fake, fake, 10, 2, 0.0, fake, _ext.F64, null)
+    assert rc == EINVAL and "dtype" in msg()
+
+
 # ----------------------------------------------------------------------------------------------- multi-rank
 _GLOO = r"""
 import os, sys
