@@ -37,6 +37,12 @@ K1_DRAM_BYTES_PER_LAUNCH = 1708.3e6  # dram__bytes_read.sum + dram__bytes_write.
 FP64_EXECUTED_PER_SAMPLE = 31.7  # FP64 thread-instructions the column-rolling kernel executes per pixel-sample = the
 #                                  algorithmic count of ITS formulation (ncu: DADD + DMUL + DFMA of
 #                                  one launch / pixel-samples, profiles/r1_roll_kernel.md)
+# mixed-arithmetic rolling kernel (FP64 projection, FP32 spline; the default when the small image is float32), from one
+# ncu --set full capture of a config-1 launch (profiles/r1_ncu_roll_mixed_v1.txt): 2.3086e10 warp-instructions and
+# 9.80e10 FP64 thread-instructions over 1.51e10 pixel-samples = 4.72e8 warp-samples
+MIXED_INSTR_PER_WARP_SAMPLE = 48.9   # all warp-instructions per warp-sample (32 pixel-samples)
+MIXED_FP64_PER_SAMPLE = 6.5          # of which FP64 (4 per pixel for the two coordinate quadratics + per-lag set-up)
+MIXED_DRAM_BYTES_PER_LAUNCH = 842.2e6   # dram read 137.3 MB + write 704.9 MB of that launch
 BYTES_PER_SAMPLE = 8.0         # un-amortised: one f32 sample of each image per pixel-sample
 LAGS = dict(lag_crval1=np.arange(-30, 30, 1.0), lag_crval2=np.arange(-30, 30, 1.0), lag_cdelt1=np.array([0.0]),
             lag_cdelt2=np.array([0.0]), lag_crota=np.array([0.0]))
@@ -279,7 +285,7 @@ def run_gpu(args):
     n_pix = gnx * gny
 
     eng = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage,
-                            no_fast=args.no_fast)
+                            no_fast=args.no_fast, arithmetic=args.arithmetic)
     eng.set_small(a.data_small)
     eng.prepare_hpc(a.data_large, w_large, w_small)
     table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
@@ -335,7 +341,8 @@ def run_gpu(args):
 
     def e2e_step():
         e = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage,
-                              no_fast=args.no_fast)
+                              no_fast=args.no_fast, arithmetic=args.arithmetic)
+        e.pure_shift_hint = eng.pure_shift_hint     # what hpc_lag_table derived from the lag grid
         e.set_small(h_small)
         e.prepare_hpc(h_large, w_large, w_small)
         return e.search(table)
@@ -393,13 +400,65 @@ def run_gpu(args):
         per_sample = FP64_EXECUTED_PER_SAMPLE if fast else FP64_INSTR_PER_SAMPLE
         ach_exec = per_sample * samples_per_launch / (k1_avg_ms * 1e-3)
         ach_gbs = BYTES_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3) / 1e9
+        mixed = fast and eng.arithmetic == "mixed" and eng.small32 is not None
+        roof_fp64 = {"bound": "fp64", "achieved": ach_exec / 1e12, "peak": fp64_peak / 1e12,
+                     "unit": "T FP64-instr/s", "frac": ach_exec / fp64_peak,
+                     "traffic": K1_DRAM_BYTES_PER_LAUNCH * (hi - lo) / 3600.0 if (fast and n_lags == 3600) else None,
+                     "traffic_unit": "B per launch (ncu DRAM read + write of one full 3600-lag launch, scaled by "
+                                     "this rank's share of the lags)",
+                     "kernel": "lag_corr_roll_kernel" if fast else "lag_corr_kernel<TanCoord>",
+                     "kernel_ms": k1_avg_ms,
+                     "algorithmic": f"{per_sample:.1f} FP64 instr/pixel-sample x {samples_per_launch:.3e} "
+                                    "pixel-samples/launch (homography + shared-floor formulation, DESIGN.md 5)"
+                                    if fast else f"{per_sample:.0f} FP64 instr/pixel-sample (SURVEY 8d)",
+                     "peak_source": "coreg_fp64_peak DFMA microbenchmark, this run",
+                     "note": "the FP64 pipe is the binding unit but a DFMA blocks the warp scheduler's dispatch "
+                             "port for 2 cycles and every other instruction for 1, so the reachable fraction "
+                             "for this instruction mix is about 0.8 (profiles/r1_roll_kernel.md)"}
+        extra = {}
+        if mixed:
+            # The mixed kernel took the spline off the FP64 pipe; what bounds it is the warp scheduler's dispatch
+            # port (one instruction per cycle and SM sub-partition, an FP64 instruction holds it for two:
+            # profiles/r1_fp64_issue_model.md). Needed dispatch cycles per warp-sample = all instructions + the
+            # FP64 ones once more; peak = SMs x 4 sub-partitions x the SM clock sampled during the timed region.
+            sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+            sms = _ext.load().coreg_device_sm_count()
+            sms = sms if sms > 0 else 148
+            slots_peak = sms * 4 * sm_hz
+            need = (MIXED_INSTR_PER_WARP_SAMPLE + MIXED_FP64_PER_SAMPLE) * samples_per_launch / 32.0
+            ach_slots = need / (k1_avg_ms * 1e-3)
+            ach_f = MIXED_FP64_PER_SAMPLE * samples_per_launch / (k1_avg_ms * 1e-3)
+            roof = {"bound": "issue", "achieved": ach_slots / 1e9, "peak": slots_peak / 1e9,
+                    "unit": "G warp-dispatch cycles/s", "frac": ach_slots / slots_peak,
+                    "traffic": MIXED_DRAM_BYTES_PER_LAUNCH * (hi - lo) / 3600.0 if n_lags == 3600 else None,
+                    "traffic_unit": roof_fp64["traffic_unit"],
+                    "kernel": "lag_corr_roll_kernel<MIXED>", "kernel_ms": k1_avg_ms,
+                    "algorithmic": f"({MIXED_INSTR_PER_WARP_SAMPLE} instr + {MIXED_FP64_PER_SAMPLE} FP64 counted "
+                                   f"twice) dispatch cycles per warp-sample x {samples_per_launch / 32.0:.3e} "
+                                   "warp-samples/launch (ncu instruction mix of this kernel, DESIGN.md 5)",
+                    "peak_source": f"{sms} SMs x 4 sub-partitions x {sm_hz / 1e6:.0f} MHz (nvidia-smi median under "
+                                   "load, this run)",
+                    "note": "neither HBM nor tensor cores nor, after the FP32 spline, the FP64 pipe binds this "
+                            "kernel: the warp scheduler does. roofline_fp64 gives the FP64 pipe's share, "
+                            "roofline_survey the rate on SURVEY 8d's 69-instruction count"}
+            extra["roofline_fp64"] = {"bound": "fp64", "achieved": ach_f / 1e12, "peak": fp64_peak / 1e12,
+                                      "unit": "T FP64-instr/s", "frac": ach_f / fp64_peak,
+                                      "algorithmic": f"{MIXED_FP64_PER_SAMPLE} FP64 instr/pixel-sample executed by "
+                                                     "the mixed kernel (the all-FP64 kernel needs 31.7 and reaches "
+                                                     "0.64 of this peak: --arithmetic fp64)",
+                                      "peak_source": roof_fp64["peak_source"]}
+        else:
+            roof = roof_fp64
+        arith_name = ("strict (scipy op order)" if args.strict else
+                      ("mixed: fp64 projection, fp32 spline + segment sums" if mixed else "fp64 fma"))
         line = {
             "metric": "lag_evals_per_s", "value": value, "unit": "lag-evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64+f32" if mixed else "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "lags": n_lags, "grid": [gny, gnx], "spline_order": 2,
-                       "arithmetic": "strict (scipy op order)" if args.strict else "fp64 fma", "variant": args.variant, "kernel": "generic" if (args.no_fast or args.strict) else "fast", "small_storage": str(eng.small.dtype).replace("torch.", ""),
+                       "arithmetic": arith_name, "variant": args.variant, "kernel": "generic" if (args.no_fast or args.strict) else "fast", "small_storage": str(eng.small.dtype).replace("torch.", ""),
                        "parallelism": f"lag-sharded x{world}",
                        "l2": "flushed: a 256 MiB device buffer is rewritten before every timed step (inside the timed "
                              f"region); every step also rewrites its {eng._work.numel() * 8 / 1e6:.0f} MB partials "
@@ -417,20 +476,8 @@ def run_gpu(args):
             # lag kernel and the finalize kernel (the L2 flush memset and the NCCL all-gather are not ours)
             "gpu_launches": int(k1_launches * (3 if fast else 2)),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": ach_exec / 1e12, "peak": fp64_peak / 1e12,
-                         "unit": "T FP64-instr/s", "frac": ach_exec / fp64_peak,
-                         "traffic": K1_DRAM_BYTES_PER_LAUNCH * (hi - lo) / 3600.0 if (fast and n_lags == 3600) else None,
-                         "traffic_unit": "B per launch (ncu DRAM read + write of one full 3600-lag launch, scaled by "
-                                         "this rank's share of the lags)",
-                         "kernel": "lag_corr_roll_kernel" if fast else "lag_corr_kernel<TanCoord>",
-                         "kernel_ms": k1_avg_ms,
-                         "algorithmic": f"{per_sample:.1f} FP64 instr/pixel-sample x {samples_per_launch:.3e} "
-                                        "pixel-samples/launch (homography + shared-floor formulation, DESIGN.md 5)"
-                                        if fast else f"{per_sample:.0f} FP64 instr/pixel-sample (SURVEY 8d)",
-                         "peak_source": "coreg_fp64_peak DFMA microbenchmark, this run",
-                         "note": "the FP64 pipe is the binding unit but a DFMA blocks the warp scheduler's dispatch "
-                                 "port for 2 cycles and every other instruction for 1, so the reachable fraction "
-                                 "for this instruction mix is about 0.8 (profiles/r1_roll_kernel.md)"},
+            "roofline": roof,
+            **extra,
             "roofline_survey": {"bound": "fp64", "achieved": ach_instr / 1e12, "peak": fp64_peak / 1e12,
                                 "unit": "T FP64-instr/s", "frac": ach_instr / fp64_peak,
                                 "algorithmic": f"{FP64_INSTR_PER_SAMPLE:.0f} FP64 instr/pixel-sample: SURVEY 8d's count "
@@ -460,6 +507,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--strict", action="store_true", help="scipy operation order in the spline (no FMA)")
     ap.add_argument("--variant", type=int, default=0, help="kernel tuning variant (tile/occupancy)")
+    ap.add_argument("--arithmetic", default=None, choices=["fp64", "mixed"],
+                    help="homography kernel: everything in FP64, or FP64 projection + FP32 spline (engine default)")
     ap.add_argument("--no-fast", action="store_true", help="force the generic fused kernel")
     ap.add_argument("--small-storage", default="f64", choices=["auto", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
 F32, F64, I32 = 0, 1, 2
 FLAG_STRICT = 1
 FLAG_NO_FAST = 4
+FLAG_MIXED = 8      # coreg_hpc_search_host: mixed-arithmetic kernel when the small payload is float32
 
 
 def make_flags(strict=False, variant=0, no_fast=False):
@@ -63,6 +64,9 @@ _SIGNATURES = {
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                          _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_hpc_lag_corr_wcs_mixed": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P,
+                                               _P, C.c_int, _P]),
     "coreg_tan_homography_emax": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P]),
     "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
@@ -297,9 +301,11 @@ def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
                                       int(flags), _stream()), "coreg_hpc_lag_corr")
 
 
-def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_out, nvalid_out=None, flags=0):
+def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_out, nvalid_out=None, flags=0,
+                     small32=None):
     """K1, homography form. `lag_wcs`: device float64 [n_lags, 11] (CoregTanWcs rows of the shifted headers);
-    `grid_wcs`: `_compat.wcs.TanWcs` of the common grid."""
+    `grid_wcs`: `_compat.wcs.TanWcs` of the common grid. `small32` (the float32 payload `small` was widened from)
+    selects the mixed-arithmetic kernel: FP64 projection, FP32 spline."""
     torch = _torch()
     lib = load()
     _require_cuda(ref, small, lag_wcs, pivots, work, corr_out)
@@ -309,6 +315,18 @@ def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_ou
         raise TypeError("the homography kernel reads a float64 small image")
     gny, gnx = ref.shape
     g = tan_struct(grid_wcs)
+    if small32 is not None:
+        _require_cuda(small32)
+        if small32.dtype != torch.float32 or small32.shape != small.shape or not small32.is_contiguous():
+            raise TypeError("small32 must be the contiguous float32 twin of small")
+        with torch.cuda.device(ref.device):
+            _check(lib.coreg_hpc_lag_corr_wcs_mixed(
+                _ptr(ref), _ptr(small), _ptr(small32), small.shape[1], small.shape[0], gnx, gny, C.byref(g),
+                _ptr(lag_wcs), lag_wcs.shape[0], int(order), _ptr(pivots), _ptr(work),
+                work.numel() * work.element_size(), _ptr(corr_out),
+                _ptr(nvalid_out) if nvalid_out is not None else None, int(flags), _stream()),
+                "coreg_hpc_lag_corr_wcs_mixed")
+        return
     with torch.cuda.device(ref.device):
         _check(lib.coreg_hpc_lag_corr_wcs(_ptr(ref), _ptr(small), small.shape[1], small.shape[0], gnx, gny,
                                           C.byref(g), _ptr(lag_wcs), lag_wcs.shape[0], int(order), _ptr(pivots),

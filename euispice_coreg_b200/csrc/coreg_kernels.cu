@@ -1273,6 +1273,82 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
   }
 }
 
+// The same segment in MIXED arithmetic: coordinates in FP64 (7 instructions per pixel), the spline and the segment's
+// moments in FP32 on a float32 copy of the small image. The reference rounds every sample to float32 anyway
+// (`alignment.py:1024`), so an FP32 spline differs from it by about one float32 ulp per sample, unbiased; the
+// Pearson sums average that over 4e6 samples (|dr| ~ 1e-9 measured, bar 1e-6). A DFMA occupies the dispatch port
+// for two cycles and an FFMA for one (profiles/r1_fp64_issue_model.md), so moving the 23 spline / moment
+// instructions off the FP64 pipe is what shortens the issue-bound loop.
+// The fractional parts leave the FP64 domain without a conversion instruction: the coordinate FMA adds
+// kFracMagic = 1.5 * 2^29, whose ulp is 2^-23, so the low word of the result is round((x - floor_x0) * 2^23): bits
+// 23.. must be zero for x (p for y: the row index inside the segment), the low 23 bits are the float32 mantissa of
+// 1 + frac. `vbad` collects the bits that must be zero; the caller re-evaluates the segment pixel by pixel when
+// vbad >= 2^23 (a floor changed inside the segment, or a fraction rounded up to 1).
+constexpr double kFracMagic = 805306368.0;   // 1.5 * 2^29
+template <int MODE, int P>
+__device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ small32, unsigned tap,
+                                                   unsigned row_elems, double be, double bnx, double bny, double he1,
+                                                   double hx1, double hy1, double inv0, double xoffm, double yoffm,
+                                                   float pivot_b, const float (&a_c)[P], float& sb, float& sbb,
+                                                   float& sab, unsigned& vbad) {
+  auto row = [&](unsigned t, float& ca, float& cb, float& cc) {
+    const float ta = __ldg(small32 + t), tb = __ldg(small32 + t + 1), tc = __ldg(small32 + t + 2);
+    ca = 0.5f * (ta + tb);
+    cb = tb - ta;
+    cc = fmaf(0.5f, ta + tc, -tb);
+  };
+  float r0a, r0b, r0c, r1a, r1b, r1c, r2a, r2b, r2c;
+  row(tap, r0a, r0b, r0c);
+  row(tap += row_elems, r1a, r1b, r1c);
+  row(tap += row_elems, r2a, r2b, r2c);
+  double qx0 = 0, qx1 = 0, qx2 = 0, qy0 = 0, qy1 = 0, qy2 = 0;
+  if (MODE == 0) {
+    const double dinv = fma(be + be, he1, he1);   // d(1 + e + e^2) / dp at the first pixel
+    qx0 = fma(bnx, inv0, xoffm);
+    qy0 = fma(bny, inv0, yoffm);
+    qx1 = fma(hx1, inv0, bnx * dinv);
+    qy1 = fma(hy1, inv0, bny * dinv);
+    qx2 = hx1 * dinv;
+    qy2 = hy1 * dinv;
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    float r3a = 0.f, r3b = 0.f, r3c = 0.f;
+    if (p + 1 < P) row(tap += row_elems, r3a, r3b, r3c);
+    double cx, cy;   // coordinate - shared floor + kFracMagic
+    if (MODE == 0) {
+      // |e| <= 2^-18 over the whole grid: along the segment 1 / (1 - e) is linear in p to 5e-13 (its slope
+      // he1 (1 + 2 e) is below 4e-9 per row), so numerator x reciprocal is a quadratic in p whose coefficients the
+      // caller formed once per lag: two FMAs per coordinate instead of seven instructions for both
+      cx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
+      cy = (p == 0) ? qy0 : fma(fma(qy2, (double)p, qy1), (double)p, qy0);
+    } else {
+      const double e = (p == 0) ? be : fma(he1, (double)p, be);
+      const double inv = (p == 0) ? inv0 : recip_1me_small(e);
+      const double nx = (p == 0) ? bnx : fma(hx1, (double)p, bnx);
+      const double ny = (p == 0) ? bny : fma(hy1, (double)p, bny);
+      cx = fma(nx, inv, xoffm);
+      cy = fma(ny, inv, yoffm);
+    }
+    const unsigned ux = (unsigned)__double2loint(cx);
+    const unsigned uy = (unsigned)__double2loint(cy) ^ ((unsigned)p << 23);
+    vbad |= ux | uy;
+    const float vx = __uint_as_float(ux | 0x3F800000u) - 1.0f;
+    const float vy = __uint_as_float(uy | 0x3F800000u) - 1.0f;
+    const float q0 = fmaf(fmaf(r0c, vx, r0b), vx, r0a);
+    const float q1 = fmaf(fmaf(r1c, vx, r1b), vx, r1a);
+    const float q2 = fmaf(fmaf(r2c, vx, r2b), vx, r2a);
+    // sample - pivot in one go: the pivot rides in the constant term of the y quadratic
+    const float bc = fmaf(fmaf(fmaf(0.5f, q0 + q2, -q1), vy, q1 - q0), vy, fmaf(0.5f, q0 + q1, -pivot_b));
+    sb += bc;
+    sbb = fmaf(bc, bc, sbb);
+    sab = fmaf(a_c[p], bc, sab);
+    r0a = r1a; r0b = r1b; r0c = r1c;
+    r1a = r2a; r1b = r2b; r1c = r2c;
+    r2a = r3a; r2b = r3b; r2c = r3c;
+  }
+}
+
 // One pixel by the per-pixel rules: own floors, 9 taps when they are all inside the image, otherwise the exact
 // out-of-line sampler. (sx, sy) are the coordinates + 0.5. Returns false when the sample is missing.
 template <bool ROUND32>
@@ -1310,11 +1386,11 @@ __device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ sma
 // segment or -- image borders, irregular columns (rotated lags), missing pixels, division-mode lags -- the segment
 // pixel by pixel. Out: the thread's Sb, Sbb, Sab over its valid samples and the mask of pixels that have a finite
 // reference value but no valid sample.
-template <bool ROUND32, int P>
-__device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small, int snx, int sny,
-                                         unsigned row_elems, double di, double dj0, const double (&a_c)[P],
-                                         unsigned a_ok, bool all_ref, double pivot_b, double& sb, double& sbb,
-                                         double& sab, unsigned& miss) {
+template <bool ROUND32, int P, bool MIXED, typename AT>
+__device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small,
+                                         const float* __restrict__ small32, int snx, int sny, unsigned row_elems,
+                                         double di, double dj0, const AT (&a_c)[P], unsigned a_ok, bool all_ref,
+                                         double pivot_b, double& sb, double& sbb, double& sab, unsigned& miss) {
   const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
   const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
   // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
@@ -1332,7 +1408,32 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
   bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
               ((unsigned)(ix0 - 1) < (unsigned)(snx - 2)) && (iy0 >= 1) && (iy0 + P <= sny - 1);
-  if (fast) {
+  if constexpr (MIXED) {
+    // the low word of coordinate + kFracMagic holds the offset from the shared floor only while that offset stays
+    // below 2^9 pixels: true for any sane lag, guaranteed here by bounding the per-row slopes (block-uniform test)
+    fast = fast && (fabs(hx1) < 8.0) && (fabs(hy1) < 8.0);
+    if (fast) {
+      const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
+      // xoff + kFracMagic rounds to 2^-23 pixel; the residual (exact) goes into the numerator, whose factor inv is
+      // 1 + O(2^-7): what is lost is below 1e-9 pixel, the same for every pixel of the lag
+      const double xoffm = xoff + kFracMagic, yoffm = yoff + kFracMagic;
+      const double bnx2 = bnx + (xoff - (xoffm - kFracMagic)), bny2 = bny + (yoff - (yoffm - kFracMagic));
+      float fsb = 0.f, fsbb = 0.f, fsab = 0.f;
+      unsigned vbad = 0;
+      if (mode == 0)
+        roll_segment_mixed<0, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+                                 (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
+      else
+        roll_segment_mixed<1, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+                                 (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
+      // every offset inside its cell, every sample finite (a non-finite sample makes Sbb non-finite; so does a
+      // finite sample beyond 1.8e19, which then just takes the exact path)
+      fast = (vbad < 0x00800000u) && ((__float_as_uint(fsbb) & 0x7F800000u) != 0x7F800000u);
+      sb = (double)fsb;
+      sbb = (double)fsbb;
+      sab = (double)fsab;
+    }
+  } else if (fast) {
     const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
     unsigned vmax = 0, bmax = 0;
     if (mode == 0)
@@ -1357,10 +1458,11 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
       const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
       const double sx = fma(fma(hx1, (double)p, bnx), inv, x0h);
       const double sy = fma(fma(hy1, (double)p, bny), inv, y0h);
-      double ac = a_c[0];
+      AT acs = a_c[0];
 #pragma unroll
       for (int q = 1; q < P; ++q)
-        if (q == p) ac = a_c[q];
+        if (q == p) acs = a_c[q];
+      const double ac = (double)acs;
       double b;
       if (sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, &b)) {
         const double bc = b - pivot_b;
@@ -1394,9 +1496,10 @@ struct RollWShared {
   HomLag lag[kWarps][kRollChunk];
 };
 
-template <typename RefT, bool ROUND32, int P, int MINB>
+template <typename RefT, bool ROUND32, int P, int MINB, bool MIXED>
 __global__ void __launch_bounds__(kThreads, MINB)
-lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small, int snx, int sny, int gnx,
+lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small,
+                      const float* __restrict__ small32, int snx, int sny, int gnx,
                       int gny, const HomLag* __restrict__ lags, int n_lags, int lags_per_block,
                       const double* __restrict__ pivots, double* __restrict__ wrec, double* __restrict__ wcorr,
                       double* __restrict__ wconst, unsigned* __restrict__ wmask) {
@@ -1411,29 +1514,35 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
   const int tx = tid & (kTileW - 1), rg = tid / kTileW;
   const int gx = tile_x * kTileW + tx;
   const int gy0 = tile_y * TILE_H + rg * P;
-  const double pivot_a = pivots[0], pivot_b = pivots[1];
+  // MIXED: float32-representable pivots, so that the float32 segment sums and the FP64 fallback subtract the same
+  // numbers and a - pivot_a is (nearly always) exact in float32. r does not depend on the pivots.
+  const double pivot_a = MIXED ? (double)(float)pivots[0] : pivots[0];
+  const double pivot_b = MIXED ? (double)(float)pivots[1] : pivots[1];
   const unsigned row_elems = (unsigned)snx;
   const double di = (double)gx, dj0 = (double)gy0;
   const size_t wid = (size_t)tile * kWarps + warp;   // this warp's record row
 
-  double a_c[P];
+  using AT = typename std::conditional<MIXED, float, double>::type;
+  AT a_c[P];
   unsigned a_ok = 0;
   double sa_all = 0.0, saa_all = 0.0;
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const int gy = gy0 + p;
-    a_c[p] = 0.0;
+    a_c[p] = (AT)0;
     if (gx < gnx && gy < gny) {
       const double a = (double)ref[(int64_t)gy * gnx + gx];
       if (isfinite(a)) {
-        a_c[p] = a - pivot_a;
+        a_c[p] = (AT)(a - pivot_a);
         a_ok |= 1u << p;
-        sa_all += a_c[p];
-        saa_all = fma(a_c[p], a_c[p], saa_all);
+        // MIXED: every sum sees the float32 value of a - pivot_a, i.e. one consistent reference image
+        const double ac = (double)a_c[p];
+        sa_all += ac;
+        saa_all = fma(ac, ac, saa_all);
       }
     }
   }
-  const bool all_ref = a_ok == ((1u << P) - 1u);
+  const bool all_ref = a_ok == ((P >= 32) ? 0xFFFFFFFFu : ((1u << (P & 31)) - 1u));
   if (blockIdx.y == 0) {
     // lag-independent reference moments of this warp's pixels (n, Sa, Saa): one record per warp, written once
     double wsa = sa_all, wsaa = saa_all;
@@ -1466,8 +1575,8 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
     for (int l = 0; l < cnt; ++l) {
       double sb, sbb, sab;
       unsigned miss;
-      roll_lag<ROUND32, P>(S.lag[warp][l], small, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb, sbb,
-                           sab, miss);
+      roll_lag<ROUND32, P, MIXED, AT>(S.lag[warp][l], small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref,
+                                      pivot_b, sb, sbb, sab, miss);
       S.acc[warp][l][0][lane] = sb;
       S.acc[warp][l][1][lane] = sbb;
       S.acc[warp][l][2][lane] = sab;
@@ -1476,8 +1585,9 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
 #pragma unroll
         for (int p = 0; p < P; ++p)
           if (miss & (1u << p)) {
-            m[1] += a_c[p];
-            m[2] = fma(a_c[p], a_c[p], m[2]);
+            const double ac = (double)a_c[p];
+            m[1] += ac;
+            m[2] = fma(ac, ac, m[2]);
           }
         const double tot = warp_transpose_reduce4(m, lane);  // lanes 0, 8, 16: n, Sa, Saa of the missing pixels
         if ((lane & 7) == 0 && lane < 24) wcorr[(wid * n_lags + (l0 + l)) * 3 + (lane >> 3)] = tot;
@@ -1628,12 +1738,17 @@ int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
 }
 
 // rolling kernel + its finalize. Tuning variants (flags bits 8..11): rows per thread 12 (default), 16, 14; the
-// workspace layout is sized for 12 (fewer rows per thread would need more record rows)
+// workspace layout is sized for 12 (fewer rows per thread would need more record rows). small32 != nullptr selects
+// the mixed-arithmetic kernel (FP64 coordinates, FP32 spline on the float32 copy of the small image); its variants
+// 3 / 4 are 12 / 16 rows per thread at 3 resident CTAs per SM.
 template <typename RefT, bool ROUND32>
 int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
-                     const double* small, int snx, int sny, const HomLag* ft, const double* pivots, void* work,
-                     double* corr, int64_t* nvalid, bool prof) {
-  const int rows_per_thread = (variant == 1) ? 16 : ((variant == 2) ? 14 : kRollWRows);
+                     const double* small, const float* small32, int snx, int sny, const HomLag* ft,
+                     const double* pivots, void* work, double* corr, int64_t* nvalid, bool prof) {
+  const bool mixed = small32 != nullptr;
+  const int minb = (mixed && (variant == 3 || variant == 4)) ? 3 : 2;
+  const int rows_per_thread = (variant == 1 || variant == 4) ? 16 : ((variant == 2 && !mixed) ? 14 :
+                              ((mixed && variant == 5) ? 24 : ((mixed && variant == 6) ? 32 : kRollWRows)));
   const RollWLayout L = rollw_layout(gnx, gny, n_lags);
   char* base = static_cast<char*>(work);
   double* wrec = reinterpret_cast<double*>(base + L.rec);
@@ -1642,18 +1757,28 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
   unsigned* wmask = reinterpret_cast<unsigned*>(base + L.mask);
   dim3 grid;
   int lpb, tiles;
-  if (!lag_grid(kRowsPerPass * rows_per_thread, 2, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk))
+  if (!lag_grid(kRowsPerPass * rows_per_thread, minb, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk))
     return fail(COREG_EINVAL, "lag grid too large for one launch");
   CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
   if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
-#define RW(P_)                                                                                                       \
+#define RW(P_, MINB_, MIXED_)                                                                                        \
   {                                                                                                                  \
-    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2>;                                                          \
+    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, MINB_, MIXED_>;                                              \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));               \
-    kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, snx, sny, gnx, gny, ft, (int)n_lags, lpb, pivots,   \
-                                                     wrec, wcorr, wconst, wmask);                                    \
+    kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, small32, snx, sny, gnx, gny, ft, (int)n_lags, lpb,  \
+                                                     pivots, wrec, wcorr, wconst, wmask);                            \
   }
-  if (rows_per_thread == 16) RW(16) else if (rows_per_thread == 14) RW(14) else RW(kRollWRows)
+  if (mixed) {
+    if (minb == 3) {
+      if (rows_per_thread == 16) RW(16, 3, true) else RW(kRollWRows, 3, true)
+    } else {
+      if (rows_per_thread == 16) RW(16, 2, true) else if (rows_per_thread == 24) RW(24, 2, true)
+      else if (rows_per_thread == 32) RW(32, 2, true) else RW(kRollWRows, 2, true)
+    }
+  } else {
+    if (rows_per_thread == 16) RW(16, 2, false) else if (rows_per_thread == 14) RW(14, 2, false)
+    else RW(kRollWRows, 2, false)
+  }
 #undef RW
   CK_LAUNCH("lag_corr_roll_kernel");
   if (prof) {
@@ -2158,7 +2283,8 @@ inline int grid_for(int64_t n, int threads = 256) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
 }
 
-int hpc_lag_corr_wcs_impl(const float* ref, const double* small, int snx, int sny, int gnx, int gny,
+int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* small32, int snx, int sny, int gnx,
+                          int gny,
                           const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags,
                           const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s) {
   HomGrid g;
@@ -2174,8 +2300,8 @@ int hpc_lag_corr_wcs_impl(const float* ref, const double* small, int snx, int sn
     CK(cudaEventCreate(&g_prof[g_prof_n].a));
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
   }
-  return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, snx, sny, ft, pivots, work,
-                                       corr, nvalid, prof);
+  return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, small32, snx, sny, ft,
+                                       pivots, work, corr, nvalid, prof);
 }
 
 }  // namespace
@@ -2303,8 +2429,25 @@ int coreg_hpc_lag_corr_wcs(const float* ref, const double* small, int snx, int s
   if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
   if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
   if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
-  return hpc_lag_corr_wcs_impl(ref, small, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr, nvalid,
-                               flags, (cudaStream_t)stream);
+  return hpc_lag_corr_wcs_impl(ref, small, nullptr, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
+                               nvalid, flags, (cudaStream_t)stream);
+}
+
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const float* small32, int snx, int sny,
+                                 int gnx, int gny, const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs,
+                                 int64_t n_lags, int order, const double* pivots, void* work, size_t work_bytes,
+                                 double* corr, int64_t* nvalid, int flags, void* stream) {
+  if (!ref || !small || !small32 || !grid_wcs || !lag_wcs || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs_mixed: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  if (order != 2 || (flags & COREG_FLAG_STRICT))
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs_mixed: only order 2 with FMA arithmetic; use coreg_hpc_lag_corr");
+  if (gnx <= 0 || gny <= 0 || snx < 3 || sny < 3) return fail(COREG_EINVAL, "image too small for the fast kernel");
+  if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  return hpc_lag_corr_wcs_impl(ref, small, small32, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
+                               nvalid, flags, (cudaStream_t)stream);
 }
 
 int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs, int gnx, int gny, const CoregTanWcs* lag_wcs, int64_t n_lags,
@@ -2615,7 +2758,10 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   TRYRC(coreg_map_coordinates(d_large, large_dtype, lny, lnx, d_y, d_x, ns, order, (double)NAN, d_ref, COREG_F32, s));
   TRYRC(coreg_finite_mean(d_ref, COREG_F32, ns, d_piv, s));
   TRYRC(coreg_finite_mean(d_small, COREG_F64, ns, d_piv + 1, s));
-  if (fast) {
+  if (fast && (flags & COREG_FLAG_MIXED) && d_small_in) {
+    TRYRC(coreg_hpc_lag_corr_wcs_mixed(d_ref, d_small, (const float*)d_small_in, snx, sny, snx, sny, wcs_small, d_lagw,
+                                       n_lags, order, d_piv, d_work, work_bytes, d_corr, d_nv, flags, s));
+  } else if (fast) {
     TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv, d_work,
                                  work_bytes, d_corr, d_nv, flags, s));
   } else {

@@ -43,8 +43,14 @@ class Alignment:
                  small_fov_window: object = -1,
                  path_save_figure: str = None, reprojection_order=2, force_crota_0=False,
                  unit_lag="arcsec", cdelt_semantics="reference", strict_arithmetic=False, lag_search="dense",
-                 coarse_stride=None):
-        """Same parameters as the reference (`hdrshift/alignment.py:47-83`). Two additions:
+                 coarse_stride=None, arithmetic=None):
+        """Same parameters as the reference (`hdrshift/alignment.py:47-83`). Additions:
+
+        arithmetic: "mixed" (default of the helioprojective order-2 search when the small image holds float32
+            values, e.g. a BITPIX -32 file): projection in FP64, spline and per-segment sums in FP32 -- the
+            reference stores every sample as float32 anyway (`alignment.py:1024`); |dr| ~ 1e-9 against "fp64"
+            (everything in FP64, |dr| ~ 1e-13 against the reference's arithmetic). None: COREG_ARITHMETIC or the
+            engine's default.
 
         cdelt_semantics: "reference" reproduces the reference's handling of CDELT lags (a CDELT1 lag only
             rebuilds PCi_j, a non-zero CDELT2 lag leaves 0.0 in the cube because the reference's worker dies,
@@ -101,6 +107,7 @@ class Alignment:
         self.use_sunpy = False
         self.cdelt_semantics = cdelt_semantics
         self.strict_arithmetic = strict_arithmetic
+        self.arithmetic = arithmetic
         if lag_search not in ("dense", "coarse_to_fine"):
             raise ValueError("lag_search must be 'dense' or 'coarse_to_fine'")
         self.lag_search = lag_search
@@ -417,7 +424,8 @@ class Alignment:
         # conversion); float32, when the file holds float32, for the Carrington kernel, whose gather is sparse in the
         # small image (several detector pixels per Carrington pixel) and therefore bound by L1 wavefronts, not FP64
         storage = "auto" if self.coordinate_frame == "final_carrington" else "f64"
-        eng = _engine.LagSearchEngine(order=self.order, strict=self.strict_arithmetic, small_storage=storage)
+        eng = _engine.LagSearchEngine(order=self.order, strict=self.strict_arithmetic, small_storage=storage,
+                                      arithmetic=getattr(self, "arithmetic", None))
         self.engine = eng
         eng.set_small(self.data_small)
         n_r = len(self.lag_solar_r)

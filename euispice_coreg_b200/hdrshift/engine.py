@@ -183,8 +183,22 @@ class LagSearchEngine:
 
     max_workspace_bytes = 2 << 30   # 3968 lags of a 2048^2 grid per launch (535 KB of warp records per lag)
 
-    def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64", no_fast=False):
+    default_arithmetic = "mixed"
+
+    def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64", no_fast=False,
+                 arithmetic=None):
+        """arithmetic: "mixed" (FP64 projection, FP32 spline on the float32 payload of the small image; applies to
+        the homography kernel when every small-image pixel is a float32 value) or "fp64" (everything in FP64).
+        None: the COREG_ARITHMETIC environment variable, else `default_arithmetic`."""
         torch = _torch()
+        arithmetic = arithmetic or os.environ.get("COREG_ARITHMETIC") or self.default_arithmetic
+        if arithmetic not in ("fp64", "mixed"):
+            raise ValueError('arithmetic must be "fp64" or "mixed"')
+        self.arithmetic = arithmetic
+        self.small32 = None
+        # launch-shape hint for the mixed kernel, set by `hpc_lag_table` from the WHOLE lag grid (never from a slice
+        # of it: every shard must launch the same shape for the cube to be bit-identical for any GPU count)
+        self.pure_shift_hint = False
         _ext.load()  # fail loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _ext.CoregLibraryError("no CUDA device: the pointing search has no CPU fallback")
@@ -225,9 +239,20 @@ class LagSearchEngine:
         as float64 on the device (a float32 input is uploaded as float32 and widened there); "auto": kept as float32
         when the input is float32 -- half the gather traffic, same values, but 9 f32->f64 conversions per sample on the
         quarter-rate conversion pipe and no homography kernel: measured slower on B200 (profiles/r1_k1_tuning.md)."""
+        torch = _torch()
         small = self._upload(self._native_float(data_small), pinned=pinned)
-        if small.dtype == _torch().float32 and self.small_storage == "f64":
+        self.small32 = None
+        mixed = self.arithmetic == "mixed" and self.small_storage == "f64" and not self.strict and self.order == 2
+        if small.dtype == torch.float32 and self.small_storage == "f64":
+            if mixed:
+                self.small32 = small
             small = _ext.widen_f32(small)
+        elif mixed and small.dtype == torch.float64:
+            # a float64 input whose pixels are all float32 values (an integer FITS payload, a float32 image the
+            # caller widened): the mixed kernel sees exactly the same image
+            s32 = small.to(torch.float32)
+            if bool(((s32.to(torch.float64) == small) | torch.isnan(small)).all()):
+                self.small32 = s32.contiguous()
         self.small = small
         _ext.finite_mean(self.small, self.pivots[1:2])
 
@@ -303,6 +328,9 @@ class LagSearchEngine:
     def hpc_lag_table(self, hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics="reference"):
         """Host lag table for `search` in the helioprojective frame + the mask of lags the reference cannot
         evaluate: candidate-header rows for the homography kernel when it applies, `CoregLagTan` rows otherwise."""
+        # launch shape of the mixed kernel: 16 rows per thread when every lag is a pure CRVAL shift (no segment changes
+        # a floor), 12 when CROTA / CDELT lags make some segments irregular (measured: tools/mixed_lab.py)
+        self.pure_shift_hint = not (np.any(np.asarray(d3)) or np.any(np.asarray(d4)) or np.any(np.asarray(d5)))
         if self.hpc_fast_eligible():
             return tan_wcs_table(hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics)
         return tan_lag_table(hdr_small, refs, d1, d2, d3, d4, d5, self.alpha_ref_deg, cdelt_semantics)
@@ -385,8 +413,13 @@ class LagSearchEngine:
                 hi = min(n, lo + step)
                 nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
                 if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
+                    mixed = self.arithmetic == "mixed" and self.small32 is not None
+                    flags = self.flags
+                    if mixed and self.variant == 0 and self.pure_shift_hint:
+                        flags = _ext.make_flags(self.strict, 1, no_fast=self.no_fast)
                     _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
-                                          self.pivots, work, out_dev[lo:hi], nv, self.flags)
+                                          self.pivots, work, out_dev[lo:hi], nv, flags,
+                                          small32=self.small32 if mixed else None)
                 elif self.frame == "car":
                     _ext.car_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order,
                                       self.pivots, work, out_dev[lo:hi], nv, self.flags)

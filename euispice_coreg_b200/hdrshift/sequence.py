@@ -39,7 +39,8 @@ class SequenceAlignment:
     def __init__(self, large_fov_known_pointing: str, list_small_fov_to_correct, lag_crval1, lag_crval2,
                  lag_cdelt1=None, lag_cdelt2=None, lag_crota=None, small_fov_value_min=None,
                  small_fov_value_max=None, large_fov_window=-1, small_fov_window=-1, reprojection_order=2,
-                 force_crota_0=False, unit_lag="arcsec", cdelt_semantics="reference", strict_arithmetic=False):
+                 force_crota_0=False, unit_lag="arcsec", cdelt_semantics="reference", strict_arithmetic=False,
+                 arithmetic=None):
         self.large_fov_known_pointing = large_fov_known_pointing
         self.list_small = list(list_small_fov_to_correct)
         self.kw = dict(lag_crval1=lag_crval1, lag_crval2=lag_crval2, lag_cdelt1=lag_cdelt1, lag_cdelt2=lag_cdelt2,
@@ -47,7 +48,7 @@ class SequenceAlignment:
                        small_fov_value_max=small_fov_value_max, large_fov_window=large_fov_window,
                        small_fov_window=small_fov_window, reprojection_order=reprojection_order,
                        force_crota_0=force_crota_0, unit_lag=unit_lag, cdelt_semantics=cdelt_semantics,
-                       strict_arithmetic=strict_arithmetic, parallelism=True)
+                       strict_arithmetic=strict_arithmetic, parallelism=True, arithmetic=arithmetic)
         self.engine = None
         self.frames_per_s = None
 
@@ -79,7 +80,8 @@ class SequenceAlignment:
         # two engines = two sets of per-frame device buffers (small image, cut of the large image, pivots, workspace)
         # sharing the one resident large image: frame k+1 is uploaded and prepared on a side stream while frame k is
         # being searched on the main stream
-        engs = [_engine.LagSearchEngine(order=self.kw["reprojection_order"], strict=self.kw["strict_arithmetic"])
+        engs = [_engine.LagSearchEngine(order=self.kw["reprojection_order"], strict=self.kw["strict_arithmetic"],
+                                        arithmetic=self.kw["arithmetic"])
                 for _ in range(2)]
         eng = engs[0]
         self.engine = eng

@@ -40,6 +40,9 @@ extern "C" {
 #define COREG_FLAG_STRICT 1
 /* COREG_FLAG_NO_FAST (value 4; 2 is reserved): force the generic kernel (testing / comparison). */
 #define COREG_FLAG_NO_FAST 4
+/* COREG_FLAG_MIXED: coreg_hpc_search_host only -- run the mixed-arithmetic kernel (coreg_hpc_lag_corr_wcs_mixed) when
+ * the small image is COREG_F32 and the fast form applies. */
+#define COREG_FLAG_MIXED 8
 #define COREG_FLAG_VARIANT(v) (((v) & 15) << 8)
 
 /* Constants of a 2-axis gnomonic (TAN) WCS. Replaces `astropy.wcs.WCS(hdr)`:
@@ -188,6 +191,20 @@ int coreg_hpc_lag_corr_wcs(const float* ref_dev, const double* small_dev, int sn
                            const CoregTanWcs* grid_wcs_host, const CoregTanWcs* lag_wcs_dev, int64_t n_lags,
                            int order, const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
                            int64_t* nvalid_dev, int flags, void* stream);
+
+/* ---- K1 (fast form, mixed arithmetic) -------------------------------------------------------------------------------
+ * coreg_hpc_lag_corr_wcs with the projection in FP64 and the spline + per-segment moments in FP32, for a small image
+ * whose pixels are float32 values (a BITPIX -32 FITS payload: what `Fits.open(...)[w].data` holds before the
+ * reference widens it, hdrshift/alignment.py:299-316). small32_dev is that payload, small_dev its float64 widening
+ * (used where a segment touches the image border, a missing pixel or an irregular column and is evaluated by the
+ * exact per-pixel rules). The reference stores every sample as float32 (alignment.py:1024), so the FP32 spline moves
+ * a sample by about one float32 ulp, unbiased: |dr| ~ 1e-9 against the FP64 kernel (bar: 1e-6). Variants
+ * (COREG_FLAG_VARIANT): 0 = 12 rows per thread, 1 = 16, at 2 CTAs / SM; 3 = 12, 4 = 16 at 3 CTAs / SM. */
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref_dev, const double* small_dev, const float* small32_dev, int snx,
+                                 int sny, int gnx, int gny, const CoregTanWcs* grid_wcs_host,
+                                 const CoregTanWcs* lag_wcs_dev, int64_t n_lags, int order, const double* pivots_dev,
+                                 void* work_dev, size_t work_bytes, double* corr_dev, int64_t* nvalid_dev, int flags,
+                                 void* stream);
 
 /* Diagnostic: max |e| = max |1 - D| of each candidate header's homography over the gnx x gny common grid (what selects
  * the reciprocal form per lag inside coreg_hpc_lag_corr_wcs). scratch_dev: at least 96 * n_lags bytes.

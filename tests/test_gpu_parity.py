@@ -13,6 +13,11 @@ from conftest import load_pair
 pytestmark = pytest.mark.gpu
 
 R_TOL = 1e-6  # tolerance stated by BASELINE.json north_star
+# what the two arithmetic modes of the homography kernel actually deliver against the oracle (both far inside R_TOL):
+# "fp64" repeats the reference's FP64 tap arithmetic (FMA-contracted); "mixed" (the default when the small image
+# holds float32 values) evaluates the spline in FP32 -- one float32 ulp per sample, averaged over the Pearson sums
+OBSERVED = {"fp64": 1e-10, "mixed": 5e-8}
+ARITH = pytest.mark.parametrize("arithmetic", ["fp64", "mixed"])
 
 
 @pytest.fixture(scope="module")
@@ -98,6 +103,7 @@ def _oracle_cube(pair, **kw):
     kw["order"] = kw.pop("reprojection_order", 2)
     kw["cdelt_mode"] = kw.pop("cdelt_semantics", "reference")
     kw.pop("strict_arithmetic", None)
+    kw.pop("arithmetic", None)
     s = HpcSearch(dl, hl, ds, hs, **kw)
     return s.cube(), s
 
@@ -115,11 +121,13 @@ LAGS = dict(lag_crval1=np.arange(20, 29, 2.0), lag_crval2=np.arange(2, 11, 2.0),
             lag_crota=[0])
 
 
-def test_hpc_cube_parity_basic(torch_cuda, toy_pair):
-    gpu, a = _gpu_cube(toy_pair, **LAGS)
+@ARITH
+def test_hpc_cube_parity_basic(torch_cuda, toy_pair, arithmetic):
+    gpu, a = _gpu_cube(toy_pair, arithmetic=arithmetic, **LAGS)
+    assert (a.engine.small32 is not None) == (arithmetic == "mixed")   # the toy files are BITPIX -32
     ref, s = _oracle_cube(toy_pair, **LAGS)
     err = _assert_parity(gpu, ref)
-    assert err < 1e-10  # what FP64 + identical tap arithmetic actually delivers
+    assert err < OBSERVED[arithmetic]
     i, j = np.unravel_index(np.nanargmax(gpu), gpu.shape)[:2]
     assert (LAGS["lag_crval1"][i], LAGS["lag_crval2"][j]) == (24.0, 6.0)
     # the one-time cut of the large image (K2): same NaN pattern; the coordinates come from device trig (<= 1e-11 px
@@ -201,9 +209,12 @@ def test_hpc_cube_deg_units(torch_cuda, toy_pair, tmp_path):
 def test_strict_arithmetic_mode(torch_cuda, toy_pair):
     """scipy's exact tap arithmetic; the default FMA mode differs from it by far less than the tolerance."""
     gpu, _ = _gpu_cube(toy_pair, strict_arithmetic=True, **LAGS)
-    fma, _ = _gpu_cube(toy_pair, **LAGS)
-    # default path = homography kernel with FMA arithmetic; strict = generic kernel, scipy operation order
+    fma, _ = _gpu_cube(toy_pair, arithmetic="fp64", **LAGS)
+    # homography kernel with FMA arithmetic vs strict = generic kernel, scipy operation order
     assert np.nanmax(np.abs(gpu - fma)) < 1e-10
+    mixed, a = _gpu_cube(toy_pair, **LAGS)      # the default: FP64 projection, FP32 spline
+    assert a.engine.arithmetic == "mixed" and a.engine.small32 is not None
+    assert np.nanmax(np.abs(gpu - mixed)) < OBSERVED["mixed"]
     ref, _ = _oracle_cube(toy_pair, **LAGS)
     _assert_parity(gpu, ref)
 
@@ -213,7 +224,7 @@ def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     from euispice_coreg_b200 import _ext
     from euispice_coreg_b200._compat.wcs import TanWcs
     from euispice_coreg_b200.hdrshift import engine
-    gpu, a = _gpu_cube(toy_pair, **LAGS)
+    gpu, a = _gpu_cube(toy_pair, arithmetic="fp64", **LAGS)
     dl, hl, ds, hs = load_pair(*toy_pair[:2])
     d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
     w_small = TanWcs.from_header(a.hdr_small)
@@ -231,6 +242,17 @@ def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     corr_g, nv_g = _ext.hpc_search_host(dl, TanWcs.from_header(hl), ds, w_small, table,
                                         flags=_ext.make_flags(no_fast=True))
     assert np.nanmax(np.abs(corr_g - corr)) < 1e-11 and np.array_equal(nv_g, nvalid)
+    # mixed arithmetic through the same entry (COREG_FLAG_MIXED, float32 payload; 16 rows per thread is what the
+    # engine launches for pure CRVAL lags) == the torch-plumbed default path, bit for bit
+    gpu_m, a_m = _gpu_cube(toy_pair, arithmetic="mixed", **LAGS)
+    corr_m, nv_m = _ext.hpc_search_host(dl, TanWcs.from_header(hl), ds, w_small, table,
+                                        flags=_ext.make_flags(variant=1) | _ext.FLAG_MIXED)
+    assert np.array_equal(corr_m.reshape(gpu_m.shape), gpu_m) and np.array_equal(nv_m, nvalid)
+    assert not np.array_equal(corr_m, corr) and np.nanmax(np.abs(corr_m - corr)) < OBSERVED["mixed"]
+    # a float64 payload has no float32 twin on this entry: the flag is ignored, FP64 kernel
+    corr_d, _ = _ext.hpc_search_host(dl, TanWcs.from_header(hl), ds.astype(np.float64), w_small, table,
+                                     flags=flags | _ext.FLAG_MIXED)
+    assert np.array_equal(corr_d, corr)
 
 
 def test_results_and_written_header_match_oracle_cube(torch_cuda, toy_pair, tmp_path):
@@ -258,12 +280,13 @@ def test_results_and_written_header_match_oracle_cube(torch_cuda, toy_pair, tmp_
     assert LAGS["lag_crval1"][res.max_index[0]] == LAGS["lag_crval1"][res_o.max_index[0]]
 
 
-def test_determinism_and_lag_sharding_invariance(torch_cuda, toy_pair):
+@ARITH
+def test_determinism_and_lag_sharding_invariance(torch_cuda, toy_pair, arithmetic):
     """Same bits run to run, and the same bits whether the lag list is evaluated whole or in slices
     (what makes the cube independent of the GPU count)."""
     from euispice_coreg_b200.hdrshift import engine
-    gpu, a = _gpu_cube(toy_pair, **LAGS)
-    gpu2, _ = _gpu_cube(toy_pair, **LAGS)
+    gpu, a = _gpu_cube(toy_pair, arithmetic=arithmetic, **LAGS)
+    gpu2, _ = _gpu_cube(toy_pair, arithmetic=arithmetic, **LAGS)
     assert np.array_equal(gpu, gpu2)
     eng = a.engine
     d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
@@ -278,10 +301,14 @@ def test_determinism_and_lag_sharding_invariance(torch_cuda, toy_pair):
     eng_g.alpha_ref_deg, eng_g.delta_ref_deg = eng.alpha_ref_deg, eng.delta_ref_deg
     table_g, _ = eng_g.hpc_lag_table(a.hdr_small, a, *d)
     assert table_g.shape[1] == 10
-    assert np.nanmax(np.abs(eng_g.search(table_g) - gpu.ravel())) < 1e-11
+    assert np.nanmax(np.abs(eng_g.search(table_g) - gpu.ravel())) < (1e-11 if arithmetic == "fp64" else OBSERVED["mixed"])
 
 
-def test_config1_full_size_bounded_sample_vs_oracle(torch_cuda):
+_CFG1_REF = {}
+
+
+@ARITH
+def test_config1_full_size_bounded_sample_vs_oracle(torch_cuda, arithmetic):
     """BASELINE.json configs[0] at full size (2048^2 vs 3072^2, 60x60 CRVAL lags): the whole GPU cube through the
     public API against the oracle on a bounded sample of lags (the oracle needs ~5 s per lag per core).
 
@@ -294,9 +321,10 @@ def test_config1_full_size_bounded_sample_vs_oracle(torch_cuda):
     from euispice_coreg_b200.hdrshift import Alignment
     from oracle.hpc import HpcSearch, cube_multiprocess
     pl, ps = bench.ensure_config1()
-    a = Alignment(pl, ps, parallelism=True, **bench.LAGS)
+    a = Alignment(pl, ps, parallelism=True, arithmetic=arithmetic, **bench.LAGS)
     cube = a.align_using_helioprojective(return_type="corr")
     assert cube.shape == (60, 60, 1, 1, 1, 1)
+    assert (a.engine.small32 is not None) == (arithmetic == "mixed")
     gpu = cube.ravel()
     nvalid = a.nvalid.ravel()
     dl, hl, ds, hs = load_pair(pl, ps)
@@ -305,10 +333,12 @@ def test_config1_full_size_bounded_sample_vs_oracle(torch_cuda):
     sel = np.array([0, 59, 3540, 3599, 54 * 60 + 36, 1000, 2500, zero])   # corners, the peak (24, 6), interior, (0, 0)
     assert bench.LAGS["lag_crval1"][30] == 0.0
     cores = max(1, min(len(sel), len(os.sched_getaffinity(0))))
-    ref = cube_multiprocess(search, cores, sel)
+    if "ref" not in _CFG1_REF:       # the oracle sample is the slow part: once for both arithmetic modes
+        _CFG1_REF["ref"] = cube_multiprocess(search, cores, sel)
+    ref = _CFG1_REF["ref"]
     err = np.abs(gpu[sel] - ref)
     assert np.all(err[:-1] <= R_TOL), err
-    assert err[:-1].max() < 1e-10
+    assert err[:-1].max() < OBSERVED[arithmetic]
     assert err[-1] < 1e-3 and 2048 * 2048 - nvalid[zero] <= 2 * (2048 + 2048)
     assert int(np.nanargmax(gpu)) == 54 * 60 + 36
 
@@ -323,7 +353,8 @@ def wide_pair(tmp_path_factory):
     return make_pair(str(d), spec, tag="wide")
 
 
-def test_hpc_cube_parity_all_three_reciprocal_modes(torch_cuda, wide_pair):
+@ARITH
+def test_hpc_cube_parity_all_three_reciprocal_modes(torch_cuda, wide_pair, arithmetic):
     """Per lag the rolling kernel picks 1 + e + e^2 (|e| <= 2^-18), the three-factor product (|e| <= 2^-7) or a true
     division from the exact range of e = 1 - D over the grid. One cube that needs all three, against the oracle."""
     import torch
@@ -332,7 +363,7 @@ def test_hpc_cube_parity_all_three_reciprocal_modes(torch_cuda, wide_pair):
     # (no exact (0, 0, 0) lag: that one is the closed-bound knife edge of DESIGN.md section 4)
     kw = dict(lag_crval1=np.array([0.5, 3.0, 600.0, 2400.0, 9000.0, 30000.0]), lag_crval2=np.array([0.0, 600.0, -20000.0]),
               lag_cdelt1=None, lag_cdelt2=None, lag_crota=[0.0, 2.0])
-    gpu, a = _gpu_cube(wide_pair, **kw)
+    gpu, a = _gpu_cube(wide_pair, arithmetic=arithmetic, **kw)
     ref, _ = _oracle_cube(wide_pair, **kw)
     _assert_parity(gpu, ref)
     # which series each lag got: e_max of the device-built homographies
@@ -344,7 +375,7 @@ def test_hpc_cube_parity_all_three_reciprocal_modes(torch_cuda, wide_pair):
     assert set(modes.tolist()) == {0, 1, 2}, (emax.min(), emax.max())
     # and the generic kernel (per-lag trig, true division everywhere) agrees with all of them
     gen, _ = _gpu_cube(wide_pair, strict_arithmetic=True, **kw)
-    assert np.nanmax(np.abs(gen - gpu)) < 1e-9
+    assert np.nanmax(np.abs(gen - gpu)) < (1e-9 if arithmetic == "fp64" else OBSERVED["mixed"])
 
 
 def test_small_image_with_holes_and_all_nan(torch_cuda, toy_pair, tmp_path):
@@ -407,7 +438,9 @@ def test_config1_full_size_properties(torch_cuda):
     eng.set_small((small * 2.0).cpu().numpy())
     assert np.array_equal(eng.search(table), cube)
     eng.set_small((small * 3.0 + 100.0).cpu().numpy())
-    assert np.max(np.abs(eng.search(table) - cube)) < 1e-9
+    # (3 a + 100 is not a float32 image any more: this search runs the all-FP64 kernel, `cube` came from the mixed
+    # one -- rounding of the map + the difference between the two arithmetic modes, ~1e-9)
+    assert np.max(np.abs(eng.search(table) - cube)) < 1e-8
     eng.small, eng.pivots = small, piv
 
 
