@@ -1,0 +1,61 @@
+"""The mixed-arithmetic kernel's way out of the FP64 domain (csrc/coreg_kernels.cu, roll_segment_mixed), restated in
+numpy: the coordinate FMA adds kFracMagic = 1.5 * 2^29, whose ulp is 2^-23, so the LOW word of the double is
+round((x - floor_x0) * 2^23) modulo 2^32 -- the row index inside the segment in the bits above bit 22 and the
+float32 mantissa of 1 + fraction below. This pins the encoding the CUDA code relies on (CPU test, no GPU)."""
+import numpy as np
+
+MAGIC = 805306368.0   # 1.5 * 2^29
+
+
+def _low_word(offset):
+    v = np.asarray(offset, dtype=np.float64) + MAGIC          # one rounding of the exact sum, like the FMA's
+    return (v.view(np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+def _fraction(lo, p):
+    """What the kernel computes: validity word and float32 fraction for a pixel expected in row p of the segment."""
+    u = lo ^ np.uint32(p << 23)
+    frac = ((u | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0))
+    return u, frac
+
+
+def test_magic_has_ulp_2_pow_minus_23():
+    assert MAGIC == 1.5 * 2.0 ** 29 and np.spacing(np.float64(MAGIC)) == 2.0 ** -23
+    assert np.spacing(np.float64(MAGIC + 511.999)) == 2.0 ** -23     # holds for offsets below 2^9 pixels
+
+
+def test_fraction_and_row_index_come_out_of_the_low_word():
+    rng = np.random.default_rng(7)
+    for p in (0, 1, 5, 15, 31):
+        s = p + rng.random(200000)                       # offset from the shared floor: row p, fraction in [0, 1)
+        u, frac = _fraction(_low_word(s), p)
+        true = s - p
+        up = np.round(true * 2.0 ** 23) == 2.0 ** 23    # a fraction that rounds up to 1 leaves its cell: flagged
+        ok = u < np.uint32(0x00800000)
+        assert np.array_equal(ok, ~up)
+        assert np.max(np.abs(frac[ok].astype(np.float64) - true[ok])) <= 2.0 ** -24
+        assert frac[ok].min() >= 0.0 and frac[ok].max() < 1.0
+
+
+def test_offsets_outside_the_cell_are_flagged():
+    # a floor changed inside the segment (rotated lags): wrong row, negative offsets, far-away coordinates
+    for p, s in ((0, 1.25), (3, 2.999), (3, 4.0), (0, -1e-7), (0, -0.75), (7, -3.5), (2, 300.0), (0, 511.5)):
+        u, _ = _fraction(_low_word(np.array([s])), p)
+        assert u[0] >= 0x00800000, (p, s)
+    # an offset less than 2^-24 pixel below the cell rounds to fraction 0 of the cell: the spline is C1 across cell
+    # boundaries, so that is the same rounding as anywhere else, not a misclassification
+    u, frac = _fraction(_low_word(np.array([-1e-9])), 0)
+    assert u[0] < 0x00800000 and frac[0] == 0.0
+    # exactly on a cell boundary from above is row p with fraction 0
+    u, frac = _fraction(_low_word(np.array([4.0])), 4)
+    assert u[0] < 0x00800000 and frac[0] == 0.0
+
+
+def test_residual_folding_keeps_the_lag_offset_exact():
+    # xoff + MAGIC rounds to 2^-23 pixel; the kernel moves the residual into the numerator (roll_lag): check that
+    # hi + residual reproduces xoff exactly
+    rng = np.random.default_rng(11)
+    xoff = -rng.random(1000) * 2048.0
+    xm = xoff + MAGIC
+    resid = xoff - (xm - MAGIC)
+    assert np.all(np.abs(resid) <= 2.0 ** -24) and np.array_equal((xm - MAGIC) + resid, xoff)
