@@ -64,8 +64,7 @@ _SIGNATURES = {
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                          _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
-    "coreg_spline_row_coefficients": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
-    "coreg_hpc_lag_corr_wcs_mixed": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+    "coreg_hpc_lag_corr_wcs_mixed": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P,
                                                _P, C.c_int, _P]),
     "coreg_tan_homography_emax": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P]),
@@ -302,22 +301,8 @@ def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
                                       int(flags), _stream()), "coreg_hpc_lag_corr")
 
 
-def spline_row_coefficients(small32):
-    """float32 image [ny, nx] -> float32 [ny, nx, 4]: the order-2 row coefficients (A, B, C, 0) per centre tap."""
-    torch = _torch()
-    lib = load()
-    _require_cuda(small32)
-    if small32.dtype != torch.float32 or not small32.is_contiguous():
-        raise TypeError("small32 must be a contiguous float32 image")
-    out = torch.empty(small32.shape + (4,), dtype=torch.float32, device=small32.device)
-    with torch.cuda.device(small32.device):
-        _check(lib.coreg_spline_row_coefficients(_ptr(small32), small32.shape[1], small32.shape[0], _ptr(out),
-                                                 _stream()), "coreg_spline_row_coefficients")
-    return out
-
-
 def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_out, nvalid_out=None, flags=0,
-                     small32=None, rowcoef=None):
+                     small32=None):
     """K1, homography form. `lag_wcs`: device float64 [n_lags, 11] (CoregTanWcs rows of the shifted headers);
     `grid_wcs`: `_compat.wcs.TanWcs` of the common grid. `small32` (the float32 payload `small` was widened from)
     selects the mixed-arithmetic kernel: FP64 projection, FP32 spline."""
@@ -336,8 +321,7 @@ def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_ou
             raise TypeError("small32 must be the contiguous float32 twin of small")
         with torch.cuda.device(ref.device):
             _check(lib.coreg_hpc_lag_corr_wcs_mixed(
-                _ptr(ref), _ptr(small), _ptr(small32), _ptr(rowcoef) if rowcoef is not None else None,
-                small.shape[1], small.shape[0], gnx, gny, C.byref(g),
+                _ptr(ref), _ptr(small), _ptr(small32), small.shape[1], small.shape[0], gnx, gny, C.byref(g),
                 _ptr(lag_wcs), lag_wcs.shape[0], int(order), _ptr(pivots), _ptr(work),
                 work.numel() * work.element_size(), _ptr(corr_out),
                 _ptr(nvalid_out) if nvalid_out is not None else None, int(flags), _stream()),

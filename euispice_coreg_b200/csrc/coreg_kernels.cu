@@ -1286,44 +1286,20 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
 // vbad >= 2^23 (a floor changed inside the segment, or a fraction rounded up to 1).
 constexpr double kFracMagic = 805306368.0;   // 1.5 * 2^29
 
-// The row coefficients (A, B, C) of roll_segment depend on the image only: one float4 {A, B, C, 0} per pixel, indexed
-// by the centre tap (x in [1, nx - 2]; the border columns are never read by a regular window).
-__global__ void spline_row_coef_kernel(const float* __restrict__ img, int nx, int ny, float4* __restrict__ out) {
-  const int64_t n = (int64_t)nx * ny;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % nx);
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x >= 1 && x <= nx - 2) {
-      const float ta = __ldg(img + i - 1), tb = __ldg(img + i), tc = __ldg(img + i + 1);
-      c.x = 0.5f * (ta + tb);
-      c.y = tb - ta;
-      c.z = fmaf(0.5f, ta + tc, -tb);
-    }
-    out[i] = c;
-  }
-}
-
-template <int MODE, int P, bool COEF>
+template <int MODE, int P>
 __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ small32, unsigned tap,
                                                    unsigned row_elems, double be, double bnx, double bny, double he1,
                                                    double hx1, double hy1, double inv0, double xoffm, double yoffm,
                                                    float pivot_b, const float (&a_c)[P], float& sb, float& sbb,
                                                    float& sab, unsigned& vbad) {
-  // (a 64-bit row pointer, walked or formed as base + k * stride, compiles to four IADD3 per row; the 32-bit index
-  // + IMAD.WIDE form below costs two)
+  // (Measured and dropped, profiles/r1_mixed_kernel.md: a per-image plane of these coefficients, one 16-byte load
+  // per row and no arithmetic, is slower -- four times the L1 footprint; a 64-bit row pointer, walked or formed as
+  // base + k * stride, compiles to four IADD3 per row where the 32-bit index + IMAD.WIDE form below costs two.)
   auto row = [&](unsigned t, float& ca, float& cb, float& cc) {
-    if (COEF) {
-      // small32 is the float4 coefficient plane of spline_row_coef_kernel: one 16-byte load, no arithmetic
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(small32) + (t + 1));
-      ca = c4.x;
-      cb = c4.y;
-      cc = c4.z;
-    } else {
-      const float ta = __ldg(small32 + t), tb = __ldg(small32 + t + 1), tc = __ldg(small32 + t + 2);
-      ca = 0.5f * (ta + tb);
-      cb = tb - ta;
-      cc = fmaf(0.5f, ta + tc, -tb);
-    }
+    const float ta = __ldg(small32 + t), tb = __ldg(small32 + t + 1), tc = __ldg(small32 + t + 2);
+    ca = 0.5f * (ta + tb);
+    cb = tb - ta;
+    cc = fmaf(0.5f, ta + tc, -tb);
   };
   float r0a, r0b, r0c, r1a, r1b, r1c, r2a, r2b, r2c;
   row(tap, r0a, r0b, r0c);
@@ -1414,7 +1390,7 @@ __device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ sma
 // segment or -- image borders, irregular columns (rotated lags), missing pixels, division-mode lags -- the segment
 // pixel by pixel. Out: the thread's Sb, Sbb, Sab over its valid samples and the mask of pixels that have a finite
 // reference value but no valid sample.
-template <bool ROUND32, int P, bool MIXED, bool COEF, typename AT>
+template <bool ROUND32, int P, bool MIXED, typename AT>
 __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small,
                                          const float* __restrict__ small32, int snx, int sny, unsigned row_elems,
                                          double di, double dj0, const AT (&a_c)[P], unsigned a_ok, bool all_ref,
@@ -1449,10 +1425,10 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
       float fsb = 0.f, fsbb = 0.f, fsab = 0.f;
       unsigned vbad = 0;
       if (mode == 0)
-        roll_segment_mixed<0, P, COEF>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+        roll_segment_mixed<0, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
                                  (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
       else
-        roll_segment_mixed<1, P, COEF>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+        roll_segment_mixed<1, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
                                  (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
       // every offset inside its cell, every sample finite (a non-finite sample makes Sbb non-finite; so does a
       // finite sample beyond 1.8e19, which then just takes the exact path)
@@ -1540,7 +1516,7 @@ struct RollWShared {
   HomLag lag[kWarps][kRollChunk];
 };
 
-template <typename RefT, bool ROUND32, int P, int MINB, bool MIXED, bool COEF = false>
+template <typename RefT, bool ROUND32, int P, int MINB, bool MIXED>
 __global__ void __launch_bounds__(kThreads, MINB)
 lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small,
                       const float* __restrict__ small32, int snx, int sny, int gnx,
@@ -1619,7 +1595,7 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
     for (int l = 0; l < cnt; ++l) {
       double sb, sbb, sab;
       unsigned miss;
-      roll_lag<ROUND32, P, MIXED, COEF, AT>(S.lag[warp][l], small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref,
+      roll_lag<ROUND32, P, MIXED, AT>(S.lag[warp][l], small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref,
                                       pivot_b, sb, sbb, sab, miss);
       S.acc[warp][l][0][lane] = sb;
       S.acc[warp][l][1][lane] = sbb;
@@ -1784,15 +1760,14 @@ int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cuda
 // rolling kernel + its finalize. Tuning variants (flags bits 8..11): rows per thread 12 (default), 16, 14; the
 // workspace layout is sized for 12 (fewer rows per thread would need more record rows). small32 != nullptr selects
 // the mixed-arithmetic kernel (FP64 coordinates, FP32 spline on the float32 copy of the small image), variants 0 / 1
-// = 12 / 16 rows per thread; rowcoef != nullptr makes it read the precomputed row coefficients (float4 per pixel)
-// instead of forming them from three taps. (Measured and dropped: 3 CTAs per SM at 80 registers -- spills; 24 and 32
-// rows per thread -- spills and partial tiles: tools/mixed_lab.py, profiles/r1_mixed_kernel.md.)
+// = 12 / 16 rows per thread. (Measured and dropped: 3 CTAs per SM at 80 registers -- spills; 24 and 32 rows per
+// thread -- spills and partial tiles; a precomputed row-coefficient plane: tools/mixed_lab.py,
+// profiles/r1_mixed_kernel.md.)
 template <typename RefT, bool ROUND32>
 int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
-                     const double* small, const float* small32, const float* rowcoef, int snx, int sny,
+                     const double* small, const float* small32, int snx, int sny,
                      const HomLag* ft, const double* pivots, void* work, double* corr, int64_t* nvalid, bool prof) {
   const bool mixed = small32 != nullptr;
-  const bool coef = mixed && rowcoef != nullptr;
   const int minb = 2;
   const int rows_per_thread = (variant == 1) ? 16 : ((variant == 2 && !mixed) ? 14 : kRollWRows);
   const RollWLayout L = rollw_layout(gnx, gny, n_lags);
@@ -1807,20 +1782,17 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
     return fail(COREG_EINVAL, "lag grid too large for one launch");
   CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
   if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
-#define RW(P_, MIXED_, COEF_)                                                                                        \
+#define RW(P_, MIXED_)                                                                                               \
   {                                                                                                                  \
-    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2, MIXED_, COEF_>;                                           \
+    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2, MIXED_>;                                                  \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));               \
-    kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, COEF_ ? rowcoef : small32, snx, sny, gnx, gny, ft,  \
-                                                     (int)n_lags, lpb, pivots, wrec, wcorr, wconst, wmask);          \
+    kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, small32, snx, sny, gnx, gny, ft, (int)n_lags, lpb,  \
+                                                     pivots, wrec, wcorr, wconst, wmask);                            \
   }
-  if (coef) {
-    if (rows_per_thread == 16) RW(16, true, true) else RW(kRollWRows, true, true)
-  } else if (mixed) {
-    if (rows_per_thread == 16) RW(16, true, false) else RW(kRollWRows, true, false)
+  if (mixed) {
+    if (rows_per_thread == 16) RW(16, true) else RW(kRollWRows, true)
   } else {
-    if (rows_per_thread == 16) RW(16, false, false) else if (rows_per_thread == 14) RW(14, false, false)
-    else RW(kRollWRows, false, false)
+    if (rows_per_thread == 16) RW(16, false) else if (rows_per_thread == 14) RW(14, false) else RW(kRollWRows, false)
   }
 #undef RW
   CK_LAUNCH("lag_corr_roll_kernel");
@@ -2326,8 +2298,8 @@ inline int grid_for(int64_t n, int threads = 256) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
 }
 
-int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* small32, const float* rowcoef, int snx,
-                          int sny, int gnx, int gny,
+int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* small32, int snx, int sny, int gnx,
+                          int gny,
                           const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags,
                           const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s) {
   HomGrid g;
@@ -2343,8 +2315,8 @@ int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* sm
     CK(cudaEventCreate(&g_prof[g_prof_n].a));
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
   }
-  return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, small32, rowcoef, snx,
-                                       sny, ft, pivots, work, corr, nvalid, prof);
+  return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, small32, snx, sny, ft,
+                                       pivots, work, corr, nvalid, prof);
 }
 
 }  // namespace
@@ -2472,23 +2444,12 @@ int coreg_hpc_lag_corr_wcs(const float* ref, const double* small, int snx, int s
   if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
   if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
   if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
-  return hpc_lag_corr_wcs_impl(ref, small, nullptr, nullptr, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
+  return hpc_lag_corr_wcs_impl(ref, small, nullptr, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
                                nvalid, flags, (cudaStream_t)stream);
 }
 
-int coreg_spline_row_coefficients(const float* img, int nx, int ny, float* rowcoef, void* stream) {
-  if (!img || !rowcoef) return fail(COREG_EINVAL, "coreg_spline_row_coefficients: null pointer");
-  if (nx < 3 || ny < 1) return fail(COREG_EINVAL, "coreg_spline_row_coefficients: image too small");
-  if ((reinterpret_cast<uintptr_t>(rowcoef) & 15) != 0)
-    return fail(COREG_EINVAL, "coreg_spline_row_coefficients: rowcoef must be 16-byte aligned");
-  spline_row_coef_kernel<<<grid_for((int64_t)nx * ny), 256, 0, (cudaStream_t)stream>>>(
-      img, nx, ny, reinterpret_cast<float4*>(rowcoef));
-  CK_LAUNCH("spline_row_coef_kernel");
-  return COREG_OK;
-}
-
-int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const float* small32, const float* rowcoef,
-                                 int snx, int sny, int gnx, int gny, const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs,
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const float* small32, int snx, int sny,
+                                 int gnx, int gny, const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs,
                                  int64_t n_lags, int order, const double* pivots, void* work, size_t work_bytes,
                                  double* corr, int64_t* nvalid, int flags, void* stream) {
   if (!ref || !small || !small32 || !grid_wcs || !lag_wcs || !pivots || !work || !corr)
@@ -2500,10 +2461,8 @@ int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const fl
   if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
   if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
   if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
-  if (rowcoef && (reinterpret_cast<uintptr_t>(rowcoef) & 15) != 0)
-    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs_mixed: rowcoef must be 16-byte aligned");
-  return hpc_lag_corr_wcs_impl(ref, small, small32, rowcoef, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work,
-                               corr, nvalid, flags, (cudaStream_t)stream);
+  return hpc_lag_corr_wcs_impl(ref, small, small32, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
+                               nvalid, flags, (cudaStream_t)stream);
 }
 
 int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs, int gnx, int gny, const CoregTanWcs* lag_wcs, int64_t n_lags,
@@ -2815,7 +2774,7 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   TRYRC(coreg_finite_mean(d_ref, COREG_F32, ns, d_piv, s));
   TRYRC(coreg_finite_mean(d_small, COREG_F64, ns, d_piv + 1, s));
   if (fast && (flags & COREG_FLAG_MIXED) && d_small_in) {
-    TRYRC(coreg_hpc_lag_corr_wcs_mixed(d_ref, d_small, (const float*)d_small_in, nullptr, snx, sny, snx, sny, wcs_small, d_lagw,
+    TRYRC(coreg_hpc_lag_corr_wcs_mixed(d_ref, d_small, (const float*)d_small_in, snx, sny, snx, sny, wcs_small, d_lagw,
                                        n_lags, order, d_piv, d_work, work_bytes, d_corr, d_nv, flags, s));
   } else if (fast) {
     TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv, d_work,

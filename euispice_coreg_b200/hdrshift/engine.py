@@ -256,17 +256,6 @@ class LagSearchEngine:
         self.small = small
         _ext.finite_mean(self.small, self.pivots[1:2])
 
-    use_rowcoef = os.environ.get("COREG_ROWCOEF", "0") == "1"
-
-    def _rowcoef(self):
-        """Row-coefficient plane of the mixed kernel (16 B per pixel), built on first use per small image."""
-        if not self.use_rowcoef or self.small32 is None:
-            return None
-        if getattr(self, "_rowcoef_of", None) is not self.small32:
-            self._rowcoef_t = _ext.spline_row_coefficients(self.small32)
-            self._rowcoef_of = self.small32
-        return self._rowcoef_t
-
     # ---- helioprojective ------------------------------------------------------------------------
     def set_large(self, data_large, wcs_large: TanWcs):
         """Upload the large image once; it stays resident for any number of `cut_large` calls (frame sequences)."""
@@ -430,8 +419,7 @@ class LagSearchEngine:
                         flags = _ext.make_flags(self.strict, 1, no_fast=self.no_fast)
                     _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
                                           self.pivots, work, out_dev[lo:hi], nv, flags,
-                                          small32=self.small32 if mixed else None,
-                                          rowcoef=self._rowcoef() if mixed else None)
+                                          small32=self.small32 if mixed else None)
                 elif self.frame == "car":
                     _ext.car_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order,
                                       self.pivots, work, out_dev[lo:hi], nv, self.flags)

@@ -199,14 +199,9 @@ int coreg_hpc_lag_corr_wcs(const float* ref_dev, const double* small_dev, int sn
  * (used where a segment touches the image border, a missing pixel or an irregular column and is evaluated by the
  * exact per-pixel rules). The reference stores every sample as float32 (alignment.py:1024), so the FP32 spline moves
  * a sample by about one float32 ulp, unbiased: |dr| ~ 1e-9 against the FP64 kernel (bar: 1e-6). Variants
- * (COREG_FLAG_VARIANT): 0 = 12 rows per thread, 1 = 16 (faster when no lag rotates or rescales the grid).
- * rowcoef_dev (may be NULL): the output of coreg_spline_row_coefficients for small32_dev; the kernel then loads the
- * three row coefficients of a tap row with one 16-byte load instead of forming them from three taps. */
-int coreg_spline_row_coefficients(const float* img_dev, int nx, int ny, float* rowcoef_dev /* [ny*nx*4], 16-B aligned */,
-                                  void* stream);
-int coreg_hpc_lag_corr_wcs_mixed(const float* ref_dev, const double* small_dev, const float* small32_dev,
-                                 const float* rowcoef_dev, int snx, int sny, int gnx, int gny,
-                                 const CoregTanWcs* grid_wcs_host,
+ * (COREG_FLAG_VARIANT): 0 = 12 rows per thread, 1 = 16 (faster when no lag rotates or rescales the grid). */
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref_dev, const double* small_dev, const float* small32_dev, int snx,
+                                 int sny, int gnx, int gny, const CoregTanWcs* grid_wcs_host,
                                  const CoregTanWcs* lag_wcs_dev, int64_t n_lags, int order, const double* pivots_dev,
                                  void* work_dev, size_t work_bytes, double* corr_dev, int64_t* nvalid_dev, int flags,
                                  void* stream);

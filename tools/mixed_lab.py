@@ -46,8 +46,7 @@ def main():
         base = None
         for combo in args.combos.split(","):
             arith, v = combo.split(":")
-            eng = E.LagSearchEngine(order=2, variant=int(v), arithmetic="mixed" if arith == "mixedc" else arith)
-            eng.use_rowcoef = arith == "mixedc"      # "mixedc": precomputed row-coefficient plane
+            eng = E.LagSearchEngine(order=2, variant=int(v), arithmetic=arith)
             eng.set_small(a.data_small)
             eng.prepare_hpc(a.data_large, w_large, w_small)
             table, _ = eng.hpc_lag_table(a.hdr_small, a, *d, kw.get("cdelt_semantics", "reference"))
