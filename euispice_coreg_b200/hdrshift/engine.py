@@ -256,6 +256,34 @@ class LagSearchEngine:
         self.small = small
         _ext.finite_mean(self.small, self.pivots[1:2])
 
+    # float32 moments need headroom on both sides: the mixed kernel squares pivot-subtracted pixel values and sums
+    # 16 of them in float32, so images whose magnitudes sit near the ends of the float32 range (|v| beyond 1e12, or
+    # nothing above 1e-9: flux units far from DN/s or W/m2/sr/nm) are searched by the all-FP64 kernel instead
+    MIXED_ABS_RANGE = (1e-9, 1e12)
+
+    @classmethod
+    def _float32_headroom(cls, *images):
+        torch = _torch()
+        lo, hi = cls.MIXED_ABS_RANGE
+        for img in images:
+            mag = torch.where(torch.isfinite(img), img.abs(), torch.zeros((), dtype=img.dtype, device=img.device))
+            m = float(mag.max()) if mag.numel() else 0.0
+            if not (lo < m < hi):
+                return False
+        return True
+
+    def _mixed_applies(self):
+        """Mixed arithmetic for the current (small, ref) pair: requested, a float32 twin of the small image exists,
+        and both images leave the float32 sums enough range. Decided once per pair (one device reduction + sync)."""
+        if self.arithmetic != "mixed" or self.small32 is None or self.ref is None:
+            return False
+        # (the pair is identified by the tensor objects themselves: a new image may land on a recycled address)
+        if getattr(self, "_mixed_pair", None) is None or self._mixed_pair[0] is not self.small32 \
+                or self._mixed_pair[1] is not self.ref:
+            self._mixed_pair = (self.small32, self.ref)
+            self._mixed_ok = self._float32_headroom(self.small32, self.ref)
+        return self._mixed_ok
+
     # ---- helioprojective ------------------------------------------------------------------------
     def set_large(self, data_large, wcs_large: TanWcs):
         """Upload the large image once; it stays resident for any number of `cut_large` calls (frame sequences)."""
@@ -413,7 +441,7 @@ class LagSearchEngine:
                 hi = min(n, lo + step)
                 nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
                 if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
-                    mixed = self.arithmetic == "mixed" and self.small32 is not None
+                    mixed = self._mixed_applies()
                     flags = self.flags
                     if mixed and self.variant == 0 and self.pure_shift_hint:
                         flags = _ext.make_flags(self.strict, 1, no_fast=self.no_fast)

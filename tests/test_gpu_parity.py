@@ -219,6 +219,26 @@ def test_strict_arithmetic_mode(torch_cuda, toy_pair):
     _assert_parity(gpu, ref)
 
 
+def test_mixed_arithmetic_needs_float32_headroom(torch_cuda, toy_pair):
+    """The float32 segment sums of the mixed kernel square pixel values: an image in units that push them towards the
+    ends of the float32 range is searched by the all-FP64 kernel, whatever was requested. Scaling by 2^-70 is exact
+    in binary floating point and r is scale-invariant, so that cube equals the all-FP64 cube of the original image
+    bit for bit."""
+    from euispice_coreg_b200.hdrshift import engine
+    f64, _ = _gpu_cube(toy_pair, arithmetic="fp64", **LAGS)
+    mixed, a = _gpu_cube(toy_pair, arithmetic="mixed", **LAGS)
+    eng = a.engine
+    assert eng._mixed_applies() and not np.array_equal(mixed, f64)
+    d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
+    table, _ = eng.hpc_lag_table(a.hdr_small, a, *d)
+    small = eng.small.cpu().numpy()
+    eng.set_small(small * 2.0 ** -70)          # ~1e-19: float32 values still, but their squares are not
+    assert eng.small32 is not None and not eng._mixed_applies()
+    assert np.array_equal(eng.search(table), f64.ravel())
+    eng.set_small(small)
+    assert eng._mixed_applies() and np.array_equal(eng.search(table), mixed.ravel())
+
+
 def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     """coreg_hpc_search_host (the non-Python caller's entry) == the torch-plumbed path, bit for bit."""
     from euispice_coreg_b200 import _ext
