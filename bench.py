@@ -38,11 +38,11 @@ FP64_EXECUTED_PER_SAMPLE = 31.7  # FP64 thread-instructions the column-rolling k
 #                                  algorithmic count of ITS formulation (ncu: DADD + DMUL + DFMA of
 #                                  one launch / pixel-samples, profiles/r1_roll_kernel.md)
 # mixed-arithmetic rolling kernel (FP64 projection, FP32 spline; the default when the small image is float32), from one
-# ncu --set full capture of a config-1 launch (profiles/r1_ncu_roll_mixed_v1.txt): 2.3086e10 warp-instructions and
-# 9.80e10 FP64 thread-instructions over 1.51e10 pixel-samples = 4.72e8 warp-samples
-MIXED_INSTR_PER_WARP_SAMPLE = 48.9   # all warp-instructions per warp-sample (32 pixel-samples)
-MIXED_FP64_PER_SAMPLE = 6.5          # of which FP64 (4 per pixel for the two coordinate quadratics + per-lag set-up)
-MIXED_DRAM_BYTES_PER_LAUNCH = 842.2e6   # dram read 137.3 MB + write 704.9 MB of that launch
+# ncu --set full capture of a config-1 launch (profiles/r1_ncu_roll_mixed_v2.txt): 2.2539e10 warp-instructions and
+# 9.42e10 FP64 thread-instructions over 1.51e10 pixel-samples = 4.72e8 warp-samples
+MIXED_INSTR_PER_WARP_SAMPLE = 47.8   # all warp-instructions per warp-sample (32 pixel-samples)
+MIXED_FP64_PER_SAMPLE = 6.2          # of which FP64 (4 per pixel for the two coordinate quadratics + per-lag set-up)
+MIXED_DRAM_BYTES_PER_LAUNCH = 849.1e6   # dram read 144.0 MB + write 705.0 MB of that launch
 BYTES_PER_SAMPLE = 8.0         # un-amortised: one f32 sample of each image per pixel-sample
 LAGS = dict(lag_crval1=np.arange(-30, 30, 1.0), lag_crval2=np.arange(-30, 30, 1.0), lag_cdelt1=np.array([0.0]),
             lag_cdelt2=np.array([0.0]), lag_crota=np.array([0.0]))
@@ -368,7 +368,7 @@ def run_gpu(args):
     # the "align() wall time" metric. It contains a collective, so all ranks take part.
     barrier()
     t0 = time.perf_counter()
-    res = Alignment(pl, ps, parallelism=True, **LAGS).align_using_helioprojective()
+    res = Alignment(pl, ps, parallelism=True, arithmetic=args.arithmetic, **LAGS).align_using_helioprojective()
     torch.cuda.synchronize()
     align_wall = time.perf_counter() - t0
     carr = None if args.no_carrington else carrington_secondary(pl, ps, args.steps, world, barrier, torch, dist,
