@@ -1712,7 +1712,7 @@ lag_corr_finalize_kernel(const double* __restrict__ work, int n_tiles, int n_lag
 // grid for a (rows per tile, resident blocks per SM) choice: blockIdx.x = tile, blockIdx.y = slice of the lag list,
 // enough slices for a few waves of resident blocks; returns false when the lag list does not fit one launch
 inline bool lag_grid(int tile_h, int minb, int gnx, int gny, int64_t n_lags, int sms, dim3* grid, int* lags_per_block,
-                     int* tiles_out, int lag_sub) {
+                     int* tiles_out, int lag_sub, bool amortise_block_setup = false) {
   const int tiles = ((gnx + kTileW - 1) / kTileW) * ((gny + tile_h - 1) / tile_h);
   *tiles_out = tiles;
   // many more blocks than resident slots: border tiles take the per-pixel path and run longer, so a fine
@@ -1722,6 +1722,15 @@ inline bool lag_grid(int tile_h, int minb, int gnx, int gny, int64_t n_lags, int
   int splits = (want_blocks + tiles - 1) / tiles;
   const int max_splits = (int)((n_lags + lag_sub - 1) / lag_sub);
   splits = std::max(1, std::min(splits, max_splits));
+  // ... but not so fine that a block's own set-up (its pixels of the reference image, their moments: worth about
+  // two lags) stops being amortised. Tail ~ 1 / waves and set-up ~ splits / n_lags balance at
+  // splits ~ sqrt(1.3 * resident blocks * n_lags / tiles): the 128-wave value for a 3600-lag search of a 2048^2 grid,
+  // fewer slices for short lag lists (one rank's share of a sharded search). Measured on 450-lag slices of config 1
+  // (tools/shard_lab.py): 29 slices of 16 lags 4.06 ms, 19 of 24 3.95, 12 of 40 3.86, 4 of 120 4.07.
+  if (amortise_block_setup) {
+    const double s = sqrt(1.315 * (double)(sms * minb) * (double)n_lags / (double)tiles);
+    splits = std::max(1, std::min(splits, (int)lround(s)));
+  }
   int lpb = (int)((n_lags + splits - 1) / splits);
   lpb = ((lpb + lag_sub - 1) / lag_sub) * lag_sub;
   splits = (int)((n_lags + lpb - 1) / lpb);
@@ -1778,7 +1787,7 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
   unsigned* wmask = reinterpret_cast<unsigned*>(base + L.mask);
   dim3 grid;
   int lpb, tiles;
-  if (!lag_grid(kRowsPerPass * rows_per_thread, minb, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk))
+  if (!lag_grid(kRowsPerPass * rows_per_thread, minb, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk, true))
     return fail(COREG_EINVAL, "lag grid too large for one launch");
   CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
   if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
