@@ -1321,9 +1321,9 @@ __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ sma
     if (p + 1 < P) row(tap += row_elems, r3a, r3b, r3c);
     double cx, cy;   // coordinate - shared floor + kFracMagic
     if (MODE == 0) {
-      // |e| <= 2^-18 over the whole grid: along the segment 1 / (1 - e) is linear in p to 5e-13 (its slope
-      // he1 (1 + 2 e) is below 4e-9 per row), so numerator x reciprocal is a quadratic in p whose coefficients the
-      // caller formed once per lag: two FMAs per coordinate instead of seven instructions for both
+      // |e| <= 2^-18 over the whole grid and |he1| < 2.2e-8 (the caller's test): along the segment 1 / (1 - e) is
+      // linear in p to p^2 he1^2 < 1.3e-13, so numerator x reciprocal is a quadratic in p whose coefficients are
+      // formed once per lag: two FMAs per coordinate instead of seven instructions for both
       cx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
       cy = (p == 0) ? qy0 : fma(fma(qy2, (double)p, qy1), (double)p, qy0);
     } else {
@@ -1424,7 +1424,10 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
       const double bnx2 = bnx + (xoff - (xoffm - kFracMagic)), bny2 = bny + (yoff - (yoffm - kFracMagic));
       float fsb = 0.f, fsbb = 0.f, fsab = 0.f;
       unsigned vbad = 0;
-      if (mode == 0)
+      // the quadratic form of the coordinates drops p^2 he1^2 of the reciprocal: below 1e-9 pixel for |he1| < 2.2e-8
+      // (P <= 16 rows, numerators below 8192 pixels) -- any 2048-row grid in this mode has |he1| < 4e-9; a small grid
+      // with a steep denominator takes the per-pixel series instead (block-uniform choice)
+      if (mode == 0 && fabs(he1) < 2.2e-8)
         roll_segment_mixed<0, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
                                  (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
       else

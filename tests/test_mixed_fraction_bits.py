@@ -59,3 +59,31 @@ def test_residual_folding_keeps_the_lag_offset_exact():
     xm = xoff + MAGIC
     resid = xoff - (xm - MAGIC)
     assert np.all(np.abs(resid) <= 2.0 ** -24) and np.array_equal((xm - MAGIC) + resid, xoff)
+
+
+def test_quadratic_coordinates_stay_within_a_nanopixel():
+    """roll_segment_mixed, MODE 0 (|e| <= 2^-18 over the grid, |he1| < 2.2e-8): along a 16-row segment the coordinate
+    numerator(p) / (1 - e(p)) is evaluated as the quadratic q0 + p (q1 + p q2) with
+    q1 = h1 * inv0 + n0 * dinv, q2 = h1 * dinv, dinv = he1 (1 + 2 e0), inv0 = 1 + e0 + e0^2.
+    Restated in numpy against exact rational arithmetic for the worst cases the mode admits."""
+    from fractions import Fraction as F
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for _ in range(200):
+        gny = int(rng.choice([64, 512, 2048, 4096]))
+        emax = 2.0 ** -18
+        he1 = float(rng.uniform(-1, 1)) * 2 * emax / gny          # e is linear over the grid and bounded by emax
+        if abs(he1) >= 2.2e-8:
+            continue                                              # the kernel takes the per-pixel series there
+        e0 = float(rng.uniform(-1, 1)) * (emax - abs(he1) * 16)
+        n0 = float(rng.uniform(-4096, 4096))                      # numerator of the first pixel (pixels)
+        h1 = float(rng.uniform(-2, 2))                            # its slope per row
+        inv0 = 1.0 + e0 + e0 * e0
+        dinv = he1 * (1.0 + 2.0 * e0)
+        q0, q1, q2 = n0 * inv0, h1 * inv0 + n0 * dinv, h1 * dinv
+        for p in range(16):
+            exact = (F(n0) + p * F(h1)) / (1 - (F(e0) + p * F(he1)))
+            quad = F(q0) + p * (F(q1) + p * F(q2))
+            worst = max(worst, abs(float(quad - exact)))
+    # e^3 of the series (5.5e-17 relative = 2e-13 px) + the neglected curvature of the reciprocal along the segment
+    assert worst < 1e-9, worst
