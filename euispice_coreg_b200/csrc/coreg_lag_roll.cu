@@ -1,0 +1,750 @@
+// coreg_lag_roll.cu -- helioprojective frame: per-lag homographies and the column-rolling fused lag kernel (all-FP64 and mixed arithmetic).
+#include "coreg_common.cuh"
+
+namespace coreg {
+// ---------------------------------------------------------------------------------------------------------
+// Fast variant of the fused lag kernel: order-2 spline, FMA arithmetic.
+//
+// Helioprojective frame = homography. The common grid and every candidate header are gnomonic (TAN) projections
+// of the same sphere from its centre, so pixel (i, j) of the common grid maps to the candidate's pixel through a
+// plane projective transformation, exactly:
+//      (nx, ny, D) = H (i, j, 1)^T ,   x = x0 + nx / D ,   y = y0 + ny / D ,
+// H = [plane'->pixel'] . E(lag)^T Rz(alpha0 - alpha') E(grid) . [pixel->plane]   (3x3, one per lag, built by
+// tan_homography_kernel from the two CoregTanWcs). No per-pixel trig, no world-coordinate planes; per sample the
+// map costs 3 FMA + the reciprocal. D = cos(angle to the lag's reference point) * sqrt(1 + r^2) is within 2^-7 of 1
+// for fields smaller than ~6 deg, where 1/D is the product form of the geometric series (1+e)(1+e^2)(1+e^4),
+// e = 1 - D, exact to 2^-56 (COREG_FLAG_SMALL_ANGLE, guaranteed by the caller); otherwise a true division is used.
+//
+// Both functors deliver coordinates already offset by +0.5, so floor(x + 0.5) is one magic-number add, and
+// "strictly interior" (all 9 taps inside the image: no closed-bound test, no mirroring) is one unsigned integer
+// compare per axis on the floor index. Groups of pixels take the branch-free path together; anything else (image
+// borders, missing reference pixels) falls back to the exact generic sampler with the same coordinates.
+// ---------------------------------------------------------------------------------------------------------
+struct HomGrid {  // pixel (i, j, 1) -> native direction (-Y, X, 1), and the grid's Euler matrix
+  double c[3][3];
+  double e[3][3];
+  double a0_rad;
+  double xmax, ymax;  // gnx - 1, gny - 1
+};
+
+// E(delta0, lonpole): native unit vector -> celestial frame whose x axis points at longitude alpha0
+__host__ __device__ inline void euler_matrix(double sin_d, double cos_d, double sin_lp, double cos_lp, double (&e)[3][3]) {
+  e[0][0] = -sin_d * cos_lp; e[0][1] = -sin_d * sin_lp; e[0][2] = cos_d;
+  e[1][0] = sin_lp;          e[1][1] = -cos_lp;         e[1][2] = 0.0;
+  e[2][0] = cos_d * cos_lp;  e[2][1] = cos_d * sin_lp;  e[2][2] = sin_d;
+}
+
+int make_hom_grid(const CoregTanWcs* w, int gnx, int gny, HomGrid* g) {
+  TanDev t;
+  int rc = make_tan(w, &t);
+  if (rc) return rc;
+  const double cx = t.f11 * (1.0 - t.crpix1) + t.f12 * (1.0 - t.crpix2);
+  const double cy = t.f21 * (1.0 - t.crpix1) + t.f22 * (1.0 - t.crpix2);
+  // d_native = (-Y, X, 1) with X = f11 i + f12 j + cx, Y = f21 i + f22 j + cy
+  g->c[0][0] = -t.f21; g->c[0][1] = -t.f22; g->c[0][2] = -cy;
+  g->c[1][0] = t.f11;  g->c[1][1] = t.f12;  g->c[1][2] = cx;
+  g->c[2][0] = 0.0;    g->c[2][1] = 0.0;    g->c[2][2] = 1.0;
+  euler_matrix(t.s0, t.c0, sin(t.lonpole_rad), cos(t.lonpole_rad), g->e);
+  g->a0_rad = t.a0_rad;
+  g->xmax = (double)(gnx - 1);
+  g->ymax = (double)(gny - 1);
+  return COREG_OK;
+}
+
+__global__ void tan_homography_kernel(HomGrid g, const CoregTanWcs* __restrict__ lag_wcs, int n,
+                                      HomLag* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const CoregTanWcs w = lag_wcs[idx];
+  double sd, cd, sl, cl, sa, ca;
+  sincos(w.crval2 * kD2R, &sd, &cd);
+  sincos(w.lonpole * kD2R, &sl, &cl);
+  sincos(g.a0_rad - w.crval1 * kD2R, &sa, &ca);  // Rz(alpha0 - alpha')
+  double e2[3][3];
+  euler_matrix(sd, cd, sl, cl, e2);
+  // m = Rz * E(grid) * C   (celestial direction in the lag's alpha frame, as a function of (i, j, 1))
+  double ec[3][3], m[3][3], r[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) ec[a][b] = g.e[a][0] * g.c[0][b] + g.e[a][1] * g.c[1][b] + g.e[a][2] * g.c[2][b];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    m[0][b] = ca * ec[0][b] - sa * ec[1][b];
+    m[1][b] = sa * ec[0][b] + ca * ec[1][b];
+    m[2][b] = ec[2][b];
+  }
+  // r = E(lag)^T m : native direction of the lag's projection
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) r[a][b] = e2[0][a] * m[0][b] + e2[1][a] * m[1][b] + e2[2][a] * m[2][b];
+  // plane' = (r1 / r2, -r0 / r2) [rad]; pixel' = inv(cdelt pc) plane' + crpix - 1
+  const double f11 = w.cdelt1 * w.pc11 * kD2R, f12 = w.cdelt1 * w.pc12 * kD2R;
+  const double f21 = w.cdelt2 * w.pc21 * kD2R, f22 = w.cdelt2 * w.pc22 * kD2R;
+  const double det = f11 * f22 - f12 * f21;
+  const double i11 = f22 / det, i12 = -f12 / det, i21 = -f21 / det, i22 = f11 / det;
+  HomLag h;
+  h.hx0 = i11 * r[1][0] - i12 * r[0][0]; h.hx1 = i11 * r[1][1] - i12 * r[0][1]; h.hx2 = i11 * r[1][2] - i12 * r[0][2];
+  h.hy0 = i21 * r[1][0] - i22 * r[0][0]; h.hy1 = i21 * r[1][1] - i22 * r[0][1]; h.hy2 = i21 * r[1][2] - i22 * r[0][2];
+  h.he0 = -r[2][0]; h.he1 = -r[2][1]; h.he2 = 1.0 - r[2][2];
+  h.x0h = (w.crpix1 - 1.0) + 0.5;
+  h.y0h = (w.crpix2 - 1.0) + 0.5;
+  // e = he0 i + he1 j + he2 is linear over the grid: its extreme values sit at the four corners
+  const double e00 = h.he2, e10 = fma(h.he0, g.xmax, h.he2), e01 = fma(h.he1, g.ymax, h.he2),
+               e11 = fma(h.he0, g.xmax, fma(h.he1, g.ymax, h.he2));
+  double em = fmax(fmax(fabs(e00), fabs(e10)), fmax(fabs(e01), fabs(e11)));
+  if (!(em == em) || !isfinite(h.hx0 + h.hx1 + h.hx2 + h.hy0 + h.hy1 + h.hy2)) em = CUDART_INF;
+  h.emax = em;
+  out[idx] = h;
+}
+
+// reciprocal of the projective denominator D = 1 - e, chosen per lag (block-uniform) from the lag's emax:
+//   |e| <= 2^-18 : 1 + e + e^2                    (2 ops, truncation e^3 <= 2^-54)
+//   |e| <= 2^-7  : (1 + e)(1 + e^2)(1 + e^4)      (5 ops, truncation e^8 <= 2^-56)
+//   otherwise    : true division; D <= 0 (behind the tangent hemisphere) -> NaN
+constexpr double kTinyE = 3.814697265625e-06;  // 2^-18
+constexpr double kSmallE = 0.0078125;          // 2^-7
+
+__device__ __forceinline__ double recip_1me_tiny(double e) { return fma(e, e, 1.0 + e); }
+__device__ __forceinline__ double recip_1me_small(double e) {
+  const double e2 = e * e;
+  double inv = 1.0 + e;
+  inv = fma(e2, inv, inv);
+  const double e4 = e2 * e2;
+  return fma(e4, inv, inv);
+}
+__device__ __forceinline__ double recip_1me_div(double e) {
+  const double den = 1.0 - e;
+  return (den > 0.0) ? 1.0 / den : CUDART_NAN;
+}
+
+// exact order-2 sample at (sx - 0.5, sy - 0.5) with float32 rounding / masking, kept out of line: only image
+// borders, irregular columns and missing reference pixels come here
+template <bool ROUND32>
+__device__ __noinline__ bool sample_exact_half(const double* __restrict__ small, int sny, int snx, double sy,
+                                               double sx, double* out) {
+  double v;
+  bool ok = spline_sample<2, false, double>(small, sny, snx, sy - 0.5, sx - 0.5, v);
+  if (ROUND32) {
+    const float bf = __double2float_rn(v);
+    ok = ok && isfinite(bf);
+    v = (double)bf;
+  } else {
+    ok = ok && isfinite(v) && (v != -32762.0);
+  }
+  *out = v;
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Column-rolling form of the fused helioprojective lag kernel (order-2 spline, FMA arithmetic, float64 small image).
+//
+// A thread owns P CONSECUTIVE rows of one common-grid column. Under a candidate header the homography moves that
+// column segment almost rigidly: x is constant to a small fraction of a pixel and y advances by one pixel per row,
+// so floor(x + 0.5) is shared by the P pixels and floor(y + 0.5) increases by exactly one per row ("regular"
+// column). The 3x3 tap windows of consecutive pixels then overlap in two of their three rows: the thread keeps a
+// rolling window of three tap rows in registers and loads 3 new taps per pixel instead of 9 (3 (P + 2) / P per pixel
+// overall) -- the L1 data pipe, not FP64 issue, bounded the per-pixel kernel. The fractional parts come from the
+// shared floors (x - floor_x0, y - (floor_y0 + p)); whether they really lie in [0, 1) is checked per pixel with one
+// integer compare on the high word, and a pixel that fails (a floor changed inside the segment: rotated lags, or a
+// coordinate within 1e-7 of a half-integer) is re-evaluated by the exact out-of-line sampler, as is every pixel of
+// a thread whose window touches the image border or whose reference pixels are not all finite. Results therefore
+// equal the per-pixel kernel's up to the rounding of the reciprocal series.
+// ---------------------------------------------------------------------------------------------------------
+// The P pixels of a regular window, fully unrolled and free of branches, selects and predicates so that the
+// independent dependency chains of consecutive pixels interleave (the FP64 pipe has an 8-cycle dependent-issue
+// latency). MODE selects the reciprocal series (0: 1 + e + e^2, 1: three-factor product). Validity is tracked for the
+// segment as a whole with two integer maxima: `vmax` over the high words of the fractional parts (all in [0, 1) <=>
+// vmax < 0x3FF00000) and `bmax` over the magnitude bits of the float32 samples (all finite <=> bmax < 0x7F800000);
+// the caller discards the sums and re-evaluates the segment pixel by pixel when either test fails.
+template <int MODE, bool ROUND32, int P>
+__device__ __forceinline__ void roll_segment(const double* __restrict__ small, unsigned tap, unsigned row_elems,
+                                             double be, double bnx, double bny, double he1, double hx1, double hy1,
+                                             double inv0, double xoff, double yoff, double pivot_b,
+                                             const double (&a_c)[P], double& sb, double& sbb, double& sab,
+                                             unsigned& vmax, unsigned& bmax) {
+  // A tap row (a, b, c) enters the result only through  a w0 + b w1 + c w2  with the order-2 B-spline weights
+  // w0 = (1 - v)^2 / 2, w1 = 1/2 + v - v^2, w2 = v^2 / 2 of v = d + 0.5, i.e. through the quadratic
+  //   A + v (B + v C),   A = (a + b) / 2,  B = b - a,  C = (a + c) / 2 - b.
+  // A row serves three consecutive pixels of the column (each with its own v), so its coefficients are formed once
+  // (5 operations per row) and every pixel evaluates three Horner forms in x (6 FMAs) and, the same way, one in y
+  // (5 + 2): 13 + 5 (P + 2) / P operations per pixel instead of 12 for the weights plus 12 for the taps.
+  // (Forming the coefficients once per image into three planes was measured slower: three times the L1 footprint.)
+  auto row = [&](unsigned t, double& ca, double& cb, double& cc) {
+    const double ta = __ldg(small + t), tb = __ldg(small + t + 1), tc = __ldg(small + t + 2);
+    ca = 0.5 * (ta + tb);
+    cb = tb - ta;
+    cc = fma(0.5, ta + tc, -tb);
+  };
+  double r0a, r0b, r0c, r1a, r1b, r1c, r2a, r2b, r2c;
+  row(tap, r0a, r0b, r0c);
+  row(tap += row_elems, r1a, r1b, r1c);
+  row(tap += row_elems, r2a, r2b, r2c);
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    // next row first: it is consumed one pixel later
+    double r3a = 0.0, r3b = 0.0, r3c = 0.0;
+    if (p + 1 < P) row(tap += row_elems, r3a, r3b, r3c);
+    const double e = (p == 0) ? be : fma(he1, (double)p, be);
+    const double inv = (p == 0) ? inv0 : ((MODE == 0) ? recip_1me_tiny(e) : recip_1me_small(e));
+    const double nx = (p == 0) ? bnx : fma(hx1, (double)p, bnx);
+    const double ny = (p == 0) ? bny : fma(hy1, (double)p, bny);
+    // fractional parts (+0.5) relative to the shared floors: v = d + 0.5 in [0, 1) on a regular column
+    const double vx = fma(nx, inv, xoff);
+    const double vy = fma(ny, inv, yoff - (double)p);
+    vmax = max(vmax, max((unsigned)__double2hiint(vx), (unsigned)__double2hiint(vy)));
+    const double q0 = fma(fma(r0c, vx, r0b), vx, r0a);
+    const double q1 = fma(fma(r1c, vx, r1b), vx, r1a);
+    const double q2 = fma(fma(r2c, vx, r2b), vx, r2a);
+    const double t = fma(fma(fma(0.5, q0 + q2, -q1), vy, q1 - q0), vy, 0.5 * (q0 + q1));
+    double b;
+    if (ROUND32) {
+      // a non-finite float32 sample makes Sbb non-finite: the caller tests that once per segment
+      b = (double)__double2float_rn(t);
+    } else {
+      // finite and not the -32762 fill: fold both into the same flag (the fill marks the sample as missing)
+      const unsigned hi = (unsigned)__double2hiint(t) & 0x7FFFFFFFu;
+      bmax = max(bmax, (t == -32762.0) ? 0x7F800000u : ((hi >= 0x7FF00000u) ? 0x7F800000u : 0u));
+      b = t;
+    }
+    const double bc = b - pivot_b;
+    sb += bc;
+    sbb = fma(bc, bc, sbb);
+    sab = fma(a_c[p], bc, sab);
+    r0a = r1a; r0b = r1b; r0c = r1c;
+    r1a = r2a; r1b = r2b; r1c = r2c;
+    r2a = r3a; r2b = r3b; r2c = r3c;
+  }
+}
+
+// The same segment in MIXED arithmetic: coordinates in FP64 (7 instructions per pixel), the spline and the segment's
+// moments in FP32 on a float32 copy of the small image. The reference rounds every sample to float32 anyway
+// (`alignment.py:1024`), so an FP32 spline differs from it by about one float32 ulp per sample, unbiased; the
+// Pearson sums average that over 4e6 samples (|dr| ~ 1e-9 measured, bar 1e-6). A DFMA occupies the dispatch port
+// for two cycles and an FFMA for one (profiles/r1_fp64_issue_model.md), so moving the 23 spline / moment
+// instructions off the FP64 pipe is what shortens the issue-bound loop.
+// The fractional parts leave the FP64 domain without a conversion instruction: the coordinate FMA adds
+// kFracMagic = 1.5 * 2^29, whose ulp is 2^-23, so the low word of the result is round((x - floor_x0) * 2^23): bits
+// 23.. must be zero for x (p for y: the row index inside the segment), the low 23 bits are the float32 mantissa of
+// 1 + frac. `vbad` collects the bits that must be zero; the caller re-evaluates the segment pixel by pixel when
+// vbad >= 2^23 (a floor changed inside the segment, or a fraction rounded up to 1).
+constexpr double kFracMagic = 805306368.0;   // 1.5 * 2^29
+
+template <int MODE, int P>
+__device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ small32, unsigned tap,
+                                                   unsigned row_elems, double be, double bnx, double bny, double he1,
+                                                   double hx1, double hy1, double inv0, double xoffm, double yoffm,
+                                                   float pivot_b, const float (&a_c)[P], float& sb, float& sbb,
+                                                   float& sab, unsigned& vbad) {
+  // (Measured and dropped, profiles/r1_mixed_kernel.md: a per-image plane of these coefficients, one 16-byte load
+  // per row and no arithmetic, is slower -- four times the L1 footprint; a 64-bit row pointer, walked or formed as
+  // base + k * stride, compiles to four IADD3 per row where the 32-bit index + IMAD.WIDE form below costs two.)
+  auto row = [&](unsigned t, float& ca, float& cb, float& cc) {
+    const float ta = __ldg(small32 + t), tb = __ldg(small32 + t + 1), tc = __ldg(small32 + t + 2);
+    ca = 0.5f * (ta + tb);
+    cb = tb - ta;
+    cc = fmaf(0.5f, ta + tc, -tb);
+  };
+  float r0a, r0b, r0c, r1a, r1b, r1c, r2a, r2b, r2c;
+  row(tap, r0a, r0b, r0c);
+  row(tap += row_elems, r1a, r1b, r1c);
+  row(tap += row_elems, r2a, r2b, r2c);
+  double qx0 = 0, qx1 = 0, qx2 = 0, qy0 = 0, qy1 = 0, qy2 = 0;
+  if (MODE == 0) {
+    const double dinv = fma(be + be, he1, he1);   // d(1 + e + e^2) / dp at the first pixel
+    qx0 = fma(bnx, inv0, xoffm);
+    qy0 = fma(bny, inv0, yoffm);
+    qx1 = fma(hx1, inv0, bnx * dinv);
+    qy1 = fma(hy1, inv0, bny * dinv);
+    qx2 = hx1 * dinv;
+    qy2 = hy1 * dinv;
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    float r3a = 0.f, r3b = 0.f, r3c = 0.f;
+    if (p + 1 < P) row(tap += row_elems, r3a, r3b, r3c);
+    double cx, cy;   // coordinate - shared floor + kFracMagic
+    if (MODE == 0) {
+      // |e| <= 2^-18 over the whole grid and |he1| < 2.2e-8 (the caller's test): along the segment 1 / (1 - e) is
+      // linear in p to p^2 he1^2 < 1.3e-13, so numerator x reciprocal is a quadratic in p whose coefficients are
+      // formed once per lag: two FMAs per coordinate instead of seven instructions for both
+      cx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
+      cy = (p == 0) ? qy0 : fma(fma(qy2, (double)p, qy1), (double)p, qy0);
+    } else {
+      const double e = (p == 0) ? be : fma(he1, (double)p, be);
+      const double inv = (p == 0) ? inv0 : recip_1me_small(e);
+      const double nx = (p == 0) ? bnx : fma(hx1, (double)p, bnx);
+      const double ny = (p == 0) ? bny : fma(hy1, (double)p, bny);
+      cx = fma(nx, inv, xoffm);
+      cy = fma(ny, inv, yoffm);
+    }
+    const unsigned ux = (unsigned)__double2loint(cx);
+    const unsigned uy = (unsigned)__double2loint(cy) ^ ((unsigned)p << 23);
+    vbad |= ux | uy;
+    const float vx = __uint_as_float(ux | 0x3F800000u) - 1.0f;
+    const float vy = __uint_as_float(uy | 0x3F800000u) - 1.0f;
+    const float q0 = fmaf(fmaf(r0c, vx, r0b), vx, r0a);
+    const float q1 = fmaf(fmaf(r1c, vx, r1b), vx, r1a);
+    const float q2 = fmaf(fmaf(r2c, vx, r2b), vx, r2a);
+    // sample - pivot in one go: the pivot rides in the constant term of the y quadratic
+    const float bc = fmaf(fmaf(fmaf(0.5f, q0 + q2, -q1), vy, q1 - q0), vy, fmaf(0.5f, q0 + q1, -pivot_b));
+    sb += bc;
+    sbb = fmaf(bc, bc, sbb);
+    sab = fmaf(a_c[p], bc, sab);
+    r0a = r1a; r0b = r1b; r0c = r1c;
+    r1a = r2a; r1b = r2b; r1c = r2c;
+    r2a = r3a; r2b = r3b; r2c = r3c;
+  }
+}
+
+// One pixel by the per-pixel rules: own floors, 9 taps when they are all inside the image, otherwise the exact
+// out-of-line sampler. (sx, sy) are the coordinates + 0.5. Returns false when the sample is missing.
+template <bool ROUND32>
+__device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ small, int sny, int snx,
+                                                  unsigned row_elems, double sx, double sy, double* out) {
+  const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+  const int ix = __double2loint(mx), iy = __double2loint(my);
+  const bool interior = small_magnitude(sx) && small_magnitude(sy) && ((unsigned)(ix - 1) < (unsigned)(snx - 2)) &&
+                        ((unsigned)(iy - 1) < (unsigned)(sny - 2));
+  if (!interior) return sample_exact_half<ROUND32>(small, sny, snx, sy, sx, out);
+  const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);
+  const double wx2 = (0.5 * vx) * vx;
+  const double wx0 = (wx2 + 0.5) - vx;
+  const double wx1 = fma(-2.0, wx2, vx + 0.5);
+  const double wy2 = (0.5 * vy) * vy;
+  const double wy0 = (wy2 + 0.5) - vy;
+  const double wy1 = fma(-2.0, wy2, vy + 0.5);
+  const double* r0p = small + ((unsigned)(iy - 1) * row_elems + (unsigned)(ix - 1));
+  const double* r1p = r0p + row_elems;
+  const double* r2p = r1p + row_elems;
+  const double q0 = fma(__ldg(r0p + 2), wx2, fma(__ldg(r0p + 1), wx1, __ldg(r0p) * wx0));
+  const double q1 = fma(__ldg(r1p + 2), wx2, fma(__ldg(r1p + 1), wx1, __ldg(r1p) * wx0));
+  const double q2 = fma(__ldg(r2p + 2), wx2, fma(__ldg(r2p + 1), wx1, __ldg(r2p) * wx0));
+  const double t = fma(q2, wy2, fma(q1, wy1, q0 * wy0));
+  if (ROUND32) {
+    const float bf = __double2float_rn(t);
+    *out = (double)bf;
+    return isfinite(bf);
+  }
+  *out = t;
+  return isfinite(t) && (t != -32762.0);
+}
+
+// One lag for one thread's column segment: first-pixel coordinates, shared floors, window test, the regular rolling
+// segment or -- image borders, irregular columns (rotated lags), missing pixels, division-mode lags -- the segment
+// pixel by pixel. Out: the thread's Sb, Sbb, Sab over its valid samples and the mask of pixels that have a finite
+// reference value but no valid sample.
+template <bool ROUND32, int P, bool MIXED, typename AT>
+__device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small,
+                                         const float* __restrict__ small32, int snx, int sny, unsigned row_elems,
+                                         double di, double dj0, const AT (&a_c)[P], unsigned a_ok, bool all_ref,
+                                         double pivot_b, double& sb, double& sbb, double& sab, unsigned& miss) {
+  const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
+  const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
+  // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
+  const double bnx = fma(hx1, dj0, fma(C.hx0, di, C.hx2));
+  const double bny = fma(hy1, dj0, fma(C.hy0, di, C.hy2));
+  const double be = fma(he1, dj0, fma(C.he0, di, C.he2));
+  const double inv0 = (mode == 0) ? recip_1me_tiny(be) : ((mode == 1) ? recip_1me_small(be) : recip_1me_div(be));
+  const double sx0 = fma(bnx, inv0, x0h), sy0 = fma(bny, inv0, y0h);  // coordinates + 0.5
+  // floors shared by the segment
+  const double mx0 = __dadd_rd(sx0, kMagic), my0 = __dadd_rd(sy0, kMagic);
+  const int ix0 = __double2loint(mx0), iy0 = __double2loint(my0);
+  const double xoff = x0h - (mx0 - kMagic), yoff = y0h - (my0 - kMagic);
+  sb = sbb = sab = 0.0;
+  // whole window inside the image: columns ix0-1 .. ix0+1, rows iy0-1 .. iy0+P; |coordinate| < 2^30 keeps the
+  // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
+  bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
+              ((unsigned)(ix0 - 1) < (unsigned)(snx - 2)) && (iy0 >= 1) && (iy0 + P <= sny - 1);
+  if constexpr (MIXED) {
+    // the low word of coordinate + kFracMagic holds the offset from the shared floor only while that offset stays
+    // below 2^9 pixels: true for any sane lag, guaranteed here by bounding the per-row slopes (block-uniform test)
+    fast = fast && (fabs(hx1) < 8.0) && (fabs(hy1) < 8.0);
+    if (fast) {
+      const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
+      // xoff + kFracMagic rounds to 2^-23 pixel; the residual (exact) goes into the numerator, whose factor inv is
+      // 1 + O(2^-7): what is lost is below 1e-9 pixel, the same for every pixel of the lag
+      const double xoffm = xoff + kFracMagic, yoffm = yoff + kFracMagic;
+      const double bnx2 = bnx + (xoff - (xoffm - kFracMagic)), bny2 = bny + (yoff - (yoffm - kFracMagic));
+      float fsb = 0.f, fsbb = 0.f, fsab = 0.f;
+      unsigned vbad = 0;
+      // the quadratic form of the coordinates drops p^2 he1^2 of the reciprocal: below 1e-9 pixel for |he1| < 2.2e-8
+      // (P <= 16 rows, numerators below 8192 pixels) -- any 2048-row grid in this mode has |he1| < 4e-9; a small grid
+      // with a steep denominator takes the per-pixel series instead (block-uniform choice)
+      if (mode == 0 && fabs(he1) < 2.2e-8)
+        roll_segment_mixed<0, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+                                 (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
+      else
+        roll_segment_mixed<1, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+                                 (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
+      // every offset inside its cell, every sample finite (a non-finite sample makes Sbb non-finite; so does a
+      // finite sample beyond 1.8e19, which then just takes the exact path)
+      fast = (vbad < 0x00800000u) && ((__float_as_uint(fsbb) & 0x7F800000u) != 0x7F800000u);
+      sb = (double)fsb;
+      sbb = (double)fsbb;
+      sab = (double)fsab;
+    }
+  } else if (fast) {
+    const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
+    unsigned vmax = 0, bmax = 0;
+    if (mode == 0)
+      roll_segment<0, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
+                                  a_c, sb, sbb, sab, vmax, bmax);
+    else
+      roll_segment<1, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
+                                  a_c, sb, sbb, sab, vmax, bmax);
+    // all fractional parts in [0, 1), every sample finite (|bc| < 2^129 keeps bc^2 finite, so Sbb is finite
+    // exactly when all samples are)
+    fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u) &&
+           (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
+  }
+  miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
+  if (!fast && a_ok && mode != 2) {
+    // A segment that lies outside the small image as a whole has no sample at all. Along the segment each
+    // coordinate is numerator / (1 - e) with both linear in p and 1 - e > 0, hence monotonic: it stays between its
+    // values at the first and the last pixel. (1e-6 pixel covers the rounding of the reciprocal series; NaN
+    // coordinates fail every compare and go pixel by pixel.)
+    const double eL = fma(he1, (double)(P - 1), be);
+    const double invL = (mode == 0) ? recip_1me_tiny(eL) : recip_1me_small(eL);
+    const double sxL = fma(fma(hx1, (double)(P - 1), bnx), invL, x0h);
+    const double syL = fma(fma(hy1, (double)(P - 1), bny), invL, y0h);
+    const double lo = 0.5 - 1e-6, hix = (double)snx - 0.5 + 1e-6, hiy = (double)sny - 0.5 + 1e-6;
+    if ((fmax(sx0, sxL) < lo) || (fmin(sx0, sxL) > hix) || (fmax(sy0, syL) < lo) || (fmin(sy0, syL) > hiy)) {
+      sb = sbb = sab = 0.0;
+      miss = a_ok;
+      return;
+    }
+  }
+  if (!fast && a_ok) {
+    // image borders, irregular columns (rotated lags), missing pixels: the segment pixel by pixel
+    sb = sbb = sab = 0.0;
+#pragma unroll 1
+    for (int p = 0; p < P; ++p) {
+      if (!(a_ok & (1u << p))) continue;
+      const double e = fma(he1, (double)p, be);
+      const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
+      const double sx = fma(fma(hx1, (double)p, bnx), inv, x0h);
+      const double sy = fma(fma(hy1, (double)p, bny), inv, y0h);
+      AT acs = a_c[0];
+#pragma unroll
+      for (int q = 1; q < P; ++q)
+        if (q == p) acs = a_c[q];
+      const double ac = (double)acs;
+      double b;
+      if (sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, &b)) {
+        const double bc = b - pivot_b;
+        sb += bc;
+        sbb = fma(bc, bc, sbb);
+        sab = fma(ac, bc, sab);
+      } else {
+        miss |= 1u << p;
+      }
+    }
+  }
+}
+
+#ifndef COREG_ROLL_CHUNK
+#define COREG_ROLL_CHUNK 8
+#endif
+constexpr int kRollChunk = COREG_ROLL_CHUNK;  // lags whose per-lane sums wait in a warp's shared-memory slice for one fold
+
+// ---------------------------------------------------------------------------------------------------------
+// The rolling kernel proper. Warps are independent: no block barrier inside the lag walk. Every warp keeps its own
+// shared-memory slice (its lanes' Sb, Sbb, Sab for kRollChunk lags, and its own copy of the chunk's 3x3 matrices),
+// folds it with __syncwarp only, and writes one 24-byte record per (warp, lag) straight to the workspace; the
+// finalize kernel sums 8 records per tile instead of one. Corrections for missing samples (rare) go to a second
+// array that is only read where a bit of the per-(tile, lag) mask is set, so it needs no initialisation; the
+// mask itself (4 B per tile and lag) is cleared by the launcher.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAccPad = 33;   // lane stride of the per-warp accumulators (bank-conflict-free transposed reads)
+
+struct RollWShared {
+  double acc[kWarps][kRollChunk][3][kAccPad];
+  HomLag lag[kWarps][kRollChunk];
+};
+
+template <typename RefT, bool ROUND32, int P, int MINB, bool MIXED>
+__global__ void __launch_bounds__(kThreads, MINB)
+lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small,
+                      const float* __restrict__ small32, int snx, int sny, int gnx,
+                      int gny, const HomLag* __restrict__ lags, int n_lags, int lags_per_block,
+                      const double* __restrict__ pivots, double* __restrict__ wrec, double* __restrict__ wcorr,
+                      double* __restrict__ wconst, unsigned* __restrict__ wmask) {
+  constexpr int TILE_H = kRowsPerPass * P;
+  extern __shared__ __align__(16) unsigned char roll_smem[];
+  RollWShared& S = *reinterpret_cast<RollWShared*>(roll_smem);
+
+  const int tiles_x = (gnx + kTileW - 1) / kTileW;
+  const int tile = blockIdx.x;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & (kTileW - 1), rg = tid / kTileW;
+  const int gx = tile_x * kTileW + tx;
+  const int gy0 = tile_y * TILE_H + rg * P;
+  // MIXED: float32-representable pivots, so that the float32 segment sums and the FP64 fallback subtract the same
+  // numbers and a - pivot_a is (nearly always) exact in float32. r does not depend on the pivots.
+  const double pivot_a = MIXED ? (double)(float)pivots[0] : pivots[0];
+  const double pivot_b = MIXED ? (double)(float)pivots[1] : pivots[1];
+  const unsigned row_elems = (unsigned)snx;
+  const double di = (double)gx, dj0 = (double)gy0;
+  const size_t wid = (size_t)tile * kWarps + warp;   // this warp's record row
+
+  using AT = typename std::conditional<MIXED, float, double>::type;
+  AT a_c[P];
+  unsigned a_ok = 0;
+  double sa_all = 0.0, saa_all = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int gy = gy0 + p;
+    a_c[p] = (AT)0;
+    if (gx < gnx && gy < gny) {
+      const double a = (double)ref[(int64_t)gy * gnx + gx];
+      if (isfinite(a)) {
+        a_c[p] = (AT)(a - pivot_a);
+        a_ok |= 1u << p;
+        // MIXED: every sum sees the float32 value of a - pivot_a, i.e. one consistent reference image
+        const double ac = (double)a_c[p];
+        sa_all += ac;
+        saa_all = fma(ac, ac, saa_all);
+      }
+    }
+  }
+  const bool all_ref = a_ok == ((P >= 32) ? 0xFFFFFFFFu : ((1u << (P & 31)) - 1u));
+  if (blockIdx.y == 0) {
+    // lag-independent reference moments of this warp's pixels (n, Sa, Saa): one record per warp, written once
+    double wsa = sa_all, wsaa = saa_all;
+    int wn = __popc(a_ok);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
+      wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
+      wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    }
+    if (lane == 0) {
+      wconst[wid * 3 + 0] = (double)wn;
+      wconst[wid * 3 + 1] = wsa;
+      wconst[wid * 3 + 2] = wsaa;
+    }
+  }
+
+  const int lag_begin = blockIdx.y * lags_per_block;
+  const int lag_end = min(n_lags, lag_begin + lags_per_block);
+  for (int l0 = lag_begin; l0 < lag_end; l0 += kRollChunk) {
+    const int cnt = min(kRollChunk, lag_end - l0);
+    __syncwarp();   // previous chunk folded
+    {
+      const double* src = reinterpret_cast<const double*>(lags + l0);
+      double* dst = reinterpret_cast<double*>(&S.lag[warp][0]);
+      const int nd = cnt * (int)(sizeof(HomLag) / sizeof(double));
+      for (int i = lane; i < nd; i += 32) dst[i] = __ldg(src + i);
+    }
+    __syncwarp();
+    for (int l = 0; l < cnt; ++l) {
+      double sb, sbb, sab;
+      unsigned miss;
+      roll_lag<ROUND32, P, MIXED, AT>(S.lag[warp][l], small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref,
+                                      pivot_b, sb, sbb, sab, miss);
+      S.acc[warp][l][0][lane] = sb;
+      S.acc[warp][l][1][lane] = sbb;
+      S.acc[warp][l][2][lane] = sab;
+      if (__any_sync(0xffffffffu, miss != 0)) {
+        double m[4] = {(double)__popc(miss), 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (miss & (1u << p)) {
+            const double ac = (double)a_c[p];
+            m[1] += ac;
+            m[2] = fma(ac, ac, m[2]);
+          }
+        const double tot = warp_transpose_reduce4(m, lane);  // lanes 0, 8, 16: n, Sa, Saa of the missing pixels
+        if ((lane & 7) == 0 && lane < 24) wcorr[(wid * n_lags + (l0 + l)) * 3 + (lane >> 3)] = tot;
+        if (lane == 0) atomicOr(wmask + ((size_t)tile * n_lags + (l0 + l)), 1u << warp);
+      }
+    }
+    __syncwarp();
+    if (lane < cnt * 3) {
+      const int l = lane / 3, v = lane - 3 * l;
+      const double* src = &S.acc[warp][l][v][0];
+      double t = src[0];
+#pragma unroll
+      for (int k = 1; k < 32; ++k) t += src[k];
+      wrec[(wid * n_lags + (l0 + l)) * 3 + v] = t;
+    }
+  }
+}
+
+// one block per lag: sum the warp records in a fixed order, moments -> Pearson r
+__global__ void __launch_bounds__(128)
+lag_corr_finalize_w_kernel(const double* __restrict__ wrec, const double* __restrict__ wcorr,
+                           const double* __restrict__ wconst, const unsigned* __restrict__ wmask, int n_rows,
+                           int n_lags, double* __restrict__ corr, int64_t* __restrict__ nvalid) {
+  __shared__ double s[128][6];
+  const int lag = blockIdx.x;
+  double m[6] = {0, 0, 0, 0, 0, 0};   // n, Sa, Sb, Saa, Sbb, Sab
+  for (int r = threadIdx.x; r < n_rows; r += 128) {
+    const double* p = wrec + ((size_t)r * n_lags + lag) * 3;
+    m[2] += p[0];
+    m[4] += p[1];
+    m[5] += p[2];
+    m[0] += wconst[(size_t)r * 3 + 0];
+    m[1] += wconst[(size_t)r * 3 + 1];
+    m[3] += wconst[(size_t)r * 3 + 2];
+    if ((wmask[(size_t)(r / kWarps) * n_lags + lag] >> (r % kWarps)) & 1u) {
+      const double* c = wcorr + ((size_t)r * n_lags + lag) * 3;
+      m[0] -= c[0];
+      m[1] -= c[1];
+      m[3] -= c[2];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s[threadIdx.x][q] = m[q];
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s[threadIdx.x][q] += s[threadIdx.x + o][q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = s[0][0], sa = s[0][1], sb = s[0][2], saa = s[0][3], sbb = s[0][4], sab = s[0][5];
+    double r = CUDART_NAN;
+    if (n > 0.0) {
+      const double cov = sab - sa * sb / n;
+      const double va = saa - sa * sa / n;
+      const double vb = sbb - sb * sb / n;
+      r = cov / sqrt(va * vb);
+    }
+    corr[lag] = r;
+    if (nvalid) nvalid[lag] = (int64_t)n;
+  }
+}
+
+// rolling kernel + its finalize. Tuning variants (flags bits 8..11): rows per thread 12 (default), 16, 14; the
+// workspace layout is sized for 12 (fewer rows per thread would need more record rows). small32 != nullptr selects
+// the mixed-arithmetic kernel (FP64 coordinates, FP32 spline on the float32 copy of the small image), variants 0 / 1
+// = 12 / 16 rows per thread. (Measured and dropped: 3 CTAs per SM at 80 registers -- spills; 24 and 32 rows per
+// thread -- spills and partial tiles; a precomputed row-coefficient plane: tools/mixed_lab.py,
+// profiles/r1_mixed_kernel.md.)
+template <typename RefT, bool ROUND32>
+int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
+                     const double* small, const float* small32, int snx, int sny,
+                     const HomLag* ft, const double* pivots, void* work, double* corr, int64_t* nvalid, bool prof) {
+  const bool mixed = small32 != nullptr;
+  const int minb = 2;
+  const int rows_per_thread = (variant == 1) ? 16 : ((variant == 2 && !mixed) ? 14 : kRollWRows);
+  const RollWLayout L = rollw_layout(gnx, gny, n_lags);
+  char* base = static_cast<char*>(work);
+  double* wrec = reinterpret_cast<double*>(base + L.rec);
+  double* wcorr = reinterpret_cast<double*>(base + L.corr);
+  double* wconst = reinterpret_cast<double*>(base + L.cst);
+  unsigned* wmask = reinterpret_cast<unsigned*>(base + L.mask);
+  dim3 grid;
+  int lpb, tiles;
+  if (!lag_grid(kRowsPerPass * rows_per_thread, minb, gnx, gny, n_lags, sms, &grid, &lpb, &tiles, kRollChunk, true))
+    return fail(COREG_EINVAL, "lag grid too large for one launch");
+  CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
+  if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
+#define RW(P_, MIXED_)                                                                                               \
+  {                                                                                                                  \
+    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2, MIXED_>;                                                  \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));               \
+    kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, small32, snx, sny, gnx, gny, ft, (int)n_lags, lpb,  \
+                                                     pivots, wrec, wcorr, wconst, wmask);                            \
+  }
+  if (mixed) {
+    if (rows_per_thread == 16) RW(16, true) else RW(kRollWRows, true)
+  } else {
+    if (rows_per_thread == 16) RW(16, false) else if (rows_per_thread == 14) RW(14, false) else RW(kRollWRows, false)
+  }
+#undef RW
+  CK_LAUNCH("lag_corr_roll_kernel");
+  if (prof) {
+    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+    ++g_prof_n;
+  }
+  // record rows actually written: 8 warps per tile of this variant (<= L.rows)
+  lag_corr_finalize_w_kernel<<<(unsigned)n_lags, 128, 0, s>>>(wrec, wcorr, wconst, wmask, tiles * kWarps, (int)n_lags,
+                                                              corr, nvalid);
+  CK_LAUNCH("lag_corr_finalize_w_kernel");
+  return COREG_OK;
+}
+
+int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* small32, int snx, int sny, int gnx,
+                          int gny,
+                          const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags,
+                          const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s) {
+  HomGrid g;
+  int rc = make_hom_grid(grid_wcs, gnx, gny, &g);
+  if (rc) return rc;
+  int sms = coreg_device_sm_count();
+  if (sms <= 0) sms = 148;
+  HomLag* ft = reinterpret_cast<HomLag*>(static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags));
+  tan_homography_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(g, lag_wcs, (int)n_lags, ft);
+  CK_LAUNCH("tan_homography_kernel");
+  const bool prof = g_prof_on && g_prof_n < 4096;
+  if (prof) {
+    CK(cudaEventCreate(&g_prof[g_prof_n].a));
+    CK(cudaEventCreate(&g_prof[g_prof_n].b));
+  }
+  return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, small32, snx, sny, ft,
+                                       pivots, work, corr, nvalid, prof);
+}
+}  // namespace coreg
+
+using namespace coreg;
+
+extern "C" {
+
+int coreg_hpc_lag_corr_wcs(const float* ref, const double* small, int snx, int sny, int gnx, int gny,
+                           const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags, int order,
+                           const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid,
+                           int flags, void* stream) {
+  if (!ref || !small || !grid_wcs || !lag_wcs || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  if (order != 2 || (flags & COREG_FLAG_STRICT))
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs: only order 2 with FMA arithmetic; use coreg_hpc_lag_corr");
+  if (gnx <= 0 || gny <= 0 || snx < 3 || sny < 3) return fail(COREG_EINVAL, "image too small for the fast kernel");
+  if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  return hpc_lag_corr_wcs_impl(ref, small, nullptr, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
+                               nvalid, flags, (cudaStream_t)stream);
+}
+
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const float* small32, int snx, int sny,
+                                 int gnx, int gny, const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs,
+                                 int64_t n_lags, int order, const double* pivots, void* work, size_t work_bytes,
+                                 double* corr, int64_t* nvalid, int flags, void* stream) {
+  if (!ref || !small || !small32 || !grid_wcs || !lag_wcs || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs_mixed: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  if (order != 2 || (flags & COREG_FLAG_STRICT))
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs_mixed: only order 2 with FMA arithmetic; use coreg_hpc_lag_corr");
+  if (gnx <= 0 || gny <= 0 || snx < 3 || sny < 3) return fail(COREG_EINVAL, "image too small for the fast kernel");
+  if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  return hpc_lag_corr_wcs_impl(ref, small, small32, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
+                               nvalid, flags, (cudaStream_t)stream);
+}
+
+int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs, int gnx, int gny, const CoregTanWcs* lag_wcs, int64_t n_lags,
+                              void* scratch, double* emax, void* stream) {
+  if (!grid_wcs || !lag_wcs || !scratch || !emax) return fail(COREG_EINVAL, "coreg_tan_homography_emax: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  HomGrid g;
+  int rc = make_hom_grid(grid_wcs, gnx, gny, &g);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  HomLag* ft = static_cast<HomLag*>(scratch);
+  tan_homography_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(g, lag_wcs, (int)n_lags, ft);
+  CK_LAUNCH("tan_homography_kernel");
+  CK(cudaMemcpy2DAsync(emax, sizeof(double), &ft[0].emax, sizeof(HomLag), sizeof(double), (size_t)n_lags,
+                       cudaMemcpyDeviceToDevice, s));
+  return COREG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,426 @@
+// coreg_wcs.cu -- one-shot kernels: TAN / CAR pixel <-> world, map_coordinates, pivots, Carrington planes, synthetic raster.
+#include "coreg_common.cuh"
+
+namespace coreg {
+__device__ __forceinline__ double wrap_pipi_deg(double a) {
+  // -((-a + 180) % 360 - 180) with Python's floor-mod (utils/Util.py:76-80)
+  double m = fmod(-a + 180.0, 360.0);
+  if (m != 0.0 && m < 0.0) m += 360.0;
+  return -(m - 180.0);
+}
+
+__global__ void tan_pix2world_kernel(TanDev w, int nx, int ny, int wrap, double* __restrict__ lng,
+                                     double* __restrict__ lat) {
+  const int64_t n = (int64_t)nx * ny;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % nx), j = (int)(idx / nx);
+    const double u1 = ((double)i + 1.0) - w.crpix1;
+    const double u2 = ((double)j + 1.0) - w.crpix2;
+    const double px = w.f11 * u1 + w.f12 * u2;
+    const double py = w.f21 * u1 + w.f22 * u2;
+    const double r2 = px * px + py * py;
+    const double r = sqrt(r2);
+    const double phi = (r == 0.0) ? 0.0 : atan2(px, -py);
+    const double st = rsqrt(1.0 + r2);  // sin(theta), theta = atan2(1, r)
+    const double ct = r * st;
+    double sp, cp;
+    sincos(phi - w.lonpole_rad, &sp, &cp);
+    const double xx = st * w.c0 - ct * w.s0 * cp;
+    const double yy = -ct * sp;
+    const double zz = st * w.s0 + ct * w.c0 * cp;
+    double lo = w.a0_deg + atan2(yy, xx) * kR2D;
+    if (w.a0_deg >= 0.0) {
+      if (lo < 0.0) lo += 360.0;
+    } else {
+      if (lo > 0.0) lo -= 360.0;
+    }
+    double la = atan2(zz, sqrt(xx * xx + yy * yy)) * kR2D;
+    if (wrap) {
+      lo = wrap_pipi_deg(lo);
+      la = wrap_pipi_deg(la);
+    }
+    lng[idx] = lo;
+    lat[idx] = la;
+  }
+}
+
+__device__ __forceinline__ void tan_world2pix_dev(const TanDev& w, double lng_deg, double lat_deg, double& x,
+                                                  double& y) {
+  double sl, cl, sa, ca;
+  sincos(lat_deg * kD2R, &sl, &cl);
+  sincos(lng_deg * kD2R - w.a0_rad, &sa, &ca);
+  const double den = sl * w.s0 + cl * w.c0 * ca;
+  const double xs = sl * w.c0 - cl * w.s0 * ca;
+  const double ys = -cl * sa;
+  // phi = lonpole + atan2(ys, xs); plane = (r sin phi, -r cos phi), r = hypot(xs, ys) / den
+  double sp, cp;
+  sincos(w.lonpole_rad, &sp, &cp);
+  // sin(phi) * hypot = sp*xs + cp*ys ; cos(phi) * hypot = cp*xs - sp*ys
+  const double inv = 1.0 / den;
+  const double xi = (sp * xs + cp * ys) * inv;
+  const double eta = -(cp * xs - sp * ys) * inv;
+  x = w.i11 * xi + w.i12 * eta + (w.crpix1 - 1.0);
+  y = w.i21 * xi + w.i22 * eta + (w.crpix2 - 1.0);
+  if (!(den > 0.0)) {
+    x = CUDART_NAN;
+    y = CUDART_NAN;
+  }
+}
+
+__global__ void tan_world2pix_kernel(TanDev w, const double* __restrict__ lng, const double* __restrict__ lat,
+                                     int64_t n, double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double xx, yy;
+    tan_world2pix_dev(w, lng[idx], lat[idx], xx, yy);
+    x[idx] = xx;
+    y[idx] = yy;
+  }
+}
+
+__global__ void tan_trig_planes_kernel(const double* __restrict__ lng, const double* __restrict__ lat, int64_t n,
+                                       double alpha_ref_rad, double* __restrict__ planes) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double sl, cl, sa, ca;
+    sincos(lat[idx] * kD2R, &sl, &cl);
+    sincos(lng[idx] * kD2R - alpha_ref_rad, &sa, &ca);
+    planes[idx] = sl;
+    planes[n + idx] = cl * sa;
+    planes[2 * n + idx] = cl * ca;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// map_coordinates at explicit coordinates (one-shot resampling: K2, K5 large image, host API interpol2d)
+// ---------------------------------------------------------------------------------------------------------
+template <int ORDER, typename TI, typename TO>
+__global__ void map_coordinates_kernel(const TI* __restrict__ img, int ny, int nx, const double* __restrict__ yc,
+                                       const double* __restrict__ xc, int64_t n, double cval, TO* __restrict__ out) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double v;
+    if (!spline_sample<ORDER, true, TI>(img, ny, nx, yc[idx], xc[idx], v)) v = cval;
+    out[idx] = (TO)v;
+  }
+}
+
+template <typename TI, typename TO>
+int launch_map_coordinates(const TI* img, int ny, int nx, const double* y, const double* x, int64_t n, int order,
+                           double cval, TO* out, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 16);
+  if (n == 0) return COREG_OK;
+  switch (order) {
+    case 0: map_coordinates_kernel<0, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    case 1: map_coordinates_kernel<1, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    case 2: map_coordinates_kernel<2, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    case 3: map_coordinates_kernel<3, TI, TO><<<blocks, threads, 0, s>>>(img, ny, nx, y, x, n, cval, out); break;
+    default: return fail(COREG_EINVAL, "spline order must be 0..3");
+  }
+  CK_LAUNCH("map_coordinates_kernel");
+  return COREG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mean of finite values (pivot). One block, fixed traversal order -> deterministic.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void finite_mean_kernel(const T* __restrict__ img, int64_t n, double* __restrict__ mean) {
+  __shared__ double ssum[1024];
+  __shared__ unsigned long long scnt[1024];
+  double s = 0.0;
+  unsigned long long c = 0;
+  // coarse sample (every 4th element) is plenty for a pivot and keeps this one-block kernel short
+  for (int64_t i = (int64_t)threadIdx.x * 4; i < n; i += (int64_t)blockDim.x * 4) {
+    const double v = (double)img[i];
+    if (isfinite(v)) {
+      s += v;
+      ++c;
+    }
+  }
+  ssum[threadIdx.x] = s;
+  scnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + o];
+      scnt[threadIdx.x] += scnt[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mean[0] = scnt[0] ? ssum[0] / (double)scnt[0] : 0.0;
+}
+
+__global__ void car_pix2world_kernel(CoregLagCar L, double f11, double f12, double f21, double f22, int nx, int ny,
+                                     double* __restrict__ lng, double* __restrict__ lat) {
+  const int64_t n = (int64_t)nx * ny;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % nx), j = (int)(idx / nx);
+    const double u1 = (double)i - L.x0, u2 = (double)j - L.y0;
+    const double phi = (f11 * u1 + f12 * u2) * kD2R, theta = (f21 * u1 + f22 * u2) * kD2R;
+    double sp, cp, st, ct;
+    sincos(phi, &sp, &cp);
+    sincos(theta, &st, &ct);
+    const double nx_ = ct * cp, ny_ = ct * sp, nz_ = st;
+    // celestial = R^T native
+    const double cx = L.r[0] * nx_ + L.r[3] * ny_ + L.r[6] * nz_;
+    const double cy = L.r[1] * nx_ + L.r[4] * ny_ + L.r[7] * nz_;
+    const double cz = L.r[2] * nx_ + L.r[5] * ny_ + L.r[8] * nz_;
+    double lo = atan2(cy, cx) * kR2D;
+    if (L.lng_ref >= 0.0) {
+      if (lo < 0.0) lo += 360.0;
+    } else {
+      if (lo > 0.0) lo -= 360.0;
+    }
+    lng[idx] = lo;
+    lat[idx] = atan2(cz, sqrt(cx * cx + cy * cy)) * kR2D;
+  }
+}
+
+__global__ void car_world2pix_kernel(CoregLagCar L, const double* __restrict__ lng, const double* __restrict__ lat,
+                                     int64_t n, double* __restrict__ x, double* __restrict__ y) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double sl, cl, sa, ca, xx, yy;
+    sincos(lat[idx] * kD2R, &sl, &cl);
+    sincos(lng[idx] * kD2R, &sa, &ca);
+    car_map_unit(L, cl * ca, cl * sa, sl, xx, yy);
+    x[idx] = xx;
+    y[idx] = yy;
+  }
+}
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)in[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Carrington planes
+// ---------------------------------------------------------------------------------------------------------
+__global__ void carrington_planes_kernel(CoregCarrington c, double cosb0, double sinb0, double cosr, double sinr,
+                                         const double* __restrict__ sinlon, const double* __restrict__ coslon,
+                                         int n_lon, const double* __restrict__ sinlat,
+                                         const double* __restrict__ coslat, int n_lat, double* __restrict__ tx,
+                                         double* __restrict__ ty) {
+  const int64_t n = (int64_t)n_lon * n_lat;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % n_lon), j = (int)(idx / n_lon);
+    // utils/rectify.py:345-363, numpy evaluation order, no FMA
+    const double X = __dmul_rn(coslat[j], sinlon[i]);
+    const double Y = sinlat[j];
+    const double Z = __dmul_rn(coslat[j], coslon[i]);
+    const double zz = __dadd_rn(__dmul_rn(Z, cosb0), __dmul_rn(Y, sinb0));
+    const double yy = __dsub_rn(__dmul_rn(Y, cosb0), __dmul_rn(Z, sinb0));
+    double ox = CUDART_NAN, oy = CUDART_NAN;
+    if (zz >= 0.0) {
+      const double y2 = __dsub_rn(__dmul_rn(yy, cosr), __dmul_rn(X, sinr));
+      const double x2 = __dadd_rn(__dmul_rn(X, cosr), __dmul_rn(yy, sinr));
+      const double z2 = __dsub_rn(c.dist, zz);
+      ox = __ddiv_rn(__dmul_rn(__dmul_rn(atan(__ddiv_rn(x2, z2)), kR2D), 3600.0), c.cdelt1);
+      oy = __ddiv_rn(__dmul_rn(__dmul_rn(atan(__ddiv_rn(y2, z2)), kR2D), 3600.0), c.cdelt2);
+    }
+    tx[idx] = ox;
+    ty[idx] = oy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// synthetic raster
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxSynrasFrames = 64;
+struct SynrasWcs {
+  TanDev w[kMaxSynrasFrames];
+};
+
+template <int ORDER, typename T>
+__global__ void synras_kernel(const T* __restrict__ frames, int fnx, int fny, const TanDev* __restrict__ wcs,
+                              const int* __restrict__ frame_of_col, const double* __restrict__ lng,
+                              const double* __restrict__ lat, int n_rows, int n_cols, double* __restrict__ out) {
+  const int64_t n = (int64_t)n_rows * n_cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % n_cols);
+    const int f = frame_of_col[col];
+    double v = CUDART_NAN;
+    if (f >= 0) {
+      double x, y, s;
+      tan_world2pix_dev(wcs[f], lng[idx], lat[idx], x, y);
+      // interpol2d(dst=None) returns the imager's dtype (utils/Util.py:95-97): float32 frames give float32-rounded
+      // samples, which the reference then stores into its float64 raster
+      if (spline_sample<ORDER, true, T>(frames + (size_t)f * fnx * fny, fny, fnx, y, x, s))
+        v = (sizeof(T) == 4) ? (double)__double2float_rn(s) : s;
+    }
+    out[idx] = v;
+  }
+}
+}  // namespace coreg
+
+using namespace coreg;
+
+extern "C" {
+
+int coreg_tan_pix2world(const CoregTanWcs* wcs, int nx, int ny, int wrap_pipi, double* lng, double* lat,
+                        void* stream) {
+  TanDev t;
+  int rc = make_tan(wcs, &t);
+  if (rc) return rc;
+  if (nx <= 0 || ny <= 0) return COREG_OK;
+  if (!lng || !lat) return fail(COREG_EINVAL, "null output plane");
+  const int64_t n = (int64_t)nx * ny;
+  tan_pix2world_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(t, nx, ny, wrap_pipi, lng, lat);
+  CK_LAUNCH("tan_pix2world_kernel");
+  return COREG_OK;
+}
+
+int coreg_tan_world2pix(const CoregTanWcs* wcs, const double* lng, const double* lat, int64_t n, double* x,
+                        double* y, void* stream) {
+  TanDev t;
+  int rc = make_tan(wcs, &t);
+  if (rc) return rc;
+  if (n <= 0) return COREG_OK;
+  if (!lng || !lat || !x || !y) return fail(COREG_EINVAL, "null pointer");
+  tan_world2pix_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(t, lng, lat, n, x, y);
+  CK_LAUNCH("tan_world2pix_kernel");
+  return COREG_OK;
+}
+
+int coreg_map_coordinates(const void* img, int img_dtype, int img_ny, int img_nx, const double* y, const double* x,
+                          int64_t n, int order, double cval, void* out, int out_dtype, void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!img || !y || !x || !out) return fail(COREG_EINVAL, "null pointer");
+  if (img_ny <= 0 || img_nx <= 0) return fail(COREG_EINVAL, "empty image");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (img_dtype == COREG_F32 && out_dtype == COREG_F32)
+    return launch_map_coordinates((const float*)img, img_ny, img_nx, y, x, n, order, cval, (float*)out, s);
+  if (img_dtype == COREG_F32 && out_dtype == COREG_F64)
+    return launch_map_coordinates((const float*)img, img_ny, img_nx, y, x, n, order, cval, (double*)out, s);
+  if (img_dtype == COREG_F64 && out_dtype == COREG_F32)
+    return launch_map_coordinates((const double*)img, img_ny, img_nx, y, x, n, order, cval, (float*)out, s);
+  if (img_dtype == COREG_F64 && out_dtype == COREG_F64)
+    return launch_map_coordinates((const double*)img, img_ny, img_nx, y, x, n, order, cval, (double*)out, s);
+  return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_tan_trig_planes(const double* lng, const double* lat, int64_t n, double alpha_ref_deg, double* planes,
+                          void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!lng || !lat || !planes) return fail(COREG_EINVAL, "null pointer");
+  tan_trig_planes_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(lng, lat, n, alpha_ref_deg * kD2R, planes);
+  CK_LAUNCH("tan_trig_planes_kernel");
+  return COREG_OK;
+}
+
+int coreg_widen_f32(const float* in, int64_t n, double* out, void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!in || !out) return fail(COREG_EINVAL, "coreg_widen_f32: null pointer");
+  f32_to_f64_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, n, out);
+  CK_LAUNCH("f32_to_f64_kernel");
+  return COREG_OK;
+}
+
+int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void* stream) {
+  if (!img || !mean || n <= 0) return fail(COREG_EINVAL, "coreg_finite_mean: bad argument");
+  if (dtype == COREG_F32)
+    finite_mean_kernel<float><<<1, 1024, 0, (cudaStream_t)stream>>>((const float*)img, n, mean);
+  else if (dtype == COREG_F64)
+    finite_mean_kernel<double><<<1, 1024, 0, (cudaStream_t)stream>>>((const double*)img, n, mean);
+  else
+    return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+  CK_LAUNCH("finite_mean_kernel");
+  return COREG_OK;
+}
+
+int coreg_carrington_planes(const CoregCarrington* c, const double* sinlon, const double* coslon, int n_lon,
+                            const double* sinlat, const double* coslat, int n_lat, double* tx, double* ty,
+                            void* stream) {
+  if (!c || !sinlon || !coslon || !sinlat || !coslat || !tx || !ty)
+    return fail(COREG_EINVAL, "coreg_carrington_planes: null pointer");
+  if (n_lon <= 0 || n_lat <= 0) return COREG_OK;
+  const int64_t n = (int64_t)n_lon * n_lat;
+  carrington_planes_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+      *c, cos(c->lat0), sin(c->lat0), cos(c->roll), sin(c->roll), sinlon, coslon, n_lon, sinlat, coslat, n_lat, tx,
+      ty);
+  CK_LAUNCH("carrington_planes_kernel");
+  return COREG_OK;
+}
+
+static int car_forward(const CoregLagCar* m, double* f) {
+  if (!m) return fail(COREG_EINVAL, "null CoregLagCar");
+  const double det = m->m11 * m->m22 - m->m12 * m->m21;
+  if (!(det != 0.0) || det != det) return fail(COREG_EINVAL, "singular CDELT*PC matrix");
+  f[0] = m->m22 / det;
+  f[1] = -m->m12 / det;
+  f[2] = -m->m21 / det;
+  f[3] = m->m11 / det;
+  return COREG_OK;
+}
+
+int coreg_car_pix2world(const CoregLagCar* map, int nx, int ny, double* lng, double* lat, void* stream) {
+  double f[4];
+  int rc = car_forward(map, f);
+  if (rc) return rc;
+  if (nx <= 0 || ny <= 0) return COREG_OK;
+  if (!lng || !lat) return fail(COREG_EINVAL, "null output plane");
+  const int64_t n = (int64_t)nx * ny;
+  car_pix2world_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*map, f[0], f[1], f[2], f[3], nx, ny, lng, lat);
+  CK_LAUNCH("car_pix2world_kernel");
+  return COREG_OK;
+}
+
+int coreg_car_world2pix(const CoregLagCar* map, const double* lng, const double* lat, int64_t n, double* x, double* y,
+                        void* stream) {
+  if (!map) return fail(COREG_EINVAL, "null CoregLagCar");
+  if (n <= 0) return COREG_OK;
+  if (!lng || !lat || !x || !y) return fail(COREG_EINVAL, "null pointer");
+  car_world2pix_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*map, lng, lat, n, x, y);
+  CK_LAUNCH("car_world2pix_kernel");
+  return COREG_OK;
+}
+
+int coreg_synras_build(const void* frames, int frame_dtype, int n_frames, int fnx, int fny, const CoregTanWcs* wcs,
+                       const int* frame_of_col, const double* lng, const double* lat, int n_rows, int n_cols,
+                       int order, double* out, void* stream) {
+  if (!frames || !wcs || !frame_of_col || !lng || !lat || !out)
+    return fail(COREG_EINVAL, "coreg_synras_build: null pointer");
+  if (n_frames <= 0 || n_frames > kMaxSynrasFrames) return fail(COREG_EINVAL, "n_frames must be in 1..64 per call");
+  if (n_rows <= 0 || n_cols <= 0) return COREG_OK;
+  if (order < 0 || order > 3) return fail(COREG_EINVAL, "spline order must be 0..3");
+  cudaStream_t s = (cudaStream_t)stream;
+  TanDev hw[kMaxSynrasFrames];
+  for (int f = 0; f < n_frames; ++f) {
+    int rc = make_tan(wcs + f, hw + f);
+    if (rc) return rc;
+  }
+  for (int c = 0; c < n_cols; ++c)
+    if (frame_of_col[c] >= n_frames) return fail(COREG_EINVAL, "frame_of_col entry out of range");
+  TanDev* dw = nullptr;
+  int* dcol = nullptr;
+  CK(cudaMallocAsync(&dw, sizeof(TanDev) * n_frames, s));
+  CK(cudaMallocAsync(&dcol, sizeof(int) * n_cols, s));
+  CK(cudaMemcpyAsync(dw, hw, sizeof(TanDev) * n_frames, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dcol, frame_of_col, sizeof(int) * n_cols, cudaMemcpyHostToDevice, s));
+  // hw / frame_of_col are pageable: the async copies above have consumed them when the call returns
+  const int64_t n = (int64_t)n_rows * n_cols;
+  const int g = grid_for(n);
+#define SYN(ORD, T) \
+  synras_kernel<ORD, T><<<g, 256, 0, s>>>((const T*)frames, fnx, fny, dw, dcol, lng, lat, n_rows, n_cols, out)
+  if (frame_dtype == COREG_F32) {
+    switch (order) { case 0: SYN(0, float); break; case 1: SYN(1, float); break; case 2: SYN(2, float); break; default: SYN(3, float); }
+  } else if (frame_dtype == COREG_F64) {
+    switch (order) { case 0: SYN(0, double); break; case 1: SYN(1, double); break; case 2: SYN(2, double); break; default: SYN(3, double); }
+  } else {
+    return fail(COREG_EINVAL, "frame_dtype must be COREG_F32 or COREG_F64");
+  }
+#undef SYN
+  CK_LAUNCH("synras_kernel");
+  CK(cudaFreeAsync(dw, s));
+  CK(cudaFreeAsync(dcol, s));
+  return COREG_OK;
+}
+
+}  // extern "C"
