@@ -8,7 +8,7 @@ Only what that path needs is modelled: two celestial axes with a `-TAN` projecti
 CUNIT in {deg, arcsec, arcmin, rad}, PCi_j (or CROTA/CROTA2 in the AIPS convention, or CDi_j),
 LONPOLE. wcslib rescales CRVAL/CDELT to degrees when the WCS is set up; so does `TanWcs`.
 
-The *per-pixel* work is done on the device (csrc/coreg_kernels.cu, `coreg_tan_pix2world`,
+The *per-pixel* work is done on the device (csrc/coreg_wcs.cu, `coreg_tan_pix2world`,
 `coreg_tan_world2pix`). The numpy evaluator at the bottom of this file is for a handful of points
 (synras bookkeeping, FOV limits) and is written in closed form; the wcslib-structured restatement
 used as the checker lives in `oracle/`, not here.

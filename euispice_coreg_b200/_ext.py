@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcoreg_b200.so")
 F32, F64, I32 = 0, 1, 2
 FLAG_STRICT = 1
 FLAG_NO_FAST = 4
-FLAG_MIXED = 8      # coreg_hpc_search_host: mixed-arithmetic kernel when the small payload is float32
+FLAG_MIXED = 8      # coreg_hpc_search_host: opt in to the mixed-arithmetic kernel (float32 small payload, guarded)
 
 
 def make_flags(strict=False, variant=0, no_fast=False):
@@ -58,7 +58,9 @@ _SIGNATURES = {
     "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_rice_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                     C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
-    "coreg_finite_mean": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
+    "coreg_image_stats_scratch_bytes": (C.c_size_t, []),
+    "coreg_image_stats": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_int, _P, _P]),
+    "coreg_center_f32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, _P, _P]),
     "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
@@ -66,7 +68,7 @@ _SIGNATURES = {
                                          _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_hpc_lag_corr_wcs_mixed": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P,
-                                               _P, C.c_int, _P]),
+                                               _P, _P, C.c_int, _P]),
     "coreg_tan_homography_emax": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P]),
     "coreg_carrington_planes": (C.c_int, [C.POINTER(CoregCarrington), _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "coreg_offset_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64,
@@ -271,13 +273,58 @@ def widen_f32(img):
     return out
 
 
-def finite_mean(img, out):
-    """mean of finite values of `img` -> out[0] (device double, view into the pivots tensor)."""
+STATS_ROWS = 4   # rows of a statistics block: mean (the pivot), count, max |v|, RMS about the pivot
+
+
+def _stats_scratch(device):
+    torch = _torch()
+    n = int(load().coreg_image_stats_scratch_bytes())
+    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+def image_stats(img, stats, column=0, widen=False):
+    """One deterministic multi-block pass over `img`: stats[0, column] = mean of the finite values (the pivot),
+    stats[1, column] = their count, stats[2, column] = max |v|. `stats`: device float64 [4, k]. widen=True (float32
+    image) also returns the float64 copy written by the same pass."""
     torch = _torch()
     lib = load()
-    _require_cuda(img, out)
+    _require_cuda(img, stats)
+    if stats.dtype != torch.float64 or stats.dim() != 2 or stats.shape[0] != STATS_ROWS:
+        raise TypeError("stats must be a float64 [4, k] device tensor")
+    wide = torch.empty(img.shape, dtype=torch.float64, device=img.device) if widen else None
     with torch.cuda.device(img.device):
-        _check(lib.coreg_finite_mean(_ptr(img), _dt(img), img.numel(), _ptr(out), _stream()), "coreg_finite_mean")
+        scratch = _stats_scratch(img.device)
+        _check(lib.coreg_image_stats(_ptr(img), _dt(img), img.numel(), _ptr(wide) if widen else None,
+                                     C.c_void_p(stats.data_ptr() + 8 * int(column)), int(stats.shape[1]),
+                                     _ptr(scratch), _stream()), "coreg_image_stats")
+    return wide
+
+
+def center_f32(img32, stats, column=1):
+    """Float32 twin of a float32 image centred on the float32-rounded pivot stats[0, column]; stats[3, column] = RMS of
+    the centred finite values (input of the mixed kernel's guard)."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(img32, stats)
+    if img32.dtype != torch.float32:
+        raise TypeError("float32 tensor expected")
+    out = torch.empty_like(img32)
+    with torch.cuda.device(img32.device):
+        scratch = _stats_scratch(img32.device)
+        _check(lib.coreg_center_f32(_ptr(img32), img32.numel(), _ptr(out),
+                                    C.c_void_p(stats.data_ptr() + 8 * int(column)), int(stats.shape[1]),
+                                    _ptr(scratch), _stream()), "coreg_center_f32")
+    return out
+
+
+def finite_mean(img, out):
+    """mean of finite values of `img` -> out[0] (device double, e.g. a view into a pivots tensor)."""
+    torch = _torch()
+    _require_cuda(img, out)
+    st = torch.empty((STATS_ROWS, 1), dtype=torch.float64, device=img.device)
+    image_stats(img, st)
+    with torch.cuda.device(img.device):
+        out[0:1].copy_(st[0])
 
 
 def lag_corr_workspace_bytes(gnx, gny, n_lags):
@@ -302,10 +349,12 @@ def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
 
 
 def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_out, nvalid_out=None, flags=0,
-                     small32=None):
+                     small32c=None, flagged=None):
     """K1, homography form. `lag_wcs`: device float64 [n_lags, 11] (CoregTanWcs rows of the shifted headers);
-    `grid_wcs`: `_compat.wcs.TanWcs` of the common grid. `small32` (the float32 payload `small` was widened from)
-    selects the mixed-arithmetic kernel: FP64 projection, FP32 spline."""
+    `grid_wcs`: `_compat.wcs.TanWcs` of the common grid. `small32c` (the float32 payload `small` was widened from,
+    centred on its float32 pivot: `center_f32`) selects the mixed-arithmetic kernel -- FP64 projection, FP32 spline --;
+    `pivots` must then be the [4, 2] statistics block and `flagged` a zeroed int32 device counter that receives the
+    number of lags tripping the kernel's error-model guard."""
     torch = _torch()
     lib = load()
     _require_cuda(ref, small, lag_wcs, pivots, work, corr_out)
@@ -315,16 +364,18 @@ def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_ou
         raise TypeError("the homography kernel reads a float64 small image")
     gny, gnx = ref.shape
     g = tan_struct(grid_wcs)
-    if small32 is not None:
-        _require_cuda(small32)
-        if small32.dtype != torch.float32 or small32.shape != small.shape or not small32.is_contiguous():
-            raise TypeError("small32 must be the contiguous float32 twin of small")
+    if small32c is not None:
+        _require_cuda(small32c, flagged)
+        if small32c.dtype != torch.float32 or small32c.shape != small.shape:
+            raise TypeError("small32c must be the contiguous centred float32 twin of small")
+        if pivots.shape != (STATS_ROWS, 2) or flagged.dtype != torch.int32:
+            raise TypeError("mixed arithmetic needs the [4, 2] statistics block and an int32 flag counter")
         with torch.cuda.device(ref.device):
             _check(lib.coreg_hpc_lag_corr_wcs_mixed(
-                _ptr(ref), _ptr(small), _ptr(small32), small.shape[1], small.shape[0], gnx, gny, C.byref(g),
+                _ptr(ref), _ptr(small), _ptr(small32c), small.shape[1], small.shape[0], gnx, gny, C.byref(g),
                 _ptr(lag_wcs), lag_wcs.shape[0], int(order), _ptr(pivots), _ptr(work),
                 work.numel() * work.element_size(), _ptr(corr_out),
-                _ptr(nvalid_out) if nvalid_out is not None else None, int(flags), _stream()),
+                _ptr(nvalid_out) if nvalid_out is not None else None, _ptr(flagged), int(flags), _stream()),
                 "coreg_hpc_lag_corr_wcs_mixed")
         return
     with torch.cuda.device(ref.device):

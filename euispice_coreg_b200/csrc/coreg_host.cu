@@ -47,7 +47,10 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   const size_t lsz = large_dtype == COREG_F32 ? 4 : 8;
   const size_t work_bytes = coreg_lag_corr_workspace_bytes(snx, sny, n_lags);
   const bool fast = (order == 2) && !(flags & (COREG_FLAG_STRICT | COREG_FLAG_NO_FAST)) && snx >= 3 && sny >= 3;
-  void *d_large = nullptr, *d_small_in = nullptr;
+  void *d_large = nullptr, *d_small_in = nullptr, *d_scr = nullptr;
+  float* d_small32c = nullptr;
+  int* d_flag = nullptr;
+  bool mixed_done = false;
   double *d_small = nullptr, *d_lng = nullptr, *d_lat = nullptr, *d_x = nullptr, *d_y = nullptr, *d_planes = nullptr,
          *d_piv = nullptr, *d_corr = nullptr;
   float* d_ref = nullptr;
@@ -77,7 +80,9 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   TRY(cudaMalloc(&d_x, ns * sizeof(double)));
   TRY(cudaMalloc(&d_y, ns * sizeof(double)));
   TRY(cudaMalloc(&d_ref, ns * sizeof(float)));
-  TRY(cudaMalloc(&d_piv, 2 * sizeof(double)));
+  TRY(cudaMalloc(&d_piv, 8 * sizeof(double)));   // [4][2] statistics block; its first row is the pivots
+  TRY(cudaMalloc(&d_scr, coreg_image_stats_scratch_bytes()));
+  TRY(cudaMemsetAsync(d_scr, 0, coreg_image_stats_scratch_bytes(), s));
   TRY(cudaMalloc(&d_corr, n_lags * sizeof(double)));
   TRY(cudaMalloc(&d_nv, n_lags * sizeof(int64_t)));
   TRY(cudaMalloc(&d_lagw, n_lags * sizeof(CoregTanWcs)));
@@ -85,21 +90,44 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
   TRY(cudaMemcpyAsync(d_large, large, nl * lsz, cudaMemcpyHostToDevice, s));
   if (small_dtype == COREG_F64) {
     TRY(cudaMemcpyAsync(d_small, small, ns * sizeof(double), cudaMemcpyHostToDevice, s));
+    TRYRC(coreg_image_stats(d_small, COREG_F64, ns, nullptr, d_piv + 1, 2, d_scr, s));
   } else {
-    // the lag kernels run fastest on float64 storage (no per-tap conversion): widen once on the device
+    // the lag kernels run fastest on float64 storage (no per-tap conversion): widen once on the device, in the same
+    // pass that takes the pivot
     TRY(cudaMalloc(&d_small_in, ns * sizeof(float)));
     TRY(cudaMemcpyAsync(d_small_in, small, ns * sizeof(float), cudaMemcpyHostToDevice, s));
-    TRYRC(coreg_widen_f32((const float*)d_small_in, ns, d_small, s));
+    TRYRC(coreg_image_stats(d_small_in, COREG_F32, ns, d_small, d_piv + 1, 2, d_scr, s));
   }
   TRY(cudaMemcpyAsync(d_lagw, lag_wcs, n_lags * sizeof(CoregTanWcs), cudaMemcpyHostToDevice, s));
   TRYRC(coreg_tan_pix2world(wcs_small, snx, sny, 1, d_lng, d_lat, s));
   TRYRC(coreg_tan_world2pix(wcs_large, d_lng, d_lat, ns, d_x, d_y, s));
   TRYRC(coreg_map_coordinates(d_large, large_dtype, lny, lnx, d_y, d_x, ns, order, (double)NAN, d_ref, COREG_F32, s));
-  TRYRC(coreg_finite_mean(d_ref, COREG_F32, ns, d_piv, s));
-  TRYRC(coreg_finite_mean(d_small, COREG_F64, ns, d_piv + 1, s));
+  TRYRC(coreg_image_stats(d_ref, COREG_F32, ns, nullptr, d_piv, 2, d_scr, s));
   if (fast && (flags & COREG_FLAG_MIXED) && d_small_in) {
-    TRYRC(coreg_hpc_lag_corr_wcs_mixed(d_ref, d_small, (const float*)d_small_in, snx, sny, snx, sny, wcs_small, d_lagw,
-                                       n_lags, order, d_piv, d_work, work_bytes, d_corr, d_nv, flags, s));
+    // opt-in mixed arithmetic: centred float32 payload, guarded per lag; any flagged lag -> the whole search in FP64
+    double h_stats[8];
+    TRY(cudaMalloc(&d_small32c, ns * sizeof(float)));
+    TRY(cudaMalloc(&d_flag, n_lags * sizeof(int)));
+    TRYRC(coreg_center_f32((const float*)d_small_in, ns, d_small32c, d_piv + 1, 2, d_scr, s));
+    TRY(cudaMemcpyAsync(h_stats, d_piv, sizeof(h_stats), cudaMemcpyDeviceToHost, s));
+    TRY(cudaStreamSynchronize(s));
+    // float32 headroom of the segment sums (same rule as the Python engine's MIXED_ABS_RANGE)
+    if (h_stats[4] > 1e-9 && h_stats[4] < 1e12 && h_stats[5] > 1e-9 && h_stats[5] < 1e12) {
+      TRYRC(coreg_hpc_lag_corr_wcs_mixed(d_ref, d_small, d_small32c, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order,
+                                         d_piv, d_work, work_bytes, d_corr, d_nv, d_flag, flags, s));
+      int* h_flag = (int*)malloc(n_lags * sizeof(int));
+      if (!h_flag) { rc = fail(COREG_ENOMEM, "coreg_hpc_search_host: out of host memory"); goto done; }
+      cudaError_t e = cudaMemcpyAsync(h_flag, d_flag, n_lags * sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      int64_t tripped = 0;
+      for (int64_t i = 0; i < n_lags; ++i) tripped += h_flag[i];
+      free(h_flag);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "flag readback"); goto done; }
+      mixed_done = tripped == 0;
+    }
+  }
+  if (mixed_done) {
+    // cube complete
   } else if (fast) {
     TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv, d_work,
                                  work_bytes, d_corr, d_nv, flags, s));
@@ -118,7 +146,7 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
 done:
   cudaFree(d_large); cudaFree(d_small_in); cudaFree(d_small); cudaFree(d_lng); cudaFree(d_lat); cudaFree(d_x);
   cudaFree(d_y); cudaFree(d_planes); cudaFree(d_ref); cudaFree(d_piv); cudaFree(d_corr); cudaFree(d_nv);
-  cudaFree(d_lagw); cudaFree(d_lags); cudaFree(d_work);
+  cudaFree(d_lagw); cudaFree(d_lags); cudaFree(d_work); cudaFree(d_scr); cudaFree(d_small32c); cudaFree(d_flag);
 #undef TRY
 #undef TRYRC
   return rc;

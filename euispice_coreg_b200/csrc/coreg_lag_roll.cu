@@ -218,12 +218,18 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
   }
 }
 
-// The same segment in MIXED arithmetic: coordinates in FP64 (7 instructions per pixel), the spline and the segment's
-// moments in FP32 on a float32 copy of the small image. The reference rounds every sample to float32 anyway
-// (`alignment.py:1024`), so an FP32 spline differs from it by about one float32 ulp per sample, unbiased; the
-// Pearson sums average that over 4e6 samples (|dr| ~ 1e-9 measured, bar 1e-6). A DFMA occupies the dispatch port
-// for two cycles and an FFMA for one (profiles/r1_fp64_issue_model.md), so moving the 23 spline / moment
-// instructions off the FP64 pipe is what shortens the issue-bound loop.
+// The same segment in MIXED arithmetic: coordinates in FP64 (4 - 7 instructions per pixel), the spline and the segment's
+// moments in FP32. The reference evaluates the spline in FP64 and then STORES the sample as float32
+// (`alignment.py:1024`); what the Pearson sums see is round32(S). Here the FP32 spline runs on the small image
+// CENTRED on the float32-rounded pivot p (c = v - p, exact by Sterbenz's lemma wherever p/2 <= v <= 2p and otherwise
+// rounded to one float32 ulp of the DEVIATION), so its rounding errors scale with the local deviation from the
+// pivot, not with the pixel value: t = spline(c) = S - p to ~4 ulp32(|c|). The reference's float32 store is then
+// reproduced on the uncentred value: b = round32(t + p), bc = b - p -- two FADDs; b differs from the reference's
+// sample only where S sits within ~4 ulp32(|c|) of a float32 rounding boundary of S (a fraction ~ulp32(|c|) /
+// ulp32(S) of the samples, by one ulp32(S)). An image with mean 3e4 and sigma 1 therefore behaves like one with
+// mean 0: the error model is data-independent and checked per lag by the finalize kernel (`mixed_guard`).
+// A DFMA occupies the dispatch port for two cycles and an FFMA for one (profiles/r1_fp64_issue_model.md), so moving
+// the spline / moment instructions off the FP64 pipe is what shortens the issue-bound loop.
 // The fractional parts leave the FP64 domain without a conversion instruction: the coordinate FMA adds
 // kFracMagic = 1.5 * 2^29, whose ulp is 2^-23, so the low word of the result is round((x - floor_x0) * 2^23): bits
 // 23.. must be zero for x (p for y: the row index inside the segment), the low 23 bits are the float32 mantissa of
@@ -232,7 +238,7 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
 constexpr double kFracMagic = 805306368.0;   // 1.5 * 2^29
 
 template <int MODE, int P>
-__device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ small32, unsigned tap,
+__device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ small32c, unsigned tap,
                                                    unsigned row_elems, double be, double bnx, double bny, double he1,
                                                    double hx1, double hy1, double inv0, double xoffm, double yoffm,
                                                    float pivot_b, const float (&a_c)[P], float& sb, float& sbb,
@@ -241,7 +247,7 @@ __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ sma
   // per row and no arithmetic, is slower -- four times the L1 footprint; a 64-bit row pointer, walked or formed as
   // base + k * stride, compiles to four IADD3 per row where the 32-bit index + IMAD.WIDE form below costs two.)
   auto row = [&](unsigned t, float& ca, float& cb, float& cc) {
-    const float ta = __ldg(small32 + t), tb = __ldg(small32 + t + 1), tc = __ldg(small32 + t + 2);
+    const float ta = __ldg(small32c + t), tb = __ldg(small32c + t + 1), tc = __ldg(small32c + t + 2);
     ca = 0.5f * (ta + tb);
     cb = tb - ta;
     cc = fmaf(0.5f, ta + tc, -tb);
@@ -287,8 +293,9 @@ __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ sma
     const float q0 = fmaf(fmaf(r0c, vx, r0b), vx, r0a);
     const float q1 = fmaf(fmaf(r1c, vx, r1b), vx, r1a);
     const float q2 = fmaf(fmaf(r2c, vx, r2b), vx, r2a);
-    // sample - pivot in one go: the pivot rides in the constant term of the y quadratic
-    const float bc = fmaf(fmaf(fmaf(0.5f, q0 + q2, -q1), vy, q1 - q0), vy, fmaf(0.5f, q0 + q1, -pivot_b));
+    // t = sample - pivot (the taps are centred); the reference's float32 store happens on the uncentred value
+    const float t = fmaf(fmaf(fmaf(0.5f, q0 + q2, -q1), vy, q1 - q0), vy, 0.5f * (q0 + q1));
+    const float bc = __fadd_rn(__fadd_rn(t, pivot_b), -pivot_b);
     sb += bc;
     sbb = fmaf(bc, bc, sbb);
     sab = fmaf(a_c[p], bc, sab);
@@ -574,50 +581,84 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
   }
 }
 
-// one block per lag: sum the warp records in a fixed order, moments -> Pearson r
-__global__ void __launch_bounds__(128)
+// Finalize: one block per chunk of kRollChunk consecutive lags. A record row holds the chunk's (Sb, Sbb, Sab) as 24
+// contiguous doubles, so 24 adjacent threads read one row's 192 bytes together (the first version read 24 bytes per
+// 86 KB stride: 0.41 ms per 3600-lag search, now bounded by the records' HBM read). Ten row groups walk the rows in
+// a fixed order, are folded in a fixed order, and the moments become Pearson r. The lag-independent reference moments
+// (n, Sa, Saa per row) and their rare per-lag corrections ride in a second accumulator of the same threads.
+// `guard` (mixed arithmetic only) points at the image statistics: per lag, the error model of the FP32 spline is
+// compared with the sampled image's own variance and flagged[lag] = 1 marks the lags that cannot be trusted to 1e-7
+// (the caller re-evaluates those with the all-FP64 kernel).
+constexpr int kFinGroups = 10, kFinElems = kRollChunk * 3;
+
+__device__ __forceinline__ bool mixed_guard_trips(const double* __restrict__ guard, double n, double vb) {
+  // guard = [4][2] statistics block: row 2 = max |v|, row 3 = RMS of (v - pivot); column 1 = the small image.
+  //   s_t   RMS error of the centred FP32 spline sample. Measured (numpy emulation of this arithmetic on smooth and
+  //         noisy scenes, profiles/r2_mixed_error_model.md): 0.8 - 0.9 x 2^-24 x rms; taken as 2 x 2^-24 x rms
+  //   ulpS  float32 spacing of the uncentred sample (what the reference's float32 store rounds to) at max |v|
+  //   a sample within s_t of a rounding boundary of S (probability ~ s_t / ulpS) lands one ulpS away from the
+  //   reference's: s_eff^2 = s_t^2 + s_t * ulpS (measured 1.06e-5 sigma against 1.08e-5 predicted for mean 3e4, sigma 1).
+  //   Independent errors of that size move r by ~ s_eff / (sigma_b sqrt(n)) (random part, taken at 4 sigma) +
+  //   (s_eff / sigma_b)^2 (the variance they add to Sbb). Bar: 1e-7, ten times under the contract.
+  const double rms = guard[3 * 2 + 1], mx = guard[2 * 2 + 1];
+  const double st = 2.0 * 5.9604644775390625e-08 * rms;
+  int ex = 0;
+  frexp(mx, &ex);                                   // mx = m * 2^ex, 0.5 <= m < 1: ulp32(mx) = 2^(ex - 24)
+  const double ulps = (mx > 0.0) ? ldexp(1.0, ex - 24) : 0.0;
+  const double q = (st * st + st * ulps) * n / vb;   // (s_eff / sigma_b)^2 with vb = n sigma_b^2
+  return !(4.0 * sqrt(q / n) + q <= 1e-7);
+}
+
+__global__ void __launch_bounds__(256)
 lag_corr_finalize_w_kernel(const double* __restrict__ wrec, const double* __restrict__ wcorr,
                            const double* __restrict__ wconst, const unsigned* __restrict__ wmask, int n_rows,
-                           int n_lags, double* __restrict__ corr, int64_t* __restrict__ nvalid) {
-  __shared__ double s[128][6];
-  const int lag = blockIdx.x;
-  double m[6] = {0, 0, 0, 0, 0, 0};   // n, Sa, Sb, Saa, Sbb, Sab
-  for (int r = threadIdx.x; r < n_rows; r += 128) {
-    const double* p = wrec + ((size_t)r * n_lags + lag) * 3;
-    m[2] += p[0];
-    m[4] += p[1];
-    m[5] += p[2];
-    m[0] += wconst[(size_t)r * 3 + 0];
-    m[1] += wconst[(size_t)r * 3 + 1];
-    m[3] += wconst[(size_t)r * 3 + 2];
-    if ((wmask[(size_t)(r / kWarps) * n_lags + lag] >> (r % kWarps)) & 1u) {
-      const double* c = wcorr + ((size_t)r * n_lags + lag) * 3;
-      m[0] -= c[0];
-      m[1] -= c[1];
-      m[3] -= c[2];
+                           int n_lags, double* __restrict__ corr, int64_t* __restrict__ nvalid,
+                           const double* __restrict__ guard, int* __restrict__ flagged) {
+  __shared__ double s_var[kFinGroups][kFinElems], s_cst[kFinGroups][kFinElems];
+  __shared__ double s_tot[2][kFinElems];
+  const int l0 = blockIdx.x * kRollChunk;
+  const int t = threadIdx.x, e = t % kFinElems, g = t / kFinElems;
+  const int lag = l0 + e / 3, v = e % 3;
+  if (g < kFinGroups) {
+    double av = 0.0, ac = 0.0;
+    if (lag < n_lags) {
+      for (int r = g; r < n_rows; r += kFinGroups) {
+        const size_t o = ((size_t)r * n_lags + lag) * 3 + v;
+        av += wrec[o];
+        ac += wconst[(size_t)r * 3 + v];
+        if ((wmask[(size_t)(r / kWarps) * n_lags + lag] >> (r % kWarps)) & 1u) ac -= wcorr[o];
+      }
     }
+    s_var[g][e] = av;
+    s_cst[g][e] = ac;
   }
-#pragma unroll
-  for (int q = 0; q < 6; ++q) s[threadIdx.x][q] = m[q];
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
+  if (t < kFinElems) {
+    double av = s_var[0][t], ac = s_cst[0][t];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) s[threadIdx.x][q] += s[threadIdx.x + o][q];
+    for (int k = 1; k < kFinGroups; ++k) {
+      av += s_var[k][t];
+      ac += s_cst[k][t];
     }
-    __syncthreads();
+    s_tot[0][t] = av;
+    s_tot[1][t] = ac;
   }
-  if (threadIdx.x == 0) {
-    const double n = s[0][0], sa = s[0][1], sb = s[0][2], saa = s[0][3], sbb = s[0][4], sab = s[0][5];
+  __syncthreads();
+  if (t < kRollChunk && l0 + t < n_lags) {
+    const double sb = s_tot[0][3 * t], sbb = s_tot[0][3 * t + 1], sab = s_tot[0][3 * t + 2];
+    const double n = s_tot[1][3 * t], sa = s_tot[1][3 * t + 1], saa = s_tot[1][3 * t + 2];
     double r = CUDART_NAN;
     if (n > 0.0) {
       const double cov = sab - sa * sb / n;
       const double va = saa - sa * sa / n;
       const double vb = sbb - sb * sb / n;
       r = cov / sqrt(va * vb);
+      if (guard != nullptr) flagged[l0 + t] = mixed_guard_trips(guard, n, vb) ? 1 : 0;
+    } else if (guard != nullptr) {
+      flagged[l0 + t] = 0;
     }
-    corr[lag] = r;
-    if (nvalid) nvalid[lag] = (int64_t)n;
+    corr[l0 + t] = r;
+    if (nvalid) nvalid[l0 + t] = (int64_t)n;
   }
 }
 
@@ -630,7 +671,8 @@ lag_corr_finalize_w_kernel(const double* __restrict__ wrec, const double* __rest
 template <typename RefT, bool ROUND32>
 int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
                      const double* small, const float* small32, int snx, int sny,
-                     const HomLag* ft, const double* pivots, void* work, double* corr, int64_t* nvalid, bool prof) {
+                     const HomLag* ft, const double* pivots, void* work, double* corr, int64_t* nvalid, bool prof,
+                     int* flagged) {
   const bool mixed = small32 != nullptr;
   const int minb = 2;
   const int rows_per_thread = (variant == 1) ? 16 : ((variant == 2 && !mixed) ? 14 : kRollWRows);
@@ -665,8 +707,9 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
     ++g_prof_n;
   }
   // record rows actually written: 8 warps per tile of this variant (<= L.rows)
-  lag_corr_finalize_w_kernel<<<(unsigned)n_lags, 128, 0, s>>>(wrec, wcorr, wconst, wmask, tiles * kWarps, (int)n_lags,
-                                                              corr, nvalid);
+  // mixed arithmetic: `pivots` is the head of the [4][2] statistics block (coreg_image_stats / coreg_center_f32)
+  lag_corr_finalize_w_kernel<<<(unsigned)((n_lags + kRollChunk - 1) / kRollChunk), 256, 0, s>>>(
+      wrec, wcorr, wconst, wmask, tiles * kWarps, (int)n_lags, corr, nvalid, (mixed && flagged) ? pivots : nullptr, flagged);
   CK_LAUNCH("lag_corr_finalize_w_kernel");
   return COREG_OK;
 }
@@ -674,7 +717,8 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
 int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* small32, int snx, int sny, int gnx,
                           int gny,
                           const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs, int64_t n_lags,
-                          const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s) {
+                          const double* pivots, void* work, double* corr, int64_t* nvalid, int flags, cudaStream_t s,
+                          int* flagged = nullptr) {
   HomGrid g;
   int rc = make_hom_grid(grid_wcs, gnx, gny, &g);
   if (rc) return rc;
@@ -689,7 +733,7 @@ int hpc_lag_corr_wcs_impl(const float* ref, const double* small, const float* sm
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
   }
   return launch_lag_rollw<float, true>((flags >> 8) & 15, gnx, gny, n_lags, sms, s, ref, small, small32, snx, sny, ft,
-                                       pivots, work, corr, nvalid, prof);
+                                       pivots, work, corr, nvalid, prof, flagged);
 }
 }  // namespace coreg
 
@@ -714,11 +758,11 @@ int coreg_hpc_lag_corr_wcs(const float* ref, const double* small, int snx, int s
                                nvalid, flags, (cudaStream_t)stream);
 }
 
-int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const float* small32, int snx, int sny,
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const float* small32c, int snx, int sny,
                                  int gnx, int gny, const CoregTanWcs* grid_wcs, const CoregTanWcs* lag_wcs,
-                                 int64_t n_lags, int order, const double* pivots, void* work, size_t work_bytes,
-                                 double* corr, int64_t* nvalid, int flags, void* stream) {
-  if (!ref || !small || !small32 || !grid_wcs || !lag_wcs || !pivots || !work || !corr)
+                                 int64_t n_lags, int order, const double* stats, void* work, size_t work_bytes,
+                                 double* corr, int64_t* nvalid, int* flagged, int flags, void* stream) {
+  if (!ref || !small || !small32c || !grid_wcs || !lag_wcs || !stats || !work || !corr || !flagged)
     return fail(COREG_EINVAL, "coreg_hpc_lag_corr_wcs_mixed: null pointer");
   if (n_lags <= 0) return COREG_OK;
   if (order != 2 || (flags & COREG_FLAG_STRICT))
@@ -727,8 +771,8 @@ int coreg_hpc_lag_corr_wcs_mixed(const float* ref, const double* small, const fl
   if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
   if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
   if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
-  return hpc_lag_corr_wcs_impl(ref, small, small32, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, pivots, work, corr,
-                               nvalid, flags, (cudaStream_t)stream);
+  return hpc_lag_corr_wcs_impl(ref, small, small32c, snx, sny, gnx, gny, grid_wcs, lag_wcs, n_lags, stats, work, corr,
+                               nvalid, flags, (cudaStream_t)stream, flagged);
 }
 
 int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs, int gnx, int gny, const CoregTanWcs* lag_wcs, int64_t n_lags,

@@ -124,33 +124,90 @@ int launch_map_coordinates(const TI* img, int ny, int nx, const double* y, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// mean of finite values (pivot). One block, fixed traversal order -> deterministic.
+// Image statistics in one pass over the image (multi-block, deterministic): mean of the finite values (the pivot of
+// the single-pass Pearson moments), their count and max |v|, optionally widening a float32 image to float64 on the
+// way (the host-side `np.array(..., dtype=float64)` of hdrshift/alignment.py:299-316). A second pass, for the mixed-
+// arithmetic kernel only, writes the float32 image centred on the float32-rounded pivot and takes the RMS of the
+// centred values. Every block leaves one partial; the block that finishes last folds the partials in index order,
+// so the result does not depend on scheduling. The grid is fixed (kStatBlocks x kStatThreads) on every device.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void finite_mean_kernel(const T* __restrict__ img, int64_t n, double* __restrict__ mean) {
-  __shared__ double ssum[1024];
-  __shared__ unsigned long long scnt[1024];
-  double s = 0.0;
-  unsigned long long c = 0;
-  // coarse sample (every 4th element) is plenty for a pivot and keeps this one-block kernel short
-  for (int64_t i = (int64_t)threadIdx.x * 4; i < n; i += (int64_t)blockDim.x * 4) {
-    const double v = (double)img[i];
-    if (isfinite(v)) {
-      s += v;
-      ++c;
-    }
-  }
-  ssum[threadIdx.x] = s;
-  scnt[threadIdx.x] = c;
+constexpr int kStatBlocks = 592, kStatThreads = 256;
+struct StatPart { double sum, cnt, maxabs, sumsq; };
+struct StatScratch { StatPart part[kStatBlocks]; unsigned done; unsigned pad[3]; };
+
+__device__ __forceinline__ void stat_block_fold(StatPart& v, StatPart* sh) {
+  sh[threadIdx.x] = v;
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      ssum[threadIdx.x] += ssum[threadIdx.x + o];
-      scnt[threadIdx.x] += scnt[threadIdx.x + o];
+  for (int o = kStatThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[threadIdx.x].sum += sh[threadIdx.x + o].sum;
+      sh[threadIdx.x].cnt += sh[threadIdx.x + o].cnt;
+      sh[threadIdx.x].sumsq += sh[threadIdx.x + o].sumsq;
+      sh[threadIdx.x].maxabs = fmax(sh[threadIdx.x].maxabs, sh[threadIdx.x + o].maxabs);
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) mean[0] = scnt[0] ? ssum[0] / (double)scnt[0] : 0.0;
+  v = sh[0];
+  __syncthreads();
+}
+
+// CENTER = false: sum / count / max|v| (+ optional widening);  CENTER = true (T = float): out32 = v - (float)mean, RMS
+template <typename T, bool CENTER>
+__global__ void __launch_bounds__(kStatThreads)
+image_stats_kernel(const T* __restrict__ img, int64_t n, double* __restrict__ widen, float* __restrict__ out32,
+                   StatScratch* __restrict__ scr, double* __restrict__ stats, int stride) {
+  __shared__ StatPart sh[kStatThreads];
+  __shared__ bool last;
+  StatPart v{0.0, 0.0, 0.0, 0.0};
+  const float p32 = CENTER ? (float)stats[0] : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t)kStatBlocks * kStatThreads) {
+    const T raw = img[i];
+    if (CENTER) {
+      const float c = (float)raw - p32;
+      out32[i] = c;
+      if (isfinite(c)) {
+        v.sumsq = fma((double)c, (double)c, v.sumsq);
+        v.cnt += 1.0;
+      }
+    } else {
+      const double x = (double)raw;
+      if (widen) widen[i] = x;
+      if (isfinite(x)) {
+        v.sum += x;
+        v.cnt += 1.0;
+        v.maxabs = fmax(v.maxabs, fabs(x));
+      }
+    }
+  }
+  stat_block_fold(v, sh);
+  if (threadIdx.x == 0) {
+    scr->part[blockIdx.x] = v;
+    __threadfence();
+    last = atomicAdd(&scr->done, 1u) == (unsigned)(kStatBlocks - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  StatPart t{0.0, 0.0, 0.0, 0.0};
+  for (int b = threadIdx.x; b < kStatBlocks; b += kStatThreads) {
+    const volatile StatPart* q = &scr->part[b];
+    t.sum += q->sum;
+    t.cnt += q->cnt;
+    t.sumsq += q->sumsq;
+    t.maxabs = fmax(t.maxabs, q->maxabs);
+  }
+  stat_block_fold(t, sh);
+  if (threadIdx.x == 0) {
+    if (CENTER) {
+      stats[3 * stride] = (t.cnt > 0.0) ? sqrt(t.sumsq / t.cnt) : 0.0;
+    } else {
+      stats[0] = (t.cnt > 0.0) ? t.sum / t.cnt : 0.0;
+      stats[stride] = t.cnt;
+      stats[2 * stride] = t.maxabs;
+      stats[3 * stride] = 0.0;
+    }
+    scr->done = 0;   // ready for the next call on this scratch
+  }
 }
 
 __global__ void car_pix2world_kernel(CoregLagCar L, double f11, double f12, double f21, double f22, int nx, int ny,
@@ -323,15 +380,35 @@ int coreg_widen_f32(const float* in, int64_t n, double* out, void* stream) {
   return COREG_OK;
 }
 
-int coreg_finite_mean(const void* img, int dtype, int64_t n, double* mean, void* stream) {
-  if (!img || !mean || n <= 0) return fail(COREG_EINVAL, "coreg_finite_mean: bad argument");
+size_t coreg_image_stats_scratch_bytes(void) { return sizeof(StatScratch); }
+
+int coreg_image_stats(const void* img, int dtype, int64_t n, double* widen, double* stats, int stats_stride,
+                      void* scratch, void* stream) {
+  if (!img || !stats || !scratch || n <= 0 || stats_stride <= 0) return fail(COREG_EINVAL, "coreg_image_stats: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StatScratch* scr = static_cast<StatScratch*>(scratch);
+  CK(cudaMemsetAsync(&scr->done, 0, sizeof(unsigned), s));
   if (dtype == COREG_F32)
-    finite_mean_kernel<float><<<1, 1024, 0, (cudaStream_t)stream>>>((const float*)img, n, mean);
-  else if (dtype == COREG_F64)
-    finite_mean_kernel<double><<<1, 1024, 0, (cudaStream_t)stream>>>((const double*)img, n, mean);
+    image_stats_kernel<float, false><<<kStatBlocks, kStatThreads, 0, s>>>((const float*)img, n, widen, nullptr, scr, stats,
+                                                                          stats_stride);
+  else if (dtype == COREG_F64 && !widen)
+    image_stats_kernel<double, false><<<kStatBlocks, kStatThreads, 0, s>>>((const double*)img, n, nullptr, nullptr, scr,
+                                                                           stats, stats_stride);
   else
-    return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
-  CK_LAUNCH("finite_mean_kernel");
+    return fail(COREG_EINVAL, "coreg_image_stats: dtype must be COREG_F32 or COREG_F64 (widening needs COREG_F32)");
+  CK_LAUNCH("image_stats_kernel");
+  return COREG_OK;
+}
+
+int coreg_center_f32(const float* img, int64_t n, float* out, double* stats, int stats_stride, void* scratch,
+                     void* stream) {
+  if (!img || !out || !stats || !scratch || n <= 0 || stats_stride <= 0)
+    return fail(COREG_EINVAL, "coreg_center_f32: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StatScratch* scr = static_cast<StatScratch*>(scratch);
+  CK(cudaMemsetAsync(&scr->done, 0, sizeof(unsigned), s));
+  image_stats_kernel<float, true><<<kStatBlocks, kStatThreads, 0, s>>>(img, n, nullptr, out, scr, stats, stats_stride);
+  CK_LAUNCH("image_stats_kernel<center>");
   return COREG_OK;
 }
 

@@ -3,7 +3,7 @@
 Public signatures mirror `hdrshift/alignment.py:47-55, 144-148, 263-269`. What changes is everything
 below `_find_best_header_parameters` (`:613-797`): instead of forking `counts_cpu_max` workers that each
 rebuild two WCS objects, call scipy and numba per lag, the lag grid is turned into a table of per-lag
-constants and evaluated by the fused CUDA kernels of `csrc/coreg_kernels.cu` (see `engine.py`).
+constants and evaluated by the fused CUDA kernels of `csrc/coreg_lag_*.cu` (see `engine.py`).
 
 Semantics follow the reference's `parallelism=True` branch (the contract of SURVEY.md section 0):
 the common grid of the helioprojective search is the UNSHIFTED small grid. `parallelism`,
@@ -46,11 +46,13 @@ class Alignment:
                  coarse_stride=None, arithmetic=None):
         """Same parameters as the reference (`hdrshift/alignment.py:47-83`). Additions:
 
-        arithmetic: "mixed" (default of the helioprojective order-2 search when the small image holds float32
-            values, e.g. a BITPIX -32 file): projection in FP64, spline and per-segment sums in FP32 -- the
-            reference stores every sample as float32 anyway (`alignment.py:1024`); |dr| ~ 1e-9 against "fp64"
-            (everything in FP64, |dr| ~ 1e-13 against the reference's arithmetic). None: COREG_ARITHMETIC or the
-            engine's default.
+        arithmetic: "fp64" (default): every sample is evaluated in FP64 like the reference does (scipy accumulates in
+            double, `utils/Util.py:98-102`) and then rounded to float32 (`alignment.py:1024`); |dr| ~ 1e-13 against
+            the reference's operation order. "mixed" (opt-in, helioprojective order-2 search of a small image that
+            holds float32 values, e.g. a BITPIX -32 file): projection in FP64, spline and per-segment sums in FP32 on
+            the image centred on its pivot, the float32 store reproduced on the uncentred value; a per-lag error
+            model (checked on the device) sends any lag that cannot be trusted to 1e-7 back through the FP64
+            kernel. None: the COREG_ARITHMETIC environment variable, else "fp64".
 
         cdelt_semantics: "reference" reproduces the reference's handling of CDELT lags (a CDELT1 lag only
             rebuilds PCi_j, a non-zero CDELT2 lag leaves 0.0 in the cube because the reference's worker dies,

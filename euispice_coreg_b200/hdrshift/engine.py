@@ -183,19 +183,25 @@ class LagSearchEngine:
 
     max_workspace_bytes = 2 << 30   # 3968 lags of a 2048^2 grid per launch (535 KB of warp records per lag)
 
-    default_arithmetic = "mixed"
+    # the reference evaluates every sample in FP64 (scipy accumulates in double, utils/Util.py:98-102) and only then
+    # stores it as float32 (alignment.py:1024): FP64 is the default, "mixed" an explicit opt-in
+    default_arithmetic = "fp64"
 
     def __init__(self, order=2, strict=False, device=None, variant=0, small_storage="f64", no_fast=False,
                  arithmetic=None):
-        """arithmetic: "mixed" (FP64 projection, FP32 spline on the float32 payload of the small image; applies to
-        the homography kernel when every small-image pixel is a float32 value) or "fp64" (everything in FP64).
-        None: the COREG_ARITHMETIC environment variable, else `default_arithmetic`."""
+        """arithmetic: "fp64" (default: everything in FP64, the reference's arithmetic) or "mixed" (opt-in: FP64
+        projection, FP32 spline on the pivot-centred float32 payload of the small image; applies to the homography
+        kernel when every small-image pixel is a float32 value; lags whose error model exceeds 1e-7 in r are
+        re-evaluated in FP64, see `resolve_flags`). None: the COREG_ARITHMETIC environment variable, else
+        `default_arithmetic`."""
         torch = _torch()
         arithmetic = arithmetic or os.environ.get("COREG_ARITHMETIC") or self.default_arithmetic
         if arithmetic not in ("fp64", "mixed"):
             raise ValueError('arithmetic must be "fp64" or "mixed"')
         self.arithmetic = arithmetic
-        self.small32 = None
+        self.small32 = None      # float32 payload of the small image, centred on its float32 pivot (mixed arithmetic)
+        self.lag_flags = None    # int32 [n]: lags of the last mixed `evaluate` that tripped the kernel's guard
+        self.flagged_lags = 0    # how many lags `resolve_flags` re-evaluated in FP64 (diagnostic)
         # launch-shape hint for the mixed kernel, set by `hpc_lag_table` from the WHOLE lag grid (never from a slice
         # of it: every shard must launch the same shape for the cube to be bit-identical for any GPU count)
         self.pure_shift_hint = False
@@ -208,7 +214,9 @@ class LagSearchEngine:
         self.variant, self.no_fast = int(variant), bool(no_fast)
         self.flags = _ext.make_flags(strict, variant, no_fast=no_fast)
         self.small_storage = small_storage
-        self.pivots = torch.zeros(2, dtype=torch.float64, device=self.device)
+        # statistics block [4, 2]: rows = mean (the pivot), count, max |v|, RMS about the pivot; columns = ref, small
+        self.stats = torch.zeros((_ext.STATS_ROWS, 2), dtype=torch.float64, device=self.device)
+        self.pivots = self.stats[0]
         self.ref = None        # large image on the common grid
         self.small = None
         self.planes = None     # TAN: [3, gny, gnx]; Carrington: (tx, ty)
@@ -242,46 +250,43 @@ class LagSearchEngine:
         torch = _torch()
         small = self._upload(self._native_float(data_small), pinned=pinned)
         self.small32 = None
+        self._mixed_pair = None
         mixed = self.arithmetic == "mixed" and self.small_storage == "f64" and not self.strict and self.order == 2
-        if small.dtype == torch.float32 and self.small_storage == "f64":
-            if mixed:
-                self.small32 = small
-            small = _ext.widen_f32(small)
-        elif mixed and small.dtype == torch.float64:
-            # a float64 input whose pixels are all float32 values (an integer FITS payload, a float32 image the
-            # caller widened): the mixed kernel sees exactly the same image
-            s32 = small.to(torch.float32)
-            if bool(((s32.to(torch.float64) == small) | torch.isnan(small)).all()):
-                self.small32 = s32.contiguous()
+        with torch.cuda.device(self.device):
+            if small.dtype == torch.float32 and self.small_storage == "f64":
+                s32 = small
+                small = _ext.image_stats(s32, self.stats, 1, widen=True)    # pivot + float64 copy in one pass
+                if mixed:
+                    self.small32 = _ext.center_f32(s32, self.stats, 1)
+            else:
+                _ext.image_stats(small, self.stats, 1)
+                if mixed and small.dtype == torch.float64:
+                    # a float64 input whose pixels are all float32 values (an integer FITS payload, a float32 image
+                    # the caller widened): the mixed kernel sees exactly the same image
+                    s32 = small.to(torch.float32)
+                    if bool(((s32.to(torch.float64) == small) | torch.isnan(small)).all()):
+                        self.small32 = _ext.center_f32(s32.contiguous(), self.stats, 1)
         self.small = small
-        _ext.finite_mean(self.small, self.pivots[1:2])
 
-    # float32 moments need headroom on both sides: the mixed kernel squares pivot-subtracted pixel values and sums
-    # 16 of them in float32, so images whose magnitudes sit near the ends of the float32 range (|v| beyond 1e12, or
-    # nothing above 1e-9: flux units far from DN/s or W/m2/sr/nm) are searched by the all-FP64 kernel instead
+    # float32 moments need headroom on both sides: the mixed kernel squares pivot-centred pixel values and sums 16 of
+    # them in float32, so images whose magnitudes sit near the ends of the float32 range (|v| beyond 1e12, or nothing
+    # above 1e-9: flux units far from DN/s or W/m2/sr/nm) are searched by the all-FP64 kernel from the start. (The
+    # per-lag guard of the finalize kernel would catch them too -- underflowing squares make the sampled variance
+    # vanish -- at the price of running the search twice.)
     MIXED_ABS_RANGE = (1e-9, 1e12)
 
-    @classmethod
-    def _float32_headroom(cls, *images):
-        torch = _torch()
-        lo, hi = cls.MIXED_ABS_RANGE
-        for img in images:
-            mag = torch.where(torch.isfinite(img), img.abs(), torch.zeros((), dtype=img.dtype, device=img.device))
-            m = float(mag.max()) if mag.numel() else 0.0
-            if not (lo < m < hi):
-                return False
-        return True
-
     def _mixed_applies(self):
-        """Mixed arithmetic for the current (small, ref) pair: requested, a float32 twin of the small image exists,
-        and both images leave the float32 sums enough range. Decided once per pair (one device reduction + sync)."""
+        """Mixed arithmetic for the current (small, ref) pair: requested, a centred float32 twin of the small image
+        exists, and both images leave the float32 sums enough range. Decided once per pair (one 64-byte D2H + sync)."""
         if self.arithmetic != "mixed" or self.small32 is None or self.ref is None:
             return False
         # (the pair is identified by the tensor objects themselves: a new image may land on a recycled address)
         if getattr(self, "_mixed_pair", None) is None or self._mixed_pair[0] is not self.small32 \
                 or self._mixed_pair[1] is not self.ref:
             self._mixed_pair = (self.small32, self.ref)
-            self._mixed_ok = self._float32_headroom(self.small32, self.ref)
+            lo, hi = self.MIXED_ABS_RANGE
+            mags = self.stats[2].tolist()
+            self._mixed_ok = all(lo < m < hi for m in mags)
         return self._mixed_ok
 
     # ---- helioprojective ------------------------------------------------------------------------
@@ -306,7 +311,7 @@ class LagSearchEngine:
             self.grid_wcs = wcs_small
             self.alpha_ref_deg = wcs_small.crval1
             self.delta_ref_deg = wcs_small.crval2
-            _ext.finite_mean(self.ref, self.pivots[0:1])
+            _ext.image_stats(self.ref, self.stats, 0)
         self.frame = "hpc"
 
     def prepare_hpc(self, data_large, wcs_large: TanWcs, wcs_small: TanWcs):
@@ -329,7 +334,7 @@ class LagSearchEngine:
             self.planes = _ext.tan_trig_planes(lng, lat, 0.0)
             del x, y, lng, lat, d_large
             self.grid_wcs = wcs_small
-            _ext.finite_mean(self.ref, self.pivots[0:1])
+            _ext.image_stats(self.ref, self.stats, 0)
         self.frame = "car"
         # launch shape of the generic kernel: the default 4 pixels x 4 CTAs / SM (64 registers, the atan2 temporaries
         # spill to L1-resident local memory) measured faster than 8 x 2 with 128 registers: 101.9 vs 115.7 ms on
@@ -408,7 +413,7 @@ class LagSearchEngine:
             ref = _ext.map_coordinates(d_large, ny, nx, self.order, -32762.0, torch.float64)
             ref = torch.where(ref == -32762.0, torch.full_like(ref, float("nan")), ref)
             self.ref = ref.contiguous()
-            _ext.finite_mean(self.ref, self.pivots[0:1])
+            _ext.image_stats(self.ref, self.stats, 0)
         self.frame = "carrington"
 
     # ---- evaluation ------------------------------------------------------------------------------------
@@ -426,28 +431,32 @@ class LagSearchEngine:
         per_lag = max(1, (_ext.lag_corr_workspace_bytes(gnx, gny, 1025) - fixed) // 1024)
         return max(64, ((self.max_workspace_bytes - fixed) // per_lag) // 64 * 64)
 
-    def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None):
+    def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None, allow_mixed=True):
         """Run the fused kernel over a device lag table [n, k]; results into out_dev[n]. Helioprojective frame:
         k = 11 (`CoregTanWcs` rows, `tan_wcs_table`) selects the homography kernel, k = 10 (`CoregLagTan` rows,
-        `tan_lag_table`) the generic one."""
+        `tan_lag_table`) the generic one. Asynchronous. With mixed arithmetic `self.lag_flags` receives the per-lag
+        guard verdicts: follow with `resolve_flags` (which synchronises) before trusting `out_dev`."""
         torch = _torch()
         n = table_dev.shape[0]
         gny, gnx = self.ref.shape
         step = self.lags_per_launch(gnx, gny)
         self.last_launches = 0
+        mixed = (allow_mixed and self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES
+                 and self._mixed_applies())
         with torch.cuda.device(self.device):
+            self.lag_flags = torch.zeros(n, dtype=torch.int32, device=self.device) if mixed else None
             work = self._workspace(gnx, gny, min(n, step))
             for lo in range(0, n, step):
                 hi = min(n, lo + step)
                 nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
                 if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
-                    mixed = self._mixed_applies()
                     flags = self.flags
                     if mixed and self.variant == 0 and self.pure_shift_hint:
                         flags = _ext.make_flags(self.strict, 1, no_fast=self.no_fast)
                     _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
-                                          self.pivots, work, out_dev[lo:hi], nv, flags,
-                                          small32=self.small32 if mixed else None)
+                                          self.stats if mixed else self.pivots, work, out_dev[lo:hi], nv, flags,
+                                          small32c=self.small32 if mixed else None,
+                                          flagged=self.lag_flags[lo:hi] if mixed else None)
                 elif self.frame == "car":
                     _ext.car_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order,
                                       self.pivots, work, out_dev[lo:hi], nv, self.flags)
@@ -461,6 +470,29 @@ class LagSearchEngine:
                 self.last_launches += 2  # lag kernel + finalize
         return out_dev
 
+    def resolve_flags(self, table_dev, out_dev, nvalid_dev=None):
+        """After a mixed-arithmetic `evaluate`: re-evaluate, with the all-FP64 kernel, every lag whose error model
+        (FP32 rounding of the centred spline against the variance of the sampled image, `mixed_guard_trips` in
+        csrc/coreg_lag_roll.cu) exceeded 1e-7 in r. The decision is per lag, so the cube does not depend on how the
+        lag list was sharded. Synchronises on the flag count. Returns the number of lags re-evaluated."""
+        torch = _torch()
+        if self.lag_flags is None:
+            return 0
+        with torch.cuda.device(self.device):
+            idx = torch.nonzero(self.lag_flags, as_tuple=False).flatten()   # (synchronises)
+            self.lag_flags = None
+            k = int(idx.numel())
+            if k:
+                sub = table_dev.index_select(0, idx).contiguous()
+                out = torch.empty(k, dtype=torch.float64, device=self.device)
+                nv = torch.empty(k, dtype=torch.int64, device=self.device) if nvalid_dev is not None else None
+                self.evaluate(sub, out, nv, allow_mixed=False)
+                out_dev.index_copy_(0, idx, out)
+                if nvalid_dev is not None:
+                    nvalid_dev.index_copy_(0, idx, nv)
+            self.flagged_lags = k
+        return k
+
     def search(self, table, planes=None, return_nvalid=False):
         """Host lag table [n_lags, k] -> numpy corr[n_lags]; shards over ranks when torch.distributed is up."""
         torch = _torch()
@@ -473,7 +505,9 @@ class LagSearchEngine:
             nvalid = torch.zeros(chunk, dtype=torch.int64, device=self.device) if return_nvalid else None
             if hi > lo:
                 tab_dev = self._upload(table[lo:hi])
-                self.evaluate(tab_dev, local[:hi - lo], None if nvalid is None else nvalid[:hi - lo], planes)
+                nv = None if nvalid is None else nvalid[:hi - lo]
+                self.evaluate(tab_dev, local[:hi - lo], nv, planes)
+                self.resolve_flags(tab_dev, local[:hi - lo], nv)
             full = gather_slices(local, n, chunk)
             corr = full.cpu().numpy()
             if return_nvalid:

@@ -34,6 +34,35 @@ def _side_stream(device):
     return _SIDE[key]
 
 
+def frames_of_rank(n_frames, rank, world):
+    """Round-robin frame sharding: rank r searches frames r, r + world, ..."""
+    return list(range(rank, n_frames, world))
+
+
+def gather_frame_cubes(cubes, n_frames, n_lags, device):
+    """{frame index: flat cube} of this rank's frames -> the same for ALL frames, on every rank: one all-gather of a
+    [frames per rank, n_lags] block (NCCL: `all_gather_into_tensor`; gloo, for the CPU tests of this logic: list
+    `all_gather`). A rank without frames (more ranks than frames) contributes an all-NaN block of the same shape."""
+    torch = _engine._torch()
+    dist, rank, world = _engine._dist_info()
+    if dist is None or world == 1 or n_frames == 0:
+        return cubes
+    per = (n_frames + world - 1) // world
+    width = max(n_lags, 1)
+    local = torch.full((per, width), float("nan"), dtype=torch.float64, device=device)
+    for j, k in enumerate(frames_of_rank(n_frames, rank, world)):
+        local[j, :n_lags] = torch.from_numpy(np.ascontiguousarray(cubes[k], dtype=np.float64).ravel()).to(device)
+    if local.is_cuda:
+        full = torch.empty((world * per, width), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(full, local)
+    else:
+        parts = [torch.empty((per, width), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, local)
+        full = torch.cat(parts)
+    full = full.cpu().numpy().reshape(world, per, -1)
+    return {r + world * j: full[r, j, :n_lags] for r in range(world) for j in range(per) if r + world * j < n_frames}
+
+
 class SequenceAlignment:
 
     def __init__(self, large_fov_known_pointing: str, list_small_fov_to_correct, lag_crval1, lag_crval2,
@@ -76,7 +105,7 @@ class SequenceAlignment:
         torch = _engine._torch()
         dist, rank, world = _engine._dist_info()
         n_frames = len(self.list_small)
-        mine = list(range(rank, n_frames, world))          # frames of this rank (round robin)
+        mine = frames_of_rank(n_frames, rank, world)
         # two engines = two sets of per-frame device buffers (small image, cut of the large image, pivots, workspace)
         # sharing the one resident large image: frame k+1 is uploaded and prepared on a side stream while frame k is
         # being searched on the main stream
@@ -92,17 +121,26 @@ class SequenceAlignment:
         a0._check_ant_create_pcij_matrix(hdr_large)
         eng.set_large(a0._float_image(f_large[a0.large_fov_window].data), TanWcs.from_header(hdr_large))
         engs[1].d_large, engs[1].wcs_large = eng.d_large, eng.wcs_large
+        # the cube shape depends on the lag arrays only: every rank needs it for the all-gather, also one that gets no
+        # frame (more ranks than frames)
         shape5 = None
-        pending = None                                      # (frame index, device cube, dead mask, Alignment)
+        if n_frames and not mine:
+            a = self._host_prepare(self.list_small[0])
+            shape5 = (len(a.lag_crval1), len(a.lag_crval2), len(a.lag_cdelt1), len(a.lag_cdelt2), len(a.lag_crota))
+            del a
+        pending = None                                      # (frame index, device cube, dead mask, Alignment, ...)
         cubes = {}
         aligns = {}
 
         def finish(item):
             # fetch on the side stream, ordered after THIS frame's search only: the main stream may already be busy
             # with the next frame, and a copy enqueued there would make the host wait for that one too
-            k, out_dev, dead, a, evt = item
+            k, out_dev, dead, a, evt, e, tab_dev = item
             with torch.cuda.device(out_dev.device), torch.cuda.stream(side):
                 side.wait_event(evt)
+                # mixed arithmetic (opt-in): lags that tripped the kernel's guard are redone in FP64, here on the side
+                # stream; this engine's buffers are not touched again before the side stream reaches its next frame
+                e.resolve_flags(tab_dev, out_dev)
                 host = out_dev.cpu()
             cubes[k] = np.where(dead, 0.0, host.numpy())
             aligns[k] = a
@@ -137,7 +175,7 @@ class SequenceAlignment:
             a.data_small = None
             if pending is not None:
                 finish(pending)
-            pending = (k, out_dev, dead, a, searched[n & 1])
+            pending = (k, out_dev, dead, a, searched[n & 1], e, tab_dev)
         if pending is not None:
             finish(pending)
         torch.cuda.synchronize()
@@ -145,16 +183,7 @@ class SequenceAlignment:
         self.frames_per_s = len(mine) / dt if dt > 0 and mine else None
         # assemble: every rank ends with all cubes (one all-gather of [frames per rank, n_lags])
         n_lags = int(np.prod(shape5)) if shape5 is not None else 0
-        if dist is not None and world > 1:
-            per = (n_frames + world - 1) // world
-            local = torch.full((per, max(n_lags, 1)), float("nan"), dtype=torch.float64, device=eng.device)
-            for j, k in enumerate(mine):
-                local[j, :n_lags] = torch.from_numpy(cubes[k]).to(eng.device)
-            full = torch.empty((world * per, max(n_lags, 1)), dtype=torch.float64, device=eng.device)
-            dist.all_gather_into_tensor(full, local)
-            full = full.cpu().numpy().reshape(world, per, -1)
-            cubes = {r + world * j: full[r, j, :n_lags] for r in range(world) for j in range(per)
-                     if r + world * j < n_frames}
+        cubes = gather_frame_cubes(cubes, n_frames, n_lags, eng.device)
         out = []
         for k in range(n_frames):
             cube = cubes[k].reshape(shape5 + (1,))

@@ -40,8 +40,9 @@ extern "C" {
 #define COREG_FLAG_STRICT 1
 /* COREG_FLAG_NO_FAST (value 4; 2 is reserved): force the generic kernel (testing / comparison). */
 #define COREG_FLAG_NO_FAST 4
-/* COREG_FLAG_MIXED: coreg_hpc_search_host only -- run the mixed-arithmetic kernel (coreg_hpc_lag_corr_wcs_mixed) when
- * the small image is COREG_F32 and the fast form applies. */
+/* COREG_FLAG_MIXED: coreg_hpc_search_host only -- opt in to the mixed-arithmetic kernel (coreg_hpc_lag_corr_wcs_mixed) when
+ * the small image is COREG_F32 and the fast form applies; the entry checks the kernel's per-lag guard and repeats the
+ * search in FP64 when any lag trips it. Default (flag clear): all FP64, the reference's arithmetic. */
 #define COREG_FLAG_MIXED 8
 #define COREG_FLAG_VARIANT(v) (((v) & 15) << 8)
 
@@ -154,9 +155,22 @@ int coreg_rice_decode(const unsigned char* heap_dev, const long long* offsets_de
  * kernels read the small image fastest as float64 (no per-tap conversion). */
 int coreg_widen_f32(const float* in_dev, int64_t n, double* out_dev, void* stream);
 
-/* mean of the finite values of an image -> mean_dev[0] (device double); deterministic. Used as the pivot of the
- * single-pass moments (the Pearson coefficient is invariant under it). */
-int coreg_finite_mean(const void* img_dev, int dtype, int64_t n, double* mean_dev, void* stream);
+/* ---- image statistics (pivots of the single-pass Pearson moments) ------------------------------------------------
+ * One deterministic multi-block pass over an image: stats_dev[0] = mean of the finite values (the pivot: the Pearson
+ * coefficient is invariant under it, it only keeps the single-pass moments well conditioned), stats_dev[stride] = their
+ * count, stats_dev[2 stride] = max |v| over them, stats_dev[3 stride] = 0. With a COREG_F32 image and widen_dev != NULL
+ * the same pass also writes the float64 copy (what coreg_widen_f32 does): the reference's
+ * `np.array(hdul[w].data.copy(), dtype=np.float64)`, hdrshift/alignment.py:299-316, fused with the pivot.
+ * The search kernels take `pivots_dev` = two such means side by side (ref, small): a [4][2] block filled with stride 2.
+ * scratch_dev: coreg_image_stats_scratch_bytes() bytes, private to the call's stream while it runs. */
+size_t coreg_image_stats_scratch_bytes(void);
+int coreg_image_stats(const void* img_dev, int dtype, int64_t n, double* widen_dev, double* stats_dev, int stats_stride,
+                      void* scratch_dev, void* stream);
+/* Float32 twin of a float32 image CENTRED on the float32-rounded pivot, for the mixed-arithmetic kernel:
+ * out_dev[i] = img_dev[i] - (float)stats_dev[0] (exact wherever pivot/2 <= v <= 2 pivot), and stats_dev[3 stride] =
+ * RMS of the centred finite values. stats_dev[0] must hold the pivot (coreg_image_stats on the same stream before). */
+int coreg_center_f32(const float* img_dev, int64_t n, float* out_dev, double* stats_dev, int stats_stride,
+                     void* scratch_dev, void* stream);
 
 /* ---- K1: fused helioprojective lag search ---------------------------------------------------------------------
  * For every lag: shift header -> world->pixel of every common-grid pixel -> order-k spline sample of the small
@@ -192,19 +206,28 @@ int coreg_hpc_lag_corr_wcs(const float* ref_dev, const double* small_dev, int sn
                            int order, const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
                            int64_t* nvalid_dev, int flags, void* stream);
 
-/* ---- K1 (fast form, mixed arithmetic) -------------------------------------------------------------------------------
+/* ---- K1 (fast form, mixed arithmetic; opt-in) ------------------------------------------------------------------------
  * coreg_hpc_lag_corr_wcs with the projection in FP64 and the spline + per-segment moments in FP32, for a small image
  * whose pixels are float32 values (a BITPIX -32 FITS payload: what `Fits.open(...)[w].data` holds before the
- * reference widens it, hdrshift/alignment.py:299-316). small32_dev is that payload, small_dev its float64 widening
- * (used where a segment touches the image border, a missing pixel or an irregular column and is evaluated by the
- * exact per-pixel rules). The reference stores every sample as float32 (alignment.py:1024), so the FP32 spline moves
- * a sample by about one float32 ulp, unbiased: |dr| ~ 1e-9 against the FP64 kernel (bar: 1e-6). Variants
- * (COREG_FLAG_VARIANT): 0 = 12 rows per thread, 1 = 16 (faster when no lag rotates or rescales the grid). */
-int coreg_hpc_lag_corr_wcs_mixed(const float* ref_dev, const double* small_dev, const float* small32_dev, int snx,
+ * reference widens it, hdrshift/alignment.py:299-316).
+ *   small32c_dev  the payload centred on the float32-rounded pivot (coreg_center_f32); small_dev its float64 widening
+ *                 (segments that touch the image border, a missing pixel or an irregular column are evaluated by the
+ *                 exact per-pixel rules in FP64)
+ *   stats_dev     the [4][2] statistics block (column 0 = ref, column 1 = small) of coreg_image_stats + coreg_center_f32;
+ *                 its first row is the pivots
+ *   flagged_dev   [n_lags] int32 out: 1 for every lag whose error model (FP32 rounding of the centred spline
+ *                 against the sampled image's own variance, see coreg_lag_roll.cu:mixed_guard_trips) exceeds 1e-7 in
+ *                 r, else 0. The caller re-evaluates the flagged lags with coreg_hpc_lag_corr_wcs (all FP64); the
+ *                 decision is per lag, so a cube does not depend on how its lags were sharded. The reference computes every sample in FP64 and then stores it
+ *                 as float32 (alignment.py:1024); this kernel reproduces that float32 store on the uncentred value,
+ *                 so its samples equal the reference's except within a few float32 ulps OF THE DEVIATION FROM THE
+ *                 PIVOT of a rounding boundary: |dr| <= 1e-7 by the model, ~1e-10 observed, independent of the image's
+ *                 mean level. Variants (COREG_FLAG_VARIANT): 0 = 12 rows per thread, 1 = 16 (pure CRVAL lag grids). */
+int coreg_hpc_lag_corr_wcs_mixed(const float* ref_dev, const double* small_dev, const float* small32c_dev, int snx,
                                  int sny, int gnx, int gny, const CoregTanWcs* grid_wcs_host,
-                                 const CoregTanWcs* lag_wcs_dev, int64_t n_lags, int order, const double* pivots_dev,
-                                 void* work_dev, size_t work_bytes, double* corr_dev, int64_t* nvalid_dev, int flags,
-                                 void* stream);
+                                 const CoregTanWcs* lag_wcs_dev, int64_t n_lags, int order, const double* stats_dev,
+                                 void* work_dev, size_t work_bytes, double* corr_dev, int64_t* nvalid_dev,
+                                 int* flagged_dev, int flags, void* stream);
 
 /* Diagnostic: max |e| = max |1 - D| of each candidate header's homography over the gnx x gny common grid (what selects
  * the reciprocal form per lag inside coreg_hpc_lag_corr_wcs). scratch_dev: at least 96 * n_lags bytes.

@@ -56,7 +56,7 @@ def test_timeutil():
 
 # ----------------------------------------------------------------------------------------------- lag tables
 def _kernel_map(table_row, lng, lat, alpha_ref_deg):
-    """numpy emulation of TanCoord::map (csrc/coreg_kernels.cu) from the lag-table row."""
+    """numpy emulation of TanCoord::map (csrc/coreg_common.cuh) from the lag-table row."""
     s_da, c_da, s_d0, c_d0, m11, m12, m21, m22, x0, y0 = table_row
     p0 = np.sin(np.deg2rad(lat))
     a = np.deg2rad(lng) - np.deg2rad(alpha_ref_deg)
@@ -367,17 +367,28 @@ for n in (25, 7, 2, 1, 3600):
     local[:hi - lo] = torch.arange(lo, hi, dtype=torch.float64) * 0.5      # stands in for the rank's r values
     full = engine.gather_slices(local, n, chunk)
     assert full.shape == (n,) and torch.equal(full, torch.arange(n, dtype=torch.float64) * 0.5), (n, full)
+# frame sharding of a sequence (hdrshift/sequence.py): round robin, one all-gather of the cubes -- also with more
+# ranks than frames (a rank without frames must still contribute a block of the common shape)
+from euispice_coreg_b200.hdrshift import sequence
+for n_frames, n_lags in ((5, 12), (1, 7), (world + 3, 4), (world - 1, 6), (0, 3)):
+    mine = sequence.frames_of_rank(n_frames, rank, world)
+    cubes = {{k: np.full(n_lags, 100.0 * k) + np.arange(n_lags) for k in mine}}
+    allc = sequence.gather_frame_cubes(cubes, n_frames, n_lags, torch.device("cpu"))
+    assert sorted(allc) == list(range(n_frames)), (n_frames, sorted(allc))
+    for k in range(n_frames):
+        assert np.array_equal(allc[k], np.full(n_lags, 100.0 * k) + np.arange(n_lags)), (n_frames, k)
 dist.barrier()
 if rank == 0:
     print("GLOO_OK")
 """
 
 
-def test_lag_sharding_and_gather_world_size_2_gloo(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_lag_and_frame_sharding_gather_gloo(tmp_path, world):
     script = tmp_path / "gloo_worker.py"
     script.write_text(_GLOO.format(root=ROOT))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29531 + world), str(script)],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout

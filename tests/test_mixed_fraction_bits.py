@@ -1,4 +1,4 @@
-"""The mixed-arithmetic kernel's way out of the FP64 domain (csrc/coreg_kernels.cu, roll_segment_mixed), restated in
+"""The mixed-arithmetic kernel's way out of the FP64 domain (csrc/coreg_lag_roll.cu, roll_segment_mixed), restated in
 numpy: the coordinate FMA adds kFracMagic = 1.5 * 2^29, whose ulp is 2^-23, so the LOW word of the double is
 round((x - floor_x0) * 2^23) modulo 2^32 -- the row index inside the segment in the bits above bit 22 and the
 float32 mantissa of 1 + fraction below. This pins the encoding the CUDA code relies on (CPU test, no GPU)."""
