@@ -206,13 +206,21 @@ def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0):
     rank = dist.get_rank() if world > 1 else 0
     chunk, bounds = E.shard_bounds(n, world)
     lo, hi = bounds[rank]
-    tab_dev = eng._upload(table[lo:hi])
+    # the kernel takes its lags in detector-plane patches (engine.offset_patch_order), padded with dummy lags
+    i1, i2 = np.unravel_index(np.arange(lo, hi), (len(a.lag_crval1), len(a.lag_crval2)))
+    slot, n_slots = E.offset_patch_order(i1, i2)
+    padded = np.full((n_slots, 2), np.nan)
+    padded[slot] = table[lo:hi]
+    tab_dev = eng._upload(padded)
+    slot_dev = torch.from_numpy(slot).to(eng.device)
+    out_p = torch.empty(n_slots, dtype=torch.float64, device=eng.device)
+    nv_p = torch.zeros(n_slots, dtype=torch.int64, device=eng.device)
     out = torch.full((chunk,), float("nan"), dtype=torch.float64, device=eng.device)
-    nv = torch.zeros(chunk, dtype=torch.int64, device=eng.device)
     full = torch.empty(chunk * world, dtype=torch.float64, device=eng.device)
 
     def step():
-        eng.evaluate(tab_dev, out[:hi - lo], nv[:hi - lo], planes)
+        eng.evaluate(tab_dev, out_p, nv_p, planes)
+        out[:hi - lo] = out_p.index_select(0, slot_dev)
         if world > 1:
             dist.all_gather_into_tensor(full, out)
 
@@ -228,7 +236,7 @@ def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0):
     torch.cuda.synchronize()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=eng.device)
-    eff = nv[:hi - lo].sum().to(torch.float64).reshape(1)
+    eff = nv_p.index_select(0, slot_dev).sum().to(torch.float64).reshape(1)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(eff, op=dist.ReduceOp.SUM)

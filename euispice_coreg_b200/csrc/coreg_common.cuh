@@ -443,8 +443,9 @@ struct HomLag {
 // ---- launchers defined in one translation unit and used from another ----
 // fixed-order fold of [tile][lag][kMom] partials -> Pearson r (coreg_lag_generic.cu)
 int launch_finalize_tiles(const double* work, int tiles, int64_t n_lags, double* corr, int64_t* nvalid, cudaStream_t s);
-// Carrington-frame fast kernel (coreg_lag_offset.cu); small_dtype COREG_F32 / COREG_F64
-int launch_offset_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const double* ref,
-                       const void* small, int small_dtype, int snx, int sny, const double* tx, const double* ty,
-                       const CoregLagOffset* lags, const double* pivots, void* work, int* tiles_out);
+// Carrington-frame lag kernel + its finalize (coreg_lag_offset.cu); small_dtype COREG_F32 / COREG_F64
+int launch_offset_fast(int gnx, int gny, int64_t n_lags, cudaStream_t s, const double* ref, const void* small,
+                       int small_dtype, int snx, int sny, const double* tx, const double* ty,
+                       const CoregLagOffset* lags, const double* pivots, void* work, double* corr, int64_t* nvalid);
+size_t offset_workspace_bytes(int gnx, int gny, int64_t n_lags);
 }  // namespace coreg

@@ -190,6 +190,14 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
   const bool strict = (flags & COREG_FLAG_STRICT) != 0;
   const int variant = (flags >> 8) & 15;
   double* w = static_cast<double*>(work);
+  // window kernel for the offset (Carrington) functor: order 2, FMA arithmetic, image of at least 3x3
+  const bool fast_ok = std::is_same<Coord, OffsetCoord>::value && (order == 2) && !strict && snx >= 3 && sny >= 3 &&
+                       !(flags & COREG_FLAG_NO_FAST);
+  if constexpr (std::is_same<Coord, OffsetCoord>::value) {
+    if (fast_ok)
+      return launch_offset_fast(gnx, gny, n_lags, s, ref, small, sizeof(SmallT) == 4 ? COREG_F32 : COREG_F64, snx, sny,
+                                planes.tx, planes.ty, lags, pivots, work, corr, nvalid);
+  }
   const bool prof = g_prof_on && g_prof_n < 4096;
   if (prof) {
     CK(cudaEventCreate(&g_prof[g_prof_n].a));
@@ -197,21 +205,6 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
     CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
   int tiles = 0, rc = COREG_OK;
-  // fast kernel for the offset (Carrington) functor: order 2, FMA arithmetic, image of at least 3x3
-  const bool fast_ok = std::is_same<Coord, OffsetCoord>::value && (order == 2) && !strict && snx >= 3 && sny >= 3 &&
-                       !(flags & COREG_FLAG_NO_FAST);
-  if constexpr (std::is_same<Coord, OffsetCoord>::value) {
-    if (fast_ok) {
-      rc = launch_offset_fast(variant, gnx, gny, n_lags, sms, s, ref, small, sizeof(SmallT) == 4 ? COREG_F32 : COREG_F64, snx,
-                              sny, planes.tx, planes.ty, lags, pivots, work, &tiles);
-      if (rc) return rc;
-      if (prof) {
-        CK(cudaEventRecord(g_prof[g_prof_n].b, s));
-        ++g_prof_n;
-      }
-      return launch_finalize_tiles(w, tiles, n_lags, corr, nvalid, s);
-    }
-  }
 #define LAUNCH(ORD, STR)                                                                                          \
   rc = launch_lag_variant<Coord, ORD, STR, SmallT, RefT, ROUND32>(variant, dim3(), gnx, gny, n_lags, sms, s, ref, \
                                                                    small, snx, sny, planes, lags, pivots, w, &tiles)
@@ -241,7 +234,8 @@ extern "C" {
 
 size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags) {
   if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;
-  return partials_bytes(gnx, gny, n_lags) + (size_t)n_lags * sizeof(HomLag);
+  return std::max(partials_bytes(gnx, gny, n_lags), offset_workspace_bytes(gnx, gny, n_lags)) +
+         (size_t)n_lags * sizeof(HomLag);
 }
 
 int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,

@@ -1,39 +1,87 @@
-// coreg_lag_offset.cu -- Carrington-frame lag kernel (order-2 spline, FMA arithmetic): per-pixel detector-plane offsets + per-lag shift.
+// coreg_lag_offset.cu -- Carrington-frame lag kernel (K4): order-2 spline, FMA arithmetic, FP64 throughout.
+//
+// Replaces `Alignment._step` with function_to_apply = `_carrington_transform_fa` for a list of CRVAL lags
+// (hdrshift/alignment.py:509-542, 889-901; utils/rectify.py:340-374, 865-888). For such lags the detector coordinate
+// of a Carrington-grid pixel is  x = x0(lag) + Tx[pixel],  y = y0(lag) + Ty[pixel]  (SURVEY App. A.3): a translated
+// gather. Neighbouring grid pixels land several detector pixels apart (4.4 x 1.7 at BASELINE configs[1]), so a warp
+// that walks a grid row scatters its nine taps per sample over 4 - 5 cache lines each: the first version of this
+// kernel kept the L1 data pipe 94 % busy and the FP64 pipe 29 % (profiles/r1_ncu_carrington_v0.txt).
+//
+// This version turns the warp around: LANES ARE LAGS. A block owns a super-tile of the grid (four stacked tiles of
+// 32 x 16 pixels) and a chunk of 256 consecutive lags (one per thread; the caller orders the lag list so that
+// consecutive lags are neighbours in the detector plane -- 16 x 16 patches, 8 x 4 per warp). For each tile
+//   * the live pixels (finite reference value, in front of the limb) are compacted into a shared-memory table
+//     (Tx, Ty, ref - pivot): every lane reads the same entry, a broadcast;
+//   * the part of the small image that ANY (pixel, lag) pair of the tile and chunk can touch -- the tile's detector
+//     footprint grown by the chunk's offset spread plus the spline support -- is staged in shared memory by ONE TMA
+//     tile load (cp.async.bulk.tensor.2d, completion on an mbarrier; the box starts on a 16-byte boundary of the image
+//     row; out-of-image parts arrive as zeros and are never read). A window that does not fit the box (coarse grids, unordered lags) falls back to global loads; an image
+//     whose row pitch is not a multiple of 16 bytes is staged by a cooperative copy instead of TMA;
+//   * every lane walks the pixel table for its own lag: coordinates, floors by magic-number add, one unsigned
+//     compare per axis for "all nine taps inside image and window", weights, nine LDS.32 -- the 32 lanes of a warp
+//     now touch a 16 x 8 pixel neighbourhood of the window instead of a 140-pixel row --, moments. Samples on the
+//     image border take the exact out-of-line sampler on global memory, as before.
+// The six moments of a (super-tile, lag) pair therefore accumulate in the registers of one thread, in a fixed order:
+// no warp shuffles, no shared-memory accumulators, one 64-byte partial per (live super-tile, lag). Super-tiles that
+// cannot reach the small image under any lag of the launch (87 % of the grid at configs[1]) get no partial at all:
+// a pre-pass marks them and a single-block scan assigns partial slots in ascending order, so the finalize kernel
+// adds the partials of a lag in the same order whatever the launch contained (bit-identical cubes for any sharding).
+#include <cuda.h>
+
 #include "coreg_common.cuh"
 
 namespace coreg {
-struct OffsetFastLag {
-  double x0h, y0h;
+
+constexpr int kOffThreads = 256;          // = lags per chunk (one lag per thread)
+constexpr int kOffWarps = kOffThreads / 32;
+constexpr int kOffTileW = 32, kOffTileH = 16, kOffTilePx = kOffTileW * kOffTileH;
+constexpr int kOffTilesPerBlock = 4;      // stacked vertically: super-tile = 32 x 64 grid pixels
+constexpr int kOffSuperH = kOffTileH * kOffTilesPerBlock;
+
+template <typename T>
+struct OffBox {   // shared-memory window = TMA box. Row pitch = 8 (mod 32) words: lanes two rows apart do not alias.
+  static constexpr int W = sizeof(T) == 4 ? 200 : 100;
+  static constexpr int H = sizeof(T) == 4 ? 64 : 56;
+  static constexpr int kBytes = W * H * (int)sizeof(T);
 };
 
-__global__ void offset_fast_table_kernel(const CoregLagOffset* __restrict__ lags, int n, OffsetFastLag* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  OffsetFastLag f;
-  f.x0h = lags[i].x0 + 0.5;
-  f.y0h = lags[i].y0 + 0.5;
-  out[i] = f;
-}
+struct OffPx {   // one live pixel of the current tile (32 B: one LDS.128 + one LDS.64, broadcast)
+  double tx, ty, ac, pad;
+};
 
-// per lag slice (blockIdx.y of the fast kernel): range of the offsets, so that a tile whose whole bounding box
-// falls outside the small image for every lag of the slice can be skipped
-__global__ void offset_lag_range_kernel(const OffsetFastLag* __restrict__ ft, int n_lags, int lags_per_block,
-                                        double* __restrict__ ranges) {
-  __shared__ double s[4][128];
-  const int lo = blockIdx.x * lags_per_block, hi = min(n_lags, lo + lags_per_block);
+struct OffWork {   // byte offsets into the workspace (all 16-byte aligned)
+  size_t partials, slots, nslots, range, total;
+  int n_super;
+};
+inline OffWork offw_layout(int gnx, int gny, int64_t n_lags) {
+  OffWork L;
+  L.n_super = ((gnx + kOffTileW - 1) / kOffTileW) * ((gny + kOffSuperH - 1) / kOffSuperH);
+  L.partials = 0;
+  L.slots = (size_t)L.n_super * (size_t)n_lags * kMom * sizeof(double);
+  L.nslots = L.slots + (((size_t)L.n_super * sizeof(int) + 15) / 16) * 16;
+  L.range = L.nslots + 16;
+  L.total = L.range + 4 * sizeof(double);
+  return L;
+}
+size_t offset_workspace_bytes(int gnx, int gny, int64_t n_lags) { return offw_layout(gnx, gny, n_lags).total; }
+
+// ---- pre-pass ---------------------------------------------------------------------------------------------------
+// range of the lag offsets (+0.5) of the whole launch; NaN / absurd offsets never evaluate anything and are ignored
+__global__ void __launch_bounds__(256) offset_lag_range_kernel(const CoregLagOffset* __restrict__ lags, int n_lags,
+                                                               double* __restrict__ range) {
+  __shared__ double s[4][256];
   double x0 = CUDART_INF, x1 = -CUDART_INF, y0 = CUDART_INF, y1 = -CUDART_INF;
-  bool bad = false;
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const OffsetFastLag f = ft[i];
-    bad = bad || !(f.x0h == f.x0h) || !(f.y0h == f.y0h);
-    x0 = fmin(x0, f.x0h); x1 = fmax(x1, f.x0h);
-    y0 = fmin(y0, f.y0h); y1 = fmax(y1, f.y0h);
+  for (int i = threadIdx.x; i < n_lags; i += 256) {
+    const double x = lags[i].x0 + 0.5, y = lags[i].y0 + 0.5;
+    if (small_magnitude(x) && small_magnitude(y)) {
+      x0 = fmin(x0, x); x1 = fmax(x1, x);
+      y0 = fmin(y0, y); y1 = fmax(y1, y);
+    }
   }
-  if (bad) { x0 = y0 = -CUDART_INF; x1 = y1 = CUDART_INF; }   // NaN offsets: never skip
   s[0][threadIdx.x] = x0; s[1][threadIdx.x] = x1; s[2][threadIdx.x] = y0; s[3][threadIdx.x] = y1;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
       s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + o]);
       s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + o]);
       s[2][threadIdx.x] = fmin(s[2][threadIdx.x], s[2][threadIdx.x + o]);
@@ -41,323 +89,466 @@ __global__ void offset_lag_range_kernel(const OffsetFastLag* __restrict__ ft, in
     }
     __syncthreads();
   }
-  if (threadIdx.x < 4) ranges[blockIdx.x * 4 + threadIdx.x] = s[threadIdx.x][0];
+  if (threadIdx.x < 4) range[threadIdx.x] = s[threadIdx.x][0];
 }
 
-struct OffsetFast {
-  typedef OffsetFastLag LagC;
-  typedef OffsetCoord::Planes Planes;
-  struct Thread {};
-  typedef OffsetCoord::Pix Pix;
-  struct TL {};
-  static constexpr bool kCoordsAlwaysFinite = false;  // dead pixels carry NaN offsets -> never interior
-  __device__ static __forceinline__ Thread thread_init(int) { return Thread(); }
-  __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx, int) { return OffsetCoord::load(pl, idx); }
-  __device__ static __forceinline__ Pix dead() { return OffsetCoord::dead(); }
-  __device__ static __forceinline__ TL thread_lag(const LagC&, const Thread&) { return TL(); }
-  __device__ static __forceinline__ double plane_x(const Pix& q) { return q.tx; }
-  __device__ static __forceinline__ double plane_y(const Pix& q) { return q.ty; }
-  __device__ static __forceinline__ void map_half(const Pix& q, const TL&, const LagC& C, double& sx, double& sy) {
-    sx = C.x0h + q.tx;
-    sy = C.y0h + q.ty;
-  }
-};
-
-constexpr int kFastLagSub = 32;
-
-
-template <class Fast, typename SmallT, typename RefT, bool ROUND32, int PPT, int MINB, int GROUP>
-__global__ void __launch_bounds__(kThreads, MINB)
-lag_corr_fast_kernel(const RefT* __restrict__ ref, const SmallT* __restrict__ small, int snx, int sny, int gnx, int gny,
-                     typename Fast::Planes planes, const typename Fast::LagC* __restrict__ fast_lags, int n_lags,
-                     int lags_per_block, const double* __restrict__ pivots, double* __restrict__ work,
-                     const double* __restrict__ ranges) {
-  typedef typename Fast::Pix Pix;
-  typedef typename Fast::LagC LagC;
-  constexpr int TILE_H = kRowsPerPass * PPT;
-  __shared__ double s_box[4][kWarps];
-  // GROUP = pixels whose dependency chains are interleaved (their coordinates / indices are live together)
-  static_assert(PPT % GROUP == 0, "PPT must be a multiple of GROUP");
-  __shared__ __align__(16) LagC s_lag[kFastLagSub];
-  __shared__ double s_part[kWarps][kFastLagSub][kMom];
-  __shared__ double s_wconst[kWarps][3];                 // per warp: n, Sa, Saa over its finite reference pixels
-  __shared__ unsigned char s_miss[kWarps][kFastLagSub];  // 1 when the (warp, lag) slot carries its own n, Sa, Saa
-
-  const int tiles_x = (gnx + kTileW - 1) / kTileW;
-  const int tile = blockIdx.x;
-  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & (kTileW - 1), ty0 = tid / kTileW;
-  const int gx = tile_x * kTileW + tx;
-  const double pivot_a = pivots[0], pivot_b = pivots[1];
-  const unsigned ux = (unsigned)(snx - 2), uy = (unsigned)(sny - 2);  // launcher guarantees snx, sny >= 3
-  const unsigned row_elems = (unsigned)snx;
-
-  const typename Fast::Thread tstate = Fast::thread_init(gx);
-  Pix pix[PPT];
-  double a_c[PPT];
-  unsigned a_ok = 0;
-  double sa_all = 0.0, saa_all = 0.0;
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const int gy = tile_y * TILE_H + ty0 + k * kRowsPerPass;
-    a_c[k] = 0.0;
-    pix[k] = Fast::dead();
+// live[s] = 1 when super-tile s has a live pixel whose 3 x 3 support can touch the image under some lag of the launch
+__global__ void __launch_bounds__(256) offset_super_live_kernel(const double* __restrict__ ref,
+                                                                const double* __restrict__ tx,
+                                                                const double* __restrict__ ty, int gnx, int gny,
+                                                                int snx, int sny, const double* __restrict__ range,
+                                                                int* __restrict__ live) {
+  __shared__ double s[4][256];
+  const int sx_tiles = (gnx + kOffTileW - 1) / kOffTileW;
+  const int ox = (blockIdx.x % sx_tiles) * kOffTileW, oy = (blockIdx.x / sx_tiles) * kOffSuperH;
+  double x0 = CUDART_INF, x1 = -CUDART_INF, y0 = CUDART_INF, y1 = -CUDART_INF;
+  for (int i = threadIdx.x; i < kOffTileW * kOffSuperH; i += 256) {
+    const int gx = ox + (i & (kOffTileW - 1)), gy = oy + i / kOffTileW;
     if (gx < gnx && gy < gny) {
       const int64_t idx = (int64_t)gy * gnx + gx;
-      const double a = (double)ref[idx];
-      if (isfinite(a)) {
-        a_c[k] = a - pivot_a;
-        a_ok |= 1u << k;
-        pix[k] = Fast::load(planes, idx, gy);
-        sa_all += a_c[k];
-        saa_all = fma(a_c[k], a_c[k], saa_all);
+      const double a = ref[idx], px = tx[idx], py = ty[idx];
+      if (isfinite(a) && small_magnitude(px) && small_magnitude(py)) {
+        x0 = fmin(x0, px); x1 = fmax(x1, px);
+        y0 = fmin(y0, py); y1 = fmax(y1, py);
       }
     }
   }
-  const int n_all = __popc(a_ok);
-  // warp totals of the lag-independent reference moments (used when no sample of the warp is missing)
-  double wsa = sa_all, wsaa = saa_all;
-  int wn = n_all;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    wsa += __shfl_xor_sync(0xffffffffu, wsa, o);
-    wsaa += __shfl_xor_sync(0xffffffffu, wsaa, o);
-    wn += __shfl_xor_sync(0xffffffffu, wn, o);
+  s[0][threadIdx.x] = x0; s[1][threadIdx.x] = x1; s[2][threadIdx.x] = y0; s[3][threadIdx.x] = y1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + o]);
+      s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + o]);
+      s[2][threadIdx.x] = fmin(s[2][threadIdx.x], s[2][threadIdx.x + o]);
+      s[3][threadIdx.x] = fmax(s[3][threadIdx.x], s[3][threadIdx.x + o]);
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
-    s_wconst[warp][0] = (double)wn;
-    s_wconst[warp][1] = wsa;
-    s_wconst[warp][2] = wsaa;
+  if (threadIdx.x == 0) {
+    // sample valid <=> 0 <= x <= n - 1 <=> 0.5 <= x + 0.5 <= n - 0.5; one pixel of slack for rounding. An empty box
+    // (no live pixel: +inf / -inf) or an empty lag range fails the test.
+    const bool reach = (s[1][0] + range[1] >= -0.5) && (s[0][0] + range[0] <= (double)snx + 0.5) &&
+                       (s[3][0] + range[3] >= -0.5) && (s[2][0] + range[2] <= (double)sny + 0.5);
+    live[blockIdx.x] = reach ? 1 : 0;
   }
+}
 
-  const int lag_begin = blockIdx.y * lags_per_block;
-  const int lag_end = min(n_lags, lag_begin + lags_per_block);
-  if (ranges != nullptr) {
-    // A Carrington grid is usually far larger than the small image's footprint: when the bounding box of this
-    // tile's detector-plane offsets cannot reach the image under any lag of the slice (or the tile has no finite
-    // reference pixel), every sample is missing, all six moments are zero, and the lag walk is skipped.
-    double bx0 = CUDART_INF, bx1 = -CUDART_INF, by0 = CUDART_INF, by1 = -CUDART_INF;
-#pragma unroll
-    for (int k = 0; k < PPT; ++k)
-      if (a_ok & (1u << k)) {
-        const double px = Fast::plane_x(pix[k]), py = Fast::plane_y(pix[k]);
-        bx0 = fmin(bx0, px); bx1 = fmax(bx1, px);
-        by0 = fmin(by0, py); by1 = fmax(by1, py);
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      bx0 = fmin(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-      bx1 = fmax(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-      by0 = fmin(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-      by1 = fmax(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-    }
-    if (lane == 0) { s_box[0][warp] = bx0; s_box[1][warp] = bx1; s_box[2][warp] = by0; s_box[3][warp] = by1; }
+// in place: live flags -> partial slot (ascending over live super-tiles) or -1; *n_slots = number of live super-tiles
+__global__ void __launch_bounds__(1024) offset_slot_scan_kernel(int* __restrict__ slot, int n, int* __restrict__ n_slots) {
+  __shared__ int s[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? slot[i] : 0;
+    s[threadIdx.x] = v;
     __syncthreads();
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      bx0 = fmin(bx0, s_box[0][w]); bx1 = fmax(bx1, s_box[1][w]);
-      by0 = fmin(by0, s_box[2][w]); by1 = fmax(by1, s_box[3][w]);
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int add = ((int)threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += add;
+      __syncthreads();
     }
-    const double* rg = ranges + 4 * blockIdx.y;   // min / max of x0 + 0.5, y0 + 0.5 over the slice
-    // sample valid <=> 0 <= x <= n - 1 <=> 0.5 <= x + 0.5 <= n - 0.5 (one pixel of slack for rounding)
-    const bool reach = (bx1 + rg[1] >= -0.5) && (bx0 + rg[0] <= (double)snx + 0.5) &&
-                       (by1 + rg[3] >= -0.5) && (by0 + rg[2] <= (double)sny + 0.5);
-    if (!reach) {   // also taken when the tile has no live pixel (box stays empty: +inf / -inf)
-      for (int i = tid; i < (lag_end - lag_begin) * kMom; i += kThreads)
-        work[((size_t)tile * n_lags + lag_begin) * kMom + i] = 0.0;
-      return;
+    if (i < n) slot[i] = v ? carry + s[threadIdx.x] - 1 : -1;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_slots = carry;
+}
+
+// ---- TMA / mbarrier primitives (PTX: cp.async.bulk.tensor + mbarrier; SASS: UTMALDG, SYNCS) ----------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+// fixed-order block reductions through shared memory (8 warps): every thread returns the same value
+__device__ __forceinline__ double block_min(double v, double* s_red, int lane, int warp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double r = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kOffWarps; ++w) r = fmin(r, s_red[w]);
+  return r;
+}
+__device__ __forceinline__ double block_sum(double v, double* s_red, int lane, int warp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double r = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kOffWarps; ++w) r += s_red[w];
+  return r;
+}
+
+// One lag's walk over the live pixels of a tile. WINDOW: `img` is the staged window (shared memory, pitch `pitch`,
+// origin folded into lo_x / lo_y / base_off); otherwise the image itself in global memory.
+template <typename T, bool WINDOW>
+__device__ __forceinline__ void offset_walk(const T* __restrict__ img, int pitch, int base_off, int lo_x, int lo_y,
+                                            unsigned span_x, unsigned span_y, const T* __restrict__ small, int snx,
+                                            int sny, const OffPx* __restrict__ s_px, int n_live, double x0h,
+                                            double y0h, double pivot_b, double& sb, double& sbb, double& sab,
+                                            int& n_miss, double& sa_miss, double& saa_miss) {
+#pragma unroll 2
+  for (int k = 0; k < n_live; ++k) {
+    const double2 t2 = *reinterpret_cast<const double2*>(&s_px[k].tx);
+    const double ac = s_px[k].ac;
+    const double sx = x0h + t2.x, sy = y0h + t2.y;   // coordinates + 0.5
+    const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+    const int ix = __double2loint(mx), iy = __double2loint(my);
+    const unsigned rx = (unsigned)(ix - lo_x), ry = (unsigned)(iy - lo_y);
+    // all nine taps inside the image and, with a window, inside the window. The window covers every coordinate the
+    // tile can reach under this chunk's lags, so the magic-number floor is in range there; without a window the
+    // magnitude test keeps wrapped floors of absurd coordinates out.
+    bool fast = (rx <= span_x) && (ry <= span_y);
+    if (!WINDOW) fast = fast && small_magnitude(sx) && small_magnitude(sy);
+    double v;
+    bool ok;
+    if (fast) {
+      const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);   // = d + 0.5 in [0, 1)
+      const double wx2 = (0.5 * vx) * vx;
+      const double wx0 = (wx2 + 0.5) - vx;
+      const double wx1 = fma(-2.0, wx2, vx + 0.5);
+      const double wy2 = (0.5 * vy) * vy;
+      const double wy0 = (wy2 + 0.5) - vy;
+      const double wy1 = fma(-2.0, wy2, vy + 0.5);
+      const T* r0p = img + ((int)ry * pitch + (int)rx + base_off);
+      const T* r1p = r0p + pitch;
+      const T* r2p = r1p + pitch;
+      const double r0 = fma((double)r0p[2], wx2, fma((double)r0p[1], wx1, (double)r0p[0] * wx0));
+      const double r1 = fma((double)r1p[2], wx2, fma((double)r1p[1], wx1, (double)r1p[0] * wx0));
+      const double r2 = fma((double)r2p[2], wx2, fma((double)r2p[1], wx1, (double)r2p[0] * wx0));
+      v = fma(r2, wy2, fma(r1, wy1, r0 * wy0));
+      ok = true;
+    } else {
+      ok = spline_sample<2, false, T>(small, sny, snx, sy - 0.5, sx - 0.5, v);
+    }
+    // finite and not the -32762 fill (`np.where(image == -32762, nan, image)`, alignment.py:900-901)
+    ok = ok && (((unsigned)__double2hiint(v) & 0x7FF00000u) != 0x7FF00000u) && (v != -32762.0);
+    if (ok) {
+      const double bc = v - pivot_b;
+      sb += bc;
+      sbb = fma(bc, bc, sbb);
+      sab = fma(ac, bc, sab);
+    } else {
+      ++n_miss;
+      sa_miss += ac;
+      saa_miss = fma(ac, ac, saa_miss);
     }
   }
-  for (int l0 = lag_begin; l0 < lag_end; l0 += kFastLagSub) {
-    const int cnt = min(kFastLagSub, lag_end - l0);
-    __syncthreads();
-    {
-      const double* src = reinterpret_cast<const double*>(fast_lags + l0);
-      double* dst = reinterpret_cast<double*>(s_lag);
-      const int nd = cnt * (int)(sizeof(LagC) / sizeof(double));
-      for (int i = tid; i < nd; i += kThreads) dst[i] = src[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kOffThreads, 3)
+offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const double* __restrict__ ref,
+                     const T* __restrict__ small, int snx, int sny, int gnx, int gny, const double* __restrict__ tx,
+                     const double* __restrict__ ty, const CoregLagOffset* __restrict__ lags, int n_lags,
+                     int chunks_per_block, const double* __restrict__ pivots, const int* __restrict__ slot_of_super,
+                     double* __restrict__ work) {
+  constexpr int BW = OffBox<T>::W, BH = OffBox<T>::H;
+  extern __shared__ __align__(128) unsigned char off_smem[];
+  T* s_win = reinterpret_cast<T*>(off_smem);
+  OffPx* s_px = reinterpret_cast<OffPx*>(off_smem + OffBox<T>::kBytes);
+  double* s_red = reinterpret_cast<double*>(s_px + kOffTilePx);
+  int* s_cnt = reinterpret_cast<int*>(s_red + kOffWarps);
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_cnt + 2 * kOffWarps);
+
+  const int slot = slot_of_super[blockIdx.x];
+  if (slot < 0) return;   // cannot reach the small image under any lag of this launch: no partial
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sx_tiles = (gnx + kOffTileW - 1) / kOffTileW;
+  const int ox = (blockIdx.x % sx_tiles) * kOffTileW, oy = (blockIdx.x / sx_tiles) * kOffSuperH;
+  const double pivot_a = pivots[0], pivot_b = pivots[1];
+  unsigned phase = 0;
+  if (tid == 0) mbar_init(s_bar, 1);
+  __syncthreads();
+
+  const int n_chunks = (n_lags + kOffThreads - 1) / kOffThreads;
+  const int c_end = min(n_chunks, ((int)blockIdx.y + 1) * chunks_per_block);
+  for (int chunk = blockIdx.y * chunks_per_block; chunk < c_end; ++chunk) {
+    const int lag = chunk * kOffThreads + tid;
+    double x0h = CUDART_NAN, y0h = CUDART_NAN;
+    if (lag < n_lags) {
+      x0h = lags[lag].x0 + 0.5;
+      y0h = lags[lag].y0 + 0.5;
     }
-    __syncthreads();
-    for (int l = 0; l < cnt; ++l) {
-      const LagC C = s_lag[l];
-      const typename Fast::TL tl = Fast::thread_lag(C, tstate);
-      double sb = 0.0, sbb = 0.0, sab = 0.0, sa_miss = 0.0, saa_miss = 0.0;
-      int n_miss = 0;
+    const bool lag_ok = small_magnitude(x0h) && small_magnitude(y0h);   // false for NaN (dummy / dead lags)
+    // spread of the chunk's offsets
+    const double lx0 = block_min(lag_ok ? x0h : CUDART_INF, s_red, lane, warp);
+    const double lx1 = -block_min(lag_ok ? -x0h : CUDART_INF, s_red, lane, warp);
+    const double ly0 = block_min(lag_ok ? y0h : CUDART_INF, s_red, lane, warp);
+    const double ly1 = -block_min(lag_ok ? -y0h : CUDART_INF, s_red, lane, warp);
+    const bool any_lag = lx0 <= lx1;
+
+    double sb = 0.0, sbb = 0.0, sab = 0.0, sa_v = 0.0, saa_v = 0.0;
+    int n_v = 0;
+    for (int t = 0; t < kOffTilesPerBlock && any_lag; ++t) {
+      // ---- live pixels of the tile -> shared table, in pixel order; their detector-plane box and reference moments
+      double bx0 = CUDART_INF, bx1n = CUDART_INF, by0 = CUDART_INF, by1n = CUDART_INF, sa_t = 0.0, saa_t = 0.0;
+      int base = 0;
+      __syncthreads();   // previous tile's walk is over: table and window may be rewritten
 #pragma unroll
-      for (int g = 0; g < PPT; g += GROUP) {
-        // phase A: coordinates (+0.5), floor indices, fractional parts; branch-free
-        double sxs[GROUP], sys[GROUP], vx[GROUP], vy[GROUP];
-        int ix[GROUP], iy[GROUP];
-        bool interior = true;
-#pragma unroll
-        for (int j = 0; j < GROUP; ++j) {
-          Fast::map_half(pix[g + j], tl, C, sxs[j], sys[j]);
-          const double mx = __dadd_rd(sxs[j], kMagic), my = __dadd_rd(sys[j], kMagic);
-          ix[j] = __double2loint(mx);
-          iy[j] = __double2loint(my);
-          vx[j] = sxs[j] - (mx - kMagic);   // = d + 0.5 in [0, 1)
-          vy[j] = sys[j] - (my - kMagic);
-          interior = interior && ((unsigned)(ix[j] - 1) < ux) && ((unsigned)(iy[j] - 1) < uy) &&
-                     small_magnitude(sxs[j]) && small_magnitude(sys[j]);
+      for (int pass = 0; pass < kOffTilePx / kOffThreads; ++pass) {
+        const int i = pass * kOffThreads + tid;
+        const int gx = ox + (i & (kOffTileW - 1)), gy = oy + t * kOffTileH + i / kOffTileW;
+        double a = CUDART_NAN, px = CUDART_NAN, py = CUDART_NAN;
+        if (gx < gnx && gy < gny) {
+          const int64_t idx = (int64_t)gy * gnx + gx;
+          a = ref[idx];
+          px = __ldg(tx + idx);
+          py = __ldg(ty + idx);
         }
-        if (Fast::kCoordsAlwaysFinite) interior = interior && (((a_ok >> g) & ((1u << GROUP) - 1u)) == ((1u << GROUP) - 1u));
-        if (interior) {
-          // phase B: weights, 9 taps, float32 rounding, moments
-#pragma unroll
-          for (int j = 0; j < GROUP; ++j) {
-            // order-2 B-spline weights from v = d + 0.5: w2 = v^2/2, w0 = w2 - d, w1 = 1 - w0 - w2
-            const double wx2 = (0.5 * vx[j]) * vx[j];
-            const double wx0 = (wx2 + 0.5) - vx[j];
-            const double wx1 = fma(-2.0, wx2, vx[j] + 0.5);
-            const double wy2 = (0.5 * vy[j]) * vy[j];
-            const double wy0 = (wy2 + 0.5) - vy[j];
-            const double wy1 = fma(-2.0, wy2, vy[j] + 0.5);
-            // interior => 1 <= ix, iy, so the first tap index is a non-negative 32-bit number
-            const unsigned tap0 = (unsigned)(iy[j] - 1) * row_elems + (unsigned)(ix[j] - 1);
-            const SmallT* r0p = small + tap0;
-            const SmallT* r1p = r0p + row_elems;
-            const SmallT* r2p = r1p + row_elems;
-            const double r0 = fma(ldval(r0p + 2), wx2, fma(ldval(r0p + 1), wx1, ldval(r0p) * wx0));
-            const double r1 = fma(ldval(r1p + 2), wx2, fma(ldval(r1p + 1), wx1, ldval(r1p) * wx0));
-            const double r2 = fma(ldval(r2p + 2), wx2, fma(ldval(r2p + 1), wx1, ldval(r2p) * wx0));
-            const double t = fma(r2, wy2, fma(r1, wy1, r0 * wy0));
-            double b;
-            bool ok;
-            if (ROUND32) {
-              const float bf = __double2float_rn(t);
-              ok = isfinite(bf);
-              b = (double)bf;
-            } else {
-              ok = isfinite(t) && (t != -32762.0);
-              b = t;
-            }
-            if (ok) {
-              const double bc = b - pivot_b;
-              sb += bc;
-              sbb = fma(bc, bc, sbb);
-              sab = fma(a_c[g + j], bc, sab);
-            } else {
-              ++n_miss;   // interior => the reference pixel is present
-              sa_miss += a_c[g + j];
-              saa_miss = fma(a_c[g + j], a_c[g + j], saa_miss);
-            }
+        const bool live = isfinite(a) && small_magnitude(px) && small_magnitude(py);
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_cnt[pass * kOffWarps + warp] = __popc(bal);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += s_cnt[pass * kOffWarps + w];
+        int total = 0;
+        for (int w = 0; w < kOffWarps; ++w) total += s_cnt[pass * kOffWarps + w];
+        if (live) {
+          const double ac = a - pivot_a;
+          OffPx e;
+          e.tx = px; e.ty = py; e.ac = ac; e.pad = 0.0;
+          s_px[before + __popc(bal & ((1u << lane) - 1u))] = e;
+          bx0 = fmin(bx0, px); bx1n = fmin(bx1n, -px);
+          by0 = fmin(by0, py); by1n = fmin(by1n, -py);
+          sa_t += ac;
+          saa_t = fma(ac, ac, saa_t);
+        }
+        base += total;
+      }
+      const int n_live = base;
+      if (n_live == 0) continue;   // block-uniform
+      bx0 = block_min(bx0, s_red, lane, warp);
+      const double bx1 = -block_min(bx1n, s_red, lane, warp);
+      by0 = block_min(by0, s_red, lane, warp);
+      const double by1 = -block_min(by1n, s_red, lane, warp);
+      sa_t = block_sum(sa_t, s_red, lane, warp);
+      saa_t = block_sum(saa_t, s_red, lane, warp);
+      // ---- window: every tap any (pixel, lag) pair of this tile and chunk can touch
+      const double fx0 = floor(bx0 + lx0), fx1 = floor(bx1 + lx1), fy0 = floor(by0 + ly0), fy1 = floor(by1 + ly1);
+      // (box and offsets passed small_magnitude: |.| < 2^31, the casts are exact)
+      // TMA wants the box to start on a 16-byte boundary of the image row (a misaligned inner coordinate is an illegal
+      // instruction: tools/ubench/tma_probe.cu): the window origin is rounded down to a multiple of 4 (2) pixels
+      constexpr int kAlign = 16 / (int)sizeof(T);
+      int wx0 = (int)fx0 - 1;
+      wx0 -= ((wx0 % kAlign) + kAlign) % kAlign;
+      const int wx1 = (int)fx1 + 1, wy0 = (int)fy0 - 1, wy1 = (int)fy1 + 1;
+      if (wx1 < 0 || wx0 > snx - 1 || wy1 < 0 || wy0 > sny - 1) continue;   // nothing of it inside the image
+      const bool fits = (wx1 - wx0 + 1 <= BW) && (wy1 - wy0 + 1 <= BH);
+      int lo_x = 1, lo_y = 1, hi_x = snx - 2, hi_y = sny - 2, pitch = snx, base_off = 0;
+      if (fits) {
+        lo_x = max(1, wx0 + 1);
+        lo_y = max(1, wy0 + 1);
+        hi_x = min(snx - 2, wx0 + BW - 2);
+        hi_y = min(sny - 2, wy0 + BH - 2);
+        pitch = BW;
+        base_off = (lo_y - 1 - wy0) * BW + (lo_x - 1 - wx0);
+        if (use_tma) {
+          if (tid == 0) {
+            mbar_expect_tx(s_bar, (unsigned)OffBox<T>::kBytes);
+            tma_load_2d(s_win, &tmap, s_bar, wx0, wy0);
           }
         } else {
-          // exact generic sampler with the same coordinates (image borders, missing reference pixels)
-#pragma unroll
-          for (int j = 0; j < GROUP; ++j) {
-            if (!(a_ok & (1u << (g + j)))) continue;
-            double v;
-            bool ok = spline_sample<2, false, SmallT>(small, sny, snx, sys[j] - 0.5, sxs[j] - 0.5, v);
-            double b;
-            if (ROUND32) {
-              const float bf = __double2float_rn(v);
-              ok = ok && isfinite(bf);
-              b = (double)bf;
-            } else {
-              ok = ok && isfinite(v) && (v != -32762.0);
-              b = v;
-            }
-            if (ok) {
-              const double bc = b - pivot_b;
-              sb += bc;
-              sbb = fma(bc, bc, sbb);
-              sab = fma(a_c[g + j], bc, sab);
-            } else {
-              ++n_miss;
-              sa_miss += a_c[g + j];
-              saa_miss = fma(a_c[g + j], a_c[g + j], saa_miss);
-            }
+          const int w = wx1 - wx0 + 1, h = wy1 - wy0 + 1;
+          for (int i = tid; i < w * h; i += kOffThreads) {
+            const int yy = i / w, xx = i - yy * w;
+            const int gx = wx0 + xx, gy = wy0 + yy;
+            T val = (T)0;
+            if (gx >= 0 && gx < snx && gy >= 0 && gy < sny) val = __ldg(small + ((size_t)gy * snx + gx));
+            s_win[yy * BW + xx] = val;
           }
         }
-      }
-      if (__any_sync(0xffffffffu, n_miss != 0)) {
-        double m[8];
-        m[0] = (double)(n_all - n_miss);
-        m[1] = sa_all - sa_miss;
-        m[2] = sb;
-        m[3] = saa_all - saa_miss;
-        m[4] = sbb;
-        m[5] = sab;
-        m[6] = 0.0;
-        m[7] = 0.0;
-        const double tot = warp_transpose_reduce8(m, lane);
-        if ((lane & 3) == 0) s_part[warp][l][lane >> 2] = tot;
-        if (lane == 0) s_miss[warp][l] = 1;
       } else {
-        // common case: nothing missing in this warp -> only the three lag-dependent sums need the butterfly;
-        // n, Sa, Saa are the warp constants
-        double m[4];
-        m[0] = sb;
-        m[1] = sbb;
-        m[2] = sab;
-        m[3] = 0.0;
-        const double tot = warp_transpose_reduce4(m, lane);
-        // lanes 0, 8, 16 hold Sb, Sbb, Sab -> slots 2, 4, 5
-        if ((lane & 7) == 0 && lane < 24) s_part[warp][l][(lane >> 3) + 2 + (lane != 0)] = tot;
-        if (lane == 1) s_miss[warp][l] = 0;
+        base_off = 0;   // tap (iy - 1, ix - 1) = small[(iy - 1) * snx + ix - 1] with rx = ix - 1, ry = iy - 1
+      }
+      unsigned span_x = 0, span_y = 0;
+      if (hi_x >= lo_x && hi_y >= lo_y) {
+        span_x = (unsigned)(hi_x - lo_x);
+        span_y = (unsigned)(hi_y - lo_y);
+      } else {
+        lo_x = lo_y = 0x40000000;   // no pixel can take the fast path
+      }
+      if (fits && use_tma) {
+        mbar_wait(s_bar, phase);
+        phase ^= 1u;
+      }
+      __syncthreads();   // table complete (and the cooperative copy, if any)
+      if (lag_ok) {
+        int n_miss = 0;
+        double sa_miss = 0.0, saa_miss = 0.0, tsb = 0.0, tsbb = 0.0, tsab = 0.0;
+        if (fits)
+          offset_walk<T, true>(s_win, pitch, base_off, lo_x, lo_y, span_x, span_y, small, snx, sny, s_px, n_live, x0h,
+                               y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+        else
+          offset_walk<T, false>(small, pitch, base_off, lo_x, lo_y, span_x, span_y, small, snx, sny, s_px, n_live,
+                                x0h, y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+        // per tile, so that a tile this lag cannot reach adds exactly nothing -- whether the block skipped it for
+        // the whole chunk or walked it for the sake of other lags (sharding-invariant partials)
+        if (n_miss < n_live) {
+          n_v += n_live - n_miss;
+          sa_v += (n_miss == 0) ? sa_t : sa_t - sa_miss;
+          saa_v += (n_miss == 0) ? saa_t : saa_t - saa_miss;
+          sb += tsb;
+          sbb += tsbb;
+          sab += tsab;
+        }
       }
     }
-    __syncthreads();
-    for (int i = tid; i < cnt * kMom; i += kThreads) {
-      const int l = i / kMom, q = i % kMom;
-      double s = 0.0;
-      if (q < 6) {
-        const int c = (q == 0) ? 0 : ((q == 1) ? 1 : ((q == 3) ? 2 : -1));  // slot of a warp constant, or -1
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += (c >= 0 && !s_miss[w][l]) ? s_wconst[w][c] : s_part[w][l][q];
-      }
-      work[((size_t)tile * n_lags + (l0 + l)) * kMom + q] = s;
+    if (lag < n_lags) {
+      double* out = work + ((size_t)slot * n_lags + lag) * kMom;
+      double4* o4 = reinterpret_cast<double4*>(out);
+      o4[0] = make_double4((double)n_v, sa_v, sb, saa_v);
+      o4[1] = make_double4(sbb, sab, 0.0, 0.0);
     }
   }
 }
 
-// tuning variants (flags bits 8..11) of the per-pixel fast kernel: (pixels per thread, resident CTAs per SM, group)
-template <class Fast, typename SmallT, typename RefT, bool ROUND32>
-int launch_lag_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
-                    const SmallT* small, int snx, int sny, typename Fast::Planes planes,
-                    const typename Fast::LagC* ft, const double* pivots, double* w, int* tiles_out,
-                    double* ranges) {
-  static const int kVar[3][2] = {{4, 3}, {8, 2}, {4, 4}};
-  if (variant < 0 || variant > 2) variant = 0;
-  dim3 grid;
-  int lpb;
-  if (!lag_grid(kRowsPerPass * kVar[variant][0], kVar[variant][1], gnx, gny, n_lags, sms, &grid, &lpb, tiles_out,
-                kFastLagSub))
-    return fail(COREG_EINVAL, "lag grid too large for one launch");
-  if (ranges) offset_lag_range_kernel<<<grid.y, 128, 0, s>>>(ft, (int)n_lags, lpb, ranges);
-#define LF(PPT_, MINB_, G_)                                                                     \
-  lag_corr_fast_kernel<Fast, SmallT, RefT, ROUND32, PPT_, MINB_, G_><<<grid, kThreads, 0, s>>>( \
-      ref, small, snx, sny, gnx, gny, planes, ft, (int)n_lags, lpb, pivots, w, ranges)
-  switch (variant) {
-    case 1: LF(8, 2, 2); break;
-    case 2: LF(4, 4, 2); break;
-    default: LF(4, 3, 2); break;
+// fold the partials of the live super-tiles in slot order (= ascending super-tile index), moments -> Pearson r.
+// One block = 32 consecutive lags x 8 moments: a slot's 2 KB of partials for those lags is one coalesced read.
+__global__ void __launch_bounds__(256)
+offset_finalize_kernel(const double* __restrict__ work, const int* __restrict__ n_slots_ptr, int n_lags,
+                       double* __restrict__ corr, int64_t* __restrict__ nvalid) {
+  __shared__ double s[32][kMom + 1];
+  const int l0 = blockIdx.x * 32, t = threadIdx.x, lag = l0 + t / kMom, q = t % kMom;
+  const int n_slots = *n_slots_ptr;
+  double acc = 0.0;
+  if (lag < n_lags) {
+    const double* p = work + (size_t)lag * kMom + q;
+    for (int sl = 0; sl < n_slots; ++sl) acc += p[(size_t)sl * n_lags * kMom];
   }
-#undef LF
+  s[t / kMom][q] = acc;
+  __syncthreads();
+  if (t < 32 && l0 + t < n_lags) {
+    const double n = s[t][0], sa = s[t][1], sb = s[t][2], saa = s[t][3], sbb = s[t][4], sab = s[t][5];
+    double r = CUDART_NAN;
+    if (n > 0.0) {
+      const double cov = sab - sa * sb / n;
+      const double va = saa - sa * sa / n;
+      const double vb = sbb - sb * sb / n;
+      r = cov / sqrt(va * vb);
+    }
+    corr[l0 + t] = r;
+    if (nvalid) nvalid[l0 + t] = (int64_t)n;
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                           CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = []() -> TensorMapEncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<TensorMapEncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// TMA descriptor of the small image with the window as its box; false when the image cannot be described (row pitch
+// or base address not 16-byte aligned, driver without the entry point): the kernel then stages the window itself.
+template <typename T>
+static bool make_window_map(const T* small, int snx, int sny, CUtensorMap* map) {
+  memset(map, 0, sizeof(*map));
+  if (getenv("COREG_NO_TMA")) return false;
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(small) & 15u) || (((size_t)snx * sizeof(T)) & 15u)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)snx, (cuuint64_t)sny};
+  const cuuint64_t strides[1] = {(cuuint64_t)snx * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)OffBox<T>::W, (cuuint32_t)OffBox<T>::H};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = enc(map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                          const_cast<T*>(small), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
+template <typename T>
+static int launch_offset_window(int gnx, int gny, int64_t n_lags, cudaStream_t s, const double* ref, const T* small,
+                                int snx, int sny, const double* tx, const double* ty, const CoregLagOffset* lags,
+                                const double* pivots, void* work, double* corr, int64_t* nvalid) {
+  const OffWork L = offw_layout(gnx, gny, n_lags);
+  char* base = static_cast<char*>(work);
+  double* partials = reinterpret_cast<double*>(base + L.partials);
+  int* slots = reinterpret_cast<int*>(base + L.slots);
+  int* n_slots = reinterpret_cast<int*>(base + L.nslots);
+  double* range = reinterpret_cast<double*>(base + L.range);
+  offset_lag_range_kernel<<<1, 256, 0, s>>>(lags, (int)n_lags, range);
+  offset_super_live_kernel<<<L.n_super, 256, 0, s>>>(ref, tx, ty, gnx, gny, snx, sny, range, slots);
+  offset_slot_scan_kernel<<<1, 1024, 0, s>>>(slots, L.n_super, n_slots);
+  CK_LAUNCH("offset pre-pass");
+  CUtensorMap map;
+  const int use_tma = make_window_map(small, snx, sny, &map) ? 1 : 0;
+  const int n_chunks = (int)((n_lags + kOffThreads - 1) / kOffThreads);
+  const int cpb = (n_chunks + 65534) / 65535;
+  const dim3 grid(L.n_super, (n_chunks + cpb - 1) / cpb);
+  const size_t smem = (size_t)OffBox<T>::kBytes + kOffTilePx * sizeof(OffPx) + kOffWarps * sizeof(double) +
+                      2 * kOffWarps * sizeof(int) + 16;
+  auto kern = offset_window_kernel<T>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool prof = g_prof_on && g_prof_n < 4096;
+  if (prof) {
+    CK(cudaEventCreate(&g_prof[g_prof_n].a));
+    CK(cudaEventCreate(&g_prof[g_prof_n].b));
+    CK(cudaEventRecord(g_prof[g_prof_n].a, s));
+  }
+  kern<<<grid, kOffThreads, smem, s>>>(map, use_tma, ref, small, snx, sny, gnx, gny, tx, ty, lags, (int)n_lags, cpb,
+                                       pivots, slots, partials);
+  CK_LAUNCH("offset_window_kernel");
+  if (prof) {
+    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+    ++g_prof_n;
+  }
+  offset_finalize_kernel<<<(unsigned)((n_lags + 31) / 32), 256, 0, s>>>(partials, n_slots, (int)n_lags, corr, nvalid);
+  CK_LAUNCH("offset_finalize_kernel");
   return COREG_OK;
 }
 
-int launch_offset_fast(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const double* ref,
-                       const void* small, int small_dtype, int snx, int sny, const double* tx, const double* ty,
-                       const CoregLagOffset* lags, const double* pivots, void* work, int* tiles_out) {
-  // the per-lag fast table lives in the tail of the workspace (after the [tiles][lags][8] partials)
-  OffsetFastLag* ft = reinterpret_cast<OffsetFastLag*>(static_cast<char*>(work) + partials_bytes(gnx, gny, n_lags));
-  offset_fast_table_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(lags, (int)n_lags, ft);
-  // per-slice offset ranges right behind the table (the tail reserves 96 B per lag; the table uses 16)
-  double* ranges = reinterpret_cast<double*>(ft + n_lags);
-  double* w = static_cast<double*>(work);
-  OffsetCoord::Planes planes{tx, ty};
-  int rc;
+int launch_offset_fast(int gnx, int gny, int64_t n_lags, cudaStream_t s, const double* ref, const void* small,
+                       int small_dtype, int snx, int sny, const double* tx, const double* ty,
+                       const CoregLagOffset* lags, const double* pivots, void* work, double* corr, int64_t* nvalid) {
   if (small_dtype == COREG_F32)
-    rc = launch_lag_fast<OffsetFast, float, double, false>(variant, gnx, gny, n_lags, sms, s, ref, (const float*)small, snx,
-                                                           sny, planes, ft, pivots, w, tiles_out, ranges);
-  else
-    rc = launch_lag_fast<OffsetFast, double, double, false>(variant, gnx, gny, n_lags, sms, s, ref, (const double*)small,
-                                                            snx, sny, planes, ft, pivots, w, tiles_out, ranges);
-  if (rc) return rc;
-  CK_LAUNCH("lag_corr_fast_kernel");
-  return COREG_OK;
+    return launch_offset_window<float>(gnx, gny, n_lags, s, ref, (const float*)small, snx, sny, tx, ty, lags, pivots,
+                                       work, corr, nvalid);
+  return launch_offset_window<double>(gnx, gny, n_lags, s, ref, (const double*)small, snx, sny, tx, ty, lags, pivots,
+                                      work, corr, nvalid);
 }
+
 }  // namespace coreg

@@ -547,7 +547,12 @@ class Alignment:
             planes = eng.carrington_planes(hdr, d_solar_r, self.lonlims, self.latlims, self.shape)
             x0, y0 = eng.carrington_offset(hdr, refs.crval1_ref + d1[sel], refs.crval2_ref + d2[sel], roll)
             table = np.stack([x0, y0], axis=1).astype(np.float64)
-            c, nv = eng.search(table, planes=planes, return_nvalid=True)
+            # CRVAL grid indices of the selected lags (flat C order: crval1 slowest ... crota fastest): the kernel
+            # takes them in detector-plane patches; lags that differ only in a CDELT index never share a patch
+            shape5 = (len(self.lag_crval1), len(self.lag_crval2), len(self.lag_cdelt1), len(self.lag_cdelt2),
+                      len(self.lag_crota))
+            i1, i2, i3, i4, _ = np.unravel_index(sel, shape5)
+            c, nv = eng.search(table, planes=planes, return_nvalid=True, lag_ij=(i1, i2, i3 * shape5[3] + i4))
             corr[sel] = c
             nvalid[sel] = nv
         return corr, nvalid

@@ -145,6 +145,33 @@ def car_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_cro
     return tab, dead | bad
 
 
+OFFSET_CHUNK = 256   # lags per block of the Carrington-frame kernel (one per thread, csrc/coreg_lag_offset.cu)
+
+
+def offset_patch_order(i1, i2, group=None, patch=(16, 16), sub=(8, 4)):
+    """Order in which the Carrington-frame kernel wants a CRVAL lag list: its blocks take 256 consecutive lags (one per
+    thread) and stage the part of the small image those lags can touch, so consecutive lags must be neighbours in
+    the detector plane. Lags are grouped into patches of 16 x 16 grid indices (i1 = CRVAL1 index, i2 = CRVAL2 index),
+    inside a patch into sub-patches of 8 x 4 (one warp each); every patch is padded to 256 slots so that a block
+    never straddles two patches. `group`: optional integer key of lags that must not share a patch (e.g. the CDELT
+    index). Returns (slot_of_lag [n], n_slots): lag k goes to row slot_of_lag[k] of a [n_slots, 2] table whose
+    other rows are NaN (dummy lags: evaluate nothing)."""
+    i1 = np.asarray(i1, dtype=np.int64)
+    i2 = np.asarray(i2, dtype=np.int64)
+    g = np.zeros_like(i1) if group is None else np.asarray(group, dtype=np.int64)
+    p1, p2 = i1 // patch[0], i2 // patch[1]
+    q1, q2 = i1 % patch[0], i2 % patch[1]
+    s1, s2 = q1 // sub[0], q2 // sub[1]
+    # position inside the patch: sub-patch major, then row-major inside the 8 x 4 sub-patch (8 along CRVAL1 fastest)
+    inner = ((s2 * (patch[0] // sub[0]) + s1) * (sub[0] * sub[1]) + (q2 % sub[1]) * sub[0] + (q1 % sub[0]))
+    _, pid = np.unique(np.stack([g, p1, p2], axis=1), axis=0, return_inverse=True)
+    slot = pid.ravel() * (patch[0] * patch[1]) + inner
+    n_slots = int((pid.max() + 1) * patch[0] * patch[1]) if i1.size else 0
+    if i1.size and np.unique(slot).size != slot.size:   # repeated (i1, i2) pairs inside one group: no structure to use
+        return np.arange(i1.size, dtype=np.int64), int(i1.size)
+    return slot, n_slots
+
+
 def _dist_info():
     try:
         import torch.distributed as dist
@@ -493,8 +520,10 @@ class LagSearchEngine:
             self.flagged_lags = k
         return k
 
-    def search(self, table, planes=None, return_nvalid=False):
-        """Host lag table [n_lags, k] -> numpy corr[n_lags]; shards over ranks when torch.distributed is up."""
+    def search(self, table, planes=None, return_nvalid=False, lag_ij=None):
+        """Host lag table [n_lags, k] -> numpy corr[n_lags]; shards over ranks when torch.distributed is up.
+        lag_ij = (i1, i2[, group]): CRVAL1 / CRVAL2 grid indices of every lag (Carrington frame): each rank's slice is
+        handed to the kernel in `offset_patch_order`."""
         torch = _torch()
         n = table.shape[0]
         dist, rank, world = _dist_info()
@@ -503,7 +532,19 @@ class LagSearchEngine:
         with torch.cuda.device(self.device):
             local = torch.full((chunk,), float("nan"), dtype=torch.float64, device=self.device)
             nvalid = torch.zeros(chunk, dtype=torch.int64, device=self.device) if return_nvalid else None
-            if hi > lo:
+            if hi > lo and lag_ij is not None and self.frame == "carrington":
+                slot, n_slots = offset_patch_order(*(np.asarray(v)[lo:hi] for v in lag_ij))
+                padded = np.full((n_slots, table.shape[1]), np.nan, dtype=np.float64)
+                padded[slot] = table[lo:hi]
+                tab_dev = self._upload(padded)
+                out = torch.empty(n_slots, dtype=torch.float64, device=self.device)
+                nv = torch.empty(n_slots, dtype=torch.int64, device=self.device) if return_nvalid else None
+                self.evaluate(tab_dev, out, nv, planes)
+                idx = torch.from_numpy(slot).to(self.device)
+                local[:hi - lo] = out.index_select(0, idx)
+                if return_nvalid:
+                    nvalid[:hi - lo] = nv.index_select(0, idx)
+            elif hi > lo:
                 tab_dev = self._upload(table[lo:hi])
                 nv = None if nvalid is None else nvalid[:hi - lo]
                 self.evaluate(tab_dev, local[:hi - lo], nv, planes)

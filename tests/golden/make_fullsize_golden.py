@@ -4,8 +4,8 @@
 
 * config1_full_cube.npz   every one of the 60 x 60 = 3600 helioprojective lags of configs[0]
                           (2048^2 vs 3072^2 synthetic pair of `bench.ensure_config1`), `oracle.hpc.HpcSearch.step`
-* config2_sample.npz      320 of the 120 x 120 Carrington-grid lags of configs[1] (2048^2 grid, lon 200-300, lat +-20):
-                          a 16 x 16 sub-lattice + 64 seeded random lags, `oracle.carrington.CarringtonSearch.step`
+* config2_sample.npz      ~290 of the 120 x 120 Carrington-grid lags of configs[1] (2048^2 grid, lon 200-300, lat +-20):
+                          a 15 x 15 sub-lattice + 64 seeded random lags, `oracle.carrington.CarringtonSearch.step`
 * config4_sample.npz      288 of the 20 x 20 x 16 x 16 x 10 = 1 024 000 lags of configs[3] (intended CDELT semantics):
                           the arg-max neighbourhood + seeded random lags
 
@@ -104,7 +104,7 @@ def main():
         r = s.refs
         g = np.meshgrid(r.lag_crval1, r.lag_crval2, r.lag_cdelt1, r.lag_cdelt2, r.lag_crota, indexing="ij")
         flat = [a.ravel() for a in g]
-        lat = (np.arange(16) * 8 + 4)
+        lat = (np.arange(15) * 8 + 4)
         sub = (lat[:, None] * 120 + lat[None, :]).ravel()
         rng = np.random.default_rng(22)
         sel = np.unique(np.concatenate([sub, rng.integers(0, 14400, 64), [84 * 120 + 66, 0, 14399]]))

@@ -81,3 +81,47 @@ def test_carrington_size_deg_grid_and_results_object(torch_cuda, toy_pair):
     assert abs(res.shift_arcsec[0] - 24.0) < 1.0 and abs(res.shift_arcsec[1] - 6.0) < 1.0
     with pytest.raises(ValueError):
         Alignment(toy_pair[0], toy_pair[1], **LAGS).align_using_carrington(lonlims=(1, 2))
+
+
+def test_window_kernel_staging_paths_give_the_same_bits(torch_cuda, toy_pair, monkeypatch):
+    """The Carrington kernel stages the reachable part of the small image in shared memory with one TMA tile load per
+    (tile, lag chunk); COREG_NO_TMA=1 makes the block copy the window itself (what happens for images whose row pitch
+    is not a multiple of 16 bytes). Same arithmetic, same accumulation order: the cubes are bit-identical. A float64
+    small image (no float32 twin) goes through the float64 instantiation."""
+    from euispice_coreg_b200.hdrshift import Alignment, engine
+    lags = dict(LAGS, lag_crval1=np.arange(10, 38, 1.0), lag_crval2=np.arange(-6, 18, 1.0))
+    grid = dict(lonlims=(246.0, 254.0), latlims=(-6.0, 2.0), shape=(150, 170))
+
+    def run():
+        a = Alignment(toy_pair[0], toy_pair[1], parallelism=True, **lags)
+        return a.align_using_carrington(method="correlation", return_type="corr", **grid), a
+
+    tma, a = run()
+    assert a.engine.small.dtype == torch_cuda.float32
+    monkeypatch.setenv("COREG_NO_TMA", "1")
+    copy, _ = run()
+    monkeypatch.delenv("COREG_NO_TMA")
+    assert np.array_equal(tma, copy, equal_nan=True)
+    # lags handed over in flat order instead of detector-plane patches: chunks whose window does not fit the box read
+    # global memory -- the same samples, the same sums
+    eng = a.engine
+    d1, d2, _, _, _ = engine.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
+    roll = a.hdr_small["CROTA"]
+    planes = eng.carrington_planes(a.hdr_small, float(a.lag_solar_r[0]), a.lonlims, a.latlims, a.shape)
+    x0, y0 = eng.carrington_offset(a.hdr_small, a.crval1_ref + d1, a.crval2_ref + d2, roll)
+    flat = eng.search(np.stack([x0, y0], axis=1), planes=planes)
+    assert np.array_equal(flat, tma.ravel(), equal_nan=True)
+    from oracle.carrington import CarringtonSearch
+    dl, hl, ds, hs = load_pair(*toy_pair[:2])
+    s = CarringtonSearch(dl, hl, ds, hs, **lags, **grid)
+    sel = [(0, 0), (14, 12), (27, 23), (5, 20)]
+    for i, j in sel:
+        assert abs(tma[i, j, 0, 0, 0, 0] - s.step(lags["lag_crval1"][i], lags["lag_crval2"][j], 0.0, 0.0, 0.0)) < 1e-9
+
+
+def test_window_kernel_far_apart_lags_take_the_global_path(torch_cuda, toy_pair):
+    """Lags 30 arcsec apart: no shared-memory window holds a 16 x 16 patch of them, every chunk falls back to global
+    loads. Parity against the oracle all the same."""
+    lags = dict(LAGS, lag_crval1=np.arange(-36, 85, 30.0), lag_crval2=np.arange(-54, 67, 30.0))
+    gpu, ref, _, _ = _both(toy_pair, lags, dict(lonlims=(244.0, 256.0), latlims=(-8.0, 4.0), shape=(130, 90)))
+    assert _assert_parity(gpu, ref) < 1e-9

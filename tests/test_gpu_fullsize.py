@@ -2,7 +2,7 @@
 committed under tests/golden/ by `tests/golden/make_fullsize_golden.py` (the oracle needs 1.5 - 4 s per lag per core):
 
 * BASELINE.json configs[0]: every one of the 3600 helioprojective lags, both arithmetic modes;
-* configs[1]: 323 of the 14 400 Carrington-grid lags (a 16 x 16 sub-lattice, 64 random lags, the peak, two corners);
+* configs[1]: ~290 of the 14 400 Carrington-grid lags (a 15 x 15 sub-lattice, 64 random lags, the peak, two corners);
 * configs[3]: 290 of the 1 024 000 lags of the 5-D grid (arg-max neighbourhood + random), both arithmetic modes.
 
 Bar (north_star): |r_gpu - r_oracle| <= 1e-6 for every stored lag, identical arg-max. One documented exception: the
