@@ -99,7 +99,7 @@ def load(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("COREG_LIB_PATH") or LIB_PATH   # COREG_LIB_PATH: A/B runs of tuning builds
     if not os.path.exists(p):
         raise CoregLibraryError(
             f"{p} not found: the CUDA library is not built. Run `python -c 'import __graft_entry__ as g; "

@@ -7,9 +7,9 @@
 // that walks a grid row scatters its nine taps per sample over 4 - 5 cache lines each: the first version of this
 // kernel kept the L1 data pipe 94 % busy and the FP64 pipe 29 % (profiles/r1_ncu_carrington_v0.txt).
 //
-// This version turns the warp around: LANES ARE LAGS. A block owns a super-tile of the grid (four stacked tiles of
-// 32 x 16 pixels) and a chunk of 256 consecutive lags (one per thread; the caller orders the lag list so that
-// consecutive lags are neighbours in the detector plane -- 16 x 16 patches, 8 x 4 per warp). For each tile
+// This version turns the warp around: LANES ARE LAGS. A block owns a super-tile of the grid (eight stacked tiles of
+// 32 x 8 pixels) and a chunk of 256 consecutive lags (one per thread; the caller orders the lag list so that
+// consecutive lags are neighbours in the detector plane -- 16 x 16 patches, 16 x 2 per warp). For each tile
 //   * the live pixels (finite reference value, in front of the limb) are compacted into a shared-memory table
 //     (Tx, Ty, ref - pivot): every lane reads the same entry, a broadcast;
 //   * the part of the small image that ANY (pixel, lag) pair of the tile and chunk can touch -- the tile's detector
@@ -34,13 +34,16 @@ namespace coreg {
 
 constexpr int kOffThreads = 256;          // = lags per chunk (one lag per thread)
 constexpr int kOffWarps = kOffThreads / 32;
-constexpr int kOffTileW = 32, kOffTileH = 16, kOffTilePx = kOffTileW * kOffTileH;
-constexpr int kOffTilesPerBlock = 4;      // stacked vertically: super-tile = 32 x 64 grid pixels
+constexpr int kOffTileW = 32, kOffTileH = 8, kOffTilePx = kOffTileW * kOffTileH;   // one pixel per thread
+constexpr int kOffTilesPerBlock = 8;      // stacked vertically: super-tile = 32 x 64 grid pixels
 constexpr int kOffSuperH = kOffTileH * kOffTilesPerBlock;
 
 template <typename T>
-struct OffBox {   // shared-memory window = TMA box. Row pitch = 8 (mod 32) words: lanes two rows apart do not alias.
-  static constexpr int W = sizeof(T) == 4 ? 200 : 100;
+struct OffBox {   // shared-memory window = TMA box. With a warp's 32 lags laid out 16 x 2 (two detector pixels apart
+                  // along x at BASELINE configs[1]) a row pitch of 0 (mod 32) words gives the unavoidable 2-way bank
+                  // conflict of a stride-2 access and no more (tools/ubench/bank_model.py: 18 wavefronts for the nine
+                  // taps against 30 with 8 x 4 lags per warp and a pitch of 8 mod 32, measured 33)
+  static constexpr int W = sizeof(T) == 4 ? 192 : 96;
   static constexpr int H = sizeof(T) == 4 ? 64 : 56;
   static constexpr int kBytes = W * H * (int)sizeof(T);
 };
@@ -185,54 +188,75 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-// fixed-order block reductions through shared memory (8 warps): every thread returns the same value
-__device__ __forceinline__ double block_min(double v, double* s_red, int lane, int warp) {
+// fixed-order block reduction through shared memory (8 warps): every thread ends with the same values
+// four minima and two sums in one go (two barriers): v[0..3] -> block minima, v[4..5] -> block sums (fixed order)
+__device__ __forceinline__ void block_min4_sum2(double (&v)[6], double* s_red, int lane, int warp) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  double r = s_red[0];
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-  for (int w = 1; w < kOffWarps; ++w) r = fmin(r, s_red[w]);
-  return r;
-}
-__device__ __forceinline__ double block_sum(double v, double* s_red, int lane, int warp) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int i = 0; i < 4; ++i) v[i] = fmin(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+    v[4] += __shfl_xor_sync(0xffffffffu, v[4], o);
+    v[5] += __shfl_xor_sync(0xffffffffu, v[5], o);
+  }
   __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  double r = s_red[0];
+  if (lane < 6) {
+    double mine = v[0];
 #pragma unroll
-  for (int w = 1; w < kOffWarps; ++w) r += s_red[w];
-  return r;
+    for (int i = 1; i < 6; ++i)
+      if (lane == i) mine = v[i];
+    s_red[warp * 6 + lane] = mine;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double r = s_red[i];
+#pragma unroll
+    for (int w = 1; w < kOffWarps; ++w) r = (i < 4) ? fmin(r, s_red[w * 6 + i]) : r + s_red[w * 6 + i];
+    v[i] = r;
+  }
 }
 
-// One lag's walk over the live pixels of a tile. WINDOW: `img` is the staged window (shared memory, pitch `pitch`,
-// origin folded into lo_x / lo_y / base_off); otherwise the image itself in global memory.
-template <typename T, bool WINDOW>
-__device__ __forceinline__ void offset_walk(const T* __restrict__ img, int pitch, int base_off, int lo_x, int lo_y,
-                                            unsigned span_x, unsigned span_y, const T* __restrict__ small, int snx,
-                                            int sny, const OffPx* __restrict__ s_px, int n_live, double x0h,
-                                            double y0h, double pivot_b, double& sb, double& sbb, double& sab,
-                                            int& n_miss, double& sa_miss, double& saa_miss) {
+// explicit shared-memory loads on 32-bit shared addresses with immediate offsets: the window base is formed once per
+// tile (through a generic pointer the compiler re-derived it -- S2UR SR_CgaCtaId, UMOV, ULEA -- for every sample)
+template <int OFF>
+__device__ __forceinline__ double lds_tap(unsigned a, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+  return (double)v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_tap(unsigned a, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ void lds_px(unsigned a, double& tx, double& ty, double& ac) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(a));
+  asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(ac) : "r"(a));
+}
+
+// One lag's walk over the live pixels of a tile, nine taps from the staged window (shared address `win` already
+// offset to the tap of the first allowed floor index; row pitch = the box width). CHECK: the window holds a
+// non-finite value or the -32762 fill somewhere, so every sample is tested; a clean window needs no test.
+template <typename T, bool CHECK>
+__device__ __forceinline__ void offset_walk_window(unsigned win, int lo_x, int lo_y, unsigned span_x, unsigned span_y,
+                                                   const T* __restrict__ small, int snx, int sny, unsigned px,
+                                                   int n_live, double x0h, double y0h, double pivot_b, double& sb,
+                                                   double& sbb, double& sab, int& n_miss, double& sa_miss,
+                                                   double& saa_miss) {
+  constexpr int ROW = OffBox<T>::W * (int)sizeof(T), E = (int)sizeof(T);
 #pragma unroll 2
-  for (int k = 0; k < n_live; ++k) {
-    const double2 t2 = *reinterpret_cast<const double2*>(&s_px[k].tx);
-    const double ac = s_px[k].ac;
-    const double sx = x0h + t2.x, sy = y0h + t2.y;   // coordinates + 0.5
+  for (int k = 0; k < n_live; ++k, px += (unsigned)sizeof(OffPx)) {
+    double ptx, pty, ac;
+    lds_px(px, ptx, pty, ac);
+    const double sx = x0h + ptx, sy = y0h + pty;   // coordinates + 0.5
     const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
-    const int ix = __double2loint(mx), iy = __double2loint(my);
-    const unsigned rx = (unsigned)(ix - lo_x), ry = (unsigned)(iy - lo_y);
-    // all nine taps inside the image and, with a window, inside the window. The window covers every coordinate the
-    // tile can reach under this chunk's lags, so the magic-number floor is in range there; without a window the
-    // magnitude test keeps wrapped floors of absurd coordinates out.
-    bool fast = (rx <= span_x) && (ry <= span_y);
-    if (!WINDOW) fast = fast && small_magnitude(sx) && small_magnitude(sy);
+    const unsigned rx = (unsigned)(__double2loint(mx) - lo_x), ry = (unsigned)(__double2loint(my) - lo_y);
     double v;
     bool ok;
-    if (fast) {
+    // all nine taps inside the image and the window (which covers every coordinate this tile reaches under this
+    // chunk's lags, so the magic-number floor is in range)
+    if ((rx <= span_x) && (ry <= span_y)) {
       const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);   // = d + 0.5 in [0, 1)
       const double wx2 = (0.5 * vx) * vx;
       const double wx0 = (wx2 + 0.5) - vx;
@@ -240,18 +264,66 @@ __device__ __forceinline__ void offset_walk(const T* __restrict__ img, int pitch
       const double wy2 = (0.5 * vy) * vy;
       const double wy0 = (wy2 + 0.5) - vy;
       const double wy1 = fma(-2.0, wy2, vy + 0.5);
-      const T* r0p = img + ((int)ry * pitch + (int)rx + base_off);
-      const T* r1p = r0p + pitch;
-      const T* r2p = r1p + pitch;
-      const double r0 = fma((double)r0p[2], wx2, fma((double)r0p[1], wx1, (double)r0p[0] * wx0));
-      const double r1 = fma((double)r1p[2], wx2, fma((double)r1p[1], wx1, (double)r1p[0] * wx0));
-      const double r2 = fma((double)r2p[2], wx2, fma((double)r2p[1], wx1, (double)r2p[0] * wx0));
+      const unsigned a = win + ry * (unsigned)ROW + rx * (unsigned)E;
+      const double r0 = fma(lds_tap<2 * E>(a, T()), wx2, fma(lds_tap<E>(a, T()), wx1, lds_tap<0>(a, T()) * wx0));
+      const double r1 =
+          fma(lds_tap<ROW + 2 * E>(a, T()), wx2, fma(lds_tap<ROW + E>(a, T()), wx1, lds_tap<ROW>(a, T()) * wx0));
+      const double r2 = fma(lds_tap<2 * ROW + 2 * E>(a, T()), wx2,
+                            fma(lds_tap<2 * ROW + E>(a, T()), wx1, lds_tap<2 * ROW>(a, T()) * wx0));
+      v = fma(r2, wy2, fma(r1, wy1, r0 * wy0));
+      ok = true;
+      if (CHECK) ok = (((unsigned)__double2hiint(v) & 0x7FF00000u) != 0x7FF00000u) && (v != -32762.0);
+    } else {
+      ok = spline_sample<2, false, T>(small, sny, snx, sy - 0.5, sx - 0.5, v);
+      // finite and not the -32762 fill (`np.where(image == -32762, nan, image)`, alignment.py:900-901)
+      ok = ok && (((unsigned)__double2hiint(v) & 0x7FF00000u) != 0x7FF00000u) && (v != -32762.0);
+    }
+    if (ok) {
+      const double bc = v - pivot_b;
+      sb += bc;
+      sbb = fma(bc, bc, sbb);
+      sab = fma(ac, bc, sab);
+    } else {
+      ++n_miss;
+      sa_miss += ac;
+      saa_miss = fma(ac, ac, saa_miss);
+    }
+  }
+}
+
+// The same walk straight from the image in global memory: (tile, chunk) pairs whose window does not fit the box.
+template <typename T>
+__device__ __forceinline__ void offset_walk_global(const T* __restrict__ small, int snx, int sny,
+                                                   const OffPx* __restrict__ s_px, int n_live, double x0h, double y0h,
+                                                   double pivot_b, double& sb, double& sbb, double& sab, int& n_miss,
+                                                   double& sa_miss, double& saa_miss) {
+  const unsigned span_x = (unsigned)(snx - 3), span_y = (unsigned)(sny - 3);   // floor index in [1, n - 2]
+  for (int k = 0; k < n_live; ++k) {
+    const double ac = s_px[k].ac;
+    const double sx = x0h + s_px[k].tx, sy = y0h + s_px[k].ty;
+    const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+    const unsigned rx = (unsigned)(__double2loint(mx) - 1), ry = (unsigned)(__double2loint(my) - 1);
+    double v;
+    bool ok;
+    if ((rx <= span_x) && (ry <= span_y) && small_magnitude(sx) && small_magnitude(sy)) {
+      const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);
+      const double wx2 = (0.5 * vx) * vx;
+      const double wx0 = (wx2 + 0.5) - vx;
+      const double wx1 = fma(-2.0, wx2, vx + 0.5);
+      const double wy2 = (0.5 * vy) * vy;
+      const double wy0 = (wy2 + 0.5) - vy;
+      const double wy1 = fma(-2.0, wy2, vy + 0.5);
+      const T* r0p = small + ((size_t)ry * snx + rx);
+      const T* r1p = r0p + snx;
+      const T* r2p = r1p + snx;
+      const double r0 = fma(ldval(r0p + 2), wx2, fma(ldval(r0p + 1), wx1, ldval(r0p) * wx0));
+      const double r1 = fma(ldval(r1p + 2), wx2, fma(ldval(r1p + 1), wx1, ldval(r1p) * wx0));
+      const double r2 = fma(ldval(r2p + 2), wx2, fma(ldval(r2p + 1), wx1, ldval(r2p) * wx0));
       v = fma(r2, wy2, fma(r1, wy1, r0 * wy0));
       ok = true;
     } else {
       ok = spline_sample<2, false, T>(small, sny, snx, sy - 0.5, sx - 0.5, v);
     }
-    // finite and not the -32762 fill (`np.where(image == -32762, nan, image)`, alignment.py:900-901)
     ok = ok && (((unsigned)__double2hiint(v) & 0x7FF00000u) != 0x7FF00000u) && (v != -32762.0);
     if (ok) {
       const double bc = v - pivot_b;
@@ -266,19 +338,31 @@ __device__ __forceinline__ void offset_walk(const T* __restrict__ img, int pitch
   }
 }
 
+// does a window element force the per-sample test? (non-finite, or the reference's -32762 fill value)
+__device__ __forceinline__ bool dirty_bits(unsigned u) {   // float32
+  return ((u & 0x7F800000u) == 0x7F800000u) || (u == 0xC6FFF400u);
+}
+__device__ __forceinline__ bool dirty_value(float v) { return dirty_bits(__float_as_uint(v)); }
+__device__ __forceinline__ bool dirty_value(double v) {
+  return (((unsigned)__double2hiint(v) & 0x7FF00000u) == 0x7FF00000u) || (v == -32762.0);
+}
+
+#ifndef COREG_OFF_MINB
+#define COREG_OFF_MINB 3
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kOffThreads, 3)
+__global__ void __launch_bounds__(kOffThreads, COREG_OFF_MINB)
 offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, const double* __restrict__ ref,
                      const T* __restrict__ small, int snx, int sny, int gnx, int gny, const double* __restrict__ tx,
                      const double* __restrict__ ty, const CoregLagOffset* __restrict__ lags, int n_lags,
                      int chunks_per_block, const double* __restrict__ pivots, const int* __restrict__ slot_of_super,
-                     double* __restrict__ work) {
+                     double* __restrict__ work, unsigned long long* __restrict__ stats) {
   constexpr int BW = OffBox<T>::W, BH = OffBox<T>::H;
   extern __shared__ __align__(128) unsigned char off_smem[];
   T* s_win = reinterpret_cast<T*>(off_smem);
   OffPx* s_px = reinterpret_cast<OffPx*>(off_smem + OffBox<T>::kBytes);
   double* s_red = reinterpret_cast<double*>(s_px + kOffTilePx);
-  int* s_cnt = reinterpret_cast<int*>(s_red + kOffWarps);
+  int* s_cnt = reinterpret_cast<int*>(s_red + 6 * kOffWarps);
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_cnt + 2 * kOffWarps);
 
   const int slot = slot_of_super[blockIdx.x];
@@ -302,10 +386,10 @@ offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, cons
     }
     const bool lag_ok = small_magnitude(x0h) && small_magnitude(y0h);   // false for NaN (dummy / dead lags)
     // spread of the chunk's offsets
-    const double lx0 = block_min(lag_ok ? x0h : CUDART_INF, s_red, lane, warp);
-    const double lx1 = -block_min(lag_ok ? -x0h : CUDART_INF, s_red, lane, warp);
-    const double ly0 = block_min(lag_ok ? y0h : CUDART_INF, s_red, lane, warp);
-    const double ly1 = -block_min(lag_ok ? -y0h : CUDART_INF, s_red, lane, warp);
+    double lr[6] = {lag_ok ? x0h : CUDART_INF, lag_ok ? -x0h : CUDART_INF, lag_ok ? y0h : CUDART_INF,
+                    lag_ok ? -y0h : CUDART_INF, 0.0, 0.0};
+    block_min4_sum2(lr, s_red, lane, warp);
+    const double lx0 = lr[0], lx1 = -lr[1], ly0 = lr[2], ly1 = -lr[3];
     const bool any_lag = lx0 <= lx1;
 
     double sb = 0.0, sbb = 0.0, sab = 0.0, sa_v = 0.0, saa_v = 0.0;
@@ -348,12 +432,14 @@ offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, cons
       }
       const int n_live = base;
       if (n_live == 0) continue;   // block-uniform
-      bx0 = block_min(bx0, s_red, lane, warp);
-      const double bx1 = -block_min(bx1n, s_red, lane, warp);
-      by0 = block_min(by0, s_red, lane, warp);
-      const double by1 = -block_min(by1n, s_red, lane, warp);
-      sa_t = block_sum(sa_t, s_red, lane, warp);
-      saa_t = block_sum(saa_t, s_red, lane, warp);
+      double tr[6] = {bx0, bx1n, by0, by1n, sa_t, saa_t};
+      block_min4_sum2(tr, s_red, lane, warp);
+      bx0 = tr[0];
+      const double bx1 = -tr[1];
+      by0 = tr[2];
+      const double by1 = -tr[3];
+      sa_t = tr[4];
+      saa_t = tr[5];
       // ---- window: every tap any (pixel, lag) pair of this tile and chunk can touch
       const double fx0 = floor(bx0 + lx0), fx1 = floor(bx1 + lx1), fy0 = floor(by0 + ly0), fy1 = floor(by1 + ly1);
       // (box and offsets passed small_magnitude: |.| < 2^31, the casts are exact)
@@ -365,18 +451,35 @@ offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, cons
       const int wx1 = (int)fx1 + 1, wy0 = (int)fy0 - 1, wy1 = (int)fy1 + 1;
       if (wx1 < 0 || wx0 > snx - 1 || wy1 < 0 || wy0 > sny - 1) continue;   // nothing of it inside the image
       const bool fits = (wx1 - wx0 + 1 <= BW) && (wy1 - wy0 + 1 <= BH);
-      int lo_x = 1, lo_y = 1, hi_x = snx - 2, hi_y = sny - 2, pitch = snx, base_off = 0;
+      if (stats != nullptr && tid == 0) {   // COREG_OFFSET_STATS=1: how the (tile, chunk) pairs were served
+        atomicAdd(stats + (fits ? 0 : 1), 1ull);
+        atomicAdd(stats + 2, (unsigned long long)n_live);
+        atomicMax(stats + 3, (unsigned long long)(wx1 - wx0 + 1));
+        atomicMax(stats + 4, (unsigned long long)(wy1 - wy0 + 1));
+      }
+      int lo_x = 1, lo_y = 1, hi_x = snx - 2, hi_y = sny - 2, base_off = 0, dirty = 0;
       if (fits) {
         lo_x = max(1, wx0 + 1);
         lo_y = max(1, wy0 + 1);
         hi_x = min(snx - 2, wx0 + BW - 2);
         hi_y = min(sny - 2, wy0 + BH - 2);
-        pitch = BW;
         base_off = (lo_y - 1 - wy0) * BW + (lo_x - 1 - wx0);
         if (use_tma) {
           if (tid == 0) {
             mbar_expect_tx(s_bar, (unsigned)OffBox<T>::kBytes);
             tma_load_2d(s_win, &tmap, s_bar, wx0, wy0);
+          }
+          mbar_wait(s_bar, phase);
+          phase ^= 1u;
+          // the whole box was just rewritten: look at it once, so that the walk can skip the per-sample test
+          const uint4* w4 = reinterpret_cast<const uint4*>(s_win);
+          for (int i = tid; i < OffBox<T>::kBytes / 16; i += kOffThreads) {
+            const uint4 q = w4[i];
+            if (sizeof(T) == 4)
+              dirty |= dirty_bits(q.x) || dirty_bits(q.y) || dirty_bits(q.z) || dirty_bits(q.w);
+            else
+              dirty |= dirty_value(__hiloint2double((int)q.y, (int)q.x)) ||
+                       dirty_value(__hiloint2double((int)q.w, (int)q.z));
           }
         } else {
           const int w = wx1 - wx0 + 1, h = wy1 - wy0 + 1;
@@ -385,11 +488,10 @@ offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, cons
             const int gx = wx0 + xx, gy = wy0 + yy;
             T val = (T)0;
             if (gx >= 0 && gx < snx && gy >= 0 && gy < sny) val = __ldg(small + ((size_t)gy * snx + gx));
+            dirty |= dirty_value(val);
             s_win[yy * BW + xx] = val;
           }
         }
-      } else {
-        base_off = 0;   // tap (iy - 1, ix - 1) = small[(iy - 1) * snx + ix - 1] with rx = ix - 1, ry = iy - 1
       }
       unsigned span_x = 0, span_y = 0;
       if (hi_x >= lo_x && hi_y >= lo_y) {
@@ -398,20 +500,22 @@ offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, cons
       } else {
         lo_x = lo_y = 0x40000000;   // no pixel can take the fast path
       }
-      if (fits && use_tma) {
-        mbar_wait(s_bar, phase);
-        phase ^= 1u;
-      }
-      __syncthreads();   // table complete (and the cooperative copy, if any)
+      dirty = __syncthreads_or(dirty);   // also: table complete, cooperative copy (if any) complete
       if (lag_ok) {
         int n_miss = 0;
         double sa_miss = 0.0, saa_miss = 0.0, tsb = 0.0, tsbb = 0.0, tsab = 0.0;
-        if (fits)
-          offset_walk<T, true>(s_win, pitch, base_off, lo_x, lo_y, span_x, span_y, small, snx, sny, s_px, n_live, x0h,
-                               y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
-        else
-          offset_walk<T, false>(small, pitch, base_off, lo_x, lo_y, span_x, span_y, small, snx, sny, s_px, n_live,
-                                x0h, y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+        if (fits) {
+          const unsigned win = smem_u32(s_win) + (unsigned)base_off * (unsigned)sizeof(T);
+          if (dirty)
+            offset_walk_window<T, true>(win, lo_x, lo_y, span_x, span_y, small, snx, sny, smem_u32(s_px), n_live, x0h,
+                                        y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+          else
+            offset_walk_window<T, false>(win, lo_x, lo_y, span_x, span_y, small, snx, sny, smem_u32(s_px), n_live, x0h,
+                                         y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+        } else {
+          offset_walk_global<T>(small, snx, sny, s_px, n_live, x0h, y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss,
+                                saa_miss);
+        }
         // per tile, so that a tile this lag cannot reach adds exactly nothing -- whether the block skipped it for
         // the whole chunk or walked it for the sake of other lags (sharding-invariant partials)
         if (n_miss < n_live) {
@@ -519,7 +623,7 @@ static int launch_offset_window(int gnx, int gny, int64_t n_lags, cudaStream_t s
   const int n_chunks = (int)((n_lags + kOffThreads - 1) / kOffThreads);
   const int cpb = (n_chunks + 65534) / 65535;
   const dim3 grid(L.n_super, (n_chunks + cpb - 1) / cpb);
-  const size_t smem = (size_t)OffBox<T>::kBytes + kOffTilePx * sizeof(OffPx) + kOffWarps * sizeof(double) +
+  const size_t smem = (size_t)OffBox<T>::kBytes + kOffTilePx * sizeof(OffPx) + 6 * kOffWarps * sizeof(double) +
                       2 * kOffWarps * sizeof(int) + 16;
   auto kern = offset_window_kernel<T>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -529,9 +633,23 @@ static int launch_offset_window(int gnx, int gny, int64_t n_lags, cudaStream_t s
     CK(cudaEventCreate(&g_prof[g_prof_n].b));
     CK(cudaEventRecord(g_prof[g_prof_n].a, s));
   }
+  unsigned long long* stats = nullptr;
+  if (getenv("COREG_OFFSET_STATS")) {
+    CK(cudaMallocAsync(&stats, 8 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), s));
+  }
   kern<<<grid, kOffThreads, smem, s>>>(map, use_tma, ref, small, snx, sny, gnx, gny, tx, ty, lags, (int)n_lags, cpb,
-                                       pivots, slots, partials);
+                                       pivots, slots, partials, stats);
   CK_LAUNCH("offset_window_kernel");
+  if (stats) {   // diagnostic only (synchronises)
+    unsigned long long h[8];
+    CK(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaFreeAsync(stats, s));
+    fprintf(stderr, "[coreg offset kernel] tma=%d (tile, chunk) pairs: %llu staged, %llu global; %llu live pixel-walks; "
+            "largest window asked for %llu x %llu (box %d x %d)\n", use_tma, h[0], h[1], h[2], h[3], h[4], OffBox<T>::W,
+            OffBox<T>::H);
+  }
   if (prof) {
     CK(cudaEventRecord(g_prof[g_prof_n].b, s));
     ++g_prof_n;

@@ -148,11 +148,12 @@ def car_lag_table(hdr_small, refs, d_crval1, d_crval2, d_cdelt1, d_cdelt2, d_cro
 OFFSET_CHUNK = 256   # lags per block of the Carrington-frame kernel (one per thread, csrc/coreg_lag_offset.cu)
 
 
-def offset_patch_order(i1, i2, group=None, patch=(16, 16), sub=(8, 4)):
+def offset_patch_order(i1, i2, group=None, patch=(16, 16), sub=(16, 2)):
     """Order in which the Carrington-frame kernel wants a CRVAL lag list: its blocks take 256 consecutive lags (one per
     thread) and stage the part of the small image those lags can touch, so consecutive lags must be neighbours in
     the detector plane. Lags are grouped into patches of 16 x 16 grid indices (i1 = CRVAL1 index, i2 = CRVAL2 index),
-    inside a patch into sub-patches of 8 x 4 (one warp each); every patch is padded to 256 slots so that a block
+    inside a patch into sub-patches of 16 x 2 (one warp each: the lane layout with the fewest shared-memory bank
+    conflicts, csrc/coreg_lag_offset.cu:OffBox); every patch is padded to 256 slots so that a block
     never straddles two patches. `group`: optional integer key of lags that must not share a patch (e.g. the CDELT
     index). Returns (slot_of_lag [n], n_slots): lag k goes to row slot_of_lag[k] of a [n_slots, 2] table whose
     other rows are NaN (dummy lags: evaluate nothing)."""
@@ -162,7 +163,7 @@ def offset_patch_order(i1, i2, group=None, patch=(16, 16), sub=(8, 4)):
     p1, p2 = i1 // patch[0], i2 // patch[1]
     q1, q2 = i1 % patch[0], i2 % patch[1]
     s1, s2 = q1 // sub[0], q2 // sub[1]
-    # position inside the patch: sub-patch major, then row-major inside the 8 x 4 sub-patch (8 along CRVAL1 fastest)
+    # position inside the patch: sub-patch major, then row-major inside the sub-patch (CRVAL1 index fastest)
     inner = ((s2 * (patch[0] // sub[0]) + s1) * (sub[0] * sub[1]) + (q2 % sub[1]) * sub[0] + (q1 % sub[0]))
     _, pid = np.unique(np.stack([g, p1, p2], axis=1), axis=0, return_inverse=True)
     slot = pid.ravel() * (patch[0] * patch[1]) + inner
@@ -208,7 +209,7 @@ def gather_slices(local, n_total, chunk):
 class LagSearchEngine:
     """Resident images + workspaces for one (large, small) pair on the current CUDA device."""
 
-    max_workspace_bytes = 2 << 30   # 3968 lags of a 2048^2 grid per launch (535 KB of warp records per lag)
+    max_workspace_bytes = 4 << 30   # 8128 lags of a 2048^2 grid per launch (525 KB of warp records per lag)
 
     # the reference evaluates every sample in FP64 (scipy accumulates in double, utils/Util.py:98-102) and only then
     # stores it as float32 (alignment.py:1024): FP64 is the default, "mixed" an explicit opt-in
@@ -453,10 +454,11 @@ class LagSearchEngine:
         return self._work
 
     def lags_per_launch(self, gnx, gny):
-        """Largest multiple of 64 lags whose workspace fits `max_workspace_bytes` (the size is affine in the lags)."""
+        """Largest multiple of 256 lags whose workspace fits `max_workspace_bytes` (the size is affine in the lags;
+        256 = `OFFSET_CHUNK`: a launch boundary must not cut a patch of the Carrington-frame lag order)."""
         fixed = _ext.lag_corr_workspace_bytes(gnx, gny, 1)
         per_lag = max(1, (_ext.lag_corr_workspace_bytes(gnx, gny, 1025) - fixed) // 1024)
-        return max(64, ((self.max_workspace_bytes - fixed) // per_lag) // 64 * 64)
+        return max(OFFSET_CHUNK, ((self.max_workspace_bytes - fixed) // per_lag) // OFFSET_CHUNK * OFFSET_CHUNK)
 
     def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None, allow_mixed=True):
         """Run the fused kernel over a device lag table [n, k]; results into out_dev[n]. Helioprojective frame:
