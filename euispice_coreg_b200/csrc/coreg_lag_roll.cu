@@ -158,7 +158,10 @@ __device__ __noinline__ bool sample_exact_half(const double* __restrict__ small,
 // segment as a whole with two integer maxima: `vmax` over the high words of the fractional parts (all in [0, 1) <=>
 // vmax < 0x3FF00000) and `bmax` over the magnitude bits of the float32 samples (all finite <=> bmax < 0x7F800000);
 // the caller discards the sums and re-evaluates the segment pixel by pixel when either test fails.
-template <int MODE, bool ROUND32, int P>
+// QUAD (MODE 0 only, |he1| < 2.2e-8): numerator x reciprocal as a quadratic in the row index p, coefficients formed
+// once per lag -- two FMAs per coordinate instead of seven instructions for both (the form the mixed kernel uses;
+// what it neglects, p^2 he1^2 of the reciprocal, is below 1e-9 pixel: tests/test_mixed_fraction_bits.py).
+template <int MODE, bool ROUND32, int P, bool QUAD = false>
 __device__ __forceinline__ void roll_segment(const double* __restrict__ small, unsigned tap, unsigned row_elems,
                                              double be, double bnx, double bny, double he1, double hx1, double hy1,
                                              double inv0, double xoff, double yoff, double pivot_b,
@@ -181,18 +184,34 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
   row(tap, r0a, r0b, r0c);
   row(tap += row_elems, r1a, r1b, r1c);
   row(tap += row_elems, r2a, r2b, r2c);
+  double qx0 = 0, qx1 = 0, qx2 = 0, qy0 = 0, qy1 = 0, qy2 = 0;
+  if (QUAD) {
+    const double dinv = fma(be + be, he1, he1);   // d(1 + e + e^2) / dp at the first pixel
+    qx0 = fma(bnx, inv0, xoff);
+    qy0 = fma(bny, inv0, yoff);
+    qx1 = fma(hx1, inv0, bnx * dinv);
+    qy1 = fma(hy1, inv0, bny * dinv) - 1.0;       // the shared floor of y advances by one per row
+    qx2 = hx1 * dinv;
+    qy2 = hy1 * dinv;
+  }
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     // next row first: it is consumed one pixel later
     double r3a = 0.0, r3b = 0.0, r3c = 0.0;
     if (p + 1 < P) row(tap += row_elems, r3a, r3b, r3c);
-    const double e = (p == 0) ? be : fma(he1, (double)p, be);
-    const double inv = (p == 0) ? inv0 : ((MODE == 0) ? recip_1me_tiny(e) : recip_1me_small(e));
-    const double nx = (p == 0) ? bnx : fma(hx1, (double)p, bnx);
-    const double ny = (p == 0) ? bny : fma(hy1, (double)p, bny);
     // fractional parts (+0.5) relative to the shared floors: v = d + 0.5 in [0, 1) on a regular column
-    const double vx = fma(nx, inv, xoff);
-    const double vy = fma(ny, inv, yoff - (double)p);
+    double vx, vy;
+    if (QUAD) {
+      vx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
+      vy = (p == 0) ? qy0 : fma(fma(qy2, (double)p, qy1), (double)p, qy0);
+    } else {
+      const double e = (p == 0) ? be : fma(he1, (double)p, be);
+      const double inv = (p == 0) ? inv0 : ((MODE == 0) ? recip_1me_tiny(e) : recip_1me_small(e));
+      const double nx = (p == 0) ? bnx : fma(hx1, (double)p, bnx);
+      const double ny = (p == 0) ? bny : fma(hy1, (double)p, bny);
+      vx = fma(nx, inv, xoff);
+      vy = fma(ny, inv, yoff - (double)p);
+    }
     vmax = max(vmax, max((unsigned)__double2hiint(vx), (unsigned)__double2hiint(vy)));
     const double q0 = fma(fma(r0c, vx, r0b), vx, r0a);
     const double q1 = fma(fma(r1c, vx, r1b), vx, r1a);
@@ -395,7 +414,10 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   } else if (fast) {
     const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
     unsigned vmax = 0, bmax = 0;
-    if (mode == 0)
+    if (mode == 0 && fabs(he1) < 2.2e-8)
+      roll_segment<0, ROUND32, P, true>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff,
+                                        pivot_b, a_c, sb, sbb, sab, vmax, bmax);
+    else if (mode == 0)
       roll_segment<0, ROUND32, P>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff, pivot_b,
                                   a_c, sb, sbb, sab, vmax, bmax);
     else

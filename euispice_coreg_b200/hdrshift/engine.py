@@ -389,8 +389,8 @@ class LagSearchEngine:
     def hpc_lag_table(self, hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics="reference"):
         """Host lag table for `search` in the helioprojective frame + the mask of lags the reference cannot
         evaluate: candidate-header rows for the homography kernel when it applies, `CoregLagTan` rows otherwise."""
-        # launch shape of the mixed kernel: 16 rows per thread when every lag is a pure CRVAL shift (no segment changes
-        # a floor), 12 when CROTA / CDELT lags make some segments irregular (measured: tools/mixed_lab.py)
+        # launch shape of the rolling kernel: 16 rows per thread when every lag is a pure CRVAL shift (no segment changes
+        # a floor), 12 when CROTA / CDELT lags make some segments irregular (measured: tools/mixed_lab.py, k1_tune.py)
         self.pure_shift_hint = not (np.any(np.asarray(d3)) or np.any(np.asarray(d4)) or np.any(np.asarray(d5)))
         if self.hpc_fast_eligible():
             return tan_wcs_table(hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics)
@@ -480,7 +480,9 @@ class LagSearchEngine:
                 nv = None if nvalid_dev is None else nvalid_dev[lo:hi]
                 if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
                     flags = self.flags
-                    if mixed and self.variant == 0 and self.pure_shift_hint:
+                    if self.variant == 0 and self.pure_shift_hint:
+                        # 16 rows per thread when no lag rotates or rescales the grid (37.8 vs 40.1 ms all-FP64 on
+                        # config 1, profiles/r2_k1_tuning.md); decided on the WHOLE lag grid, never on a shard
                         flags = _ext.make_flags(self.strict, 1, no_fast=self.no_fast)
                     _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
                                           self.stats if mixed else self.pivots, work, out_dev[lo:hi], nv, flags,

@@ -321,7 +321,7 @@ def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
     w_small = TanWcs.from_header(a.hdr_small)
     table, _ = engine.tan_wcs_table(a.hdr_small, a, *d)
-    flags = _ext.make_flags()
+    flags = _ext.make_flags(variant=1)    # 16 rows per thread: what the engine launches for a pure CRVAL lag grid
     corr, nvalid = _ext.hpc_search_host(dl.astype(np.float64), TanWcs.from_header(hl), ds.astype(np.float64), w_small,
                                         table, flags=flags)
     assert np.array_equal(corr.reshape(gpu.shape), gpu)
