@@ -220,13 +220,73 @@ def _parse_header_block(raw: bytes):
 # HDUs
 # --------------------------------------------------------------------------
 class ImageHDU:
+    """Image HDU. Read from a file the pixel data stay in the (memory-mapped) file until `.data` is first touched:
+    `raw_big_endian()` hands the payload over as it is stored (for a device-side byte swap), `read_window()` converts
+    only a sub-window -- what the pointing search needs of a large image whose field the small image covers by a few
+    hundred pixels."""
     is_primary = False
 
     def __init__(self, data=None, header=None, name=None):
         self.header = Header(header) if header is not None else Header()
-        self.data = None if data is None else np.asarray(data)
+        self._data = None if data is None else np.asarray(data)
+        self._raw = None          # (big-endian ndarray view of the stored payload, bscale, bzero) until converted
         if name is not None:
             self.header["EXTNAME"] = name
+
+    @classmethod
+    def _from_file(cls, raw, header, bscale, bzero):
+        h = cls(None, header)
+        h._raw = (raw, bscale, bzero)
+        return h
+
+    @staticmethod
+    def _convert(arr, bscale, bzero):
+        """Stored (big-endian) values -> what `astropy.io.fits` returns as `.data`."""
+        dt = arr.dtype
+        scaled = float(bscale) != 1.0 or float(bzero) != 0.0
+        if scaled and dt.kind == "i" and float(bscale) == 1.0 and float(bzero) == float(2 ** (8 * dt.itemsize - 1)):
+            return (arr.astype(np.int64) + int(bzero)).astype(f"u{dt.itemsize}")   # unsigned-integer convention
+        if scaled:
+            # same promotion rule as astropy: <=16-bit ints -> float32, everything else float64
+            out_dt = np.float32 if (dt.kind in "iu" and dt.itemsize <= 2) or dt.itemsize == 4 and dt.kind == "f" \
+                else np.float64
+            return arr.astype(out_dt) * out_dt(bscale) + out_dt(bzero)
+        return arr.astype(dt.newbyteorder("="))
+
+    @property
+    def data(self):
+        if self._data is None and self._raw is not None:
+            self._data = self._convert(*self._raw)
+            self._raw = None
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = None if value is None else np.asarray(value)
+        self._raw = None
+
+    @property
+    def shape(self):
+        if self._raw is not None:
+            return self._raw[0].shape
+        return None if self._data is None else self._data.shape
+
+    def raw_big_endian(self):
+        """The stored payload as a big-endian float array (no copy, read-only) when `.data` would hold exactly these
+        values (BITPIX -32 / -64, no BSCALE / BZERO); None otherwise or once `.data` has been materialised."""
+        if self._raw is None:
+            return None
+        raw, bscale, bzero = self._raw
+        if raw.dtype.kind != "f" or float(bscale) != 1.0 or float(bzero) != 0.0:
+            return None
+        return raw
+
+    def read_window(self, y0, y1, x0, x1):
+        """`.data[y0:y1, x0:x1]` (2-D images) without converting the rest of the image."""
+        if self._raw is not None and self._raw[0].ndim == 2:
+            raw, bscale, bzero = self._raw
+            return self._convert(raw[y0:y1, x0:x1], bscale, bzero)
+        return np.array(self.data[y0:y1, x0:x1])
 
     @property
     def name(self):
@@ -425,9 +485,14 @@ def _data_nbytes(hdr: Header) -> int:
 
 
 def open(path, mode="readonly", **_):  # noqa: A001 - mirrors astropy.io.fits.open
-    """Read every HDU of a FITS file into memory. Returns an `HDUList`."""
+    """Open a FITS file: headers are parsed, image payloads stay in the memory-mapped file until used. Returns an
+    `HDUList`."""
+    import mmap
     with builtins_open(os.fspath(path), "rb") as f:
-        buf = f.read()
+        try:
+            buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        except (ValueError, OSError):       # empty file, or a file system without mmap
+            buf = f.read()
     hdus = HDUList()
     pos = 0
     first = True
@@ -455,29 +520,15 @@ def open(path, mode="readonly", **_):  # noqa: A001 - mirrors astropy.io.fits.op
             shape = tuple(int(hdr[f"NAXIS{i}"]) for i in range(naxis, 0, -1))
             dt = np.dtype(_BITPIX_DTYPE[int(hdr["BITPIX"])])
             arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape)), offset=pos).reshape(shape)
-            bscale = hdr.get("BSCALE", 1)
-            bzero = hdr.get("BZERO", 0)
-            scaled = float(bscale) != 1.0 or float(bzero) != 0.0
-            if scaled and dt.kind == "i" and float(bscale) == 1.0 \
-                    and float(bzero) == float(2 ** (8 * dt.itemsize - 1)):
-                # unsigned-integer convention (BZERO = 2**(bits-1))
-                arr = (arr.astype(np.int64) + int(bzero)).astype(f"u{dt.itemsize}")
-            elif scaled:
-                # same promotion rule as astropy: <=16-bit ints -> float32, everything else float64
-                out_dt = np.float32 if (dt.kind in "iu" and dt.itemsize <= 2) or dt.itemsize == 4 and dt.kind == "f" \
-                    else np.float64
-                arr = arr.astype(out_dt) * out_dt(bscale) + out_dt(bzero)
-            else:
-                arr = arr.astype(dt.newbyteorder("="))
-            data = arr
+            data = (arr, hdr.get("BSCALE", 1), hdr.get("BZERO", 0))
         elif nbytes and xt == "BINTABLE" and hdr.get("ZIMAGE", False):
             hdus.append(CompImageHDU(hdr, bytes(buf[pos:pos + nbytes])))
             pos += ((nbytes + BLOCK - 1) // BLOCK) * BLOCK
             first = False
             continue
         pos += ((nbytes + BLOCK - 1) // BLOCK) * BLOCK
-        hdu = PrimaryHDU(data, hdr) if first else ImageHDU(data, hdr)
-        hdus.append(hdu)
+        cls = PrimaryHDU if first else ImageHDU
+        hdus.append(cls(None, hdr) if data is None else cls._from_file(data[0], hdr, data[1], data[2]))
         first = False
     return hdus
 

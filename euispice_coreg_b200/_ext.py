@@ -58,6 +58,7 @@ _SIGNATURES = {
     "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_rice_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                     C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "coreg_bswap32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_image_stats_scratch_bytes": (C.c_size_t, []),
     "coreg_image_stats": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_int, _P, _P]),
     "coreg_center_f32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, _P, _P]),
@@ -271,6 +272,19 @@ def widen_f32(img):
     with torch.cuda.device(img.device):
         _check(lib.coreg_widen_f32(_ptr(img), img.numel(), _ptr(out), _stream()), "coreg_widen_f32")
     return out
+
+
+def bswap32_to_float32(words):
+    """Device int32 tensor holding big-endian float32 words (a FITS BITPIX -32 payload as stored) -> the float32 image,
+    swapped in place on the device."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(words)
+    if words.dtype != torch.int32:
+        raise TypeError("int32 tensor of raw big-endian words expected")
+    with torch.cuda.device(words.device):
+        _check(lib.coreg_bswap32(_ptr(words), words.numel(), _ptr(words), _stream()), "coreg_bswap32")
+    return words.view(torch.float32)
 
 
 STATS_ROWS = 4   # rows of a statistics block: mean (the pivot), count, max |v|, RMS about the pivot

@@ -250,6 +250,12 @@ __global__ void car_world2pix_kernel(CoregLagCar L, const double* __restrict__ l
   }
 }
 
+// big-endian 32-bit words (a FITS BITPIX -32 / 32 payload as stored) -> native, in place or out of place
+__global__ void bswap32_kernel(const unsigned* __restrict__ in, int64_t n, unsigned* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __byte_perm(in[i], 0u, 0x0123);
+}
+
 __global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (double)in[i];
@@ -377,6 +383,14 @@ int coreg_widen_f32(const float* in, int64_t n, double* out, void* stream) {
   if (!in || !out) return fail(COREG_EINVAL, "coreg_widen_f32: null pointer");
   f32_to_f64_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(in, n, out);
   CK_LAUNCH("f32_to_f64_kernel");
+  return COREG_OK;
+}
+
+int coreg_bswap32(const void* in, int64_t n, void* out, void* stream) {
+  if (n <= 0) return COREG_OK;
+  if (!in || !out) return fail(COREG_EINVAL, "coreg_bswap32: null pointer");
+  bswap32_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const unsigned*)in, n, (unsigned*)out);
+  CK_LAUNCH("bswap32_kernel");
   return COREG_OK;
 }
 

@@ -136,7 +136,9 @@ class Alignment:
         self.lon_ctype = "HPLN-TAN"
         self.lat_ctype = "HPLT-TAN"
         self.ang2pipi = True
-        self._load_pair()
+        masking = (self.small_fov_value_min is not None or self.small_fov_value_max is not None
+                   or fov_limits is not None or remove_fov_limits is not None)
+        self._load_pair(lazy=True, host_masking=masking)
         results = self._find_best_header_parameters(fov_limits=fov_limits, remove_fov_limits=remove_fov_limits)
         return self._wrap_results(results, return_type)
 
@@ -225,17 +227,29 @@ class Alignment:
     def _open_small(self):
         return _open_fits(self.small_fov_to_correct)
 
-    def _load_pair(self):
+    def _load_pair(self, lazy=False, host_masking=True):
+        """Open both files, copy the headers, check / create the PCi_j matrices and take the images.
+        lazy=True (helioprojective frame): the large image stays in its memory-mapped file -- the engine converts and
+        uploads only the window the small grid can reach -- and, when no host-side masking will touch it
+        (host_masking=False) and the file holds float32 (BITPIX -32), the small image is handed over as stored
+        (big-endian) for a byte swap on the device. The reference widens both images to float64 on the host
+        (alignment.py:299-316); float32 payloads are kept as they are here (float32 -> float64 is exact)."""
         f_large = self._open_large()
         f_small = self._open_small()
-        # the reference widens both images to float64 on the host (alignment.py:299-316); float32 payloads are kept
-        # as they are here (float32 -> float64 is exact) and widened on the device where a kernel wants float64
-        self.data_large = self._float_image(f_large[self.large_fov_window].data)
-        self.hdr_large = f_large[self.large_fov_window].header.copy()
-        self.hdr_small = f_small[self.small_fov_window].header.copy()
+        h_large, h_small = f_large[self.large_fov_window], f_small[self.small_fov_window]
+        if lazy and hasattr(h_large, "read_window") and h_large.shape is not None and len(h_large.shape) == 2:
+            self.data_large = h_large
+        else:
+            self.data_large = self._float_image(h_large.data)
+        self.hdr_large = h_large.header.copy()
+        self.hdr_small = h_small.header.copy()
         self._check_ant_create_pcij_matrix(self.hdr_small)
         self._check_ant_create_pcij_matrix(self.hdr_large)
-        self.data_small = self._float_image(f_small[self.small_fov_window].data)
+        raw = h_small.raw_big_endian() if (lazy and not host_masking and hasattr(h_small, "raw_big_endian")) else None
+        if raw is not None and raw.dtype == np.dtype(">f4") and raw.ndim == 2:
+            self.data_small = raw
+        else:
+            self.data_small = self._float_image(h_small.data)
         f_large.close()
         f_small.close()
 
@@ -410,8 +424,6 @@ class Alignment:
             raise NotImplementedError("only method='correlation' is on the device path")
         self._set_removed_values_to_nan_in_datasmall(fov_limits=fov_limits, remove_fov_limits=remove_fov_limits)
         self._set_initial_header_values(ang2pipi)
-        if np.isnan(self.data_small).all():
-            raise ValueError("minimum or maximum value have set all small FOV to nan")
         if self.unit_lag != self.hdr_small["CUNIT1"] or self.unit_lag != self.hdr_small["CUNIT2"]:
             raise ValueError("lag.unit and cUNIT are not the same")
         shape5 = (len(self.lag_crval1), len(self.lag_crval2), len(self.lag_cdelt1), len(self.lag_cdelt2),
@@ -430,6 +442,8 @@ class Alignment:
                                       arithmetic=getattr(self, "arithmetic", None))
         self.engine = eng
         eng.set_small(self.data_small)
+        if eng.small_count() == 0:     # `np.isnan(data_small).all()` (alignment.py:656), counted on the device
+            raise ValueError("minimum or maximum value have set all small FOV to nan")
         n_r = len(self.lag_solar_r)
         cube = np.zeros(shape5 + (n_r,), dtype=np.float64)
         if self.coordinate_frame == "final_helioprojective":

@@ -256,6 +256,18 @@ class LagSearchEngine:
     # ---- uploads -----------------------------------------------------------------------------
     def _upload(self, arr, pinned=False):
         torch = _torch()
+        arr = np.asarray(arr)
+        if arr.dtype == np.dtype(">f4"):
+            # a FITS BITPIX -32 payload as stored (possibly a read-only view of the memory-mapped file): the bytes go
+            # up as they are and are swapped on the device
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")      # "non-writable array": it is only read
+                t = torch.from_numpy(np.ascontiguousarray(arr).view("<i4"))
+            if pinned:
+                t = t.pin_memory()
+            with torch.cuda.device(self.device):
+                return _ext.bswap32_to_float32(t.to(self.device, non_blocking=pinned))
         t = torch.from_numpy(np.ascontiguousarray(arr))
         if pinned:
             t = t.pin_memory()
@@ -264,8 +276,11 @@ class LagSearchEngine:
     @staticmethod
     def _native_float(arr):
         """float32 / float64 arrays go up as they are (float32 -> float64 is exact, so FITS BITPIX -32 payloads need
-        no widening on the host); anything else is converted to float64 like the reference does."""
+        no widening on the host), big-endian float32 as stored; anything else is converted to float64 like the
+        reference does."""
         arr = np.asarray(arr)
+        if arr.dtype == np.dtype(">f4"):
+            return arr
         if arr.dtype not in (np.float32, np.float64) or not arr.dtype.isnative:
             arr = arr.astype(np.float64)
         return arr
@@ -296,6 +311,10 @@ class LagSearchEngine:
                         self.small32 = _ext.center_f32(s32.contiguous(), self.stats, 1)
         self.small = small
 
+    def small_count(self):
+        """Number of finite pixels of the small image (from its statistics pass; one 8-byte D2H)."""
+        return int(self.stats[1, 1].item())
+
     # float32 moments need headroom on both sides: the mixed kernel squares pivot-centred pixel values and sums 16 of
     # them in float32, so images whose magnitudes sit near the ends of the float32 range (|v| beyond 1e12, or nothing
     # above 1e-9: flux units far from DN/s or W/m2/sr/nm) are searched by the all-FP64 kernel from the start. (The
@@ -318,12 +337,36 @@ class LagSearchEngine:
         return self._mixed_ok
 
     # ---- helioprojective ------------------------------------------------------------------------
-    def set_large(self, data_large, wcs_large: TanWcs):
-        """Upload the large image once; it stays resident for any number of `cut_large` calls (frame sequences)."""
+    def set_large(self, data_large, wcs_large: TanWcs, origin=(0, 0)):
+        """Upload the large image once; it stays resident for any number of `cut_large` calls (frame sequences).
+        origin = (x0, y0): `data_large` is the window [y0:, x0:] of the image `wcs_large` describes."""
         torch = _torch()
         with torch.cuda.device(self.device):
             self.d_large = self._upload(self._native_float(data_large))
         self.wcs_large = wcs_large
+        self.large_origin = (int(origin[0]), int(origin[1]))
+
+    @staticmethod
+    def large_window(wcs_large: TanWcs, wcs_small: TanWcs, shape_large, margin=4):
+        """(x0, x1, y0, y1): the part of the large image the one-time cut onto the small grid can touch. Both maps are
+        gnomonic, so large-image coordinates are a projective function of small-grid coordinates and their extremes
+        over the grid lie on its boundary: the four edges are mapped on the host. `margin` covers the spline support.
+        None when the window cannot be bounded (non-finite coordinates)."""
+        nx, ny = int(wcs_small.naxis1), int(wcs_small.naxis2)
+        ny_l, nx_l = int(shape_large[0]), int(shape_large[1])
+        ex = np.concatenate([np.arange(nx), np.arange(nx), np.zeros(ny), np.full(ny, nx - 1.0)])
+        ey = np.concatenate([np.zeros(nx), np.full(nx, ny - 1.0), np.arange(ny), np.arange(ny)])
+        lon, lat = wcs_small.pixel_to_world(ex, ey)
+        xl, yl = wcs_large.world_to_pixel(lon, lat)
+        if not (np.all(np.isfinite(xl)) and np.all(np.isfinite(yl))):
+            return None
+        x0 = max(0, int(np.floor(xl.min())) - margin)
+        x1 = min(nx_l, int(np.ceil(xl.max())) + margin + 1)
+        y0 = max(0, int(np.floor(yl.min())) - margin)
+        y1 = min(ny_l, int(np.ceil(yl.max())) + margin + 1)
+        if x1 - x0 < 4 or y1 - y0 < 4:      # no overlap worth cropping to: keep the whole image
+            return None
+        return x0, x1, y0, y1
 
     def cut_large(self, wcs_small: TanWcs):
         """One-time part of a helioprojective search: world grid of the unshifted small grid (K3), the resident
@@ -333,6 +376,12 @@ class LagSearchEngine:
         with torch.cuda.device(self.device):
             lng, lat = _ext.tan_pix2world(wcs_small, wcs_small.naxis1, wcs_small.naxis2, True, self.device)
             x, y = _ext.tan_world2pix(self.wcs_large, lng, lat)
+            x0, y0 = getattr(self, "large_origin", (0, 0))
+            if x0 or y0:
+                # coordinates in the full image, computed exactly as without a window; the integer origin comes off
+                # exactly, so every tap and every weight is the one the full image would give
+                x -= float(x0)
+                y -= float(y0)
             self.ref = _ext.map_coordinates(self.d_large, y, x, self.order, float("nan"), torch.float32)
             del x, y, lng, lat
             self.planes = None          # trig planes of the generic kernel: built on first use (`_hpc_planes`)
@@ -343,10 +392,22 @@ class LagSearchEngine:
         self.frame = "hpc"
 
     def prepare_hpc(self, data_large, wcs_large: TanWcs, wcs_small: TanWcs):
-        """`set_large` + `cut_large` for a single pair; the large image is released afterwards."""
-        self.set_large(data_large, wcs_large)
+        """`set_large` + `cut_large` for a single pair; the large image is released afterwards. Only the window of
+        the large image the small grid can reach is converted (when `data_large` is a lazily read FITS HDU:
+        `fits_lite.ImageHDU.read_window`) and uploaded: a few hundred pixels across for an HRIEUV field inside a full-disc FSI image."""
+        shape = data_large.shape
+        win = self.large_window(wcs_large, wcs_small, shape) if len(shape) == 2 else None
+        if win is None:
+            full = data_large.data if hasattr(data_large, "read_window") else data_large
+            self.set_large(full, wcs_large)
+        else:
+            x0, x1, y0, y1 = win
+            part = data_large.read_window(y0, y1, x0, x1) if hasattr(data_large, "read_window") \
+                else data_large[y0:y1, x0:x1]
+            self.set_large(part, wcs_large, origin=(x0, y0))
         self.cut_large(wcs_small)
         self.d_large = None
+        self.large_origin = (0, 0)
 
     # ---- Carrington maps as inputs (CRLN-CAR / CRLT-CAR) -----------------------------------------------------
     def prepare_car(self, data_large, wcs_large: CarWcs, wcs_small: CarWcs):

@@ -89,11 +89,17 @@ class SequenceAlignment:
         f_small = a._open_small()
         a.hdr_small = f_small[a.small_fov_window].header.copy()
         a._check_ant_create_pcij_matrix(a.hdr_small)
-        a.data_small = a._float_image(f_small[a.small_fov_window].data)
-        a._set_removed_values_to_nan_in_datasmall(fov_limits=None, remove_fov_limits=None)
+        h_small = f_small[a.small_fov_window]
+        masking = a.small_fov_value_min is not None or a.small_fov_value_max is not None
+        raw = h_small.raw_big_endian() if (not masking and hasattr(h_small, "raw_big_endian")) else None
+        if raw is not None and raw.dtype == np.dtype(">f4") and raw.ndim == 2:
+            a.data_small = raw      # as stored: swapped on the device; the all-NaN check happens there too (`finish`)
+        else:
+            a.data_small = a._float_image(h_small.data)
+            a._set_removed_values_to_nan_in_datasmall(fov_limits=None, remove_fov_limits=None)
+            if np.isnan(a.data_small).all():
+                raise ValueError("minimum or maximum value have set all small FOV to nan")
         a._set_initial_header_values(True)
-        if np.isnan(a.data_small).all():
-            raise ValueError("minimum or maximum value have set all small FOV to nan")
         if a.unit_lag != a.hdr_small["CUNIT1"] or a.unit_lag != a.hdr_small["CUNIT2"]:
             raise ValueError("lag.unit and cUNIT are not the same")
         return a
@@ -142,6 +148,8 @@ class SequenceAlignment:
                 # stream; this engine's buffers are not touched again before the side stream reaches its next frame
                 e.resolve_flags(tab_dev, out_dev)
                 host = out_dev.cpu()
+                if e.small_count() == 0:     # (this engine's statistics still describe frame k: see above)
+                    raise ValueError("minimum or maximum value have set all small FOV to nan")
             cubes[k] = np.where(dead, 0.0, host.numpy())
             aligns[k] = a
 

@@ -155,6 +155,11 @@ int coreg_rice_decode(const unsigned char* heap_dev, const long long* offsets_de
  * kernels read the small image fastest as float64 (no per-tap conversion). */
 int coreg_widen_f32(const float* in_dev, int64_t n, double* out_dev, void* stream);
 
+/* Big-endian 32-bit words -> native byte order on the device (in place when out_dev == in_dev). A FITS image is stored
+ * big-endian; the reference lets astropy swap it on the host inside `hdul[w].data` (hdrshift/alignment.py:299-316).
+ * Here the BITPIX -32 payload of the small image goes up as stored and is swapped where the bandwidth is. */
+int coreg_bswap32(const void* in_dev, int64_t n_words, void* out_dev, void* stream);
+
 /* ---- image statistics (pivots of the single-pass Pearson moments) ------------------------------------------------
  * One deterministic multi-block pass over an image: stats_dev[0] = mean of the finite values (the pivot: the Pearson
  * coefficient is invariant under it, it only keeps the single-pass moments well conditioned), stats_dev[stride] = their

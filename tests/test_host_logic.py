@@ -417,3 +417,66 @@ def test_spice_solar_rotation_cdelt1_correction():
         want = 4.0 - dt * rate * np.cos(phi)
         got = a.hdr_small["CDELT1"] * (1.0 if unit == "arcsec" else 3600.0)
         assert abs(got - want) < 1e-12 and 3.8 < got < 4.0, (got, want)
+
+
+def test_fits_lite_lazy_payload_window_and_raw_view(tmp_path):
+    """Image payloads stay in the memory-mapped file until used: `read_window` converts a sub-window only,
+    `raw_big_endian` hands a float32 payload over as stored (for the device-side byte swap); both agree with `.data`,
+    also for scaled integer images; overwriting a file that is still mapped is safe."""
+    from euispice_coreg_b200._compat import fits_lite
+    rng = np.random.default_rng(3)
+    img = rng.normal(500.0, 300.0, (37, 53)).astype(np.float32)
+    img[4, 7] = np.nan
+    p = str(tmp_path / "a.fits")
+    fits_lite.writeto(p, [fits_lite.PrimaryHDU(img, fits_lite.Header())])
+    h = fits_lite.open(p)[0]
+    assert h.shape == (37, 53)
+    raw = h.raw_big_endian()
+    assert raw.dtype == np.dtype(">f4") and not raw.flags.writeable
+    assert np.array_equal(raw.astype(np.float32), img, equal_nan=True)
+    assert np.array_equal(h.read_window(3, 20, 5, 41), img[3:20, 5:41], equal_nan=True)
+    assert np.array_equal(h.data, img, equal_nan=True) and h.data.dtype == np.float32 and h.data.dtype.isnative
+    assert h.raw_big_endian() is None                     # materialised: the raw view is gone
+    assert np.array_equal(h.read_window(0, 2, 0, 3), img[:2, :3], equal_nan=True)
+    # 16-bit integers with BSCALE / BZERO: no raw float view, window == slice of the scaled data
+    ints = rng.integers(-3000, 3000, (20, 30)).astype(np.int16)
+    hdr = fits_lite.Header()
+    hdr["BSCALE"], hdr["BZERO"] = 0.5, 100.0
+    q = str(tmp_path / "b.fits")
+    fits_lite.writeto(q, [fits_lite.PrimaryHDU(ints, hdr)])
+    hq = fits_lite.open(q)[0]
+    assert hq.raw_big_endian() is None
+    win = hq.read_window(2, 9, 4, 11)
+    assert win.dtype == hq.data.dtype and np.array_equal(win, hq.data[2:9, 4:11])
+    stored = ints.astype(">i2")
+    conv = fits_lite.ImageHDU._convert
+    assert conv(stored, 0.5, 100.0).dtype == np.float32        # astropy's promotion rule for <= 16-bit integers
+    assert np.array_equal(conv(stored[2:9, 4:11], 0.5, 100.0), conv(stored, 0.5, 100.0)[2:9, 4:11])
+    assert conv(stored, 1, 32768).dtype == np.uint16           # unsigned-integer convention
+    # overwrite while mapped
+    h2 = fits_lite.open(p)
+    fits_lite.writeto(p, [fits_lite.PrimaryHDU(img * 2, h2[0].header)], overwrite=True)
+    assert np.array_equal(h2[0].data, img, equal_nan=True)
+    assert np.array_equal(fits_lite.open(p)[0].data, img * 2, equal_nan=True)
+
+
+def test_large_image_window_covers_every_cut_coordinate(toy_pair):
+    """`LagSearchEngine.large_window`: the one-time cut of the large image onto the small grid touches only a window of
+    it; the window found from the grid's four edges contains every coordinate of the full map (oracle) plus the
+    spline support."""
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    from euispice_coreg_b200.hdrshift.engine import LagSearchEngine
+    from oracle import wcs_tan
+    dl, hl, ds, hs = load_pair(*toy_pair[:2])
+    from oracle.hpc import check_and_create_pcij
+    check_and_create_pcij(hl)
+    check_and_create_pcij(hs)
+    win = LagSearchEngine.large_window(TanWcs.from_header(hl), TanWcs.from_header(hs), dl.shape)
+    x, y = wcs_tan.extract_coordinates_pixels(hs, hl)
+    x0, x1, y0, y1 = win
+    inside = (x >= 0) & (x <= dl.shape[1] - 1) & (y >= 0) & (y <= dl.shape[0] - 1)
+    assert inside.any()
+    # order-3 support reaches 2 pixels beyond floor(x); the window keeps 4
+    assert x0 <= max(0, np.floor(x[inside].min()) - 2) and x1 >= min(dl.shape[1], np.ceil(x[inside].max()) + 3)
+    assert y0 <= max(0, np.floor(y[inside].min()) - 2) and y1 >= min(dl.shape[0], np.ceil(y[inside].max()) + 3)
+    assert (x1 - x0) * (y1 - y0) < 0.5 * dl.size
