@@ -297,7 +297,8 @@ def golden(name):
         return None
 
 
-def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0, align_wall=True, fp64_peak=None):
+def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0, align_wall=True, fp64_peak=None,
+                         shard=None):
     """BASELINE.json configs[1] (same image pair on a user Carrington grid 2048^2, 120 x 120 CRVAL lags), measured
     beside the headline: device-timed search with everything resident (lags sharded like the headline) and the wall
     time of the public call. Returns a dict for the JSON line."""
@@ -322,6 +323,9 @@ def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0, 
     rank = dist.get_rank() if world > 1 else 0
     chunk, bounds = E.shard_bounds(n, world)
     lo, hi = bounds[rank]
+    if shard is not None:      # tools/carr_lab.py: the slice rank r of w ranks would get, on one GPU (no collective)
+        chunk, bounds = E.shard_bounds(n, shard[1])
+        lo, hi = bounds[shard[0]]
     # the kernel takes its lags in detector-plane patches (engine.offset_patch_order), padded with dummy lags
     i1, i2 = np.unravel_index(np.arange(lo, hi), (len(a.lag_crval1), len(a.lag_crval2)))
     slot, n_slots = E.offset_patch_order(i1, i2)
@@ -359,6 +363,9 @@ def carrington_secondary(pl, ps, steps, world, barrier, torch, dist, variant=0, 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(eff, op=dist.ReduceOp.SUM)
     ms = float(t.item()) / steps
+    if shard is not None:
+        return {"shard": list(shard), "lags": hi - lo, "ms_per_search": ms, "kernel_ms": k_ms / max(1, steps),
+                "kernel_launches_per_search": k_n // max(1, steps), "effective_pixel_samples": float(eff.item())}
     cube = (full[:n] if world > 1 else out[:n]).cpu().numpy()
     res = {"workload": "configs[1]: same pair on a Carrington grid 2048x2048 (lon 200-300 deg, lat +-20 deg), 120x120 "
                        "CRVAL lags @1arcsec, lags sharded over the ranks", "lags": n, "ms_per_search": ms,

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "coreg_image_stats": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_int, _P, _P]),
     "coreg_center_f32": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, _P, _P]),
     "coreg_lag_corr_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
+    "coreg_offset_window_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "coreg_hpc_lag_corr": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64,
                                      C.c_int, _P, _P, C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_hpc_lag_corr_wcs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
@@ -86,6 +87,15 @@ _SIGNATURES = {
                                      C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "coreg_hpc_search_host_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, _P, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int, C.c_int,
+                                              C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "coreg_carrington_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregCarrington), C.c_double,
+                                               C.c_double, _P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregCarrington),
+                                               _P, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int64, C.c_int,
+                                               C.c_int, _P, _P]),
+    "coreg_synras_build_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
+                                          C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "coreg_fp64_peak": (C.c_int, [C.POINTER(C.c_double), C.c_int, _P]),
     "coreg_profile_begin": (C.c_int, []),
     "coreg_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -341,8 +351,11 @@ def finite_mean(img, out):
         out[0:1].copy_(st[0])
 
 
-def lag_corr_workspace_bytes(gnx, gny, n_lags):
-    return int(load().coreg_lag_corr_workspace_bytes(int(gnx), int(gny), int(n_lags)))
+def lag_corr_workspace_bytes(gnx, gny, n_lags, offset_window=False):
+    """Scratch bytes of one lag-kernel launch; offset_window=True: the Carrington-frame window kernel only."""
+    lib = load()
+    fn = lib.coreg_offset_window_workspace_bytes if offset_window else lib.coreg_lag_corr_workspace_bytes
+    return int(fn(int(gnx), int(gny), int(n_lags)))
 
 
 def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid_out=None, flags=0):
@@ -566,6 +579,71 @@ def hpc_search_host(large, wcs_large, small, wcs_small, lag_wcs, order=2, flags=
                                      int(flags), corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)),
            "coreg_hpc_search_host")
     return corr, nvalid
+
+
+def hpc_search_host_multi(devices, large, wcs_large, small, wcs_small, lag_wcs, order=2, flags=0):
+    """`hpc_search_host` with the lag list split over the CUDA devices `devices` of this process (one host thread per
+    device, slices gathered in the host buffers)."""
+    lib = load()
+    large = np.ascontiguousarray(large, dtype=None if large.dtype in (np.float32, np.float64) else np.float64)
+    small = np.ascontiguousarray(small, dtype=None if small.dtype in (np.float32, np.float64) else np.float64)
+    lag_wcs = np.ascontiguousarray(lag_wcs, dtype=np.float64)
+    if lag_wcs.ndim != 2 or lag_wcs.shape[1] != TAN_WCS_DOUBLES:
+        raise ValueError("lag_wcs must be [n_lags, 11] CoregTanWcs rows")
+    n_lags = lag_wcs.shape[0]
+    corr = np.empty(n_lags, dtype=np.float64)
+    nvalid = np.empty(n_lags, dtype=np.int64)
+    sl, ss = tan_struct(wcs_large), tan_struct(wcs_small)
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    _check(lib.coreg_hpc_search_host_multi(dev, len(devices), large.ctypes.data_as(_P), _np_dt(large), large.shape[1],
+                                           large.shape[0], C.byref(sl), small.ctypes.data_as(_P), _np_dt(small),
+                                           small.shape[1], small.shape[0], C.byref(ss), lag_wcs.ctypes.data_as(_P),
+                                           n_lags, int(order), int(flags), corr.ctypes.data_as(_P),
+                                           nvalid.ctypes.data_as(_P)), "coreg_hpc_search_host_multi")
+    return corr, nvalid
+
+
+def carrington_search_host(large, c_large, xy0_large, small, c_small, vec_large, vec_small, lags, order=2, flags=0):
+    """Whole Carrington-frame search from HOST numpy buffers. c_*: `CoregCarrington`; xy0_large: the large header's
+    detector offset; vec_* = (sinlon, coslon, sinlat, coslat) of `LagSearchEngine.carrington_vectors` for each header
+    (the latitude vectors are the grid's and must agree); lags: [n_lags, 2] (x0, y0) rows."""
+    lib = load()
+    large = np.ascontiguousarray(large, dtype=None if large.dtype in (np.float32, np.float64) else np.float64)
+    small = np.ascontiguousarray(small, dtype=None if small.dtype in (np.float32, np.float64) else np.float64)
+    lags = np.ascontiguousarray(lags, dtype=np.float64)
+    v = [np.ascontiguousarray(a, dtype=np.float64) for a in (vec_large[0], vec_large[1], vec_small[0], vec_small[1],
+                                                            vec_small[2], vec_small[3])]
+    n_lon, n_lat, n_lags = v[0].size, v[4].size, lags.shape[0]
+    corr = np.empty(n_lags, dtype=np.float64)
+    nvalid = np.empty(n_lags, dtype=np.int64)
+    _check(lib.coreg_carrington_search_host(large.ctypes.data_as(_P), _np_dt(large), large.shape[1], large.shape[0],
+                                            C.byref(c_large), float(xy0_large[0]), float(xy0_large[1]),
+                                            small.ctypes.data_as(_P), _np_dt(small), small.shape[1], small.shape[0],
+                                            C.byref(c_small), v[0].ctypes.data_as(_P), v[1].ctypes.data_as(_P),
+                                            v[2].ctypes.data_as(_P), v[3].ctypes.data_as(_P), n_lon,
+                                            v[4].ctypes.data_as(_P), v[5].ctypes.data_as(_P), n_lat,
+                                            lags.ctypes.data_as(_P), n_lags, int(order), int(flags),
+                                            corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)),
+           "coreg_carrington_search_host")
+    return corr, nvalid
+
+
+def synras_build_host(frames, wcs_list, frame_of_col, lng, lat, order):
+    """Synthetic raster from HOST numpy buffers: frames [n_frames, fny, fnx] float32 / float64, lng / lat [n_rows,
+    n_cols] degrees -> float64 [n_rows, n_cols]."""
+    lib = load()
+    frames = np.ascontiguousarray(frames, dtype=None if frames.dtype in (np.float32, np.float64) else np.float64)
+    lng = np.ascontiguousarray(lng, dtype=np.float64)
+    lat = np.ascontiguousarray(lat, dtype=np.float64)
+    n_frames, fny, fnx = frames.shape
+    n_rows, n_cols = lng.shape
+    arr = (CoregTanWcs * n_frames)(*[tan_struct(w) for w in wcs_list])
+    cols = (C.c_int * n_cols)(*[int(c) for c in frame_of_col])
+    out = np.empty((n_rows, n_cols), dtype=np.float64)
+    _check(lib.coreg_synras_build_host(frames.ctypes.data_as(_P), _np_dt(frames), n_frames, fnx, fny, arr, cols,
+                                       lng.ctypes.data_as(_P), lat.ctypes.data_as(_P), n_rows, n_cols, int(order),
+                                       out.ctypes.data_as(_P)), "coreg_synras_build_host")
+    return out
 
 
 def fp64_peak(iters=20000):

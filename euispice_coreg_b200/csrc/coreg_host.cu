@@ -27,6 +27,24 @@ __global__ void tan_lag_from_wcs_kernel(const CoregTanWcs* __restrict__ lag_wcs,
   L.y0 = w.crpix2 - 1.0;
   out[idx] = L;
 }
+
+int hpc_search_host_impl(const void* large, int large_dtype, int lnx, int lny, const CoregTanWcs* wcs_large,
+                         const void* small, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,
+                         const CoregTanWcs* lag_wcs, int64_t n_lags, int order, int flags, double* corr,
+                         int64_t* nvalid);
+
+// x[i] += dx, y[i] += dy  (detector coordinates of the large image = offset + plane)
+__global__ void shift_planes_kernel(double* __restrict__ x, double* __restrict__ y, int64_t n, double dx, double dy) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += dx;
+    y[i] += dy;
+  }
+}
+// `np.where(image == -32762, np.nan, image)` (hdrshift/alignment.py:900-901)
+__global__ void fill_to_nan_kernel(double* __restrict__ img, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (img[i] == -32762.0) img[i] = CUDART_NAN;
+}
 }  // namespace coreg
 
 using namespace coreg;
@@ -37,6 +55,17 @@ int coreg_hpc_search_host(const void* large, int large_dtype, int lnx, int lny, 
                           const void* small, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,
                           const CoregTanWcs* lag_wcs, int64_t n_lags, int order, int flags, double* corr,
                           int64_t* nvalid) {
+  return hpc_search_host_impl(large, large_dtype, lnx, lny, wcs_large, small, small_dtype, snx, sny, wcs_small, lag_wcs,
+                              n_lags, order, flags, corr, nvalid);
+}
+
+}  // extern "C"
+
+namespace coreg {
+int hpc_search_host_impl(const void* large, int large_dtype, int lnx, int lny, const CoregTanWcs* wcs_large,
+                         const void* small, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,
+                         const CoregTanWcs* lag_wcs, int64_t n_lags, int order, int flags, double* corr,
+                         int64_t* nvalid) {
   if (!large || !small || !wcs_large || !wcs_small || !lag_wcs || !corr)
     return fail(COREG_EINVAL, "coreg_hpc_search_host: null pointer");
   if (lnx <= 0 || lny <= 0 || snx <= 0 || sny <= 0 || n_lags <= 0)
@@ -150,6 +179,208 @@ done:
 #undef TRY
 #undef TRYRC
   return rc;
+}
+}  // namespace coreg
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+// RAII bundle of device allocations for the host entry points
+struct DevBufs {
+  std::vector<void*> p;
+  template <typename T>
+  cudaError_t get(T** out, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+    if (e == cudaSuccess) p.push_back(q);
+    *out = static_cast<T*>(q);
+    return e;
+  }
+  ~DevBufs() {
+    for (void* q : p) cudaFree(q);
+  }
+};
+#define HTRY(call)                                   \
+  do {                                               \
+    cudaError_t _e = (call);                         \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+  } while (0)
+#define HRC(call)        \
+  do {                   \
+    int _rc = (call);    \
+    if (_rc) return _rc; \
+  } while (0)
+
+// Lag order the Carrington kernel wants (csrc/coreg_lag_offset.cu): 256 consecutive lags = neighbours in the detector
+// plane. Without knowledge of the caller's grid structure the offsets themselves are binned: cells of 32 x 32 detector
+// pixels, inside a cell bands of 4 pixels in y, x ascending; every cell is padded to a multiple of 256 slots with NaN
+// dummies so that a block never straddles two cells. slot_of[k] = row of lag k in the padded table.
+int64_t patch_order_from_offsets(const CoregLagOffset* lags, int64_t n, std::vector<int64_t>* slot_of) {
+  struct Key { long long cy, cx, band; double x; int64_t k; };
+  std::vector<Key> keys((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    const double x = lags[k].x0, y = lags[k].y0;
+    const bool ok = std::isfinite(x) && std::isfinite(y) && fabs(x) < 1e9 && fabs(y) < 1e9;
+    keys[(size_t)k] = ok ? Key{(long long)floor(y / 32.0), (long long)floor(x / 32.0), (long long)floor(y / 4.0), x, k}
+                         : Key{LLONG_MAX, LLONG_MAX, 0, 0.0, k};
+  }
+  std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+    if (a.cy != b.cy) return a.cy < b.cy;
+    if (a.cx != b.cx) return a.cx < b.cx;
+    if (a.band != b.band) return a.band < b.band;
+    if (a.x != b.x) return a.x < b.x;
+    return a.k < b.k;
+  });
+  slot_of->assign((size_t)n, 0);
+  int64_t slot = 0;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    if (i > 0 && (keys[i].cy != keys[i - 1].cy || keys[i].cx != keys[i - 1].cx)) slot = (slot + 255) / 256 * 256;
+    (*slot_of)[(size_t)keys[i].k] = slot++;
+  }
+  return (slot + 255) / 256 * 256;
+}
+}  // namespace
+
+extern "C" {
+
+int coreg_hpc_search_host_multi(const int* devices, int n_devices, const void* large, int large_dtype, int lnx, int lny,
+                                const CoregTanWcs* wcs_large, const void* small, int small_dtype, int snx, int sny,
+                                const CoregTanWcs* wcs_small, const CoregTanWcs* lag_wcs, int64_t n_lags, int order,
+                                int flags, double* corr, int64_t* nvalid) {
+  if (!devices || n_devices <= 0) return fail(COREG_EINVAL, "coreg_hpc_search_host_multi: no device given");
+  if (!lag_wcs || !corr || n_lags <= 0) return fail(COREG_EINVAL, "coreg_hpc_search_host_multi: empty lag list");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  // contiguous equal slices of the flat lag list, like np.array_split over workers (hdrshift/alignment.py:677-687)
+  const int64_t chunk = (n_lags + n_devices - 1) / n_devices;
+  std::vector<int> rcs((size_t)n_devices, COREG_OK);
+  std::vector<std::string> msgs((size_t)n_devices);
+  std::vector<std::thread> workers;
+  for (int r = 0; r < n_devices; ++r) {
+    const int64_t lo = std::min<int64_t>(r * chunk, n_lags), hi = std::min<int64_t>((r + 1) * chunk, n_lags);
+    if (hi <= lo) continue;
+    workers.emplace_back([=, &rcs, &msgs]() {
+      cudaError_t e = cudaSetDevice(devices[r]);
+      int rc = (e == cudaSuccess) ? hpc_search_host_impl(large, large_dtype, lnx, lny, wcs_large, small, small_dtype,
+                                                         snx, sny, wcs_small, lag_wcs + lo, hi - lo, order, flags,
+                                                         corr + lo, nvalid ? nvalid + lo : nullptr)
+                                  : cuda_fail(e, "cudaSetDevice");
+      rcs[(size_t)r] = rc;
+      if (rc) msgs[(size_t)r] = coreg_last_error();   // the error string is per thread
+    });
+  }
+  for (auto& w : workers) w.join();
+  cudaSetDevice(prev);
+  for (int r = 0; r < n_devices; ++r)
+    if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "device slice failed: %s", msgs[(size_t)r].c_str());
+  return COREG_OK;
+}
+
+int coreg_carrington_search_host(const void* large, int large_dtype, int lnx, int lny, const CoregCarrington* c_large,
+                                 double x0_large, double y0_large, const void* small, int small_dtype, int snx, int sny,
+                                 const CoregCarrington* c_small, const double* sinlon_large, const double* coslon_large,
+                                 const double* sinlon_small, const double* coslon_small, int n_lon,
+                                 const double* sinlat, const double* coslat, int n_lat, const CoregLagOffset* lags,
+                                 int64_t n_lags, int order, int flags, double* corr, int64_t* nvalid) {
+  if (!large || !small || !c_large || !c_small || !sinlon_large || !coslon_large || !sinlon_small || !coslon_small ||
+      !sinlat || !coslat || !lags || !corr)
+    return fail(COREG_EINVAL, "coreg_carrington_search_host: null pointer");
+  if (lnx <= 0 || lny <= 0 || snx <= 0 || sny <= 0 || n_lon <= 0 || n_lat <= 0 || n_lags <= 0)
+    return fail(COREG_EINVAL, "coreg_carrington_search_host: empty input");
+  if ((large_dtype != COREG_F32 && large_dtype != COREG_F64) || (small_dtype != COREG_F32 && small_dtype != COREG_F64))
+    return fail(COREG_EINVAL, "coreg_carrington_search_host: dtype must be COREG_F32 or COREG_F64");
+  const int64_t ng = (int64_t)n_lon * n_lat, ns = (int64_t)snx * sny, nl = (int64_t)lnx * lny;
+  const size_t lsz = large_dtype == COREG_F32 ? 4 : 8, ssz = small_dtype == COREG_F32 ? 4 : 8;
+  // lags in detector-plane patches, padded with NaN dummies
+  std::vector<int64_t> slot_of;
+  const int64_t n_slots = patch_order_from_offsets(lags, n_lags, &slot_of);
+  std::vector<CoregLagOffset> padded((size_t)n_slots, CoregLagOffset{NAN, NAN});
+  for (int64_t k = 0; k < n_lags; ++k) padded[(size_t)slot_of[(size_t)k]] = lags[k];
+  const size_t work_bytes = coreg_lag_corr_workspace_bytes(n_lon, n_lat, n_slots);
+  DevBufs B;
+  cudaStream_t s = nullptr;
+  void *d_large, *d_small, *d_work, *d_scr;
+  double *d_vec, *d_tx, *d_ty, *d_ref, *d_stats, *d_corr;
+  int64_t* d_nv;
+  CoregLagOffset* d_lags;
+  HTRY(B.get(&d_large, nl * lsz));
+  HTRY(B.get(&d_small, ns * ssz));
+  HTRY(B.get(&d_vec, (size_t)(4 * n_lon + 2 * n_lat) * sizeof(double)));
+  HTRY(B.get(&d_tx, ng * sizeof(double)));
+  HTRY(B.get(&d_ty, ng * sizeof(double)));
+  HTRY(B.get(&d_ref, ng * sizeof(double)));
+  HTRY(B.get(&d_stats, 8 * sizeof(double)));
+  HTRY(B.get(&d_scr, coreg_image_stats_scratch_bytes()));
+  HTRY(B.get(&d_corr, n_slots * sizeof(double)));
+  HTRY(B.get(&d_nv, n_slots * sizeof(int64_t)));
+  HTRY(B.get(&d_lags, n_slots * sizeof(CoregLagOffset)));
+  HTRY(B.get(&d_work, work_bytes));
+  double *d_sll = d_vec, *d_cll = d_vec + n_lon, *d_sls = d_vec + 2 * n_lon, *d_cls = d_vec + 3 * n_lon,
+         *d_slat = d_vec + 4 * n_lon, *d_clat = d_vec + 4 * n_lon + n_lat;
+  HTRY(cudaMemcpyAsync(d_large, large, nl * lsz, cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_small, small, ns * ssz, cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_sll, sinlon_large, n_lon * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_cll, coslon_large, n_lon * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_sls, sinlon_small, n_lon * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_cls, coslon_small, n_lon * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_slat, sinlat, n_lat * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_clat, coslat, n_lat * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_lags, padded.data(), n_slots * sizeof(CoregLagOffset), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemsetAsync(d_scr, 0, coreg_image_stats_scratch_bytes(), s));
+  // one-time: large image -> Carrington grid, float64, fill -32762 -> NaN (alignment.py:646-648, 889-901)
+  HRC(coreg_carrington_planes(c_large, d_sll, d_cll, n_lon, d_slat, d_clat, n_lat, d_tx, d_ty, s));
+  shift_planes_kernel<<<grid_for(ng), 256, 0, s>>>(d_tx, d_ty, ng, x0_large, y0_large);
+  HRC(coreg_map_coordinates(d_large, large_dtype, lny, lnx, d_ty, d_tx, ng, order, -32762.0, d_ref, COREG_F64, s));
+  fill_to_nan_kernel<<<grid_for(ng), 256, 0, s>>>(d_ref, ng);
+  HTRY(cudaGetLastError());
+  // the small image's planes, pivots, search
+  HRC(coreg_carrington_planes(c_small, d_sls, d_cls, n_lon, d_slat, d_clat, n_lat, d_tx, d_ty, s));
+  HRC(coreg_image_stats(d_ref, COREG_F64, ng, nullptr, d_stats, 2, d_scr, s));
+  HRC(coreg_image_stats(d_small, small_dtype, ns, nullptr, d_stats + 1, 2, d_scr, s));
+  HRC(coreg_offset_lag_corr(d_ref, d_small, small_dtype, snx, sny, n_lon, n_lat, d_tx, d_ty, d_lags, n_slots, order,
+                            d_stats, d_work, work_bytes, d_corr, d_nv, flags, s));
+  std::vector<double> h_corr((size_t)n_slots);
+  std::vector<int64_t> h_nv((size_t)n_slots);
+  HTRY(cudaMemcpyAsync(h_corr.data(), d_corr, n_slots * sizeof(double), cudaMemcpyDeviceToHost, s));
+  HTRY(cudaMemcpyAsync(h_nv.data(), d_nv, n_slots * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  HTRY(cudaStreamSynchronize(s));
+  for (int64_t k = 0; k < n_lags; ++k) {
+    corr[k] = h_corr[(size_t)slot_of[(size_t)k]];
+    if (nvalid) nvalid[k] = h_nv[(size_t)slot_of[(size_t)k]];
+  }
+  return COREG_OK;
+}
+
+int coreg_synras_build_host(const void* frames, int frame_dtype, int n_frames, int fnx, int fny, const CoregTanWcs* wcs,
+                            const int* frame_of_col, const double* lng, const double* lat, int n_rows, int n_cols,
+                            int order, double* out) {
+  if (!frames || !wcs || !frame_of_col || !lng || !lat || !out)
+    return fail(COREG_EINVAL, "coreg_synras_build_host: null pointer");
+  if (n_frames <= 0 || fnx <= 0 || fny <= 0 || n_rows <= 0 || n_cols <= 0)
+    return fail(COREG_EINVAL, "coreg_synras_build_host: empty input");
+  if (frame_dtype != COREG_F32 && frame_dtype != COREG_F64)
+    return fail(COREG_EINVAL, "coreg_synras_build_host: frame_dtype must be COREG_F32 or COREG_F64");
+  const size_t fsz = frame_dtype == COREG_F32 ? 4 : 8;
+  const int64_t n = (int64_t)n_rows * n_cols;
+  DevBufs B;
+  cudaStream_t s = nullptr;
+  void* d_frames;
+  double *d_lng, *d_lat, *d_out;
+  HTRY(B.get(&d_frames, (size_t)n_frames * fnx * fny * fsz));
+  HTRY(B.get(&d_lng, n * sizeof(double)));
+  HTRY(B.get(&d_lat, n * sizeof(double)));
+  HTRY(B.get(&d_out, n * sizeof(double)));
+  HTRY(cudaMemcpyAsync(d_frames, frames, (size_t)n_frames * fnx * fny * fsz, cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_lng, lng, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_lat, lat, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  HRC(coreg_synras_build(d_frames, frame_dtype, n_frames, fnx, fny, wcs, frame_of_col, d_lng, d_lat, n_rows, n_cols,
+                         order, d_out, s));
+  HTRY(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  HTRY(cudaStreamSynchronize(s));
+  return COREG_OK;
 }
 
 }  // extern "C"

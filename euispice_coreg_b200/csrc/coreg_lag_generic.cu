@@ -184,7 +184,6 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
   if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
   if (gnx <= 0 || gny <= 0 || snx <= 0 || sny <= 0) return fail(COREG_EINVAL, "empty image");
   if ((int64_t)snx * sny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
-  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
   int sms = coreg_device_sm_count();
   if (sms <= 0) sms = 148;
   const bool strict = (flags & COREG_FLAG_STRICT) != 0;
@@ -193,6 +192,8 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
   // window kernel for the offset (Carrington) functor: order 2, FMA arithmetic, image of at least 3x3
   const bool fast_ok = std::is_same<Coord, OffsetCoord>::value && (order == 2) && !strict && snx >= 3 && sny >= 3 &&
                        !(flags & COREG_FLAG_NO_FAST);
+  if (work_bytes < (fast_ok ? offset_workspace_bytes(gnx, gny, n_lags) : coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)))
+    return fail(COREG_ENOMEM, "workspace too small");
   if constexpr (std::is_same<Coord, OffsetCoord>::value) {
     if (fast_ok)
       return launch_offset_fast(gnx, gny, n_lags, s, ref, small, sizeof(SmallT) == 4 ? COREG_F32 : COREG_F64, snx, sny,
@@ -231,6 +232,11 @@ int launch_lag_corr(const RefT* ref, const SmallT* small, int snx, int sny, int 
 using namespace coreg;
 
 extern "C" {
+
+size_t coreg_offset_window_workspace_bytes(int gnx, int gny, int64_t n_lags) {
+  if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;
+  return offset_workspace_bytes(gnx, gny, n_lags);
+}
 
 size_t coreg_lag_corr_workspace_bytes(int gnx, int gny, int64_t n_lags) {
   if (gnx <= 0 || gny <= 0 || n_lags <= 0) return 0;

@@ -243,7 +243,7 @@ __device__ __forceinline__ void offset_walk_window(unsigned win, int lo_x, int l
                                                    const T* __restrict__ small, int snx, int sny, unsigned px,
                                                    int n_live, double x0h, double y0h, double pivot_b, double& sb,
                                                    double& sbb, double& sab, int& n_miss, double& sa_miss,
-                                                   double& saa_miss) {
+                                                   double& saa_miss, int& n_out, int& n_exact) {
   constexpr int ROW = OffBox<T>::W * (int)sizeof(T), E = (int)sizeof(T);
 #pragma unroll 2
   for (int k = 0; k < n_live; ++k, px += (unsigned)sizeof(OffPx)) {
@@ -273,7 +273,14 @@ __device__ __forceinline__ void offset_walk_window(unsigned win, int lo_x, int l
       v = fma(r2, wy2, fma(r1, wy1, r0 * wy0));
       ok = true;
       if (CHECK) ok = (((unsigned)__double2hiint(v) & 0x7FF00000u) != 0x7FF00000u) && (v != -32762.0);
+    } else if ((sx < 0.5) || (sx > (double)snx - 0.5) || (sy < 0.5) || (sy > (double)sny - 0.5)) {
+      // outside the image: exactly the closed-bound test 0 <= x <= n - 1 of the sampler on x = sx - 0.5 (the
+      // subtraction is exact), without the call -- the common case on tiles at the rim of the small image's footprint
+      ok = false;
+      v = 0.0;
+      ++n_out;
     } else {
+      ++n_exact;
       ok = spline_sample<2, false, T>(small, sny, snx, sy - 0.5, sx - 0.5, v);
       // finite and not the -32762 fill (`np.where(image == -32762, nan, image)`, alignment.py:900-901)
       ok = ok && (((unsigned)__double2hiint(v) & 0x7FF00000u) != 0x7FF00000u) && (v != -32762.0);
@@ -502,19 +509,24 @@ offset_window_kernel(const __grid_constant__ CUtensorMap tmap, int use_tma, cons
       }
       dirty = __syncthreads_or(dirty);   // also: table complete, cooperative copy (if any) complete
       if (lag_ok) {
-        int n_miss = 0;
+        int n_miss = 0, n_out = 0, n_exact = 0;
         double sa_miss = 0.0, saa_miss = 0.0, tsb = 0.0, tsbb = 0.0, tsab = 0.0;
         if (fits) {
           const unsigned win = smem_u32(s_win) + (unsigned)base_off * (unsigned)sizeof(T);
           if (dirty)
             offset_walk_window<T, true>(win, lo_x, lo_y, span_x, span_y, small, snx, sny, smem_u32(s_px), n_live, x0h,
-                                        y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+                                        y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss, n_out, n_exact);
           else
             offset_walk_window<T, false>(win, lo_x, lo_y, span_x, span_y, small, snx, sny, smem_u32(s_px), n_live, x0h,
-                                         y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss);
+                                         y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss, saa_miss, n_out, n_exact);
         } else {
           offset_walk_global<T>(small, snx, sny, s_px, n_live, x0h, y0h, pivot_b, tsb, tsbb, tsab, n_miss, sa_miss,
                                 saa_miss);
+        }
+        if (stats != nullptr) {
+          atomicAdd(stats + 5, (unsigned long long)n_out);
+          atomicAdd(stats + 6, (unsigned long long)n_exact);
+          atomicAdd(stats + 7, (unsigned long long)(dirty ? 1 : 0));
         }
         // per tile, so that a tile this lag cannot reach adds exactly nothing -- whether the block skipped it for
         // the whole chunk or walked it for the sake of other lags (sharding-invariant partials)
@@ -646,9 +658,10 @@ static int launch_offset_window(int gnx, int gny, int64_t n_lags, cudaStream_t s
     CK(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaFreeAsync(stats, s));
-    fprintf(stderr, "[coreg offset kernel] tma=%d (tile, chunk) pairs: %llu staged, %llu global; %llu live pixel-walks; "
-            "largest window asked for %llu x %llu (box %d x %d)\n", use_tma, h[0], h[1], h[2], h[3], h[4], OffBox<T>::W,
-            OffBox<T>::H);
+    fprintf(stderr, "[coreg offset kernel] tma=%d lags=%lld (tile, chunk) pairs: %llu staged, %llu global; %llu live "
+            "pixel-walks (x 256 lanes); samples outside the image %llu, exact-path %llu; lane-tiles on a dirty window "
+            "%llu; largest window asked for %llu x %llu (box %d x %d)\n", use_tma, (long long)n_lags, h[0], h[1], h[2],
+            h[5], h[6], h[7], h[3], h[4], OffBox<T>::W, OffBox<T>::H);
   }
   if (prof) {
     CK(cudaEventRecord(g_prof[g_prof_n].b, s));

@@ -160,6 +160,8 @@ def offset_patch_order(i1, i2, group=None, patch=(16, 16), sub=(16, 2)):
     i1 = np.asarray(i1, dtype=np.int64)
     i2 = np.asarray(i2, dtype=np.int64)
     g = np.zeros_like(i1) if group is None else np.asarray(group, dtype=np.int64)
+    if i1.size:      # patches start at the list's own first indices: a rank's slice of the grid gets no ragged leading patch
+        i1, i2 = i1 - i1.min(), i2 - i2.min()
     p1, p2 = i1 // patch[0], i2 // patch[1]
     q1, q2 = i1 % patch[0], i2 % patch[1]
     s1, s2 = q1 // sub[0], q2 // sub[1]
@@ -246,6 +248,7 @@ class LagSearchEngine:
         self.stats = torch.zeros((_ext.STATS_ROWS, 2), dtype=torch.float64, device=self.device)
         self.pivots = self.stats[0]
         self.ref = None        # large image on the common grid
+        self.frame = None      # "hpc" | "car" | "carrington", set by the prepare_* call
         self.small = None
         self.planes = None     # TAN: [3, gny, gnx]; Carrington: (tx, ty)
         self._work = None
@@ -469,13 +472,17 @@ class LagSearchEngine:
         return (np.sin(lon_r), np.cos(lon_r),
                 np.sin(lat_r).astype(np.float64), np.cos(lat_r).astype(np.float64))
 
+    @staticmethod
+    def carrington_struct(hdr, d_solar_r):
+        """`CoregCarrington` of one header: the constants of `CarringtonTransform.__init__` (`utils/rectify.py:377-415`)."""
+        roll_deg = hdr["CROTA"] if "CROTA" in hdr else hdr["CROTA2"]
+        return _ext.CoregCarrington(float(np.radians(hdr["CRLN_OBS"])), float(np.radians(hdr["CRLT_OBS"])),
+                                    float(np.radians(roll_deg)), float(hdr["DSUN_OBS"] / (d_solar_r * R_SUN_M)),
+                                    float(hdr["CDELT1"]), float(hdr["CDELT2"]))
+
     def carrington_planes(self, hdr, d_solar_r, lonlims, latlims, shape):
         """(tx, ty) detector-plane planes of one header on the Carrington grid (K5 coordinates)."""
-        roll_deg = hdr["CROTA"] if "CROTA" in hdr else hdr["CROTA2"]
-        c = _ext.CoregCarrington(float(np.radians(hdr["CRLN_OBS"])), float(np.radians(hdr["CRLT_OBS"])),
-                                 float(np.radians(roll_deg)),
-                                 float(hdr["DSUN_OBS"] / (d_solar_r * R_SUN_M)),
-                                 float(hdr["CDELT1"]), float(hdr["CDELT2"]))
+        c = self.carrington_struct(hdr, d_solar_r)
         vec = self.carrington_vectors(lonlims, latlims, shape, hdr["CRLN_OBS"])
         sinlon, coslon, sinlat, coslat = (self._upload(v) for v in vec)
         return _ext.carrington_planes(c, sinlon, coslon, sinlat, coslat)
@@ -506,9 +513,15 @@ class LagSearchEngine:
         self.frame = "carrington"
 
     # ---- evaluation ------------------------------------------------------------------------------------
+    def _offset_window(self):
+        """The Carrington-frame window kernel applies (order 2, FMA arithmetic): its workspace is a quarter of the
+        general one."""
+        return self.frame == "carrington" and self.order == 2 and not self.strict and not self.no_fast \
+            and self.small is not None and min(self.small.shape) >= 3
+
     def _workspace(self, gnx, gny, n_lags):
         torch = _torch()
-        need = _ext.lag_corr_workspace_bytes(gnx, gny, n_lags)
+        need = _ext.lag_corr_workspace_bytes(gnx, gny, n_lags, self._offset_window())
         if self._work is None or self._work.numel() * 8 < need:
             self._work = None
             self._work = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
@@ -517,8 +530,9 @@ class LagSearchEngine:
     def lags_per_launch(self, gnx, gny):
         """Largest multiple of 256 lags whose workspace fits `max_workspace_bytes` (the size is affine in the lags;
         256 = `OFFSET_CHUNK`: a launch boundary must not cut a patch of the Carrington-frame lag order)."""
-        fixed = _ext.lag_corr_workspace_bytes(gnx, gny, 1)
-        per_lag = max(1, (_ext.lag_corr_workspace_bytes(gnx, gny, 1025) - fixed) // 1024)
+        ow = self._offset_window()
+        fixed = _ext.lag_corr_workspace_bytes(gnx, gny, 1, ow)
+        per_lag = max(1, (_ext.lag_corr_workspace_bytes(gnx, gny, 1025, ow) - fixed) // 1024)
         return max(OFFSET_CHUNK, ((self.max_workspace_bytes - fixed) // per_lag) // OFFSET_CHUNK * OFFSET_CHUNK)
 
     def evaluate(self, table_dev, out_dev, nvalid_dev=None, planes=None, allow_mixed=True):

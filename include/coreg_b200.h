@@ -259,6 +259,13 @@ int coreg_carrington_planes(const CoregCarrington* c_host, const double* sinlon_
  * hdrshift/alignment.py:509-542, 889-901; utils/rectify.py:865-888. ref is float64 here (the reference keeps the
  * Carrington-projected large image in float64), samples are NOT rounded to float32, and a sample equal to -32762
  * is treated as missing, like `np.where(image == -32762, nan, image)`. */
+/* Workspace: coreg_lag_corr_workspace_bytes always suffices; order 2 without COREG_FLAG_STRICT / COREG_FLAG_NO_FAST (the
+ * window kernel: one 64-byte partial per 32 x 64-pixel super-tile and lag) needs only
+ * coreg_offset_window_workspace_bytes, about a quarter of it -- more lags per launch for the same memory. That kernel
+ * serves 256 consecutive lags per block from one staged window of the small image: hand the lags over so that
+ * consecutive ones are neighbours in the detector plane (e.g. 16 x 16 patches of the CRVAL grid, padded with NaN
+ * dummies; `engine.offset_patch_order`), or it falls back to global loads. */
+size_t coreg_offset_window_workspace_bytes(int gnx, int gny, int64_t n_lags);
 int coreg_offset_lag_corr(const double* ref_dev, const void* small_dev, int small_dtype, int snx, int sny, int gnx,
                           int gny, const double* tx_dev, const double* ty_dev, const CoregLagOffset* lags_dev,
                           int64_t n_lags, int order, const double* pivots_dev, void* work_dev, size_t work_bytes,
@@ -320,6 +327,48 @@ int coreg_hpc_search_host(const void* large_host, int large_dtype, int lnx, int 
                           const void* small_host, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,
                           const CoregTanWcs* lag_wcs_host, int64_t n_lags, int order, int flags, double* corr_host,
                           int64_t* nvalid_host);
+
+/* ---- the same search over several GPUs of one process ---------------------------------------------------------------
+ * The reference spreads `np.array_split` chunks of the flat lag list over `multiprocessing.Process` workers
+ * (hdrshift/alignment.py:667-744); here the chunks go to `n_devices` GPUs: one host thread per device, every device
+ * holds both images and evaluates a contiguous slice of the lag list (ceil(n_lags / n_devices) lags each), the slices
+ * land in corr_host / nvalid_host directly -- the gather is the host buffer. The cube is bit-identical to
+ * coreg_hpc_search_host's for any device list (a device may be named more than once). Other arguments as there.
+ * (Under torch.distributed the Python engine does the same with one process per GPU and one NCCL all-gather.) */
+int coreg_hpc_search_host_multi(const int* devices_host, int n_devices, const void* large_host, int large_dtype, int lnx,
+                                int lny, const CoregTanWcs* wcs_large, const void* small_host, int small_dtype, int snx,
+                                int sny, const CoregTanWcs* wcs_small, const CoregTanWcs* lag_wcs_host, int64_t n_lags,
+                                int order, int flags, double* corr_host, int64_t* nvalid_host);
+
+/* ---- whole Carrington-frame search from HOST buffers -------------------------------------------------------------------
+ * Replaces Alignment._find_best_header_parameters as driven by align_using_carrington(method_carrington_reprojection=
+ * "fa") for CRVAL lags (hdrshift/alignment.py:144-261 -- the seam is the call at :237 --, 613-797, 889-901;
+ * utils/rectify.py:377-423, 865-888): the large image is projected once onto the Carrington grid (float64, order-k
+ * spline, fill -32762 -> NaN), then every lag's projection of the small image is correlated with it.
+ *   c_large / c_small       per-image constants (CoregCarrington); x0_large, y0_large: the large header's detector
+ *                           offset (`CarringtonTransform.__init__`, utils/rectify.py:394-404)
+ *   sinlon_* / coslon_*     [n_lon] per image, sinlat / coslat [n_lat]: the float32 half of the Rectifier grid evaluated
+ *                           by the host exactly as documented at coreg_carrington_planes
+ *   lags_host               [n_lags] CoregLagOffset: x0, y0 of the small header under each CRVAL lag (same formula)
+ *   order 2 without COREG_FLAG_STRICT / COREG_FLAG_NO_FAST runs the window kernel (the entry orders the lags into
+ *   detector-plane patches itself), anything else the generic kernel. corr_host / nvalid_host: [n_lags] in the
+ *   caller's lag order. */
+int coreg_carrington_search_host(const void* large_host, int large_dtype, int lnx, int lny,
+                                 const CoregCarrington* c_large, double x0_large, double y0_large,
+                                 const void* small_host, int small_dtype, int snx, int sny,
+                                 const CoregCarrington* c_small, const double* sinlon_large_host,
+                                 const double* coslon_large_host, const double* sinlon_small_host,
+                                 const double* coslon_small_host, int n_lon, const double* sinlat_host,
+                                 const double* coslat_host, int n_lat, const CoregLagOffset* lags_host, int64_t n_lags,
+                                 int order, int flags, double* corr_host, int64_t* nvalid_host);
+
+/* ---- synthetic raster from HOST buffers ----------------------------------------------------------------------------------
+ * coreg_synras_build with the frame stack, the slit's sky coordinates and the raster in host memory: what
+ * SPICEComposedMapBuilder.process -> _create_map_from_hdu computes between reading the imager files and writing the
+ * composed FITS (synras/map_builder.py:57-79, 95-131). Arguments as coreg_synras_build. */
+int coreg_synras_build_host(const void* frames_host, int frame_dtype, int n_frames, int fnx, int fny,
+                            const CoregTanWcs* wcs_host, const int* frame_of_col_host, const double* lng_host,
+                            const double* lat_host, int n_rows, int n_cols, int order, double* out_host);
 
 /* Measurement hooks (bench.py): between begin and end every fused lag-kernel launch made by the calling thread is
  * bracketed by a CUDA event pair on its own stream; end() synchronises on them and returns the summed device time

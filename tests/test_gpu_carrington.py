@@ -125,3 +125,31 @@ def test_window_kernel_far_apart_lags_take_the_global_path(torch_cuda, toy_pair)
     lags = dict(LAGS, lag_crval1=np.arange(-36, 85, 30.0), lag_crval2=np.arange(-54, 67, 30.0))
     gpu, ref, _, _ = _both(toy_pair, lags, dict(lonlims=(244.0, 256.0), latlims=(-8.0, 4.0), shape=(130, 90)))
     assert _assert_parity(gpu, ref) < 1e-9
+
+
+def test_carrington_host_buffer_entry_point_matches_public_api(torch_cuda, toy_pair):
+    """coreg_carrington_search_host (the call a non-Python host makes at the seam `alignment.py:237`): host images,
+    per-header constants and the (x0, y0) offsets of the CRVAL lags in, cube out -- the same bits as the public API
+    (it orders the lags into detector-plane patches by itself)."""
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200.hdrshift import Alignment, engine
+    lags = dict(LAGS, lag_crval1=np.arange(10, 38, 1.0), lag_crval2=np.arange(-6, 18, 1.0))
+    grid = dict(lonlims=(246.0, 254.0), latlims=(-6.0, 2.0), shape=(150, 170))
+    a = Alignment(toy_pair[0], toy_pair[1], parallelism=True, **lags)
+    cube = a.align_using_carrington(method="correlation", return_type="corr", **grid)
+    dl, hl, ds, hs = load_pair(*toy_pair[:2])
+    E = engine.LagSearchEngine
+    r_sun = float(a.lag_solar_r[0])
+    hdr_l, hdr_s = a.hdr_large, a.hdr_small        # with the PCi_j / CROTA checks applied
+    roll_l = hdr_l["CROTA"] if "CROTA" in hdr_l else hdr_l["CROTA2"]
+    roll_s = hdr_s["CROTA"] if "CROTA" in hdr_s else hdr_s["CROTA2"]
+    d1, d2, _, _, _ = engine.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
+    x0, y0 = E.carrington_offset(hdr_s, a.crval1_ref + d1, a.crval2_ref + d2, roll_s)
+    corr, nvalid = _ext.carrington_search_host(
+        dl, E.carrington_struct(hdr_l, r_sun), E.carrington_offset(hdr_l, hdr_l["CRVAL1"], hdr_l["CRVAL2"], roll_l), ds,
+        E.carrington_struct(hdr_s, r_sun), E.carrington_vectors(grid["lonlims"], grid["latlims"], grid["shape"],
+                                                                hdr_l["CRLN_OBS"]),
+        E.carrington_vectors(grid["lonlims"], grid["latlims"], grid["shape"], hdr_s["CRLN_OBS"]),
+        np.stack([x0, y0], axis=1))
+    assert np.array_equal(corr.reshape(cube.shape), cube, equal_nan=True)
+    assert np.array_equal(nvalid.reshape(a.nvalid.shape), a.nvalid)

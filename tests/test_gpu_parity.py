@@ -347,6 +347,29 @@ def test_host_buffer_entry_point_matches_device_path(torch_cuda, toy_pair):
     assert np.array_equal(corr_d, corr)
 
 
+def test_multi_device_host_entry_point_gives_the_same_cube(torch_cuda, toy_pair):
+    """coreg_hpc_search_host_multi: one host thread per listed device, contiguous slices of the lag list, slices
+    gathered in the host buffer. Listing the one GPU of the test box three times exercises the slicing and the
+    threads; the cube has the bits of the single-device entry (it does for any device list)."""
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    from euispice_coreg_b200.hdrshift import engine
+    gpu, a = _gpu_cube(toy_pair, arithmetic="fp64", **LAGS)
+    dl, hl, ds, hs = load_pair(*toy_pair[:2])
+    d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], [0.0])
+    w_small = TanWcs.from_header(a.hdr_small)
+    table, _ = engine.tan_wcs_table(a.hdr_small, a, *d)
+    flags = _ext.make_flags(variant=1)
+    one, nv_one = _ext.hpc_search_host(dl, TanWcs.from_header(hl), ds, w_small, table, flags=flags)
+    n_dev = torch_cuda.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(n_dev)), [0] * 30):      # 30 devices for 25 lags: empty slices
+        corr, nvalid = _ext.hpc_search_host_multi(devices, dl, TanWcs.from_header(hl), ds, w_small, table, flags=flags)
+        assert np.array_equal(corr, one, equal_nan=True) and np.array_equal(nvalid, nv_one)
+    assert np.array_equal(one.reshape(gpu.shape), gpu)
+    with pytest.raises(_ext.CoregLibraryError):
+        _ext.hpc_search_host_multi([99], dl, TanWcs.from_header(hl), ds, w_small, table, flags=flags)
+
+
 def test_results_and_written_header_match_oracle_cube(torch_cuda, toy_pair, tmp_path):
     """Parity policy of SURVEY 8c(iii): both cubes through the same host post-processing."""
     from euispice_coreg_b200._compat import fits_lite

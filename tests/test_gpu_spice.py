@@ -166,3 +166,34 @@ def test_alignment_spice_parity_and_recovers_shift(spice_case, tmp_path):
     img2, _ = spice_l2_image(d4, h4, (97.68, 97.72))
     assert np.nanmax(np.abs(img2 - a2.data_small)) == 0.0 and not np.array_equal(img2, img, equal_nan=True)
     assert abs(res.shift_arcsec[0] - spec.true_shift[0]) < 2.0 and abs(res.shift_arcsec[1] - spec.true_shift[1]) < 2.0
+
+
+def test_synras_host_buffer_entry_point_matches_device_entry():
+    """coreg_synras_build_host (frame stack, slit coordinates and raster in host memory: the body of
+    `SPICEComposedMapBuilder.process`, synras/map_builder.py:57-79, 95-131) == coreg_synras_build on device tensors."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    rng = np.random.default_rng(11)
+    frames = rng.lognormal(5, 1, (3, 64, 80)).astype(np.float32)
+    frames[1, 10, 12] = np.nan
+
+    def hdr(crval, crota):
+        rho = np.deg2rad(crota)
+        return {"NAXIS1": 80, "NAXIS2": 64, "CTYPE1": "HPLN-TAN", "CTYPE2": "HPLT-TAN", "CUNIT1": "arcsec",
+                "CUNIT2": "arcsec", "CRPIX1": 40.5, "CRPIX2": 32.5, "CDELT1": 4.4, "CDELT2": 4.4, "CRVAL1": crval[0],
+                "CRVAL2": crval[1], "PC1_1": np.cos(rho), "PC1_2": -np.sin(rho), "PC2_1": np.sin(rho),
+                "PC2_2": np.cos(rho), "LONPOLE": 180.0}
+
+    wcs = [TanWcs.from_header(hdr((10.0 * k, -5.0 * k), 2.0 + k)) for k in range(3)]
+    yy, xx = np.meshgrid(np.linspace(-3, 66, 45), np.linspace(-4, 83, 12), indexing="ij")
+    lng, lat = wcs[0].pixel_to_world(xx, yy)
+    cols = [0, 1, 2, -1, 2, 1, 0, 0, 1, 2, 2, 1]
+    for order in (1, 2):
+        host = _ext.synras_build_host(frames, wcs, cols, lng, lat, order)
+        dev = _ext.synras_build(torch.from_numpy(frames).cuda(), wcs, cols, torch.from_numpy(np.ascontiguousarray(lng)).cuda(),
+                                torch.from_numpy(np.ascontiguousarray(lat)).cuda(), order).cpu().numpy()
+        assert host.shape == (45, 12) and np.array_equal(host, dev, equal_nan=True)
+        assert np.isnan(host[:, 3]).all() and np.isfinite(host).any()
