@@ -236,11 +236,12 @@ class ImageHDU:
     @classmethod
     def _from_file(cls, raw, header, bscale, bzero):
         h = cls(None, header)
-        h._raw = (raw, bscale, bzero)
+        blank = header.get("BLANK", None) if raw.dtype.kind in "iu" else None
+        h._raw = (raw, bscale, bzero) if blank is None else (raw, bscale, bzero, int(blank))
         return h
 
     @staticmethod
-    def _convert(arr, bscale, bzero):
+    def _convert(arr, bscale, bzero, blank=None):
         """Stored (big-endian) values -> what `astropy.io.fits` returns as `.data`."""
         dt = arr.dtype
         scaled = float(bscale) != 1.0 or float(bzero) != 0.0
@@ -250,7 +251,10 @@ class ImageHDU:
             # same promotion rule as astropy: <=16-bit ints -> float32, everything else float64
             out_dt = np.float32 if (dt.kind in "iu" and dt.itemsize <= 2) or dt.itemsize == 4 and dt.kind == "f" \
                 else np.float64
-            return arr.astype(out_dt) * out_dt(bscale) + out_dt(bzero)
+            out = arr.astype(out_dt) * out_dt(bscale) + out_dt(bzero)
+            if blank is not None:         # astropy: BLANK pixels of an integer image that is scaled to float are NaN
+                out[arr == blank] = np.nan
+            return out
         return arr.astype(dt.newbyteorder("="))
 
     @property
@@ -276,7 +280,7 @@ class ImageHDU:
         values (BITPIX -32 / -64, no BSCALE / BZERO); None otherwise or once `.data` has been materialised."""
         if self._raw is None:
             return None
-        raw, bscale, bzero = self._raw
+        raw, bscale, bzero = self._raw[:3]
         if raw.dtype.kind != "f" or float(bscale) != 1.0 or float(bzero) != 0.0:
             return None
         return raw
@@ -284,8 +288,7 @@ class ImageHDU:
     def read_window(self, y0, y1, x0, x1):
         """`.data[y0:y1, x0:x1]` (2-D images) without converting the rest of the image."""
         if self._raw is not None and self._raw[0].ndim == 2:
-            raw, bscale, bzero = self._raw
-            return self._convert(raw[y0:y1, x0:x1], bscale, bzero)
+            return self._convert(self._raw[0][y0:y1, x0:x1], *self._raw[1:])
         return np.array(self.data[y0:y1, x0:x1])
 
     @property
@@ -408,10 +411,48 @@ class CompImageHDU:
         o, code, sub, _ = cols["COMPRESSED_DATA"]
         dsc = np.ascontiguousarray(table[:, o:o + (8 if code == "P" else 16)]).view(">i4" if code == "P" else ">i8")
         counts, offsets = dsc[:, 0].astype(np.int64), dsc[:, 1].astype(np.int64)
-        if np.any(counts <= 0):
-            raise NotImplementedError("tiles stored uncompressed / gzip-compressed (empty COMPRESSED_DATA rows)")
         zbitpix = int(th["ZBITPIX"])
         is_float = zbitpix < 0
+        # tiles cfitsio could not quantise / compress carry an empty COMPRESSED_DATA descriptor and their pixels in
+        # GZIP_COMPRESSED_DATA (gzip of the big-endian values) or UNCOMPRESSED_DATA: decoded here on the host and
+        # patched into the device image below (the RICE kernel sees an empty stream for them)
+        fallback = {}
+        if np.any(counts <= 0):
+            import zlib
+            pix_dt = np.dtype({-32: ">f4", -64: ">f8", 8: "u1", 16: ">i2", 32: ">i4"}[zbitpix])
+            tiles_x = (nx + tw - 1) // tw
+
+            def var_column(name):
+                o2, code2, sub2, _ = cols[name]
+                d2 = np.ascontiguousarray(table[:, o2:o2 + (8 if code2 == "P" else 16)]).view(
+                    ">i4" if code2 == "P" else ">i8")
+                return d2[:, 0].astype(np.int64), d2[:, 1].astype(np.int64), sub2
+
+            alt = {k: var_column(k) for k in ("GZIP_COMPRESSED_DATA", "UNCOMPRESSED_DATA") if k in cols}
+            for row in np.nonzero(counts <= 0)[0]:
+                x0, y0 = (row % tiles_x) * tw, (row // tiles_x) * tht
+                w_, h_ = min(tw, nx - x0), min(tht, ny - y0)
+                vals = None
+                if "GZIP_COMPRESSED_DATA" in alt and alt["GZIP_COMPRESSED_DATA"][0][row] > 0:
+                    c, o2, _ = alt["GZIP_COMPRESSED_DATA"]
+                    raw = zlib.decompress(bytes(heap[o2[row]:o2[row] + c[row]]), 15 + 32)
+                    vals = np.frombuffer(raw, dtype=pix_dt, count=w_ * h_)
+                elif "UNCOMPRESSED_DATA" in alt and alt["UNCOMPRESSED_DATA"][0][row] > 0:
+                    c, o2, sub2 = alt["UNCOMPRESSED_DATA"]
+                    el = np.dtype({"E": ">f4", "D": ">f8", "J": ">i4", "I": ">i2", "B": "u1"}[sub2])
+                    vals = np.frombuffer(bytes(heap[o2[row]:o2[row] + c[row] * el.itemsize]), dtype=el, count=w_ * h_)
+                if vals is None:
+                    raise OSError(f"tile {row}: no COMPRESSED_DATA, GZIP_COMPRESSED_DATA or UNCOMPRESSED_DATA payload")
+                fallback[(int(y0), int(x0))] = vals.reshape(h_, w_)
+            counts = np.maximum(counts, 0)
+            offsets = np.where(counts > 0, offsets, 0)
+
+        def patch(dev):
+            for (y0, x0), tile in fallback.items():
+                t = torch.from_numpy(np.ascontiguousarray(tile.astype(tile.dtype.newbyteorder("="))))
+                dev[y0:y0 + tile.shape[0], x0:x0 + tile.shape[1]] = t.to(dev.device).to(dev.dtype)
+            return dev
+
         from .. import _ext   # device decode: the CUDA library is required (no host fallback)
         torch = _ext._torch()
         if not torch.cuda.is_available():
@@ -431,10 +472,10 @@ class CompImageHDU:
                 else:
                     raise NotImplementedError("per-tile ZBLANK values")
             odt = out_dtype or (torch.float32 if zbitpix == -32 else torch.float64)
-            dev = _ext.rice_decode(heap, offsets, counts, tw, tht, nx, ny, blocksize, bytepix, zscale, zzero, method,
-                                   int(th.get("ZDITHER0", 1)), blank, odt)
+            dev = patch(_ext.rice_decode(heap, offsets, counts, tw, tht, nx, ny, blocksize, bytepix, zscale, zzero,
+                                         method, int(th.get("ZDITHER0", 1)), blank, odt))
             return dev if as_device else dev.cpu().numpy()
-        dev = _ext.rice_decode(heap, offsets, counts, tw, tht, nx, ny, blocksize, bytepix)
+        dev = patch(_ext.rice_decode(heap, offsets, counts, tw, tht, nx, ny, blocksize, bytepix))
         if as_device:
             return dev
         arr = dev.cpu().numpy().astype({8: np.uint8, 16: np.int16, 32: np.int32}[zbitpix])

@@ -453,7 +453,7 @@ class Alignment:
             self.hdr_large = self.hdr_small.copy()   # alignment.py:1000
             table, dead = eng.hpc_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, self.cdelt_semantics)
             if self.lag_search == "coarse_to_fine":
-                corr, nvalid = self._coarse_to_fine(eng, table, shape5, w_large)
+                corr, nvalid = self._coarse_to_fine(eng, table, shape5, w_large, dead)
             else:
                 corr, nvalid = eng.search(table, return_nvalid=True)
                 self.lags_evaluated = int(table.shape[0])
@@ -489,9 +489,12 @@ class Alignment:
         self.data_large = None
         return cube
 
-    def _coarse_to_fine(self, eng, table, shape5, w_large):
+    def _coarse_to_fine(self, eng, table, shape5, w_large, dead=None):
         """Sub-lattice pass over the CRVAL1 x CRVAL2 plane, then dense windows around the running maximum (SURVEY.md
-        section 8f-3). Returns (corr, nvalid) over the full flat lag list, NaN / 0 where nothing was evaluated."""
+        section 8f-3). Returns (corr, nvalid) over the full flat lag list, NaN / 0 where nothing was evaluated. The
+        window follows the GLOBAL maximum over all CDELT / CROTA slices; lags the reference cannot evaluate (`dead`:
+        they read 0.0 in the final cube) never steer it; when no coarse lag yields a coefficient (no overlap, no valid
+        pixel) the search stops there and the cube is NaN where nothing could be computed, like the dense search's."""
         n1, n2 = shape5[0], shape5[1]
         rest = int(np.prod(shape5[2:]))
         stride = self.coarse_stride
@@ -521,7 +524,10 @@ class Alignment:
         evaluate(coarse)
         half = stride + 2
         for _ in range(8):
-            best = np.unravel_index(np.nanargmax(corr), (n1, n2, rest))[:2]
+            score = corr if dead is None else np.where(dead, np.nan, corr)
+            if np.isnan(score).all():
+                break
+            best = np.unravel_index(np.nanargmax(score), (n1, n2, rest))[:2]
             lo1, hi1 = max(0, best[0] - half), min(n1, best[0] + half + 1)
             lo2, hi2 = max(0, best[1] - half), min(n2, best[1] + half + 1)
             win = np.zeros((n1, n2), dtype=bool)

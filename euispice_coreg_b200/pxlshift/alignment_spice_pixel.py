@@ -64,7 +64,10 @@ class AlignmentSpicePixel(AlignmentPixels):
         print(f'Corrected solar rotation : changed SPICE CDELT1 from {dtx_old} {unit} to {dtx_new} {unit}')
 
     def _prepare_spice_from_l2(self, hdu):
-        """`pxlshift/alignment_spice_pixel.py:65-87`: spectral sum of the rows inside the slit, 2-D celestial header."""
+        """`pxlshift/alignment_spice_pixel.py:65-87`: spectral sum of the rows inside the slit, 2-D celestial header.
+        (The reference also calls `AlignSpiceUtil.recenter_crpix_in_header_L2` at :68 and
+        `AlignEUIUtil.recenter_crpix_in_header` at :77; both are `pass` in v0.4.0 -- `utils/Util.py:348-349, 565-566`,
+        bodies commented out -- so there is nothing to restate.)"""
         data_small = np.array(hdu.data.copy(), dtype=np.float64)
         header_spice = hdu.header.copy()
         ymin, ymax = Util.AlignSpiceUtil.vertical_edges_limits(header_spice)

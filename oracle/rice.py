@@ -211,9 +211,13 @@ def _card(key, value, comment=""):
 
 
 def write_compressed_image(path, data, extra_cards=(), tile=None, quantize_scale=None, zdither0=1, method=1,
-                           blank=None, bytepix=4, blocksize=32):
+                           blank=None, bytepix=4, blocksize=32, gzip_tiles=()):
     """Write `data` (2-D int16/int32, or float32/float64 with `quantize_scale`) as PRIMARY (no data) + one ZIMAGE
-    binary-table extension with RICE_1 tiles. `extra_cards`: (key, value) pairs copied into the extension header."""
+    binary-table extension with RICE_1 tiles. `extra_cards`: (key, value) pairs copied into the extension header.
+    gzip_tiles: 0-based tile numbers of a float image stored losslessly instead -- empty COMPRESSED_DATA descriptor,
+    gzip-compressed big-endian pixel values in a GZIP_COMPRESSED_DATA column: what cfitsio does with a tile it cannot
+    quantise (imcompress.c, imcomp_compress_tile)."""
+    import zlib
     data = np.asarray(data)
     ny, nx = data.shape
     tw, th = (nx, 1) if tile is None else tile
@@ -224,8 +228,17 @@ def write_compressed_image(path, data, extra_cards=(), tile=None, quantize_scale
         for tx in range(0, nx, tw):
             rows.append(data[ty:ty + th, tx:tx + tw])
     heap = bytearray()
-    desc, scales, zeros = [], [], []
+    desc, scales, zeros, gz = [], [], [], []
     for n, t in enumerate(rows, start=1):
+        if is_float and (n - 1) in gzip_tiles:
+            b = zlib.compress(np.ascontiguousarray(t).astype(t.dtype.newbyteorder(">")).tobytes())
+            desc.append((0, 0))
+            gz.append((len(b), len(heap)))
+            heap += b
+            scales.append(0.0)
+            zeros.append(0.0)
+            continue
+        gz.append((0, 0))
         if is_float:
             finite = np.isfinite(t)
             zero = float(np.min(t[finite])) if finite.any() else 0.0
@@ -239,18 +252,23 @@ def write_compressed_image(path, data, extra_cards=(), tile=None, quantize_scale
         b = rice_encode(q, blocksize, bytepix)
         desc.append((len(b), len(heap)))
         heap += b
-    ncols_bytes = 8 + (16 if is_float else 0)
+    with_gz = bool(gzip_tiles) and is_float
+    ncols_bytes = 8 + (16 if is_float else 0) + (8 if with_gz else 0)
     table = bytearray()
     for i, (cnt, off) in enumerate(desc):
         table += np.array([cnt, off], dtype=">i4").tobytes()
         if is_float:
             table += np.array([scales[i], zeros[i]], dtype=">f8").tobytes()
+        if with_gz:
+            table += np.array(gz[i], dtype=">i4").tobytes()
     cards = [_card("XTENSION", "BINTABLE"), _card("BITPIX", 8), _card("NAXIS", 2), _card("NAXIS1", ncols_bytes),
              _card("NAXIS2", len(rows)), _card("PCOUNT", len(heap)), _card("GCOUNT", 1),
-             _card("TFIELDS", 3 if is_float else 1), _card("TTYPE1", "COMPRESSED_DATA"),
+             _card("TFIELDS", (3 if is_float else 1) + (1 if with_gz else 0)), _card("TTYPE1", "COMPRESSED_DATA"),
              _card("TFORM1", f"1PB({max(c for c, _ in desc)})")]
     if is_float:
         cards += [_card("TTYPE2", "ZSCALE"), _card("TFORM2", "1D"), _card("TTYPE3", "ZZERO"), _card("TFORM3", "1D")]
+    if with_gz:
+        cards += [_card("TTYPE4", "GZIP_COMPRESSED_DATA"), _card("TFORM4", f"1PB({max(c for c, _ in gz)})")]
     zbitpix = {"f4": -32, "f8": -64, "i2": 16, "i4": 32, "u1": 8}[data.dtype.str[1:]]
     cards += [_card("ZIMAGE", True), _card("ZCMPTYPE", "RICE_1"), _card("ZBITPIX", zbitpix), _card("ZNAXIS", 2),
               _card("ZNAXIS1", nx), _card("ZNAXIS2", ny), _card("ZTILE1", tw), _card("ZTILE2", th),

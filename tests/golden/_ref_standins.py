@@ -314,9 +314,39 @@ def _plain_function():
 _plain_function.__module__ = "astropy.wcs.utils"
 
 
+def real_astropy():
+    """True when the real astropy (with its bundled wcslib) is importable: the probe every generator and
+    tests/test_wcs_pin.py run, so that the wcslib boundary gets pinned on the first box that has it."""
+    import importlib.util
+    try:
+        return importlib.util.find_spec("astropy") is not None and importlib.util.find_spec("astropy.wcs") is not None
+    except (ImportError, ValueError):
+        return False
+
+
 def install(repo_root):
+    """Make `import euispice_coreg` work. Returns "astropy" when the real astropy answered (goldens generated in that
+    process are pinned to wcslib / astropy.units / astropy.io.fits themselves) or "stand-ins" otherwise."""
     if repo_root not in sys.path:
         sys.path.insert(0, repo_root)
+    if real_astropy():
+        import importlib.util
+        for n in ("matplotlib", "matplotlib.pyplot", "matplotlib.collections", "matplotlib.gridspec",
+                  "matplotlib.patches", "matplotlib.colors", "matplotlib.backends", "matplotlib.backends.backend_pdf",
+                  "mpl_toolkits", "mpl_toolkits.axes_grid1", "multiprocess", "multiprocess.shared_memory"):
+            top = n.split(".")[0]
+            if importlib.util.find_spec(top) is None:
+                sys.modules.setdefault(n, mock.MagicMock(name=n))
+        if "multiprocess.shared_memory" in sys.modules and isinstance(sys.modules["multiprocess.shared_memory"],
+                                                                       mock.MagicMock):
+            import multiprocessing.shared_memory as std_shm
+            shm = types.ModuleType("multiprocess.shared_memory")
+            shm.SharedMemory = std_shm.SharedMemory
+            sys.modules["multiprocess.shared_memory"] = shm
+            sys.modules["multiprocess"].shared_memory = shm
+        if "/root/reference" not in sys.path:
+            sys.path.insert(0, "/root/reference")
+        return "astropy"
     from euispice_coreg_b200._compat import fits_lite
     import multiprocessing.shared_memory as std_shm
     units = types.ModuleType("astropy.units")
@@ -357,3 +387,4 @@ def install(repo_root):
             setattr(sys.modules[parent], leaf, sys.modules[name])
     if "/root/reference" not in sys.path:
         sys.path.insert(0, "/root/reference")
+    return "stand-ins"

@@ -106,3 +106,29 @@ def test_alignment_reads_compressed_inputs(cuda, toy_pair, tmp_path):
     assert np.array_equal(a, b)
     i, j = np.unravel_index(np.nanargmax(a), a.shape)[:2]
     assert (lags["lag_crval1"][i], lags["lag_crval2"][j]) == (24.0, 6.0)
+
+
+def test_lossless_fallback_tiles_are_patched_in(cuda, tmp_path):
+    """A float tile cfitsio cannot quantise is stored losslessly (empty COMPRESSED_DATA descriptor, gzip of the
+    big-endian pixels in GZIP_COMPRESSED_DATA): such tiles are decoded on the host and patched into the device image;
+    the other tiles are the RICE decoder's, bit for bit."""
+    from euispice_coreg_b200._compat import fits_lite
+    from oracle import rice
+    rng = np.random.default_rng(21)
+    img = rng.lognormal(5, 1, (24, 50)).astype(np.float32)
+    img[3, 4] = np.nan
+    plain, mixed = str(tmp_path / "plain.fits"), str(tmp_path / "mixed.fits")
+    kw = dict(tile=(25, 8), quantize_scale=0.25, zdither0=7, method=1, blank=-2147483647)
+    rice.write_compressed_image(plain, img, **kw)
+    rice.write_compressed_image(mixed, img, gzip_tiles=(1, 4), **kw)      # tiles (row 0, col 1) and (row 2, col 0)
+    a = fits_lite.open(plain)[1].data
+    b = fits_lite.open(mixed)[1].data
+    assert a.dtype == b.dtype == np.float32
+    lossless = np.zeros(img.shape, dtype=bool)
+    lossless[0:8, 25:50] = True
+    lossless[16:24, 0:25] = True
+    assert np.array_equal(b[lossless], img[lossless], equal_nan=True)          # exact pixels where stored losslessly
+    assert np.array_equal(b[~lossless], a[~lossless], equal_nan=True)          # RICE + de-quantisation elsewhere
+    assert not np.array_equal(a[lossless], img[lossless], equal_nan=True)      # (the quantised version differs)
+    dev = fits_lite.open(mixed)[1].device_data()
+    assert np.array_equal(dev.cpu().numpy(), b, equal_nan=True)

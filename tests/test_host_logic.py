@@ -453,6 +453,11 @@ def test_fits_lite_lazy_payload_window_and_raw_view(tmp_path):
     assert conv(stored, 0.5, 100.0).dtype == np.float32        # astropy's promotion rule for <= 16-bit integers
     assert np.array_equal(conv(stored[2:9, 4:11], 0.5, 100.0), conv(stored, 0.5, 100.0)[2:9, 4:11])
     assert conv(stored, 1, 32768).dtype == np.uint16           # unsigned-integer convention
+    # BLANK pixels of an integer image that is scaled to float become NaN (astropy's behaviour); unscaled stay integers
+    blank = int(stored[5, 6])
+    out = conv(stored, 0.5, 100.0, blank)
+    assert np.isnan(out[5, 6]) and np.array_equal(np.isnan(out), stored == blank)
+    assert conv(stored, 1, 0, blank).dtype == np.int16
     # overwrite while mapped
     h2 = fits_lite.open(p)
     fits_lite.writeto(p, [fits_lite.PrimaryHDU(img * 2, h2[0].header)], overwrite=True)
