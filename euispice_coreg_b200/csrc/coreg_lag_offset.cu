@@ -30,6 +30,10 @@
 
 #include "coreg_common.cuh"
 
+#ifndef COREG_OFF_UNROLL
+#define COREG_OFF_UNROLL 2     // pixels of the walk in flight per lane (tuning: tools/carr_lab.py with COREG_LIB_PATH)
+#endif
+
 namespace coreg {
 
 constexpr int kOffThreads = 256;          // = lags per chunk (one lag per thread)
@@ -245,7 +249,8 @@ __device__ __forceinline__ void offset_walk_window(unsigned win, int lo_x, int l
                                                    double& sbb, double& sab, int& n_miss, double& sa_miss,
                                                    double& saa_miss, int& n_out, int& n_exact) {
   constexpr int ROW = OffBox<T>::W * (int)sizeof(T), E = (int)sizeof(T);
-#pragma unroll 2
+  constexpr int kUnroll = COREG_OFF_UNROLL;
+#pragma unroll kUnroll
   for (int k = 0; k < n_live; ++k, px += (unsigned)sizeof(OffPx)) {
     double ptx, pty, ac;
     lds_px(px, ptx, pty, ac);

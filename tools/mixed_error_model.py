@@ -1,3 +1,13 @@
+"""NumPy emulation of the mixed-arithmetic kernel's sample arithmetic (csrc/coreg_lag_roll.cu, roll_segment_mixed):
+how far its samples are from the reference's float32-stored samples, for images whose mean is far above their
+contrast. Calibrates the per-lag guard `mixed_guard_trips`. CPU only.
+
+    python tools/mixed_error_model.py        ->  profiles/r2_mixed_error_model.md quotes the output
+
+For each mean level (sigma = 1): the reference sample S (FP64 spline of the float32 image) and its float32 store; the
+old scheme (FP32 spline on the raw values) and the new one (FP32 spline on the image centred on its float32 pivot,
+fractions quantised to 2^-23 like the kernel's, b = round32(t + p), bc = b - p).
+"""
 import numpy as np
 rng=np.random.default_rng(1)
 from scipy.ndimage import gaussian_filter
