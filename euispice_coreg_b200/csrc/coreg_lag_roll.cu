@@ -505,8 +505,31 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
   RollWShared& S = *reinterpret_cast<RollWShared*>(roll_smem);
 
   const int tiles_x = (gnx + kTileW - 1) / kTileW;
-  const int tile = blockIdx.x;
-  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const int tiles_y = (gny + TILE_H - 1) / TILE_H;
+  // Tiles on the rim of the grid run longest (segments that straddle the image border go pixel by pixel), so they are
+  // launched first: block indices 0 .. n_rim - 1 walk the rim, the rest the interior. Records are indexed by the tile,
+  // not by the block, so the order changes nothing but the tail of the launch.
+  int tile_x, tile_y;
+  {
+    const int b = blockIdx.x;
+    const int n_rim = (tiles_x <= 2 || tiles_y <= 2) ? tiles_x * tiles_y : 2 * tiles_x + 2 * (tiles_y - 2);
+    if (b >= n_rim) {
+      const int i = b - n_rim;
+      tile_x = 1 + i % (tiles_x - 2);
+      tile_y = 1 + i / (tiles_x - 2);
+    } else if (tiles_x <= 2 || tiles_y <= 2) {
+      tile_x = b % tiles_x;
+      tile_y = b / tiles_x;
+    } else if (b < 2 * tiles_x) {
+      tile_x = b % tiles_x;
+      tile_y = (b < tiles_x) ? 0 : tiles_y - 1;
+    } else {
+      const int i = b - 2 * tiles_x;
+      tile_x = (i & 1) ? tiles_x - 1 : 0;
+      tile_y = 1 + (i >> 1);
+    }
+  }
+  const int tile = tile_y * tiles_x + tile_x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & (kTileW - 1), rg = tid / kTileW;
   const int gx = tile_x * kTileW + tx;

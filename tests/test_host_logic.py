@@ -485,3 +485,36 @@ def test_large_image_window_covers_every_cut_coordinate(toy_pair):
     assert x0 <= max(0, np.floor(x[inside].min()) - 2) and x1 >= min(dl.shape[1], np.ceil(x[inside].max()) + 3)
     assert y0 <= max(0, np.floor(y[inside].min()) - 2) and y1 >= min(dl.shape[0], np.ceil(y[inside].max()) + 3)
     assert (x1 - x0) * (y1 - y0) < 0.5 * dl.size
+
+
+def test_offset_patch_order_properties():
+    """Lag order of the Carrington-frame kernel (`engine.offset_patch_order`): every lag gets its own slot; a block of
+    256 consecutive slots holds one 16 x 16 patch of the CRVAL grid; a warp's 32 slots hold 16 x 2 lags; patches
+    start at the list's own first indices (a rank's slice has no ragged leading patch); lags of different groups never
+    share a patch; a list with repeated (i1, i2) pairs is left in its own order."""
+    from euispice_coreg_b200.hdrshift.engine import OFFSET_CHUNK, offset_patch_order
+    i1, i2 = (a.ravel() for a in np.meshgrid(np.arange(120), np.arange(120), indexing="ij"))
+    slot, n_slots = offset_patch_order(i1, i2)
+    assert n_slots % OFFSET_CHUNK == 0 and n_slots == 64 * 256 and np.unique(slot).size == slot.size
+    inv = np.full(n_slots, -1)
+    inv[slot] = np.arange(slot.size)
+    for blk in range(0, n_slots, OFFSET_CHUNK):
+        k = inv[blk:blk + OFFSET_CHUNK]
+        k = k[k >= 0]
+        assert np.ptp(i1[k]) < 16 and np.ptp(i2[k]) < 16
+        for w in range(blk, blk + OFFSET_CHUNK, 32):
+            kw = inv[w:w + 32]
+            kw = kw[kw >= 0]
+            if kw.size:
+                assert np.ptp(i1[kw]) < 16 and np.ptp(i2[kw]) < 2
+    # the second half of the grid (what rank 1 of 2 gets): 60 rows -> 4 patch columns, not 5
+    half = i1 >= 60
+    _, n_half = offset_patch_order(i1[half], i2[half])
+    assert n_half == 4 * 8 * 256
+    # groups (e.g. CDELT indices) keep apart
+    g = np.repeat([0, 1], 8)
+    s, n = offset_patch_order(np.tile(np.arange(8), 2), np.zeros(16, int), g)
+    assert n == 512 and set(s[:8] // 256) == {0} and set(s[8:] // 256) == {1}
+    # repeated pairs: identity
+    s, n = offset_patch_order(np.zeros(5, int), np.zeros(5, int))
+    assert n == 5 and s.tolist() == [0, 1, 2, 3, 4]
