@@ -365,7 +365,8 @@ template <bool ROUND32, int P, bool MIXED, typename AT>
 __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small,
                                          const float* __restrict__ small32, int snx, int sny, unsigned row_elems,
                                          double di, double dj0, const AT (&a_c)[P], unsigned a_ok, bool all_ref,
-                                         double pivot_b, double& sb, double& sbb, double& sab, unsigned& miss) {
+                                         double pivot_b, double& sb, double& sbb, double& sab, unsigned& miss,
+                                         bool& slow) {
   const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
   const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
   // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
@@ -429,6 +430,7 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
            (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
   }
   miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
+  slow = false;
   if (!fast && a_ok && mode != 2) {
     // A segment that lies outside the small image as a whole has no sample at all. Along the segment each
     // coordinate is numerator / (1 - e) with both linear in p and 1 - e > 0, hence monotonic: it stays between its
@@ -445,29 +447,114 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
       return;
     }
   }
-  if (!fast && a_ok) {
-    // image borders, irregular columns (rotated lags), missing pixels: the segment pixel by pixel
-    sb = sbb = sab = 0.0;
+  // image borders, irregular columns (rotated lags), missing pixels, division-mode lags: the segment still has to be
+  // evaluated pixel by pixel -- by the warp together (`roll_pixels_warp`) or, when most lanes need it, by each thread
+  // for itself (`roll_pixels_serial`)
+  slow = !fast && a_ok;
+  if (!fast) sb = sbb = sab = 0.0;
+}
+
+// One pixel of a segment by the per-pixel rules. (gx, gy0): grid column and first row of the segment; p: row inside it.
+template <bool ROUND32>
+__device__ __forceinline__ bool roll_one_pixel(const HomLag& C, int mode, const double* __restrict__ small, int snx,
+                                               int sny, unsigned row_elems, double di, double dj0, int p, double* b) {
+  const double bnx = fma(C.hx1, dj0, fma(C.hx0, di, C.hx2));
+  const double bny = fma(C.hy1, dj0, fma(C.hy0, di, C.hy2));
+  const double be = fma(C.he1, dj0, fma(C.he0, di, C.he2));
+  const double e = fma(C.he1, (double)p, be);
+  const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
+  const double sx = fma(fma(C.hx1, (double)p, bnx), inv, C.x0h);
+  const double sy = fma(fma(C.hy1, (double)p, bny), inv, C.y0h);
+  return sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, b);
+}
+
+// The segment pixel by pixel, every thread for itself (all lanes busy: division-mode lags, tiles on the image border).
+template <bool ROUND32, int P, typename AT>
+__device__ __forceinline__ void roll_pixels_serial(const HomLag& C, int mode, const double* __restrict__ small,
+                                                   int snx, int sny, unsigned row_elems, double di, double dj0,
+                                                   const AT (&a_c)[P], unsigned a_ok, double pivot_b, double& sb,
+                                                   double& sbb, double& sab, unsigned& miss) {
+  sb = sbb = sab = 0.0;
+  miss = 0;
 #pragma unroll 1
-    for (int p = 0; p < P; ++p) {
-      if (!(a_ok & (1u << p))) continue;
-      const double e = fma(he1, (double)p, be);
-      const double inv = (mode == 0) ? recip_1me_tiny(e) : ((mode == 1) ? recip_1me_small(e) : recip_1me_div(e));
-      const double sx = fma(fma(hx1, (double)p, bnx), inv, x0h);
-      const double sy = fma(fma(hy1, (double)p, bny), inv, y0h);
-      AT acs = a_c[0];
+  for (int p = 0; p < P; ++p) {
+    if (!(a_ok & (1u << p))) continue;
+    AT acs = a_c[0];
 #pragma unroll
-      for (int q = 1; q < P; ++q)
-        if (q == p) acs = a_c[q];
-      const double ac = (double)acs;
-      double b;
-      if (sample_pixel_half<ROUND32>(small, sny, snx, row_elems, sx, sy, &b)) {
-        const double bc = b - pivot_b;
-        sb += bc;
-        sbb = fma(bc, bc, sbb);
-        sab = fma(ac, bc, sab);
-      } else {
-        miss |= 1u << p;
+    for (int q = 1; q < P; ++q)
+      if (q == p) acs = a_c[q];
+    const double ac = (double)acs;
+    double b;
+    if (roll_one_pixel<ROUND32>(C, mode, small, snx, sny, row_elems, di, dj0, p, &b)) {
+      const double bc = b - pivot_b;
+      sb += bc;
+      sbb = fma(bc, bc, sbb);
+      sab = fma(ac, bc, sab);
+    } else {
+      miss |= 1u << p;
+    }
+  }
+}
+
+// The same for the FEW lanes of a warp whose segment needs it (rotated / rescaled lags: a floor changes inside ~10 - 25 %
+// of the segments; tiles on the rim of the image), without making the other lanes wait for a 12- or 16-pixel serial
+// loop: two segments at a time, one per half-warp, one pixel per lane; the sums come back to the owner by a butterfly
+// (fixed order). A helper lane derives the owner's column and rows from the owner's lane number and re-reads the
+// reference pixel (an L1 hit). (Measured against a variant that deals the pixels of all needy segments out densely
+// over the 32 lanes through shared-memory slots: that one is slower for the all-FP64 kernel, 37.6 vs 36.4 ms on
+// config 1, profiles/r2_k1_tuning.md.)
+constexpr int kSlowOwners = 10;     // more needy lanes than this: every thread for itself
+
+template <typename RefT, bool ROUND32, int P, bool MIXED>
+__device__ __forceinline__ void roll_pixels_warp(unsigned need, const HomLag& C, int mode, const RefT* __restrict__ ref,
+                                                 const double* __restrict__ small, int snx, int sny, int gnx, int gny,
+                                                 unsigned row_elems, int gx_base, int gy_base, int lane,
+                                                 double pivot_a, double pivot_b, double& sb, double& sbb, double& sab,
+                                                 unsigned& miss) {
+  static_assert(P <= 16, "one segment per half-warp");
+  const int half = lane >> 4, p = lane & 15;
+  while (need) {   // warp-uniform
+    const int o0 = __ffs(need) - 1;
+    need &= need - 1;
+    const int o1 = need ? __ffs(need) - 1 : -1;
+    if (o1 >= 0) need &= need - 1;
+    const int owner = half ? o1 : o0;
+    double psb = 0.0, psbb = 0.0, psab = 0.0;
+    bool pmiss = false;
+    if (owner >= 0 && p < P) {
+      const int gx = gx_base + owner, gy = gy_base + p;   // a warp covers 32 consecutive columns of one row group
+      if (gx < gnx && gy < gny) {
+        const double a = (double)ref[(int64_t)gy * gnx + gx];
+        if (isfinite(a)) {
+          const double ac = MIXED ? (double)(float)(a - pivot_a) : a - pivot_a;
+          double b;
+          if (roll_one_pixel<ROUND32>(C, mode, small, snx, sny, row_elems, (double)gx, (double)gy_base, p, &b)) {
+            const double bc = b - pivot_b;
+            psb = bc;
+            psbb = bc * bc;
+            psab = ac * bc;
+          } else {
+            pmiss = true;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      psb += __shfl_xor_sync(0xffffffffu, psb, o);
+      psbb += __shfl_xor_sync(0xffffffffu, psbb, o);
+      psab += __shfl_xor_sync(0xffffffffu, psab, o);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pmiss);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double r0 = __shfl_sync(0xffffffffu, psb, 16 * k), r1 = __shfl_sync(0xffffffffu, psbb, 16 * k),
+                   r2 = __shfl_sync(0xffffffffu, psab, 16 * k);
+      if (lane == (k ? o1 : o0)) {
+        sb = r0;
+        sbb = r1;
+        sab = r2;
+        miss = (bal >> (16 * k)) & 0xFFFFu;
       }
     }
   }
@@ -595,8 +682,22 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
     for (int l = 0; l < cnt; ++l) {
       double sb, sbb, sab;
       unsigned miss;
-      roll_lag<ROUND32, P, MIXED, AT>(S.lag[warp][l], small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref,
-                                      pivot_b, sb, sbb, sab, miss);
+      bool slow;
+      const HomLag& C = S.lag[warp][l];
+      roll_lag<ROUND32, P, MIXED, AT>(C, small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb,
+                                      sbb, sab, miss, slow);
+      const unsigned need = __ballot_sync(0xffffffffu, slow);
+      if (need) {
+        const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);
+        if (__popc(need) > kSlowOwners) {      // most lanes: every thread walks its own segment, nobody waits
+          if (slow)
+            roll_pixels_serial<ROUND32, P, AT>(C, mode, small, snx, sny, row_elems, di, dj0, a_c, a_ok, pivot_b, sb, sbb,
+                                               sab, miss);
+        } else {
+          roll_pixels_warp<RefT, ROUND32, P, MIXED>(need, C, mode, ref, small, snx, sny, gnx, gny, row_elems, gx - lane,
+                                                    gy0, lane, pivot_a, pivot_b, sb, sbb, sab, miss);
+        }
+      }
       S.acc[warp][l][0][lane] = sb;
       S.acc[warp][l][1][lane] = sbb;
       S.acc[warp][l][2][lane] = sab;
