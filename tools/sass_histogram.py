@@ -54,6 +54,11 @@ def main():
                   f"TMA / mbarrier: {sum(v for k, v in ops.items() if k.startswith(('UTMALDG', 'SYNCS', 'UBLKCP')))}")
             for k, v in ops.most_common(40):
                 print(f"   {v:6d}  {k}")
+            async_ops = {k: v for k, v in ops.items() if k.startswith(('UTMALDG', 'SYNCS', 'UBLKCP', 'UTMAPF', 'FENCE'))}
+            if async_ops:
+                print("   -- TMA / mbarrier / proxy-fence opcodes:")
+                for k, v in sorted(async_ops.items()):
+                    print(f"   {v:6d}  {k}")
 
 
 if __name__ == "__main__":
