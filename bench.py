@@ -575,9 +575,9 @@ def run_gpu(args):
     def e2e_step():
         e = E.LagSearchEngine(order=2, strict=args.strict, variant=args.variant, small_storage=args.small_storage,
                               no_fast=args.no_fast, arithmetic=args.arithmetic or "fp64")
-        e.pure_shift_hint = eng.pure_shift_hint     # what hpc_lag_table derived from the lag grid
         e.set_small(h_small, pinned=True)
         e.prepare_hpc(h_large, w_large, w_small)
+        e.pure_shift_hint = eng.pure_shift_hint     # what hpc_lag_table derived from the lag grid
         return e.search(table)
 
     e2e_step()
@@ -636,7 +636,7 @@ def run_gpu(args):
         consts, withheld = measured_constants()
         fast = main["fast"]
         arith = eng.arithmetic if fast else "generic"
-        rows = 16 if ((eng.pure_shift_hint and args.variant == 0) or args.variant == 1) else (14 if args.variant == 2 else 12)
+        rows = 12 if args.variant == 3 else (14 if args.variant == 2 else 16)
         kname = ("lag_corr_roll_kernel<MIXED>" if arith == "mixed" else "lag_corr_roll_kernel") if fast \
             else "lag_corr_kernel<TanCoord>"
         kc = consts.get(kname, {})

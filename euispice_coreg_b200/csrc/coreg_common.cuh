@@ -259,7 +259,8 @@ inline RollWLayout rollw_layout(int gnx, int gny, int64_t n_lags) {
 }
 inline size_t partials_bytes(int gnx, int gny, int64_t n_lags) {
   const size_t tiles = (size_t)((gnx + kTileW - 1) / kTileW) * ((gny + kMinTileH - 1) / kMinTileH);
-  return std::max(tiles * (size_t)n_lags * kMom * sizeof(double), rollw_layout(gnx, gny, n_lags).total);
+  // a multiple of 16: the per-lag homographies (16-byte aligned records) follow the partials in the workspace
+  return (std::max(tiles * (size_t)n_lags * kMom * sizeof(double), rollw_layout(gnx, gny, n_lags).total) + 15) / 16 * 16;
 }
 
 struct TanCoord {
@@ -436,7 +437,10 @@ inline int grid_for(int64_t n, int threads = 256) {
 // per-lag 3x3 homography of the helioprojective rolling kernel (coreg_lag_roll.cu); sizes the workspace tail
 struct HomLag {
   double hx0, hx1, hx2, hy0, hy1, hy2, he0, he1, he2, x0h, y0h;  // he = (0,0,1) - (denominator row)
-  double emax;  // max |e| over the common grid (e is linear in (i, j): attained at a corner); +inf if not finite
+  // |emax| = max |e| over the common grid (e is linear in (i, j): attained at a corner), +inf if not finite. The SIGN
+  // bit marks a lag under which a column segment drifts off the one-row-per-row lattice (|hx1| or |hy1 - 1| above
+  // 2^-12 pixel per row: rotated / rescaled candidates), so that the kernel tests it with one integer compare.
+  double emax;
 };
 
 

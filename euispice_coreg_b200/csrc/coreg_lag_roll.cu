@@ -51,6 +51,16 @@ int make_hom_grid(const CoregTanWcs* w, int gnx, int gny, HomGrid* g) {
   return COREG_OK;
 }
 
+// reciprocal of the projective denominator D = 1 - e, chosen per lag (block-uniform) from the lag's emax:
+//   |e| <= 2^-18 : 1 + e + e^2                    (2 ops, truncation e^3 <= 2^-54)
+//   |e| <= 2^-7  : (1 + e)(1 + e^2)(1 + e^4)      (5 ops, truncation e^8 <= 2^-56)
+//   otherwise    : true division; D <= 0 (behind the tangent hemisphere) -> NaN
+constexpr double kTinyE = 3.814697265625e-06;  // 2^-18
+constexpr double kSmallE = 0.0078125;          // 2^-7
+// drift per row (|hx1|, |hy1 - 1|) above which a lag's segments may change a floor out of step: 2^-12 pixel, i.e. 2^-8
+// pixel over a 16-row segment -- below it that practically never happens
+constexpr double kRiskDriftPerRow = 0.000244140625;
+
 __global__ void tan_homography_kernel(HomGrid g, const CoregTanWcs* __restrict__ lag_wcs, int n,
                                       HomLag* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,16 +105,11 @@ __global__ void tan_homography_kernel(HomGrid g, const CoregTanWcs* __restrict__
                e11 = fma(h.he0, g.xmax, fma(h.he1, g.ymax, h.he2));
   double em = fmax(fmax(fabs(e00), fabs(e10)), fmax(fabs(e01), fabs(e11)));
   if (!(em == em) || !isfinite(h.hx0 + h.hx1 + h.hx2 + h.hy0 + h.hy1 + h.hy2)) em = CUDART_INF;
-  h.emax = em;
+  const bool drifts = !(fmax(fabs(h.hx1), fabs(h.hy1 - 1.0)) <= kRiskDriftPerRow);
+  h.emax = drifts ? -em : em;
   out[idx] = h;
 }
 
-// reciprocal of the projective denominator D = 1 - e, chosen per lag (block-uniform) from the lag's emax:
-//   |e| <= 2^-18 : 1 + e + e^2                    (2 ops, truncation e^3 <= 2^-54)
-//   |e| <= 2^-7  : (1 + e)(1 + e^2)(1 + e^4)      (5 ops, truncation e^8 <= 2^-56)
-//   otherwise    : true division; D <= 0 (behind the tangent hemisphere) -> NaN
-constexpr double kTinyE = 3.814697265625e-06;  // 2^-18
-constexpr double kSmallE = 0.0078125;          // 2^-7
 
 __device__ __forceinline__ double recip_1me_tiny(double e) { return fma(e, e, 1.0 + e); }
 __device__ __forceinline__ double recip_1me_small(double e) {
@@ -117,6 +122,11 @@ __device__ __forceinline__ double recip_1me_small(double e) {
 __device__ __forceinline__ double recip_1me_div(double e) {
   const double den = 1.0 - e;
   return (den > 0.0) ? 1.0 / den : CUDART_NAN;
+}
+
+__global__ void abs_inplace_kernel(double* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = fabs(v[i]);
 }
 
 // exact order-2 sample at (sx - 0.5, sy - 0.5) with float32 rounding / masking, kept out of line: only image
@@ -324,6 +334,93 @@ __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ sma
   }
 }
 
+// The rolling segment for IRREGULAR columns: every pixel takes its own floors (the per-pixel rule), the three tap rows
+// still roll. Under a rotated or rescaled candidate header x drifts by P |hx1| pixels along a segment and y by
+// P |hy1 - 1| beyond one pixel per row, so in that fraction of the segments a floor moves "out of step" once -- and
+// because neighbouring columns share the fractional parts to within the same drift, the segments of a warp do so
+// together: on the 5-D grid of BASELINE configs[3] 16 % of the warps had more than ten such lanes and walked their
+// segments pixel by pixel (9 taps each, five times the cost of a regular segment), 26 % a few
+// (tools/irregular_segments.py). Here the window (r0, r1, r2) belongs to the tap index `wtap`; a pixel whose own tap
+// index is the expected one (one row further) just rolls, any other reloads the three rows -- once or twice per
+// segment. 13 FP64 instructions per pixel for coordinates, floors and fractions instead of 4, everything else as in
+// `roll_segment`. Requires every pixel's 3 x 3 window strictly inside the image with one spare row / column (the
+// caller checks the two end pixels with that margin; the coordinates are monotonic along the segment).
+template <int MODE, bool ROUND32, int P, typename AT>
+__device__ __forceinline__ bool roll_segment_adaptive(const double* __restrict__ small, unsigned row_elems, double be,
+                                                      double bnx, double bny, double he1, double hx1, double hy1,
+                                                      double x0h, double y0h, double pivot_b, const AT (&a_c)[P],
+                                                      double& sb, double& sbb, double& sab) {
+  // Four pixels per trip of a ROLLED loop: the four row-register sets (three window rows + the prefetched one) return to
+  // their roles after four shifts, and the body stays ~6 KB. (Fully unrolled, this routine made the kernel's working
+  // set of code exceed the 32 KB instruction cache: 15 % of the stall samples were "no instruction".)
+  static_assert(P % 4 == 0, "four row-register sets");
+  auto row = [&](unsigned t, double (&c)[3]) {
+    const double ta = __ldg(small + t), tb = __ldg(small + t + 1), tc = __ldg(small + t + 2);
+    c[0] = 0.5 * (ta + tb);
+    c[1] = tb - ta;
+    c[2] = fma(0.5, ta + tc, -tb);
+  };
+  double W[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) W[k][0] = W[k][1] = W[k][2] = 0.0;
+  unsigned wtap = 0xFFFFFFFFu, bmax = 0;   // no window yet: tap indices stay below 2^31
+  double dp = 0.0;
+  sb = sbb = sab = 0.0;
+#pragma unroll 1
+  for (int p0 = 0; p0 < P; p0 += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double e = fma(he1, dp, be);
+      const double inv = (MODE == 0) ? recip_1me_tiny(e) : recip_1me_small(e);
+      const double sx = fma(fma(hx1, dp, bnx), inv, x0h);
+      const double sy = fma(fma(hy1, dp, bny), inv, y0h);
+      const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
+      const unsigned tap = (unsigned)(__double2loint(my) - 1) * row_elems + (unsigned)(__double2loint(mx) - 1);
+      const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);
+      if (tap != wtap) {   // a floor moved other than by one row (and the first pixel)
+        row(tap, W[k & 3]);
+        row(tap + row_elems, W[(k + 1) & 3]);
+        row(tap + 2u * row_elems, W[(k + 2) & 3]);
+        wtap = tap;
+      }
+      // the row the next pixel most likely needs (inside the image: one spare row)
+      row(wtap + 3u * row_elems, W[(k + 3) & 3]);
+      const double(&r0)[3] = W[k & 3];
+      const double(&r1)[3] = W[(k + 1) & 3];
+      const double(&r2)[3] = W[(k + 2) & 3];
+      const double q0 = fma(fma(r0[2], vx, r0[1]), vx, r0[0]);
+      const double q1 = fma(fma(r1[2], vx, r1[1]), vx, r1[0]);
+      const double q2 = fma(fma(r2[2], vx, r2[1]), vx, r2[0]);
+      const double t = fma(fma(fma(0.5, q0 + q2, -q1), vy, q1 - q0), vy, 0.5 * (q0 + q1));
+      double b;
+      if (ROUND32) {
+        b = (double)__double2float_rn(t);
+      } else {
+        const unsigned hi = (unsigned)__double2hiint(t) & 0x7FFFFFFFu;
+        bmax = max(bmax, (t == -32762.0) ? 0x7F800000u : ((hi >= 0x7FF00000u) ? 0x7F800000u : 0u));
+        b = t;
+      }
+      AT acs = a_c[k];
+#pragma unroll
+      for (int g = 1; g < P / 4; ++g)
+        if (p0 == 4 * g) acs = a_c[4 * g + k];
+      const double bc = b - pivot_b;
+      sb += bc;
+      sbb = fma(bc, bc, sbb);
+      sab = fma((double)acs, bc, sab);
+      wtap += row_elems;
+      dp += 1.0;
+    }
+  }
+  // every sample finite (as in the regular segment: a non-finite sample makes Sbb non-finite)
+  return (bmax < 0x7F800000u) && (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
+}
+
+#ifndef COREG_ADAPT_MIN
+#define COREG_ADAPT_MIN 1
+#endif
+constexpr int kAdaptMin = COREG_ADAPT_MIN;   // irregular lanes from which the whole warp takes the adaptive segment (measured 1 / 3 / 6: 15.0 / 15.7 / 16.6 us per lag)
+
 // One pixel by the per-pixel rules: own floors, 9 taps when they are all inside the image, otherwise the exact
 // out-of-line sampler. (sx, sy) are the coordinates + 0.5. Returns false when the sample is missing.
 template <bool ROUND32>
@@ -361,14 +458,14 @@ __device__ __forceinline__ bool sample_pixel_half(const double* __restrict__ sma
 // segment or -- image borders, irregular columns (rotated lags), missing pixels, division-mode lags -- the segment
 // pixel by pixel. Out: the thread's Sb, Sbb, Sab over its valid samples and the mask of pixels that have a finite
 // reference value but no valid sample.
-template <bool ROUND32, int P, bool MIXED, typename AT>
+template <bool ROUND32, int P, bool MIXED, bool ADAPT, typename AT>
 __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restrict__ small,
                                          const float* __restrict__ small32, int snx, int sny, unsigned row_elems,
                                          double di, double dj0, const AT (&a_c)[P], unsigned a_ok, bool all_ref,
                                          double pivot_b, double& sb, double& sbb, double& sab, unsigned& miss,
                                          bool& slow) {
   const double hx1 = C.hx1, hy1 = C.hy1, he1 = C.he1, x0h = C.x0h, y0h = C.y0h;
-  const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);  // block-uniform
+  const int mode = (fabs(C.emax) <= kTinyE) ? 0 : ((fabs(C.emax) <= kSmallE) ? 1 : 2);  // block-uniform
   // numerators and e = 1 - D of the segment's first pixel (row gy0); pixel p adds p times the row slopes
   const double bnx = fma(hx1, dj0, fma(C.hx0, di, C.hx2));
   const double bny = fma(hy1, dj0, fma(C.hy0, di, C.hy2));
@@ -384,6 +481,35 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
   bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
               ((unsigned)(ix0 - 1) < (unsigned)(snx - 2)) && (iy0 >= 1) && (iy0 + P <= sny - 1);
+  miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
+  slow = false;
+  if (ADAPT && (P % 4 == 0) && mode != 2 && __double2hiint(C.emax) < 0) {   // block-uniform: the lag rotates / rescales
+    // rotated / rescaled lag: do the floors of the last pixel follow from the first one's? If not for a few lanes of
+    // the warp, all of it takes the adaptive segment (no lane waits for another's pixel-by-pixel walk)
+    const double eL = fma(he1, (double)(P - 1), be);
+    const double invL = (mode == 0) ? recip_1me_tiny(eL) : recip_1me_small(eL);
+    const double sxL = fma(fma(hx1, (double)(P - 1), bnx), invL, x0h);
+    const double syL = fma(fma(hy1, (double)(P - 1), bny), invL, y0h);
+    const int ixL = __double2loint(__dadd_rd(sxL, kMagic)), iyL = __double2loint(__dadd_rd(syL, kMagic));
+    const unsigned wx = (snx > 4) ? (unsigned)(snx - 4) : 0u, wy = (sny > 4) ? (unsigned)(sny - 4) : 0u;
+    const bool inside2 = small_magnitude(sx0) && small_magnitude(sy0) && small_magnitude(sxL) && small_magnitude(syL) &&
+                         ((unsigned)(ix0 - 2) < wx) && ((unsigned)(ixL - 2) < wx) && ((unsigned)(iy0 - 2) < wy) &&
+                         ((unsigned)(iyL - 2) < wy);
+    const bool irregular = (ixL != ix0) || (iyL != iy0 + P - 1);
+    const unsigned b_ok = __ballot_sync(0xffffffffu, all_ref && inside2);
+    const unsigned b_irr = __ballot_sync(0xffffffffu, irregular);
+    if (b_ok == 0xffffffffu && __popc(b_irr) >= kAdaptMin) {
+      bool ok = false;
+      if constexpr (ADAPT && P % 4 == 0)
+        ok = (mode == 0) ? roll_segment_adaptive<0, ROUND32, P, AT>(small, row_elems, be, bnx, bny, he1, hx1, hy1, x0h,
+                                                                    y0h, pivot_b, a_c, sb, sbb, sab)
+                         : roll_segment_adaptive<1, ROUND32, P, AT>(small, row_elems, be, bnx, bny, he1, hx1, hy1, x0h,
+                                                                    y0h, pivot_b, a_c, sb, sbb, sab);
+      slow = !ok;   // a non-finite sample: pixel by pixel
+      if (!ok) sb = sbb = sab = 0.0;
+      return;
+    }
+  }
   if constexpr (MIXED) {
     // the low word of coordinate + kFracMagic holds the offset from the shared floor only while that offset stays
     // below 2^9 pixels: true for any sane lag, guaranteed here by bounding the per-row slopes (block-uniform test)
@@ -429,8 +555,6 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
     fast = (vmax < 0x3FF00000u) && (bmax < 0x7F800000u) &&
            (((unsigned)__double2hiint(sbb) & 0x7FF00000u) != 0x7FF00000u);
   }
-  miss = 0;  // bit p: pixel p has a finite reference value but no valid sample
-  slow = false;
   if (!fast && a_ok && mode != 2) {
     // A segment that lies outside the small image as a whole has no sample at all. Along the segment each
     // coordinate is numerator / (1 - e) with both linear in p and 1 - e > 0, hence monotonic: it stays between its
@@ -580,7 +704,7 @@ struct RollWShared {
   HomLag lag[kWarps][kRollChunk];
 };
 
-template <typename RefT, bool ROUND32, int P, int MINB, bool MIXED>
+template <typename RefT, bool ROUND32, int P, int MINB, bool MIXED, bool ADAPT>
 __global__ void __launch_bounds__(kThreads, MINB)
 lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ small,
                       const float* __restrict__ small32, int snx, int sny, int gnx,
@@ -684,11 +808,11 @@ lag_corr_roll_kernel(const RefT* __restrict__ ref, const double* __restrict__ sm
       unsigned miss;
       bool slow;
       const HomLag& C = S.lag[warp][l];
-      roll_lag<ROUND32, P, MIXED, AT>(C, small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb,
+      roll_lag<ROUND32, P, MIXED, ADAPT, AT>(C, small, small32, snx, sny, row_elems, di, dj0, a_c, a_ok, all_ref, pivot_b, sb,
                                       sbb, sab, miss, slow);
       const unsigned need = __ballot_sync(0xffffffffu, slow);
       if (need) {
-        const int mode = (C.emax <= kTinyE) ? 0 : ((C.emax <= kSmallE) ? 1 : 2);
+        const int mode = (fabs(C.emax) <= kTinyE) ? 0 : ((fabs(C.emax) <= kSmallE) ? 1 : 2);
         if (__popc(need) > kSlowOwners) {      // most lanes: every thread walks its own segment, nobody waits
           if (slow)
             roll_pixels_serial<ROUND32, P, AT>(C, mode, small, snx, sny, row_elems, di, dj0, a_c, a_ok, pivot_b, sb, sbb,
@@ -808,12 +932,20 @@ lag_corr_finalize_w_kernel(const double* __restrict__ wrec, const double* __rest
   }
 }
 
-// rolling kernel + its finalize. Tuning variants (flags bits 8..11): rows per thread 12 (default), 16, 14; the
-// workspace layout is sized for 12 (fewer rows per thread would need more record rows). small32 != nullptr selects
-// the mixed-arithmetic kernel (FP64 coordinates, FP32 spline on the float32 copy of the small image), variants 0 / 1
-// = 12 / 16 rows per thread. (Measured and dropped: 3 CTAs per SM at 80 registers -- spills; 24 and 32 rows per
-// thread -- spills and partial tiles; a precomputed row-coefficient plane: tools/mixed_lab.py,
-// profiles/r1_mixed_kernel.md.)
+// rolling kernel + its finalize. Tuning variants (flags bits 8..11):
+//   0  16 rows per thread, with the adaptive segment for rotated / rescaled lags (the default)
+//   1  16 rows per thread, without it: for lag grids of pure CRVAL shifts, where no segment drifts. The adaptive code is
+//      never executed there, but its presence in the kernel costs the regular path 1 % (all-FP64) to 3 % (mixed) through
+//      register allocation and code placement -- so the caller that knows its WHOLE lag grid holds shifts only asks for
+//      this flavour (the choice must not depend on how the grid is sharded: both flavours are correct for any lag, but
+//      they round an irregular segment differently)
+//   2  14 rows per thread (all-FP64 only), 3  12 rows per thread with the adaptive segment
+// The workspace layout is sized for 12 rows (fewer rows per thread would need more record rows). small32 != nullptr
+// selects the mixed-arithmetic kernel (FP64 coordinates, FP32 spline on the float32 copy of the small image).
+// (Until the adaptive segment existed, 12 rows were the better shape for rotated / rescaled lags -- fewer irregular
+// segments; with it 16 rows win there too: 14.0 vs 14.4 us per lag on the 5-D grid. Measured and dropped: 3 CTAs per SM
+// at 80 registers -- spills; 24 and 32 rows per thread -- spills and partial tiles; a precomputed row-coefficient
+// plane: tools/mixed_lab.py, profiles/r1_mixed_kernel.md.)
 template <typename RefT, bool ROUND32>
 int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cudaStream_t s, const RefT* ref,
                      const double* small, const float* small32, int snx, int sny,
@@ -821,7 +953,8 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
                      int* flagged) {
   const bool mixed = small32 != nullptr;
   const int minb = 2;
-  const int rows_per_thread = (variant == 1) ? 16 : ((variant == 2 && !mixed) ? 14 : kRollWRows);
+  if (mixed && variant == 2) variant = 0;
+  const int rows_per_thread = (variant == 3) ? kRollWRows : ((variant == 2) ? 14 : 16);
   const RollWLayout L = rollw_layout(gnx, gny, n_lags);
   char* base = static_cast<char*>(work);
   double* wrec = reinterpret_cast<double*>(base + L.rec);
@@ -834,17 +967,18 @@ int launch_lag_rollw(int variant, int gnx, int gny, int64_t n_lags, int sms, cud
     return fail(COREG_EINVAL, "lag grid too large for one launch");
   CK(cudaMemsetAsync(wmask, 0, (size_t)tiles * (size_t)n_lags * sizeof(unsigned), s));
   if (prof) CK(cudaEventRecord(g_prof[g_prof_n].a, s));
-#define RW(P_, MIXED_)                                                                                               \
+#define RW(P_, MIXED_, ADAPT_)                                                                                       \
   {                                                                                                                  \
-    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2, MIXED_>;                                                  \
+    auto kern = lag_corr_roll_kernel<RefT, ROUND32, P_, 2, MIXED_, ADAPT_>;                                          \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollWShared));               \
     kern<<<grid, kThreads, sizeof(RollWShared), s>>>(ref, small, small32, snx, sny, gnx, gny, ft, (int)n_lags, lpb,  \
                                                      pivots, wrec, wcorr, wconst, wmask);                            \
   }
   if (mixed) {
-    if (rows_per_thread == 16) RW(16, true) else RW(kRollWRows, true)
+    if (variant == 3) RW(kRollWRows, true, true) else if (variant == 1) RW(16, true, false) else RW(16, true, true)
   } else {
-    if (rows_per_thread == 16) RW(16, false) else if (rows_per_thread == 14) RW(14, false) else RW(kRollWRows, false)
+    if (variant == 3) RW(kRollWRows, false, true) else if (variant == 2) RW(14, false, false)
+    else if (variant == 1) RW(16, false, false) else RW(16, false, true)
   }
 #undef RW
   CK_LAUNCH("lag_corr_roll_kernel");
@@ -934,6 +1068,8 @@ int coreg_tan_homography_emax(const CoregTanWcs* grid_wcs, int gnx, int gny, con
   CK_LAUNCH("tan_homography_kernel");
   CK(cudaMemcpy2DAsync(emax, sizeof(double), &ft[0].emax, sizeof(HomLag), sizeof(double), (size_t)n_lags,
                        cudaMemcpyDeviceToDevice, s));
+  abs_inplace_kernel<<<((int)n_lags + 255) / 256, 256, 0, s>>>(emax, (int)n_lags);   // the sign bit is a flag
+  CK_LAUNCH("abs_inplace_kernel");
   return COREG_OK;
 }
 

@@ -232,9 +232,7 @@ class LagSearchEngine:
         self.small32 = None      # float32 payload of the small image, centred on its float32 pivot (mixed arithmetic)
         self.lag_flags = None    # int32 [n]: lags of the last mixed `evaluate` that tripped the kernel's guard
         self.flagged_lags = 0    # how many lags `resolve_flags` re-evaluated in FP64 (diagnostic)
-        # launch-shape hint for the mixed kernel, set by `hpc_lag_table` from the WHOLE lag grid (never from a slice
-        # of it: every shard must launch the same shape for the cube to be bit-identical for any GPU count)
-        self.pure_shift_hint = False
+        self.pure_shift_hint = False   # set by `hpc_lag_table`: the lag grid holds CRVAL shifts only
         _ext.load()  # fail loudly when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _ext.CoregLibraryError("no CUDA device: the pointing search has no CPU fallback")
@@ -453,8 +451,10 @@ class LagSearchEngine:
     def hpc_lag_table(self, hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics="reference"):
         """Host lag table for `search` in the helioprojective frame + the mask of lags the reference cannot
         evaluate: candidate-header rows for the homography kernel when it applies, `CoregLagTan` rows otherwise."""
-        # launch shape of the rolling kernel: 16 rows per thread when every lag is a pure CRVAL shift (no segment changes
-        # a floor), 12 when CROTA / CDELT lags make some segments irregular (measured: tools/mixed_lab.py, k1_tune.py)
+        # True when every lag is a pure CRVAL shift (no column segment of the rolling kernel changes a floor out of
+        # step; rotated / rescaled lags send such segments through the kernel's adaptive segment): selects the kernel
+        # flavour in `evaluate`. Set from the WHOLE lag grid: every shard must launch the same flavour for the cube to
+        # be bit-identical for any GPU count.
         self.pure_shift_hint = not (np.any(np.asarray(d3)) or np.any(np.asarray(d4)) or np.any(np.asarray(d5)))
         if self.hpc_fast_eligible():
             return tan_wcs_table(hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics)
@@ -556,8 +556,8 @@ class LagSearchEngine:
                 if self.frame == "hpc" and table_dev.shape[1] == _ext.TAN_WCS_DOUBLES:
                     flags = self.flags
                     if self.variant == 0 and self.pure_shift_hint:
-                        # 16 rows per thread when no lag rotates or rescales the grid (37.8 vs 40.1 ms all-FP64 on
-                        # config 1, profiles/r2_k1_tuning.md); decided on the WHOLE lag grid, never on a shard
+                        # a grid of pure CRVAL shifts: the kernel flavour without the adaptive segment (1 - 3 % faster
+                        # on the regular path, csrc/coreg_lag_roll.cu); decided on the WHOLE lag grid, never on a shard
                         flags = _ext.make_flags(self.strict, 1, no_fast=self.no_fast)
                     _ext.hpc_lag_corr_wcs(self.ref, self.small, self.grid_wcs, table_dev[lo:hi], self.order,
                                           self.stats if mixed else self.pivots, work, out_dev[lo:hi], nv, flags,
