@@ -575,3 +575,44 @@ def test_coarse_to_fine_search_equals_dense_where_evaluated(torch_cuda, toy_pair
     assert rc.max_index == rd.max_index and rc.shift_arcsec == rd.shift_arcsec
     with pytest.raises(ValueError):
         Alignment(toy_pair[0], toy_pair[1], lag_search="pyramid", **lags)
+
+
+def test_adaptive_segment_rotated_rescaled_lags_with_holes(torch_cuda, tmp_path):
+    """Rotated / rescaled candidate headers make column segments drift off the one-row-per-row lattice; a warp with such a
+    lane takes the rolling kernel's ADAPTIVE segment (every pixel its own floors, csrc/coreg_lag_roll.cu). A grid large
+    enough to have interior warps (448 x 448: the toy pairs are all rim), NaN holes in the small image (an adaptive
+    segment that meets a non-finite sample is redone pixel by pixel), against the oracle; and against the kernel flavour
+    WITHOUT the adaptive code (variant 1), which evaluates the same lags by the per-pixel rules."""
+    import torch
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200._compat import fits_lite
+    from euispice_coreg_b200._synth.scene import make_pair, small_spec
+    from euispice_coreg_b200.hdrshift import engine
+    pair = make_pair(str(tmp_path), small_spec(448, 512, true_crval=(-12.0, 8.0), master_n=1024), tag="adapt")
+    hd = fits_lite.open(pair[1])[0]
+    data = hd.data.copy()
+    rng = np.random.default_rng(11)
+    data[rng.integers(0, 448, 25), rng.integers(0, 448, 25)] = np.nan
+    p = str(tmp_path / "adapt_holes_small.fits")
+    fits_lite.writeto(p, [fits_lite.PrimaryHDU(data, hd.header)], overwrite=True)
+    pair = (pair[0], p)
+    cd = float(hd.header["CDELT1"])
+    kw = dict(lag_crval1=np.array([22.0, 24.0, 27.0]), lag_crval2=np.array([6.0]), lag_crota=[-0.4, 0.3],
+              lag_cdelt1=[-0.016 * cd, 0.009 * cd], lag_cdelt2=[-0.012 * cd, 0.015 * cd], cdelt_semantics="intended")
+    gpu, a = _gpu_cube(pair, **kw)
+    assert gpu.size == 24 and not a.engine.pure_shift_hint
+    ref, _ = _oracle_cube(pair, **kw)
+    err = _assert_parity(gpu, ref)
+    assert err < OBSERVED["fp64"]
+    # the same lags through the flavour without the adaptive segment, and through the generic kernel
+    d = engine.flat_lag_grid(a.lag_crval1, a.lag_crval2, a.lag_cdelt1, a.lag_cdelt2, a.lag_crota)
+    table, _ = a.engine.hpc_lag_table(a.hdr_small, a, *d, "intended")
+    c0, n0 = a.engine.search(table, return_nvalid=True)
+    assert np.array_equal(c0, gpu.ravel())
+    a.engine.variant, a.engine.flags = 1, _ext.make_flags(variant=1)
+    c1, n1 = a.engine.search(table, return_nvalid=True)
+    # (the float32 store of every sample hides the different FP64 operation order of the two paths: the cubes usually
+    # agree to the last bit)
+    assert np.array_equal(n0, n1) and np.max(np.abs(c0 - c1)) < 1e-12
+    gen, _ = _gpu_cube(pair, strict_arithmetic=True, **kw)
+    assert np.nanmax(np.abs(gen - gpu)) < 1e-9
