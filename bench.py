@@ -49,7 +49,8 @@ SEQUENCE_FRAMES, SEQUENCE_DISTINCT = 256, 16
 # Unit of work: one pixel-sample (one common-grid pixel under one lag). The binding resource is the FP64 pipe / the
 # warp scheduler's dispatch port, not HBM and not the tensor cores (gather + reduction, no dense contraction).
 # FLOOR = FP64 instructions per pixel-sample that the FORMULATION needs, counted by hand (not what the binary executes):
-#   helioprojective rolling kernel, P rows per thread: 4 (two quadratic coordinates) + 5 (P + 2) / P (coefficients of the
+#   helioprojective rolling kernel, P rows per thread: 4 (two quadratic coordinates; 3 on a grid of pure CRVAL shifts,
+#   where x is a line in the row index: `kLinXTol`, csrc/coreg_lag_roll.cu) + 5 (P + 2) / P (coefficients of the
 #   new tap row) + 6 (three Horner forms in x) + 7 (coefficients + Horner form in y) + 4 (pivot, three moments)
 #   + 28 / P (per thread and lag: first-pixel coordinates, floors, reciprocal, quadratic coefficients)
 #   Carrington kernel, per evaluated (pixel, lag) pair: 8 (coordinates, floors, fractions) + 12 (weights) + 12 (taps)
@@ -59,9 +60,9 @@ SURVEY_FP64_PER_SAMPLE_CARRINGTON = 54.0
 BYTES_PER_SAMPLE = 8.0                   # un-amortised: one f32 sample of each image per pixel-sample
 
 
-def hpc_floor(rows_per_thread):
+def hpc_floor(rows_per_thread, linear_x=False):
     p = float(rows_per_thread)
-    return 4.0 + 5.0 * (p + 2.0) / p + 6.0 + 7.0 + 4.0 + 28.0 / p
+    return (3.0 if linear_x else 4.0) + 5.0 * (p + 2.0) / p + 6.0 + 7.0 + 4.0 + 28.0 / p
 
 
 CARRINGTON_FLOOR = 36.0
@@ -642,7 +643,7 @@ def run_gpu(args):
         kc = consts.get(kname, {})
         launches_per_step = max(1, main["k_n"] // args.steps)
         samples_per_launch = n_pix * (hi - lo) / launches_per_step
-        floor = hpc_floor(rows) if fast else SURVEY_FP64_PER_SAMPLE_HPC
+        floor = hpc_floor(rows, linear_x=bool(eng.pure_shift_hint)) if fast else SURVEY_FP64_PER_SAMPLE_HPC
         # the floor is per EVALUATED pixel-sample: a few per cent of the nominal ones lie outside the small image under
         # their lag and cost nothing
         evaluated_per_launch = main["evaluated"] / launches_per_step

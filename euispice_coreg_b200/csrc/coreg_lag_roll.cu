@@ -60,6 +60,9 @@ constexpr double kSmallE = 0.0078125;          // 2^-7
 // drift per row (|hx1|, |hy1 - 1|) above which a lag's segments may change a floor out of step: 2^-12 pixel, i.e. 2^-8
 // pixel over a 16-row segment -- below it that practically never happens
 constexpr double kRiskDriftPerRow = 0.000244140625;
+// bound on hx1 he1 (P - 1)^2 [pixel] under which the rolling segment takes x as a line in the row index (1.000008 covers
+// the factor 1 + 2e of the exact coefficient)
+constexpr double kLinXTol = 0.99e-11;
 
 __global__ void tan_homography_kernel(HomGrid g, const CoregTanWcs* __restrict__ lag_wcs, int n,
                                       HomLag* __restrict__ out) {
@@ -171,7 +174,11 @@ __device__ __noinline__ bool sample_exact_half(const double* __restrict__ small,
 // QUAD (MODE 0 only, |he1| < 2.2e-8): numerator x reciprocal as a quadratic in the row index p, coefficients formed
 // once per lag -- two FMAs per coordinate instead of seven instructions for both (the form the mixed kernel uses;
 // what it neglects, p^2 he1^2 of the reciprocal, is below 1e-9 pixel: tests/test_mixed_fraction_bits.py).
-template <int MODE, bool ROUND32, int P, bool QUAD = false>
+// LINX (with QUAD): x as a LINE in the row index -- its quadratic coefficient is hx1 he1 (1 + 2e), and a lag of pure
+// CRVAL shifts has hx1 ~ 1e-7 and he1 ~ 1e-9 (x depends on the row only through the curvature of the projection), so
+// over a 16-row segment the term stays below 1e-11 pixel (`kLinXTol`, tested per lag: block-uniform): one FMA less per
+// pixel, 36.4 -> 35.2 ms on config 1.
+template <int MODE, bool ROUND32, int P, bool QUAD = false, bool LINX = false>
 __device__ __forceinline__ void roll_segment(const double* __restrict__ small, unsigned tap, unsigned row_elems,
                                              double be, double bnx, double bny, double he1, double hx1, double hy1,
                                              double inv0, double xoff, double yoff, double pivot_b,
@@ -212,7 +219,10 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
     // fractional parts (+0.5) relative to the shared floors: v = d + 0.5 in [0, 1) on a regular column
     double vx, vy;
     if (QUAD) {
-      vx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
+      if (LINX)
+        vx = (p == 0) ? qx0 : fma(qx1, (double)p, qx0);
+      else
+        vx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
       vy = (p == 0) ? qy0 : fma(fma(qy2, (double)p, qy1), (double)p, qy0);
     } else {
       const double e = (p == 0) ? be : fma(he1, (double)p, be);
@@ -266,7 +276,7 @@ __device__ __forceinline__ void roll_segment(const double* __restrict__ small, u
 // vbad >= 2^23 (a floor changed inside the segment, or a fraction rounded up to 1).
 constexpr double kFracMagic = 805306368.0;   // 1.5 * 2^29
 
-template <int MODE, int P>
+template <int MODE, int P, bool LINX = false>
 __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ small32c, unsigned tap,
                                                    unsigned row_elems, double be, double bnx, double bny, double he1,
                                                    double hx1, double hy1, double inv0, double xoffm, double yoffm,
@@ -304,7 +314,10 @@ __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ sma
       // |e| <= 2^-18 over the whole grid and |he1| < 2.2e-8 (the caller's test): along the segment 1 / (1 - e) is
       // linear in p to p^2 he1^2 < 1.3e-13, so numerator x reciprocal is a quadratic in p whose coefficients are
       // formed once per lag: two FMAs per coordinate instead of seven instructions for both
-      cx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
+      if (LINX)   // x as a line in p where its quadratic term is below kLinXTol (see roll_segment)
+        cx = (p == 0) ? qx0 : fma(qx1, (double)p, qx0);
+      else
+        cx = (p == 0) ? qx0 : fma(fma(qx2, (double)p, qx1), (double)p, qx0);
       cy = (p == 0) ? qy0 : fma(fma(qy2, (double)p, qy1), (double)p, qy0);
     } else {
       const double e = (p == 0) ? be : fma(he1, (double)p, be);
@@ -477,6 +490,8 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   const int ix0 = __double2loint(mx0), iy0 = __double2loint(my0);
   const double xoff = x0h - (mx0 - kMagic), yoff = y0h - (my0 - kMagic);
   sb = sbb = sab = 0.0;
+  // the quadratic term of x along the segment, hx1 he1 (1 + 2e) p^2 with |e| <= 2^-18, negligible? (block-uniform)
+  const bool lin_x = fabs(hx1 * he1) * (double)((P - 1) * (P - 1)) < kLinXTol;
   // whole window inside the image: columns ix0-1 .. ix0+1, rows iy0-1 .. iy0+P; |coordinate| < 2^30 keeps the
   // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
   bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
@@ -525,7 +540,10 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
       // the quadratic form of the coordinates drops p^2 he1^2 of the reciprocal: below 1e-9 pixel for |he1| < 2.2e-8
       // (P <= 16 rows, numerators below 8192 pixels) -- any 2048-row grid in this mode has |he1| < 4e-9; a small grid
       // with a steep denominator takes the per-pixel series instead (block-uniform choice)
-      if (mode == 0 && fabs(he1) < 2.2e-8)
+      if (mode == 0 && fabs(he1) < 2.2e-8 && lin_x)
+        roll_segment_mixed<0, P, true>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+                                       (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
+      else if (mode == 0 && fabs(he1) < 2.2e-8)
         roll_segment_mixed<0, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
                                  (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
       else
@@ -541,7 +559,10 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   } else if (fast) {
     const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
     unsigned vmax = 0, bmax = 0;
-    if (mode == 0 && fabs(he1) < 2.2e-8)
+    if (mode == 0 && fabs(he1) < 2.2e-8 && lin_x)
+      roll_segment<0, ROUND32, P, true, true>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff,
+                                              pivot_b, a_c, sb, sbb, sab, vmax, bmax);
+    else if (mode == 0 && fabs(he1) < 2.2e-8)
       roll_segment<0, ROUND32, P, true>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff,
                                         pivot_b, a_c, sb, sbb, sab, vmax, bmax);
     else if (mode == 0)

@@ -87,3 +87,38 @@ def test_quadratic_coordinates_stay_within_a_nanopixel():
             worst = max(worst, abs(float(quad - exact)))
     # e^3 of the series (5.5e-17 relative = 2e-13 px) + the neglected curvature of the reciprocal along the segment
     assert worst < 1e-9, worst
+
+
+def test_linear_x_coordinate_stays_within_its_tolerance():
+    """roll_segment / roll_segment_mixed with LINX: where |hx1 he1| (P - 1)^2 < kLinXTol = 0.99e-11 (csrc/coreg_lag_roll.cu)
+    the x coordinate of the quadratic form drops its p^2 term q2 = hx1 he1 (1 + 2 e0). What that neglects stays below
+    1e-11 pixel over a 16-row segment, and the line stays within the quadratic form's own nanopixel of the exact
+    numerator / (1 - e). A lag grid of pure CRVAL shifts (config 1: 0.5 arcsec pixels, 30 arcsec lags) qualifies with
+    two orders of magnitude to spare; a 0.4 degree rotation does not."""
+    from fractions import Fraction as F
+    P, tol = 16, 0.99e-11
+    rng = np.random.default_rng(5)
+    worst_drop, worst_exact, taken = 0.0, 0.0, 0
+    for _ in range(400):
+        he1 = float(rng.uniform(-1, 1)) * 2.2e-8
+        hx1 = float(10.0 ** rng.uniform(-9, -2)) * float(rng.choice([-1, 1]))
+        if not abs(hx1 * he1) * (P - 1) ** 2 < tol:
+            continue
+        taken += 1
+        e0 = float(rng.uniform(-1, 1)) * (2.0 ** -18 - abs(he1) * P)
+        n0 = float(rng.uniform(-4096, 4096))
+        inv0 = 1.0 + e0 + e0 * e0
+        dinv = he1 * (1.0 + 2.0 * e0)
+        q0, q1, q2 = n0 * inv0, hx1 * inv0 + n0 * dinv, hx1 * dinv
+        for p in range(P):
+            line = F(q0) + p * F(q1)
+            worst_drop = max(worst_drop, abs(float(p * p * F(q2))))
+            exact = (F(n0) + p * F(hx1)) / (1 - (F(e0) + p * F(he1)))
+            worst_exact = max(worst_exact, abs(float(line - exact)))
+    assert taken > 100 and worst_drop < 1e-11 and worst_exact < 1e-9, (taken, worst_drop, worst_exact)
+    # config 1: x' - x = shift (1 + O(theta^2)): hx1 ~ shift[px] * theta_x * theta_y-per-row, he1 ~ shift[rad] * pixel[rad]
+    arcsec = np.pi / 180 / 3600
+    hx1 = (30 / 0.5) * (512 * arcsec) * (0.5 * arcsec)
+    he1 = (30 * arcsec) * (0.5 * arcsec)
+    assert abs(hx1 * he1) * (P - 1) ** 2 < 1e-2 * tol
+    assert not abs(np.sin(np.radians(0.4)) * he1) * (P - 1) ** 2 < tol
