@@ -54,6 +54,8 @@ _SIGNATURES = {
     "coreg_tan_world2pix": (C.c_int, [C.POINTER(CoregTanWcs), _P, _P, C.c_int64, _P, _P, _P]),
     "coreg_map_coordinates": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_double,
                                         _P, C.c_int, _P]),
+    "coreg_hpc_cut": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
+                                C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "coreg_tan_trig_planes": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
     "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_rice_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
@@ -208,6 +210,22 @@ def map_coordinates(img, y, x, order, cval, out_dtype):
         _check(lib.coreg_map_coordinates(_ptr(img), _dt(img), img.shape[0], img.shape[1], _ptr(y), _ptr(x),
                                          x.numel(), int(order), float(cval), _ptr(out), _dt(out), _stream()),
                "coreg_map_coordinates")
+    return out
+
+
+def hpc_cut(wcs_small, wcs_large, large, origin, order):
+    """The one-time cut, fused (`coreg_hpc_cut`): the large image (or its window starting at origin = (x0, y0)) on the
+    unshifted small grid, float32 [naxis2, naxis1]."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(large)
+    nx, ny = int(wcs_small.naxis1), int(wcs_small.naxis2)
+    out = torch.empty((ny, nx), dtype=torch.float32, device=large.device)
+    ss, sl = tan_struct(wcs_small), tan_struct(wcs_large)
+    with torch.cuda.device(large.device):
+        _check(lib.coreg_hpc_cut(C.byref(ss), nx, ny, C.byref(sl), _ptr(large), _dt(large), large.shape[0],
+                                 large.shape[1], int(origin[0]), int(origin[1]), int(order), _ptr(out), _stream()),
+               "coreg_hpc_cut")
     return out
 
 

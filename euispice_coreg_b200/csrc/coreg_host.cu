@@ -104,10 +104,6 @@ int hpc_search_host_impl(const void* large, int large_dtype, int lnx, int lny, c
   } while (0)
   TRY(cudaMalloc(&d_large, nl * lsz));
   TRY(cudaMalloc(&d_small, ns * sizeof(double)));
-  TRY(cudaMalloc(&d_lng, ns * sizeof(double)));
-  TRY(cudaMalloc(&d_lat, ns * sizeof(double)));
-  TRY(cudaMalloc(&d_x, ns * sizeof(double)));
-  TRY(cudaMalloc(&d_y, ns * sizeof(double)));
   TRY(cudaMalloc(&d_ref, ns * sizeof(float)));
   TRY(cudaMalloc(&d_piv, 8 * sizeof(double)));   // [4][2] statistics block; its first row is the pivots
   TRY(cudaMalloc(&d_scr, coreg_image_stats_scratch_bytes()));
@@ -128,9 +124,8 @@ int hpc_search_host_impl(const void* large, int large_dtype, int lnx, int lny, c
     TRYRC(coreg_image_stats(d_small_in, COREG_F32, ns, d_small, d_piv + 1, 2, d_scr, s));
   }
   TRY(cudaMemcpyAsync(d_lagw, lag_wcs, n_lags * sizeof(CoregTanWcs), cudaMemcpyHostToDevice, s));
-  TRYRC(coreg_tan_pix2world(wcs_small, snx, sny, 1, d_lng, d_lat, s));
-  TRYRC(coreg_tan_world2pix(wcs_large, d_lng, d_lat, ns, d_x, d_y, s));
-  TRYRC(coreg_map_coordinates(d_large, large_dtype, lny, lnx, d_y, d_x, ns, order, (double)NAN, d_ref, COREG_F32, s));
+  // the one-time cut, fused: world grid -> large-image coordinates -> spline sample -> float32
+  TRYRC(coreg_hpc_cut(wcs_small, snx, sny, wcs_large, d_large, large_dtype, lny, lnx, 0, 0, order, d_ref, s));
   TRYRC(coreg_image_stats(d_ref, COREG_F32, ns, nullptr, d_piv, 2, d_scr, s));
   if (fast && (flags & COREG_FLAG_MIXED) && d_small_in) {
     // opt-in mixed arithmetic: centred float32 payload, guarded per lag; any flagged lag -> the whole search in FP64
@@ -161,8 +156,12 @@ int hpc_search_host_impl(const void* large, int large_dtype, int lnx, int lny, c
     TRYRC(coreg_hpc_lag_corr_wcs(d_ref, d_small, snx, sny, snx, sny, wcs_small, d_lagw, n_lags, order, d_piv, d_work,
                                  work_bytes, d_corr, d_nv, flags, s));
   } else {
+    // the generic kernel works from per-pixel trig planes of the world grid
+    TRY(cudaMalloc(&d_lng, ns * sizeof(double)));
+    TRY(cudaMalloc(&d_lat, ns * sizeof(double)));
     TRY(cudaMalloc(&d_planes, 3 * ns * sizeof(double)));
     TRY(cudaMalloc(&d_lags, n_lags * sizeof(CoregLagTan)));
+    TRYRC(coreg_tan_pix2world(wcs_small, snx, sny, 1, d_lng, d_lat, s));
     TRYRC(coreg_tan_trig_planes(d_lng, d_lat, ns, wcs_small->crval1, d_planes, s));
     tan_lag_from_wcs_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(d_lagw, (int)n_lags, wcs_small->crval1,
                                                                      wcs_small->lonpole, d_lags);

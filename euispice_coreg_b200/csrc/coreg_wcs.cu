@@ -9,37 +9,41 @@ __device__ __forceinline__ double wrap_pipi_deg(double a) {
   return -(m - 180.0);
 }
 
+__device__ __forceinline__ void tan_pix2world_dev(const TanDev& w, int i, int j, int wrap, double& lo, double& la) {
+  const double u1 = ((double)i + 1.0) - w.crpix1;
+  const double u2 = ((double)j + 1.0) - w.crpix2;
+  const double px = w.f11 * u1 + w.f12 * u2;
+  const double py = w.f21 * u1 + w.f22 * u2;
+  const double r2 = px * px + py * py;
+  const double r = sqrt(r2);
+  const double phi = (r == 0.0) ? 0.0 : atan2(px, -py);
+  const double st = rsqrt(1.0 + r2);  // sin(theta), theta = atan2(1, r)
+  const double ct = r * st;
+  double sp, cp;
+  sincos(phi - w.lonpole_rad, &sp, &cp);
+  const double xx = st * w.c0 - ct * w.s0 * cp;
+  const double yy = -ct * sp;
+  const double zz = st * w.s0 + ct * w.c0 * cp;
+  lo = w.a0_deg + atan2(yy, xx) * kR2D;
+  if (w.a0_deg >= 0.0) {
+    if (lo < 0.0) lo += 360.0;
+  } else {
+    if (lo > 0.0) lo -= 360.0;
+  }
+  la = atan2(zz, sqrt(xx * xx + yy * yy)) * kR2D;
+  if (wrap) {
+    lo = wrap_pipi_deg(lo);
+    la = wrap_pipi_deg(la);
+  }
+}
+
 __global__ void tan_pix2world_kernel(TanDev w, int nx, int ny, int wrap, double* __restrict__ lng,
                                      double* __restrict__ lat) {
   const int64_t n = (int64_t)nx * ny;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(idx % nx), j = (int)(idx / nx);
-    const double u1 = ((double)i + 1.0) - w.crpix1;
-    const double u2 = ((double)j + 1.0) - w.crpix2;
-    const double px = w.f11 * u1 + w.f12 * u2;
-    const double py = w.f21 * u1 + w.f22 * u2;
-    const double r2 = px * px + py * py;
-    const double r = sqrt(r2);
-    const double phi = (r == 0.0) ? 0.0 : atan2(px, -py);
-    const double st = rsqrt(1.0 + r2);  // sin(theta), theta = atan2(1, r)
-    const double ct = r * st;
-    double sp, cp;
-    sincos(phi - w.lonpole_rad, &sp, &cp);
-    const double xx = st * w.c0 - ct * w.s0 * cp;
-    const double yy = -ct * sp;
-    const double zz = st * w.s0 + ct * w.c0 * cp;
-    double lo = w.a0_deg + atan2(yy, xx) * kR2D;
-    if (w.a0_deg >= 0.0) {
-      if (lo < 0.0) lo += 360.0;
-    } else {
-      if (lo > 0.0) lo -= 360.0;
-    }
-    double la = atan2(zz, sqrt(xx * xx + yy * yy)) * kR2D;
-    if (wrap) {
-      lo = wrap_pipi_deg(lo);
-      la = wrap_pipi_deg(la);
-    }
+    double lo, la;
+    tan_pix2world_dev(w, (int)(idx % nx), (int)(idx / nx), wrap, lo, la);
     lng[idx] = lo;
     lat[idx] = la;
   }
@@ -120,6 +124,46 @@ int launch_map_coordinates(const TI* img, int ny, int nx, const double* y, const
     default: return fail(COREG_EINVAL, "spline order must be 0..3");
   }
   CK_LAUNCH("map_coordinates_kernel");
+  return COREG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The one-time cut of a helioprojective search in ONE kernel (`_create_submap_of_large_data`, alignment.py:987-1016):
+// world coordinates of the unshifted small grid (ang2pipi-wrapped), their pixel coordinates in the large image, the
+// integer origin of the uploaded window taken off, the spline sample, float32 store. The same device functions as the
+// three separate kernels (tan_pix2world / tan_world2pix / map_coordinates), so the same bits -- without the four
+// float64 planes (134 MB written and read back for a 2048^2 grid) and five launches in between.
+// ---------------------------------------------------------------------------------------------------------
+template <int ORDER, typename TI>
+__global__ void hpc_cut_kernel(TanDev ws, int nx, int ny, TanDev wl, const TI* __restrict__ large, int lny, int lnx,
+                               double x0, double y0, double cval, float* __restrict__ out) {
+  const int64_t n = (int64_t)nx * ny;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double lo, la, x, y, v;
+    tan_pix2world_dev(ws, (int)(idx % nx), (int)(idx / nx), 1, lo, la);
+    tan_world2pix_dev(wl, lo, la, x, y);
+    x -= x0;
+    y -= y0;
+    if (!spline_sample<ORDER, true, TI>(large, lny, lnx, y, x, v)) v = cval;
+    out[idx] = (float)v;
+  }
+}
+
+template <typename TI>
+int launch_hpc_cut(const TanDev& ws, int nx, int ny, const TanDev& wl, const TI* large, int lny, int lnx, int x0, int y0,
+                   int order, float* out, cudaStream_t s) {
+  const int64_t n = (int64_t)nx * ny;
+  const unsigned g = grid_for(n);
+  const double cval = (double)NAN;   // the quiet NaN of the host (`cval=np.nan`): the bits coreg_map_coordinates writes
+  switch (order) {
+    case 0: hpc_cut_kernel<0, TI><<<g, 256, 0, s>>>(ws, nx, ny, wl, large, lny, lnx, (double)x0, (double)y0, cval, out); break;
+    case 1: hpc_cut_kernel<1, TI><<<g, 256, 0, s>>>(ws, nx, ny, wl, large, lny, lnx, (double)x0, (double)y0, cval, out); break;
+    case 2: hpc_cut_kernel<2, TI><<<g, 256, 0, s>>>(ws, nx, ny, wl, large, lny, lnx, (double)x0, (double)y0, cval, out); break;
+    case 3: hpc_cut_kernel<3, TI><<<g, 256, 0, s>>>(ws, nx, ny, wl, large, lny, lnx, (double)x0, (double)y0, cval, out); break;
+    default: return fail(COREG_EINVAL, "spline order must be 0..3");
+  }
+  CK_LAUNCH("hpc_cut_kernel");
   return COREG_OK;
 }
 
@@ -366,6 +410,25 @@ int coreg_map_coordinates(const void* img, int img_dtype, int img_ny, int img_nx
     return launch_map_coordinates((const double*)img, img_ny, img_nx, y, x, n, order, cval, (float*)out, s);
   if (img_dtype == COREG_F64 && out_dtype == COREG_F64)
     return launch_map_coordinates((const double*)img, img_ny, img_nx, y, x, n, order, cval, (double*)out, s);
+  return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_hpc_cut(const CoregTanWcs* wcs_small, int nx, int ny, const CoregTanWcs* wcs_large, const void* large,
+                  int large_dtype, int large_ny, int large_nx, int origin_x, int origin_y, int order, float* ref,
+                  void* stream) {
+  TanDev ts, tl;
+  int rc = make_tan(wcs_small, &ts);
+  if (rc) return rc;
+  rc = make_tan(wcs_large, &tl);
+  if (rc) return rc;
+  if (nx <= 0 || ny <= 0) return COREG_OK;
+  if (!large || !ref) return fail(COREG_EINVAL, "coreg_hpc_cut: null pointer");
+  if (large_ny <= 0 || large_nx <= 0) return fail(COREG_EINVAL, "empty image");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (large_dtype == COREG_F32)
+    return launch_hpc_cut(ts, nx, ny, tl, (const float*)large, large_ny, large_nx, origin_x, origin_y, order, ref, s);
+  if (large_dtype == COREG_F64)
+    return launch_hpc_cut(ts, nx, ny, tl, (const double*)large, large_ny, large_nx, origin_x, origin_y, order, ref, s);
   return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
 }
 

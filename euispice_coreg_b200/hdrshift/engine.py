@@ -350,13 +350,16 @@ class LagSearchEngine:
     @staticmethod
     def large_window(wcs_large: TanWcs, wcs_small: TanWcs, shape_large, margin=4):
         """(x0, x1, y0, y1): the part of the large image the one-time cut onto the small grid can touch. Both maps are
-        gnomonic, so large-image coordinates are a projective function of small-grid coordinates and their extremes
-        over the grid lie on its boundary: the four edges are mapped on the host. `margin` covers the spline support.
-        None when the window cannot be bounded (non-finite coordinates)."""
+        gnomonic, so large-image coordinates are a PROJECTIVE function of small-grid coordinates: along a straight edge
+        of the grid each is a linear-fractional function of one variable, hence monotonic, and a projective map has no
+        interior extrema -- the extremes over the grid are those of its four CORNERS (mapped on the host: 4 points
+        instead of the 4 (nx + ny) edge pixels, 1 ms of numpy per pair on the GPU box's host). The denominator of the map
+        is linear over the grid, so corners in front of the large image's tangent plane (finite coordinates) put the
+        whole grid there. `margin` covers the spline support. None when the window cannot be bounded."""
         nx, ny = int(wcs_small.naxis1), int(wcs_small.naxis2)
         ny_l, nx_l = int(shape_large[0]), int(shape_large[1])
-        ex = np.concatenate([np.arange(nx), np.arange(nx), np.zeros(ny), np.full(ny, nx - 1.0)])
-        ey = np.concatenate([np.zeros(nx), np.full(nx, ny - 1.0), np.arange(ny), np.arange(ny)])
+        ex = np.array([0.0, nx - 1.0, 0.0, nx - 1.0])
+        ey = np.array([0.0, 0.0, ny - 1.0, ny - 1.0])
         lon, lat = wcs_small.pixel_to_world(ex, ey)
         xl, yl = wcs_large.world_to_pixel(lon, lat)
         if not (np.all(np.isfinite(xl)) and np.all(np.isfinite(yl))):
@@ -375,16 +378,12 @@ class LagSearchEngine:
         the ref pivot. The common grid of the search is this unshifted small grid (`alignment.py:649-651, 1000`)."""
         torch = _torch()
         with torch.cuda.device(self.device):
-            lng, lat = _ext.tan_pix2world(wcs_small, wcs_small.naxis1, wcs_small.naxis2, True, self.device)
-            x, y = _ext.tan_world2pix(self.wcs_large, lng, lat)
-            x0, y0 = getattr(self, "large_origin", (0, 0))
-            if x0 or y0:
-                # coordinates in the full image, computed exactly as without a window; the integer origin comes off
-                # exactly, so every tap and every weight is the one the full image would give
-                x -= float(x0)
-                y -= float(y0)
-            self.ref = _ext.map_coordinates(self.d_large, y, x, self.order, float("nan"), torch.float32)
-            del x, y, lng, lat
+            # world grid -> large-image coordinates (computed as in the full image; the integer origin of the uploaded
+            # window comes off exactly, so every tap and every weight is the one the full image would give) -> spline
+            # sample -> float32, in one kernel: the bits of tan_pix2world -> tan_world2pix -> map_coordinates
+            # (tests/test_gpu_parity.py), without the coordinate planes
+            self.ref = _ext.hpc_cut(wcs_small, self.wcs_large, self.d_large, getattr(self, "large_origin", (0, 0)),
+                                    self.order)
             self.planes = None          # trig planes of the generic kernel: built on first use (`_hpc_planes`)
             self.grid_wcs = wcs_small
             self.alpha_ref_deg = wcs_small.crval1

@@ -128,6 +128,17 @@ int coreg_map_coordinates(const void* img_dev, int img_dtype, int img_ny, int im
                           const double* x_dev, int64_t n, int order, double cval, void* out_dev, int out_dtype,
                           void* stream);
 
+/* ---- the one-time cut of a helioprojective search, fused ------------------------------------------------------
+ * Replaces Alignment._create_submap_of_large_data (hdrshift/alignment.py:987-1016): extract_EUI_coordinates +
+ * ang2pipi of the unshifted small grid (utils/Util.py:283-312, 76-80), WCS(hdr_large).world_to_pixel
+ * (alignment.py:1065), interpol2d (utils/Util.py:82-104, cval NaN) and the float32 store (alignment.py:1024) in one
+ * kernel: the same arithmetic as coreg_tan_pix2world -> coreg_tan_world2pix -> coreg_map_coordinates, the same bits,
+ * no coordinate planes in memory. `large_dev` may be a window [origin_y:, origin_x:] of the image wcs_large describes.
+ *   ref_dev  [ny*nx] float32: the large image on the small grid (the search's reference) */
+int coreg_hpc_cut(const CoregTanWcs* wcs_small_host, int nx, int ny, const CoregTanWcs* wcs_large_host,
+                  const void* large_dev, int large_dtype, int large_ny, int large_nx, int origin_x, int origin_y,
+                  int order, float* ref_dev, void* stream);
+
 /* ---- lag-independent per-pixel trig planes for the helioprojective search -----------------------------------
  * planes_dev: [3][n] float64 = sin(lat), cos(lat) sin(lng - alpha_ref), cos(lat) cos(lng - alpha_ref).
  * Hoists the lag-independent half of world_to_pixel out of the per-lag loop (hdrshift/alignment.py:1061-1065). */

@@ -67,6 +67,44 @@ def test_world_to_pixel_matches_oracle(torch_cuda):
 
 @pytest.mark.parametrize("order", [0, 1, 2, 3])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_cut_equals_the_three_kernels_bit_for_bit(torch_cuda, order, dtype):
+    """`coreg_hpc_cut` (one kernel: world grid -> large-image coordinates -> window origin -> spline sample -> float32)
+    against tan_pix2world -> tan_world2pix -> origin subtraction -> map_coordinates, which are pinned one by one above and
+    below: same bits, NaN pattern included (part of the small grid lies outside the large image), for the whole image
+    and for an uploaded window of it; and against the oracle's `_create_submap_of_large_data`."""
+    torch = torch_cuda
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    hs = _hdr(crval=(-100.0, 50.0), crota=3.0, n=(200, 120), cdelt=0.492)
+    hl = _hdr(crval=(-80.0, 30.0), crota=-1.5, n=(96, 80), cdelt=1.1)      # covers most, not all, of the small grid
+    ws, wl = TanWcs.from_header(hs), TanWcs.from_header(hl)
+    rng = np.random.default_rng(7)
+    large = rng.normal(500.0, 300.0, (80, 96)).astype(dtype)
+    large[10, 20] = np.nan
+    for x0, y0 in ((0, 0), (7, 5)):
+        d_large = torch.from_numpy(np.ascontiguousarray(large[y0:, x0:])).cuda()
+        lng, lat = _ext.tan_pix2world(ws, ws.naxis1, ws.naxis2, True)
+        x, y = _ext.tan_world2pix(wl, lng, lat)
+        x -= float(x0)
+        y -= float(y0)
+        ref3 = _ext.map_coordinates(d_large, y, x, order, float("nan"), torch.float32).cpu().numpy()
+        ref1 = _ext.hpc_cut(ws, wl, d_large, (x0, y0), order).cpu().numpy()
+        assert ref1.shape == (120, 200) and ref1.dtype == np.float32
+        assert np.isnan(ref1).any() and np.isfinite(ref1).sum() > 0.3 * ref1.size
+        assert np.array_equal(ref1.view(np.uint32), ref3.view(np.uint32))
+    if order == 0:
+        return      # nearest pixel: a coordinate 1e-10 pixel from a half-integer may pick the neighbour
+    from oracle import wcs_tan
+    xo, yo = wcs_tan.extract_coordinates_pixels(hs, hl)
+    want = map_coordinates(large, [yo, xo], order=order, mode="constant", cval=np.nan, prefilter=False).astype(np.float32)
+    got = _ext.hpc_cut(ws, wl, torch.from_numpy(large).cuda(), (0, 0), order).cpu().numpy()
+    both = np.isfinite(want) & np.isfinite(got)
+    assert (np.isfinite(want) != np.isfinite(got)).sum() <= 4          # closed-bound membership of border pixels
+    assert np.max(np.abs(want[both] - got[both])) <= 1e-3              # coordinates agree to ~1e-10 pixel
+
+
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_map_coordinates_bit_exact_vs_scipy(torch_cuda, order, dtype):
     """interpol2d drop-in (utils/Util.py:82-104): integer/half-integer/border/NaN coordinates included."""
     from euispice_coreg_b200.utils.Util import AlignCommonUtil

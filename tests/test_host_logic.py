@@ -350,6 +350,13 @@ def test_c_abi_argument_validation_needs_no_device():
     assert rc == ENOMEM
     rc = lib.coreg_map_coordinates(fake, 5, 4, 4, fake, fake, 10, 2, 0.0, fake, _ext.F64, null)
     assert rc == EINVAL and "dtype" in msg()
+    good = _ext.CoregTanWcs(1, 1, 1.0, 1.0, 1, 0, 0, 1, 0, 0, 180)
+    rc = lib.coreg_hpc_cut(ctypes.byref(good), 8, 8, ctypes.byref(tan), fake, _ext.F32, 8, 8, 0, 0, 2, fake, null)
+    assert rc == EINVAL and "singular" in msg()
+    rc = lib.coreg_hpc_cut(ctypes.byref(good), 8, 8, ctypes.byref(good), null, _ext.F32, 8, 8, 0, 0, 2, fake, null)
+    assert rc == EINVAL and "null" in msg()
+    rc = lib.coreg_hpc_cut(ctypes.byref(good), 8, 8, ctypes.byref(good), fake, 5, 8, 8, 0, 0, 2, fake, null)
+    assert rc == EINVAL and "dtype" in msg()
 
 
 # ----------------------------------------------------------------------------------------------- multi-rank
@@ -485,6 +492,27 @@ def test_large_image_window_covers_every_cut_coordinate(toy_pair):
     assert x0 <= max(0, np.floor(x[inside].min()) - 2) and x1 >= min(dl.shape[1], np.ceil(x[inside].max()) + 3)
     assert y0 <= max(0, np.floor(y[inside].min()) - 2) and y1 >= min(dl.shape[0], np.ceil(y[inside].max()) + 3)
     assert (x1 - x0) * (y1 - y0) < 0.5 * dl.size
+    # the window comes from the grid's four CORNERS (a projective map is monotonic along straight edges and has no interior
+    # extrema): rotated, rescaled, strongly offset small grids -- every coordinate of the full map stays inside
+    rng = np.random.default_rng(4)
+    checked = 0
+    for k in range(16):
+        h2 = dict(hs)
+        rot = np.radians(rng.uniform(-180, 180))
+        h2["PC1_1"], h2["PC1_2"], h2["PC2_1"], h2["PC2_2"] = np.cos(rot), -np.sin(rot), np.sin(rot), np.cos(rot)
+        h2["CDELT1"] = hs["CDELT1"] * rng.uniform(0.3, 1.5)
+        h2["CDELT2"] = hs["CDELT2"] * rng.uniform(0.3, 1.5)
+        h2["CRVAL1"] = hs["CRVAL1"] + rng.uniform(-400, 400) * (k % 3)
+        h2["CRVAL2"] = hs["CRVAL2"] + rng.uniform(-400, 400) * (k % 3)
+        win = LagSearchEngine.large_window(TanWcs.from_header(hl), TanWcs.from_header(h2), dl.shape)
+        x, y = wcs_tan.extract_coordinates_pixels(h2, hl)
+        if win is None:      # no overlap worth cropping to
+            continue
+        checked += 1
+        x0, x1, y0, y1 = win
+        assert x0 <= max(0, np.floor(x.min()) - 2) and x1 >= min(dl.shape[1], np.ceil(x.max()) + 3), k
+        assert y0 <= max(0, np.floor(y.min()) - 2) and y1 >= min(dl.shape[0], np.ceil(y.max()) + 3), k
+    assert checked >= 5
 
 
 def test_offset_patch_order_properties():
