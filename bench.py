@@ -595,11 +595,17 @@ def run_gpu(args):
 
     # full public API once on every rank (FITS read + host prep + sharded search + all-gather + Gaussian fit):
     # the "align() wall time" metric. It contains a collective, so all ranks take part.
-    barrier()
-    t0 = time.perf_counter()
-    res = Alignment(pl, ps, parallelism=True, arithmetic=args.arithmetic, **LAGS).align_using_helioprojective()
-    torch.cuda.synchronize()
-    align_wall = ctx.max_over_ranks(time.perf_counter() - t0)
+    # Called three times: the first call of a process pays one-time costs (page cache of the FITS files, allocator
+    # growth); `align_wall_s` is the best of the three (what a caller aligning a sequence sees per pair), the first call
+    # is reported beside it.
+    align_walls = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        res = Alignment(pl, ps, parallelism=True, arithmetic=args.arithmetic, **LAGS).align_using_helioprojective()
+        torch.cuda.synchronize()
+        align_walls.append(ctx.max_over_ranks(time.perf_counter() - t0))
+    align_wall = min(align_walls)
     fp64_peak = _ext.fp64_peak(40000)          # FP64 FMA lane-instructions / s, measured now on this GPU
     configs = {}
     if not args.no_secondary:
@@ -691,7 +697,7 @@ def run_gpu(args):
                     "what": f"LagSearchEngine from pinned host arrays ({h_large.dtype} large, {h_small.dtype} small, as "
                             "the FITS files hold them): H2D images + lag table, statistics + widening, one-time "
                             "resampling, search, all-gather, D2H cube"},
-            "align_wall_s": align_wall, "argmax_lag_arcsec": best,
+            "align_wall_s": align_wall, "align_wall_first_call_s": align_walls[0], "argmax_lag_arcsec": best,
             "mixed": mixed,
             "configs": configs,
             "widened": widened,

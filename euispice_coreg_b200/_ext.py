@@ -40,7 +40,13 @@ class CoregCarrington(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("lon0", "lat0", "roll", "dist", "cdelt1", "cdelt2")]
 
 
+class CoregSurfaceFrames(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("grid_lon", "grid_lat", "grid_dsun", "image_lon", "image_lat", "image_dsun",
+                                          "dt_days", "rsun")]
+
+
 LAG_TAN_DOUBLES = 10    # sizeof(CoregLagTan) / 8
+LAG_TAN_EDGE_DOUBLES = 12   # sizeof(CoregLagTanEdge) / 8
 TAN_WCS_DOUBLES = 11    # sizeof(CoregTanWcs) / 8
 LAG_OFFSET_DOUBLES = 2  # sizeof(CoregLagOffset) / 8
 LAG_CAR_DOUBLES = 16    # sizeof(CoregLagCar) / 8
@@ -56,6 +62,11 @@ _SIGNATURES = {
                                         _P, C.c_int, _P]),
     "coreg_hpc_cut": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "coreg_pad_edge": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "coreg_surface_cut": (C.c_int, [C.POINTER(CoregTanWcs), C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int,
+                                    C.c_int, C.POINTER(CoregSurfaceFrames), _P, _P]),
+    "coreg_hpc_lag_corr_edge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P, _P,
+                                          C.c_size_t, _P, _P, C.c_int, _P]),
     "coreg_tan_trig_planes": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
     "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_rice_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
@@ -391,6 +402,55 @@ def hpc_lag_corr(ref, small, planes, lags, order, pivots, work, corr_out, nvalid
                                       work.numel() * work.element_size(), _ptr(corr_out),
                                       _ptr(nvalid_out) if nvalid_out is not None else None,
                                       int(flags), _stream()), "coreg_hpc_lag_corr")
+
+
+def pad_edge(img):
+    """One replicated pixel around a device image, float64 (`coreg_pad_edge`: reproject's `pad_edge_pixels`)."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(img)
+    ny, nx = img.shape
+    out = torch.empty((ny + 2, nx + 2), dtype=torch.float64, device=img.device)
+    with torch.cuda.device(img.device):
+        _check(lib.coreg_pad_edge(_ptr(img), _dt(img), ny, nx, _ptr(out), _stream()), "coreg_pad_edge")
+    return out
+
+
+def surface_cut(wcs_small, wcs_large, large_pad, frames):
+    """The large image on the small grid through the solar-surface change of observer (`coreg_surface_cut`): float64
+    [naxis2, naxis1]. `large_pad`: `pad_edge` of the large image; `frames`: `CoregSurfaceFrames`."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(large_pad)
+    if large_pad.dtype != torch.float64:
+        raise TypeError("large_pad must be the float64 output of pad_edge")
+    nx, ny = int(wcs_small.naxis1), int(wcs_small.naxis2)
+    out = torch.empty((ny, nx), dtype=torch.float64, device=large_pad.device)
+    ss, sl = tan_struct(wcs_small), tan_struct(wcs_large)
+    with torch.cuda.device(large_pad.device):
+        _check(lib.coreg_surface_cut(C.byref(ss), nx, ny, C.byref(sl), _ptr(large_pad), large_pad.shape[0] - 2,
+                                     large_pad.shape[1] - 2, C.byref(frames), _ptr(out), _stream()),
+               "coreg_surface_cut")
+    return out
+
+
+def hpc_lag_corr_edge(ref, small_pad, planes, lags, pivots, work, corr_out, nvalid_out=None, flags=0):
+    """Bilinear helioprojective search with reproject's edge rule (`coreg_hpc_lag_corr_edge`). `small_pad`: `pad_edge` of
+    the small image; `lags`: device float64 [n_lags, 12] (CoregLagTanEdge rows); `ref`: float64."""
+    torch = _torch()
+    lib = load()
+    _require_cuda(ref, small_pad, planes, lags, pivots, work, corr_out)
+    if ref.dtype != torch.float64 or small_pad.dtype != torch.float64:
+        raise TypeError("ref and small_pad must be float64")
+    if lags.shape[1] != LAG_TAN_EDGE_DOUBLES:
+        raise TypeError("lags must be CoregLagTanEdge rows [n_lags, 12]")
+    gny, gnx = ref.shape
+    with torch.cuda.device(ref.device):
+        _check(lib.coreg_hpc_lag_corr_edge(_ptr(ref), _ptr(small_pad), small_pad.shape[1] - 2, small_pad.shape[0] - 2,
+                                           gnx, gny, _ptr(planes), _ptr(lags), lags.shape[0], _ptr(pivots), _ptr(work),
+                                           work.numel() * work.element_size(), _ptr(corr_out),
+                                           _ptr(nvalid_out) if nvalid_out is not None else None, int(flags),
+                                           _stream()), "coreg_hpc_lag_corr_edge")
 
 
 def hpc_lag_corr_wcs(ref, small, grid_wcs, lag_wcs, order, pivots, work, corr_out, nvalid_out=None, flags=0,

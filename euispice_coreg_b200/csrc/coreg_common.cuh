@@ -298,6 +298,22 @@ struct TanCoord {
   }
 };
 
+// TanCoord with reproject's edge rule, for an image that carries one replicated pixel of padding: coordinates within
+// half a pixel of the (unpadded) array edge are kept and moved into the padded frame, anything else is "outside".
+struct TanEdgeCoord {
+  typedef CoregLagTanEdge Lag;
+  typedef TanCoord::Planes Planes;
+  typedef TanCoord::Pix Pix;
+  __device__ static __forceinline__ Pix load(const Planes& pl, int64_t idx) { return TanCoord::load(pl, idx); }
+  __device__ static __forceinline__ Pix dead() { return TanCoord::dead(); }
+  __device__ static __forceinline__ void map(const Pix& q, const Lag& L, double& x, double& y) {
+    TanCoord::map(q, L.t, x, y);
+    const bool in = (x >= -0.5) && (x <= L.xhi) && (y >= -0.5) && (y <= L.yhi);
+    x = in ? x + 1.0 : CUDART_NAN;
+    y = y + 1.0;
+  }
+};
+
 struct OffsetCoord {
   typedef CoregLagOffset Lag;
   struct Planes {

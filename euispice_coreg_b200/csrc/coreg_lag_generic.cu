@@ -263,6 +263,31 @@ int coreg_hpc_lag_corr(const float* ref, const void* small, int small_dtype, int
   return fail(COREG_EINVAL, "small_dtype must be COREG_F32 or COREG_F64");
 }
 
+int coreg_hpc_lag_corr_edge(const double* ref, const double* small_pad, int snx, int sny, int gnx, int gny,
+                            const double* planes, const CoregLagTanEdge* lags, int64_t n_lags, const double* pivots,
+                            void* work, size_t work_bytes, double* corr, int64_t* nvalid, int flags, void* stream) {
+  if (!ref || !small_pad || !planes || !lags || !pivots || !work || !corr)
+    return fail(COREG_EINVAL, "coreg_hpc_lag_corr_edge: null pointer");
+  if (n_lags <= 0) return COREG_OK;
+  if (n_lags > (int64_t)1 << 30) return fail(COREG_EINVAL, "too many lags in one call (max 2^30)");
+  if (gnx <= 0 || gny <= 0 || snx <= 0 || sny <= 0) return fail(COREG_EINVAL, "empty image");
+  const int pnx = snx + 2, pny = sny + 2;   // the padded image the kernel reads
+  if ((int64_t)pnx * pny >= ((int64_t)1 << 31)) return fail(COREG_EINVAL, "small image too large (>= 2^31 pixels)");
+  if (work_bytes < coreg_lag_corr_workspace_bytes(gnx, gny, n_lags)) return fail(COREG_ENOMEM, "workspace too small");
+  int sms = coreg_device_sm_count();
+  if (sms <= 0) sms = 148;
+  cudaStream_t s = (cudaStream_t)stream;
+  TanCoord::Planes pl{planes, (int64_t)gnx * gny};
+  int tiles = 0;
+  // bilinear, scipy's operation order (what reproject calls), float64 reference, no float32 store
+  int rc = launch_lag_variant<TanEdgeCoord, 1, true, double, double, false>((flags >> 8) & 15, dim3(), gnx, gny, n_lags,
+                                                                            sms, s, ref, small_pad, pnx, pny, pl, lags,
+                                                                            pivots, static_cast<double*>(work), &tiles);
+  if (rc) return rc;
+  CK_LAUNCH("lag_corr_kernel<TanEdgeCoord>");
+  return launch_finalize_tiles(static_cast<double*>(work), tiles, n_lags, corr, nvalid, s);
+}
+
 int coreg_offset_lag_corr(const double* ref, const void* small, int small_dtype, int snx, int sny, int gnx, int gny,
                           const double* tx, const double* ty, const CoregLagOffset* lags, int64_t n_lags, int order,
                           const double* pivots, void* work, size_t work_bytes, double* corr, int64_t* nvalid,

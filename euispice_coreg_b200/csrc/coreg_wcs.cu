@@ -168,6 +168,76 @@ int launch_hpc_cut(const TanDev& ws, int nx, int ny, const TanDev& wl, const TI*
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Solar-surface reprojection (sunpy `reproject_to` under `propagate_with_solar_surface`, alignment.py:939-985), the
+// one-time call. See include/coreg_b200.h and oracle/surface_reproject.py for the algorithm restated here.
+// ---------------------------------------------------------------------------------------------------------
+template <typename TI>
+__global__ void pad_edge_kernel(const TI* __restrict__ img, int ny, int nx, double* __restrict__ out) {
+  const int pnx = nx + 2;
+  const int64_t n = (int64_t)(ny + 2) * pnx;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = min(max((int)(idx % pnx) - 1, 0), nx - 1), j = min(max((int)(idx / pnx) - 1, 0), ny - 1);
+    out[idx] = (double)img[(int64_t)j * nx + i];
+  }
+}
+
+struct SurfaceDev {
+  double ex[3], ey[3], ez[3];      // heliocentric-cartesian axes of the grid's observer in Stonyhurst coordinates
+  double fx[3], fy[3], fz[3];      // ... of the image's observer
+  double d_grid, d_image, rsun, dt_days;
+  int identical;                   // same observer, same time: the change of frame is the identity
+};
+
+__global__ void surface_cut_kernel(TanDev ws, int nx, int ny, TanDev wl, const double* __restrict__ large_pad, int lny,
+                                   int lnx, SurfaceDev f, double cval, double* __restrict__ out) {
+  const int64_t n = (int64_t)nx * ny;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double lo, la;
+    tan_pix2world_dev(ws, (int)(idx % nx), (int)(idx / nx), 0, lo, la);
+    bool ok = true;
+    if (!f.identical) {
+      double stx, ctx, sty, cty;
+      sincos(lo * kD2R, &stx, &ctx);
+      sincos(la * kD2R, &sty, &cty);
+      // make_3d: near intersection of the line of sight with the sphere of radius rsun (off-disc: NaN)
+      const double D = f.d_grid, cosa = cty * ctx;
+      const double d = D * cosa - sqrt(D * D * cosa * cosa - D * D + f.rsun * f.rsun);
+      const double x = d * cty * stx, y = d * sty, z = D - d * cty * ctx;
+      const double px = x * f.ex[0] + y * f.ey[0] + z * f.ez[0];
+      const double py = x * f.ex[1] + y * f.ey[1] + z * f.ez[1];
+      const double pz = x * f.ex[2] + y * f.ey[2] + z * f.ez[2];
+      const double r = sqrt(px * px + py * py + pz * pz);
+      const double lat = asin(pz / r);
+      // differential rotation, Howard et al. (urad / s), in the synodic frame of the Stonyhurst longitude
+      const double s2 = sin(lat) * sin(lat);
+      const double rate = (2.894 + -0.428 * s2 + -0.370 * s2 * s2) * 1e-6 * 86400.0;   // rad / day
+      const double lon = atan2(py, px) + (rate * f.dt_days * kR2D - 0.9856 * f.dt_days) * kD2R;
+      double sl, cl;
+      sincos(lon, &sl, &cl);
+      const double cb = cos(lat);
+      const double qx = r * cb * cl, qy = r * cb * sl, qz = r * sin(lat);
+      const double x2 = qx * f.fx[0] + qy * f.fx[1] + qz * f.fx[2];
+      const double y2 = qx * f.fy[0] + qy * f.fy[1] + qz * f.fy[2];
+      const double z2 = qx * f.fz[0] + qy * f.fz[1] + qz * f.fz[2];
+      const double D2 = f.d_image;
+      const double dist = sqrt(x2 * x2 + y2 * y2 + (D2 - z2) * (D2 - z2));
+      lo = atan2(x2, D2 - z2) * kR2D;
+      la = asin(y2 / dist) * kR2D;
+      ok = z2 * D2 > r * r;          // the surface point faces the image's observer (NaN compares false)
+    }
+    double x, y, v = cval;
+    tan_world2pix_dev(wl, lo, la, x, y);
+    ok = ok && (x >= -0.5) && (x <= (double)lnx - 0.5) && (y >= -0.5) && (y <= (double)lny - 0.5);
+    if (ok) {
+      if (!spline_sample<1, true, double>(large_pad, lny + 2, lnx + 2, y + 1.0, x + 1.0, v)) v = cval;
+    }
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Image statistics in one pass over the image (multi-block, deterministic): mean of the finite values (the pivot of
 // the single-pass Pearson moments), their count and max |v|, optionally widening a float32 image to float64 on the
 // way (the host-side `np.array(..., dtype=float64)` of hdrshift/alignment.py:299-316). A second pass, for the mixed-
@@ -430,6 +500,59 @@ int coreg_hpc_cut(const CoregTanWcs* wcs_small, int nx, int ny, const CoregTanWc
   if (large_dtype == COREG_F64)
     return launch_hpc_cut(ts, nx, ny, tl, (const double*)large, large_ny, large_nx, origin_x, origin_y, order, ref, s);
   return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+}
+
+int coreg_pad_edge(const void* img, int dtype, int ny, int nx, double* out, void* stream) {
+  if (ny <= 0 || nx <= 0) return fail(COREG_EINVAL, "empty image");
+  if (!img || !out) return fail(COREG_EINVAL, "coreg_pad_edge: null pointer");
+  const int64_t n = (int64_t)(ny + 2) * (nx + 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == COREG_F32)
+    pad_edge_kernel<float><<<grid_for(n), 256, 0, s>>>((const float*)img, ny, nx, out);
+  else if (dtype == COREG_F64)
+    pad_edge_kernel<double><<<grid_for(n), 256, 0, s>>>((const double*)img, ny, nx, out);
+  else
+    return fail(COREG_EINVAL, "dtype must be COREG_F32 or COREG_F64");
+  CK_LAUNCH("pad_edge_kernel");
+  return COREG_OK;
+}
+
+static void surface_axes(double lon, double lat, double* ex, double* ey, double* ez) {
+  ez[0] = cos(lat) * cos(lon); ez[1] = cos(lat) * sin(lon); ez[2] = sin(lat);
+  ex[0] = -sin(lon); ex[1] = cos(lon); ex[2] = 0.0;
+  ey[0] = ez[1] * ex[2] - ez[2] * ex[1];
+  ey[1] = ez[2] * ex[0] - ez[0] * ex[2];
+  ey[2] = ez[0] * ex[1] - ez[1] * ex[0];
+}
+
+int coreg_surface_cut(const CoregTanWcs* wcs_small, int nx, int ny, const CoregTanWcs* wcs_large,
+                      const double* large_pad, int large_ny, int large_nx, const CoregSurfaceFrames* fr, double* ref,
+                      void* stream) {
+  TanDev ts, tl;
+  int rc = make_tan(wcs_small, &ts);
+  if (rc) return rc;
+  rc = make_tan(wcs_large, &tl);
+  if (rc) return rc;
+  if (!fr) return fail(COREG_EINVAL, "null CoregSurfaceFrames");
+  if (nx <= 0 || ny <= 0) return COREG_OK;
+  if (!large_pad || !ref) return fail(COREG_EINVAL, "coreg_surface_cut: null pointer");
+  if (large_ny <= 0 || large_nx <= 0) return fail(COREG_EINVAL, "empty image");
+  if (!(fr->rsun > 0.0) || !(fr->grid_dsun > fr->rsun) || !(fr->image_dsun > fr->rsun))
+    return fail(COREG_EINVAL, "coreg_surface_cut: observers must be outside a sphere of positive radius");
+  SurfaceDev f;
+  surface_axes(fr->grid_lon, fr->grid_lat, f.ex, f.ey, f.ez);
+  surface_axes(fr->image_lon, fr->image_lat, f.fx, f.fy, f.fz);
+  f.d_grid = fr->grid_dsun;
+  f.d_image = fr->image_dsun;
+  f.rsun = fr->rsun;
+  f.dt_days = fr->dt_days;
+  f.identical = (fr->grid_lon == fr->image_lon && fr->grid_lat == fr->image_lat && fr->grid_dsun == fr->image_dsun &&
+                 fr->dt_days == 0.0) ? 1 : 0;
+  const int64_t n = (int64_t)nx * ny;
+  surface_cut_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ts, nx, ny, tl, large_pad, large_ny, large_nx, f,
+                                                                    (double)NAN, ref);
+  CK_LAUNCH("surface_cut_kernel");
+  return COREG_OK;
 }
 
 int coreg_tan_trig_planes(const double* lng, const double* lat, int64_t n, double alpha_ref_deg, double* planes,

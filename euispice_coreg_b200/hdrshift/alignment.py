@@ -145,18 +145,24 @@ class Alignment:
     def align_using_carrington(self, lonlims=None, latlims=None, size_deg_carrington=None, shape=None,
                                reference_date=None, method='correlation', method_carrington_reprojection="fa",
                                return_type='AlignmentResults'):
-        """Co-alignment on a user Carrington grid (`hdrshift/alignment.py:144-261`), "fa" reprojection."""
+        """Co-alignment on a user Carrington grid (`hdrshift/alignment.py:144-261`). method_carrington_reprojection:
+        "fa" (`_carrington_transform_fa`, the default) or "sunpy" (`_carrington_transform_sunpy`, `:939-985`: no grid
+        arguments needed; the search runs on the small image's own grid after a solar-surface reprojection of the large
+        image -- a restatement of sunpy / reproject's published algorithm, `_surface_search`)."""
         self.method = method
         self.coordinate_frame = "final_carrington"
         self.lon_ctype = "HPLN-TAN"
         self.lat_ctype = "HPLT-TAN"
         self.ang2pipi = True
         self.method_carrington_reprojection = method_carrington_reprojection
-        if method_carrington_reprojection == "sunpy":
-            raise NotImplementedError("the sunpy reprojection (alignment.py:939-985) is outside the device path")
-        if method_carrington_reprojection != "fa":
+        if method_carrington_reprojection not in ("fa", "sunpy"):
             raise ValueError("method_carrington_reprojection must be either 'fa' or 'sunpy")
         self._load_pair()
+        if method_carrington_reprojection == "sunpy":
+            # (the reference reads no grid argument on this path: alignment.py:198-231 is the "fa" branch)
+            self.lonlims = self.latlims = self.shape = self.reference_date = None
+            results = self._find_best_header_parameters()
+            return self._wrap_results(results, return_type)
         if reference_date is None:
             if "DATE-AVG" not in self.hdr_large:
                 raise ValueError(
@@ -481,7 +487,10 @@ class Alignment:
             if n_r != 1:
                 raise ValueError("lag_solar_r must hold exactly one value (the reference breaks on more, "
                                  "alignment.py:646-660)")
-            corr, nvalid = self._carrington_search(eng, refs, d1, d2, d3, d4, d5, float(self.lag_solar_r[0]))
+            if getattr(self, "method_carrington_reprojection", "fa") == "sunpy":
+                corr, nvalid = self._surface_search(eng, refs, d1, d2, d3, d4, d5, float(self.lag_solar_r[0]))
+            else:
+                corr, nvalid = self._carrington_search(eng, refs, d1, d2, d3, d4, d5, float(self.lag_solar_r[0]))
             cube[..., 0] = corr.reshape(shape5)
             self.nvalid = nvalid.reshape(shape5)
         else:
@@ -537,6 +546,41 @@ class Alignment:
             evaluate(win)
         self.lags_evaluated = int(done.sum()) * rest
         return corr, nvalid
+
+    @staticmethod
+    def _surface_frame(hdr):
+        """Observer (Stonyhurst longitude / latitude [rad], distance [m]) and observation time [s] of a header's
+        helioprojective frame, as sunpy's `wcs_utils` reads them: HGLN_OBS / HGLT_OBS / DSUN_OBS, DATE-AVG else DATE-OBS."""
+        from .._compat import timeutil
+        for k in ("HGLN_OBS", "HGLT_OBS", "DSUN_OBS"):
+            if k not in hdr:
+                raise ValueError(f"method_carrington_reprojection='sunpy' needs {k} in both headers")
+        date = hdr["DATE-AVG"] if "DATE-AVG" in hdr else hdr["DATE-OBS"]
+        return (float(np.radians(hdr["HGLN_OBS"])), float(np.radians(hdr["HGLT_OBS"])), float(hdr["DSUN_OBS"]),
+                timeutil.to_seconds(date))
+
+    def _surface_search(self, eng, refs, d1, d2, d3, d4, d5, d_solar_r):
+        """`_carrington_transform_sunpy` (`alignment.py:939-985`) on the device. Once: the large image reprojected onto
+        the small image's grid through sunpy's helioprojective -> helioprojective change of observer for points on the
+        solar surface (radius d_solar_r R_sun), differentially rotated over the time between the two observations
+        (`propagate_with_solar_surface`), bilinear (`reproject_interp`); then `hdr_large = hdr_small` (`:955`). Per
+        lag: `Map(data_small, hdr_shifted).reproject_to(WCS(hdr_small))` -- same observer and time on both sides, so
+        the change of frame is the identity and the call is the helioprojective search's geometry with bilinear
+        interpolation and reproject's edge rule, no float32 store. sunpy / reproject are absent from the image: the
+        algorithm is restated from its published form (oracle/surface_reproject.py), parity unpinned."""
+        from .. import _ext
+        w_small = TanWcs.from_header(self.hdr_small)
+        w_large = TanWcs.from_header(self.hdr_large)
+        g_lon, g_lat, g_d, g_t = self._surface_frame(self.hdr_small)
+        i_lon, i_lat, i_d, i_t = self._surface_frame(self.hdr_large)
+        frames = _ext.CoregSurfaceFrames(g_lon, g_lat, g_d, i_lon, i_lat, i_d, (i_t - g_t) / 86400.0,
+                                         d_solar_r * _engine.R_SUN_M)
+        eng.prepare_surface(self.data_large, w_large, w_small, frames)
+        self.hdr_large = self.hdr_small.copy()
+        table, dead = eng.surface_lag_table(self.hdr_small, refs, d1, d2, d3, d4, d5, self.cdelt_semantics)
+        corr, nvalid = eng.search(table, return_nvalid=True)
+        self.lags_evaluated = int(table.shape[0])
+        return np.where(dead, 0.0, corr), nvalid
 
     def _carrington_search(self, eng, refs, d1, d2, d3, d4, d5, d_solar_r):
         """Per CROTA-lag value one pair of detector planes; CRVAL lags are pure offsets on them

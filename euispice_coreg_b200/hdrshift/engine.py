@@ -409,6 +409,37 @@ class LagSearchEngine:
         self.d_large = None
         self.large_origin = (0, 0)
 
+    # ---- solar-surface reprojection (method_carrington_reprojection="sunpy") ------------------------------------
+    def prepare_surface(self, data_large, wcs_large: TanWcs, wcs_small: TanWcs, frames):
+        """One-time part of the "sunpy" Carrington search (`alignment.py:939-985`, first branch): the large image on the
+        grid of the small one through the solar-surface change of observer (`coreg_surface_cut`), float64; the
+        edge-padded small image and the grid's trig planes for the bilinear per-lag search. `frames`:
+        `_ext.CoregSurfaceFrames`. Restated third-party algorithm, parity unpinned (oracle/surface_reproject.py)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            d_large = self._upload(self._native_float(data_large))
+            self.ref = _ext.surface_cut(wcs_small, wcs_large, _ext.pad_edge(d_large), frames)
+            del d_large
+            lng, lat = _ext.tan_pix2world(wcs_small, wcs_small.naxis1, wcs_small.naxis2, True, self.device)
+            self.planes = _ext.tan_trig_planes(lng, lat, wcs_small.crval1)
+            del lng, lat
+            self.small_pad = _ext.pad_edge(self.small)
+            self.grid_wcs = wcs_small
+            self.alpha_ref_deg = wcs_small.crval1
+            self.delta_ref_deg = wcs_small.crval2
+            _ext.image_stats(self.ref, self.stats, 0)
+        self.frame = "surface"
+
+    def surface_lag_table(self, hdr_small, refs, d1, d2, d3, d4, d5, cdelt_semantics="reference"):
+        """`CoregLagTanEdge` rows: the candidate headers as `CoregLagTan` + the bounds of reproject's edge rule."""
+        self.pure_shift_hint = False
+        tab, dead = tan_lag_table(hdr_small, refs, d1, d2, d3, d4, d5, self.alpha_ref_deg, cdelt_semantics)
+        out = np.empty((tab.shape[0], _ext.LAG_TAN_EDGE_DOUBLES), dtype=np.float64)
+        out[:, :_ext.LAG_TAN_DOUBLES] = tab
+        out[:, _ext.LAG_TAN_DOUBLES] = self.small.shape[1] - 0.5
+        out[:, _ext.LAG_TAN_DOUBLES + 1] = self.small.shape[0] - 0.5
+        return out, dead
+
     # ---- Carrington maps as inputs (CRLN-CAR / CRLT-CAR) -----------------------------------------------------
     def prepare_car(self, data_large, wcs_large: CarWcs, wcs_small: CarWcs):
         """One-time part of `align_using_initial_carrington` (`alignment.py:344-399, 987-1016`): Carrington
@@ -562,6 +593,9 @@ class LagSearchEngine:
                                           self.stats if mixed else self.pivots, work, out_dev[lo:hi], nv, flags,
                                           small32c=self.small32 if mixed else None,
                                           flagged=self.lag_flags[lo:hi] if mixed else None)
+                elif self.frame == "surface":
+                    _ext.hpc_lag_corr_edge(self.ref, self.small_pad, self.planes, table_dev[lo:hi], self.pivots, work,
+                                           out_dev[lo:hi], nv, self.flags)
                 elif self.frame == "car":
                     _ext.car_lag_corr(self.ref, self.small, self.planes, table_dev[lo:hi], self.order,
                                       self.pivots, work, out_dev[lo:hi], nv, self.flags)

@@ -139,6 +139,42 @@ int coreg_hpc_cut(const CoregTanWcs* wcs_small_host, int nx, int ny, const Coreg
                   const void* large_dev, int large_dtype, int large_ny, int large_nx, int origin_x, int origin_y,
                   int order, float* ref_dev, void* stream);
 
+/* ---- solar-surface reprojection (method_carrington_reprojection="sunpy") ------------------------------------------
+ * Replaces Alignment._carrington_transform_sunpy (hdrshift/alignment.py:939-985), i.e. sunpy's
+ * `Map.reproject_to(wcs)` under `propagate_with_solar_surface()` = reproject.reproject_interp (bilinear) through a
+ * helioprojective -> helioprojective change of observer for points ON the solar surface, rotated differentially
+ * (Howard et al., synodic) over the time between the two frames. Third-party algorithm, absent from the image:
+ * restated from its published form, PARITY UNPINNED (oracle/surface_reproject.py).
+ *
+ * coreg_pad_edge: reproject's `pad_edge_pixels`: out_dev [(ny+2)*(nx+2)] float64 = img with one replicated pixel around.
+ * coreg_surface_cut: the one-time call -- the large image on the grid of the small one:
+ *   for every pixel of the small grid: (Tx, Ty) through wcs_small, onto the sphere of radius rsun seen from `grid`
+ *   (off-disc -> NaN), Stonyhurst longitude advanced by the differential rotation over dt_days, seen from `image`
+ *   (points that observer cannot see -> NaN: reproject's round-trip check), pixel through wcs_large, bilinear sample
+ *   of large_pad_dev (the edge-padded large image, coordinates within half a pixel of the array edge), float64.
+ * coreg_hpc_lag_corr_edge: the per-lag call -- both frames come from the small image's header, so the change of
+ *   observer is the identity and what is left is the helioprojective search's geometry with bilinear interpolation and
+ *   reproject's edge rule: coreg_hpc_lag_corr with order 1 on the edge-padded small image, float64 reference, no
+ *   float32 store; a lag row carries the bounds of the edge rule (xhi = snx - 0.5, yhi = sny - 0.5, unpadded). */
+typedef struct CoregSurfaceFrames {
+  double grid_lon, grid_lat, grid_dsun;    /* observer of the output grid: Stonyhurst lon / lat [rad], distance [m] */
+  double image_lon, image_lat, image_dsun; /* observer of the input image */
+  double dt_days;                          /* time of the input image - time of the output grid */
+  double rsun;                             /* [m] */
+} CoregSurfaceFrames;
+typedef struct CoregLagTanEdge {
+  CoregLagTan t;
+  double xhi, yhi;
+} CoregLagTanEdge;
+int coreg_pad_edge(const void* img_dev, int dtype, int ny, int nx, double* out_dev, void* stream);
+int coreg_surface_cut(const CoregTanWcs* wcs_small_host, int nx, int ny, const CoregTanWcs* wcs_large_host,
+                      const double* large_pad_dev, int large_ny, int large_nx, const CoregSurfaceFrames* frames_host,
+                      double* ref_dev, void* stream);
+int coreg_hpc_lag_corr_edge(const double* ref_dev, const double* small_pad_dev, int snx, int sny, int gnx, int gny,
+                            const double* planes_dev, const CoregLagTanEdge* lags_dev, int64_t n_lags,
+                            const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
+                            int64_t* nvalid_dev, int flags, void* stream);
+
 /* ---- lag-independent per-pixel trig planes for the helioprojective search -----------------------------------
  * planes_dev: [3][n] float64 = sin(lat), cos(lat) sin(lng - alpha_ref), cos(lat) cos(lng - alpha_ref).
  * Hoists the lag-independent half of world_to_pixel out of the per-lag loop (hdrshift/alignment.py:1061-1065). */
