@@ -490,8 +490,11 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   const int ix0 = __double2loint(mx0), iy0 = __double2loint(my0);
   const double xoff = x0h - (mx0 - kMagic), yoff = y0h - (my0 - kMagic);
   sb = sbb = sab = 0.0;
-  // the quadratic term of x along the segment, hx1 he1 (1 + 2e) p^2 with |e| <= 2^-18, negligible? (block-uniform)
-  const bool lin_x = fabs(hx1 * he1) * (double)((P - 1) * (P - 1)) < kLinXTol;
+  // the quadratic term of x along the segment, hx1 he1 (1 + 2e) p^2 with |e| <= 2^-18, negligible? (block-uniform.)
+  // Only in the flavour for lag grids of pure CRVAL shifts (!ADAPT), where every lag qualifies: in the flavour with the
+  // adaptive segment one more instantiation of the unrolled segment pushes the hot code past the instruction cache
+  // (5-D grid 14.1 -> 15.8 us per lag, measured), and its rotated / rescaled lags would not take it anyway.
+  const bool lin_x = !ADAPT && fabs(hx1 * he1) * (double)((P - 1) * (P - 1)) < kLinXTol;
   // whole window inside the image: columns ix0-1 .. ix0+1, rows iy0-1 .. iy0+P; |coordinate| < 2^30 keeps the
   // magic-number floor meaningful (NaN fails the compare as well); division-mode lags go pixel by pixel
   bool fast = all_ref && (mode != 2) && small_magnitude(sx0) && small_magnitude(sy0) &&
@@ -540,10 +543,11 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
       // the quadratic form of the coordinates drops p^2 he1^2 of the reciprocal: below 1e-9 pixel for |he1| < 2.2e-8
       // (P <= 16 rows, numerators below 8192 pixels) -- any 2048-row grid in this mode has |he1| < 4e-9; a small grid
       // with a steep denominator takes the per-pixel series instead (block-uniform choice)
-      if (mode == 0 && fabs(he1) < 2.2e-8 && lin_x)
-        roll_segment_mixed<0, P, true>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
-                                       (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
-      else if (mode == 0 && fabs(he1) < 2.2e-8)
+      if (!ADAPT && mode == 0 && fabs(he1) < 2.2e-8 && lin_x) {
+        if constexpr (!ADAPT)
+          roll_segment_mixed<0, P, true>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
+                                         (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
+      } else if (mode == 0 && fabs(he1) < 2.2e-8)
         roll_segment_mixed<0, P>(small32, tap, row_elems, be, bnx2, bny2, he1, hx1, hy1, inv0, xoffm, yoffm,
                                  (float)pivot_b, a_c, fsb, fsbb, fsab, vbad);
       else
@@ -559,10 +563,11 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
   } else if (fast) {
     const unsigned tap = (unsigned)(iy0 - 1) * row_elems + (unsigned)(ix0 - 1);
     unsigned vmax = 0, bmax = 0;
-    if (mode == 0 && fabs(he1) < 2.2e-8 && lin_x)
-      roll_segment<0, ROUND32, P, true, true>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff,
-                                              pivot_b, a_c, sb, sbb, sab, vmax, bmax);
-    else if (mode == 0 && fabs(he1) < 2.2e-8)
+    if (!ADAPT && mode == 0 && fabs(he1) < 2.2e-8 && lin_x) {
+      if constexpr (!ADAPT)
+        roll_segment<0, ROUND32, P, true, true>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff,
+                                                pivot_b, a_c, sb, sbb, sab, vmax, bmax);
+    } else if (mode == 0 && fabs(he1) < 2.2e-8)
       roll_segment<0, ROUND32, P, true>(small, tap, row_elems, be, bnx, bny, he1, hx1, hy1, inv0, xoff, yoff,
                                         pivot_b, a_c, sb, sbb, sab, vmax, bmax);
     else if (mode == 0)
