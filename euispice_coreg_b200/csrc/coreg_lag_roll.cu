@@ -355,7 +355,8 @@ __device__ __forceinline__ void roll_segment_mixed(const float* __restrict__ sma
 // segments pixel by pixel (9 taps each, five times the cost of a regular segment), 26 % a few
 // (tools/irregular_segments.py). Here the window (r0, r1, r2) belongs to the tap index `wtap`; a pixel whose own tap
 // index is the expected one (one row further) just rolls, any other reloads the three rows -- once or twice per
-// segment. 13 FP64 instructions per pixel for coordinates, floors and fractions instead of 4, everything else as in
+// segment. 10 FP64 instructions per pixel for coordinates (quadratics in the row index where the lag allows, else the
+// series: 13), floors and fractions instead of 4, everything else as in
 // `roll_segment`. Requires every pixel's 3 x 3 window strictly inside the image with one spare row / column (the
 // caller checks the two end pixels with that margin; the coordinates are monotonic along the segment).
 template <int MODE, bool ROUND32, int P, typename AT>
@@ -379,14 +380,33 @@ __device__ __forceinline__ bool roll_segment_adaptive(const double* __restrict__
   unsigned wtap = 0xFFFFFFFFu, bmax = 0;   // no window yet: tap indices stay below 2^31
   double dp = 0.0;
   sb = sbb = sab = 0.0;
+  // MODE 0 (|e| <= 2^-18 over the grid and |he1| < 2.2e-8, the caller's test): the coordinates as quadratics in the row
+  // index, the form of `roll_segment` -- two FMAs each instead of seven instructions for both
+  double qx0 = 0, qx1 = 0, qx2 = 0, qy0 = 0, qy1 = 0, qy2 = 0;
+  if (MODE == 0) {
+    const double inv0 = recip_1me_tiny(be);
+    const double dinv = fma(be + be, he1, he1);
+    qx0 = fma(bnx, inv0, x0h);
+    qy0 = fma(bny, inv0, y0h);
+    qx1 = fma(hx1, inv0, bnx * dinv);
+    qy1 = fma(hy1, inv0, bny * dinv);
+    qx2 = hx1 * dinv;
+    qy2 = hy1 * dinv;
+  }
 #pragma unroll 1
   for (int p0 = 0; p0 < P; p0 += 4) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double e = fma(he1, dp, be);
-      const double inv = (MODE == 0) ? recip_1me_tiny(e) : recip_1me_small(e);
-      const double sx = fma(fma(hx1, dp, bnx), inv, x0h);
-      const double sy = fma(fma(hy1, dp, bny), inv, y0h);
+      double sx, sy;
+      if (MODE == 0) {
+        sx = fma(fma(qx2, dp, qx1), dp, qx0);
+        sy = fma(fma(qy2, dp, qy1), dp, qy0);
+      } else {
+        const double e = fma(he1, dp, be);
+        const double inv = recip_1me_small(e);
+        sx = fma(fma(hx1, dp, bnx), inv, x0h);
+        sy = fma(fma(hy1, dp, bny), inv, y0h);
+      }
       const double mx = __dadd_rd(sx, kMagic), my = __dadd_rd(sy, kMagic);
       const unsigned tap = (unsigned)(__double2loint(my) - 1) * row_elems + (unsigned)(__double2loint(mx) - 1);
       const double vx = sx - (mx - kMagic), vy = sy - (my - kMagic);
@@ -519,7 +539,8 @@ __device__ __forceinline__ void roll_lag(const HomLag& C, const double* __restri
     if (b_ok == 0xffffffffu && __popc(b_irr) >= kAdaptMin) {
       bool ok = false;
       if constexpr (ADAPT && P % 4 == 0)
-        ok = (mode == 0) ? roll_segment_adaptive<0, ROUND32, P, AT>(small, row_elems, be, bnx, bny, he1, hx1, hy1, x0h,
+        ok = (mode == 0 && fabs(he1) < 2.2e-8)
+                 ? roll_segment_adaptive<0, ROUND32, P, AT>(small, row_elems, be, bnx, bny, he1, hx1, hy1, x0h,
                                                                     y0h, pivot_b, a_c, sb, sbb, sab)
                          : roll_segment_adaptive<1, ROUND32, P, AT>(small, row_elems, be, bnx, bny, he1, hx1, hy1, x0h,
                                                                     y0h, pivot_b, a_c, sb, sbb, sab);
