@@ -624,8 +624,9 @@ def run_gpu(args):
     if world == 1 and not args.no_secondary:
         # the SURVEY 8f-4 paths, timed for the record (single GPU only: not part of `value`)
         try:
-            from tools import car_bench, pxl_bench
-            widened = {"initial_carrington": car_bench.run(2048, 1024, 60), "pixel_shift": pxl_bench.run()}
+            from tools import car_bench, pxl_bench, surface_bench
+            widened = {"initial_carrington": car_bench.run(2048, 1024, 60), "pixel_shift": pxl_bench.run(),
+                       "sunpy_reprojection": surface_bench.run(3)}
         except Exception as exc:
             widened = {"error": repr(exc)}
     if rank == 0:

@@ -279,12 +279,22 @@ int coreg_hpc_lag_corr_edge(const double* ref, const double* small_pad, int snx,
   cudaStream_t s = (cudaStream_t)stream;
   TanCoord::Planes pl{planes, (int64_t)gnx * gny};
   int tiles = 0;
+  const bool prof = g_prof_on && g_prof_n < 4096;
+  if (prof) {
+    CK(cudaEventCreate(&g_prof[g_prof_n].a));
+    CK(cudaEventCreate(&g_prof[g_prof_n].b));
+    CK(cudaEventRecord(g_prof[g_prof_n].a, s));
+  }
   // bilinear, scipy's operation order (what reproject calls), float64 reference, no float32 store
   int rc = launch_lag_variant<TanEdgeCoord, 1, true, double, double, false>((flags >> 8) & 15, dim3(), gnx, gny, n_lags,
                                                                             sms, s, ref, small_pad, pnx, pny, pl, lags,
                                                                             pivots, static_cast<double*>(work), &tiles);
   if (rc) return rc;
   CK_LAUNCH("lag_corr_kernel<TanEdgeCoord>");
+  if (prof) {
+    CK(cudaEventRecord(g_prof[g_prof_n].b, s));
+    ++g_prof_n;
+  }
   return launch_finalize_tiles(static_cast<double*>(work), tiles, n_lags, corr, nvalid, s);
 }
 

@@ -276,7 +276,8 @@ int coreg_hpc_lag_corr_wcs(const float* ref_dev, const double* small_dev, int sn
  *                 PIVOT of a rounding boundary: |dr| <= 1e-7 by the model, ~1e-10 observed, independent of the image's
  *                 mean level. Variants (COREG_FLAG_VARIANT): 0 = 16 rows per thread with the adaptive segment for
  *                 rotated / rescaled lags (default), 1 = 16 rows without it (lag grids of pure CRVAL shifts: the same
- *                 flavour must then be used for every part of the grid), 3 = 12 rows with it. */
+ *                 flavour must then be used for every part of the grid; x is taken as a line in the row index where
+ *                 its quadratic term stays below 1e-11 pixel), 3 = 12 rows with it. */
 int coreg_hpc_lag_corr_wcs_mixed(const float* ref_dev, const double* small_dev, const float* small32c_dev, int snx,
                                  int sny, int gnx, int gny, const CoregTanWcs* grid_wcs_host,
                                  const CoregTanWcs* lag_wcs_dev, int64_t n_lags, int order, const double* stats_dev,
