@@ -67,6 +67,9 @@ _SIGNATURES = {
                                     C.c_int, C.POINTER(CoregSurfaceFrames), _P, _P]),
     "coreg_hpc_lag_corr_edge": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P, _P,
                                           C.c_size_t, _P, _P, C.c_int, _P]),
+    "coreg_surface_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
+                                            C.c_int, C.POINTER(CoregTanWcs), C.POINTER(CoregSurfaceFrames), _P,
+                                            C.c_int64, C.c_int, _P, _P]),
     "coreg_tan_trig_planes": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P]),
     "coreg_widen_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
     "coreg_rice_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
@@ -656,6 +659,27 @@ def hpc_search_host(large, wcs_large, small, wcs_small, lag_wcs, order=2, flags=
                                      small.shape[0], C.byref(ss), lag_wcs.ctypes.data_as(_P), n_lags, int(order),
                                      int(flags), corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)),
            "coreg_hpc_search_host")
+    return corr, nvalid
+
+
+def surface_search_host(large, wcs_large, small, wcs_small, frames, lag_wcs, flags=0):
+    """Whole "sunpy" Carrington search from HOST numpy buffers (`coreg_surface_search_host`). `frames`:
+    `CoregSurfaceFrames`; `lag_wcs`: [n_lags, 11] float64 `CoregTanWcs` rows (`engine.tan_wcs_table`)."""
+    lib = load()
+    large = np.ascontiguousarray(large, dtype=None if large.dtype in (np.float32, np.float64) else np.float64)
+    small = np.ascontiguousarray(small, dtype=None if small.dtype in (np.float32, np.float64) else np.float64)
+    lag_wcs = np.ascontiguousarray(lag_wcs, dtype=np.float64)
+    if lag_wcs.ndim != 2 or lag_wcs.shape[1] != TAN_WCS_DOUBLES:
+        raise ValueError("lag_wcs must be [n_lags, 11] CoregTanWcs rows")
+    n_lags = lag_wcs.shape[0]
+    corr = np.empty(n_lags, dtype=np.float64)
+    nvalid = np.empty(n_lags, dtype=np.int64)
+    sl, ss = tan_struct(wcs_large), tan_struct(wcs_small)
+    _check(lib.coreg_surface_search_host(large.ctypes.data_as(_P), _np_dt(large), large.shape[1], large.shape[0],
+                                         C.byref(sl), small.ctypes.data_as(_P), _np_dt(small), small.shape[1],
+                                         small.shape[0], C.byref(ss), C.byref(frames), lag_wcs.ctypes.data_as(_P),
+                                         n_lags, int(flags), corr.ctypes.data_as(_P), nvalid.ctypes.data_as(_P)),
+           "coreg_surface_search_host")
     return corr, nvalid
 
 

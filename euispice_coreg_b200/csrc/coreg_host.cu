@@ -33,6 +33,18 @@ int hpc_search_host_impl(const void* large, int large_dtype, int lnx, int lny, c
                          const CoregTanWcs* lag_wcs, int64_t n_lags, int order, int flags, double* corr,
                          int64_t* nvalid);
 
+// CoregLagTanEdge rows (coreg_hpc_lag_corr_edge) from CoregLagTan rows + the bounds of reproject's edge rule
+__global__ void tan_edge_rows_kernel(const CoregLagTan* __restrict__ in, int n, double xhi, double yhi,
+                                     CoregLagTanEdge* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  CoregLagTanEdge e;
+  e.t = in[idx];
+  e.xhi = xhi;
+  e.yhi = yhi;
+  out[idx] = e;
+}
+
 // x[i] += dx, y[i] += dy  (detector coordinates of the large image = offset + plane)
 __global__ void shift_planes_kernel(double* __restrict__ x, double* __restrict__ y, int64_t n, double dx, double dy) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -350,6 +362,69 @@ int coreg_carrington_search_host(const void* large, int large_dtype, int lnx, in
     corr[k] = h_corr[(size_t)slot_of[(size_t)k]];
     if (nvalid) nvalid[k] = h_nv[(size_t)slot_of[(size_t)k]];
   }
+  return COREG_OK;
+}
+
+int coreg_surface_search_host(const void* large, int large_dtype, int lnx, int lny, const CoregTanWcs* wcs_large,
+                              const void* small, int small_dtype, int snx, int sny, const CoregTanWcs* wcs_small,
+                              const CoregSurfaceFrames* frames, const CoregTanWcs* lag_wcs, int64_t n_lags, int flags,
+                              double* corr, int64_t* nvalid) {
+  if (!large || !small || !wcs_large || !wcs_small || !frames || !lag_wcs || !corr)
+    return fail(COREG_EINVAL, "coreg_surface_search_host: null pointer");
+  if (lnx <= 0 || lny <= 0 || snx <= 0 || sny <= 0 || n_lags <= 0)
+    return fail(COREG_EINVAL, "coreg_surface_search_host: empty input");
+  if ((large_dtype != COREG_F32 && large_dtype != COREG_F64) || (small_dtype != COREG_F32 && small_dtype != COREG_F64))
+    return fail(COREG_EINVAL, "coreg_surface_search_host: dtype must be COREG_F32 or COREG_F64");
+  const int64_t ns = (int64_t)snx * sny, nl = (int64_t)lnx * lny;
+  const size_t lsz = large_dtype == COREG_F32 ? 4 : 8, ssz = small_dtype == COREG_F32 ? 4 : 8;
+  const size_t work_bytes = coreg_lag_corr_workspace_bytes(snx, sny, n_lags);
+  DevBufs B;
+  cudaStream_t s = nullptr;
+  void *d_large, *d_small, *d_work, *d_scr;
+  double *d_large_pad, *d_small_pad, *d_ref, *d_lng, *d_lat, *d_planes, *d_stats, *d_corr;
+  int64_t* d_nv;
+  CoregTanWcs* d_lagw;
+  CoregLagTan* d_lags;
+  CoregLagTanEdge* d_edge;
+  HTRY(B.get(&d_large, nl * lsz));
+  HTRY(B.get(&d_small, ns * ssz));
+  HTRY(B.get(&d_large_pad, (size_t)(lnx + 2) * (lny + 2) * sizeof(double)));
+  HTRY(B.get(&d_small_pad, (size_t)(snx + 2) * (sny + 2) * sizeof(double)));
+  HTRY(B.get(&d_ref, ns * sizeof(double)));
+  HTRY(B.get(&d_lng, ns * sizeof(double)));
+  HTRY(B.get(&d_lat, ns * sizeof(double)));
+  HTRY(B.get(&d_planes, 3 * ns * sizeof(double)));
+  HTRY(B.get(&d_stats, 8 * sizeof(double)));
+  HTRY(B.get(&d_scr, coreg_image_stats_scratch_bytes()));
+  HTRY(B.get(&d_corr, n_lags * sizeof(double)));
+  HTRY(B.get(&d_nv, n_lags * sizeof(int64_t)));
+  HTRY(B.get(&d_lagw, n_lags * sizeof(CoregTanWcs)));
+  HTRY(B.get(&d_lags, n_lags * sizeof(CoregLagTan)));
+  HTRY(B.get(&d_edge, n_lags * sizeof(CoregLagTanEdge)));
+  HTRY(B.get(&d_work, work_bytes));
+  HTRY(cudaMemcpyAsync(d_large, large, nl * lsz, cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_small, small, ns * ssz, cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemcpyAsync(d_lagw, lag_wcs, n_lags * sizeof(CoregTanWcs), cudaMemcpyHostToDevice, s));
+  HTRY(cudaMemsetAsync(d_scr, 0, coreg_image_stats_scratch_bytes(), s));
+  // once: the large image on the small grid through the solar-surface change of observer (alignment.py:939-956)
+  HRC(coreg_pad_edge(d_large, large_dtype, lny, lnx, d_large_pad, s));
+  HRC(coreg_surface_cut(wcs_small, snx, sny, wcs_large, d_large_pad, lny, lnx, frames, d_ref, s));
+  // per lag: the bilinear helioprojective search with reproject's edge rule on the padded small image
+  HRC(coreg_pad_edge(d_small, small_dtype, sny, snx, d_small_pad, s));
+  HRC(coreg_tan_pix2world(wcs_small, snx, sny, 1, d_lng, d_lat, s));
+  HRC(coreg_tan_trig_planes(d_lng, d_lat, ns, wcs_small->crval1, d_planes, s));
+  tan_lag_from_wcs_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(d_lagw, (int)n_lags, wcs_small->crval1,
+                                                                   wcs_small->lonpole, d_lags);
+  tan_edge_rows_kernel<<<((int)n_lags + 127) / 128, 128, 0, s>>>(d_lags, (int)n_lags, (double)snx - 0.5,
+                                                                (double)sny - 0.5, d_edge);
+  HTRY(cudaGetLastError());
+  HRC(coreg_image_stats(d_ref, COREG_F64, ns, nullptr, d_stats, 2, d_scr, s));
+  HRC(coreg_image_stats(d_small, small_dtype, ns, nullptr, d_stats + 1, 2, d_scr, s));
+  HRC(coreg_hpc_lag_corr_edge(d_ref, d_small_pad, snx, sny, snx, sny, d_planes, d_edge, n_lags, d_stats, d_work,
+                              work_bytes, d_corr, d_nv, flags, s));
+  HTRY(cudaMemcpyAsync(corr, d_corr, n_lags * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (nvalid) HTRY(cudaMemcpyAsync(nvalid, d_nv, n_lags * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  HTRY(cudaStreamSynchronize(s));
   return COREG_OK;
 }
 

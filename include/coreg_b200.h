@@ -412,6 +412,19 @@ int coreg_carrington_search_host(const void* large_host, int large_dtype, int ln
                                  const double* coslat_host, int n_lat, const CoregLagOffset* lags_host, int64_t n_lags,
                                  int order, int flags, double* corr_host, int64_t* nvalid_host);
 
+/* ---- whole "sunpy" Carrington search from host buffers ---------------------------------------------------------------
+ * _find_best_header_parameters as driven by align_using_carrington(method_carrington_reprojection="sunpy"): the call at
+ * hdrshift/alignment.py:237 with function_to_apply = _carrington_transform_sunpy (:939-985). coreg_pad_edge +
+ * coreg_surface_cut once, then coreg_hpc_lag_corr_edge over the candidate headers (CoregTanWcs rows = the output of
+ * _shift_header, as for coreg_hpc_search_host). Restated third-party algorithm, parity unpinned (see coreg_surface_cut).
+ *   frames_host  observers of the small image (= the output grid) and of the large image, time difference, rsun
+ *   corr_host    [n_lags] float64 out; nvalid_host [n_lags] int64 out (may be NULL) */
+int coreg_surface_search_host(const void* large_host, int large_dtype, int lnx, int lny,
+                              const CoregTanWcs* wcs_large_host, const void* small_host, int small_dtype, int snx,
+                              int sny, const CoregTanWcs* wcs_small_host, const CoregSurfaceFrames* frames_host,
+                              const CoregTanWcs* lag_wcs_host, int64_t n_lags, int flags, double* corr_host,
+                              int64_t* nvalid_host);
+
 /* ---- synthetic raster from HOST buffers ----------------------------------------------------------------------------------
  * coreg_synras_build with the frame stack, the slit's sky coordinates and the raster in host memory: what
  * SPICEComposedMapBuilder.process -> _create_map_from_hdu computes between reading the imager files and writing the

@@ -124,6 +124,11 @@ def test_c_abi_rejects_bad_arguments_without_a_device():
     assert lib.coreg_hpc_lag_corr_edge(fake, fake, 4, 4, 4, 4, fake, fake, 3, fake, fake, 8, fake, null, 0,
                                        null) == E.ENOMEM and "workspace" in msg()
     assert ctypes.sizeof(_ext.CoregSurfaceFrames) == 64
+    assert lib.coreg_surface_search_host(null, _ext.F32, 4, 4, ctypes.byref(good), fake, _ext.F32, 4, 4,
+                                         ctypes.byref(good), ctypes.byref(fr), fake, 3, 0, fake,
+                                         null) == E.EINVAL and "null" in msg()
+    assert lib.coreg_surface_search_host(fake, 9, 4, 4, ctypes.byref(good), fake, _ext.F32, 4, 4, ctypes.byref(good),
+                                         ctypes.byref(fr), fake, 3, 0, fake, null) == E.EINVAL and "dtype" in msg()
 
 
 # ------------------------------------------------------------------------------------------------ device
@@ -191,6 +196,32 @@ def test_sunpy_carrington_search_matches_the_oracle(torch_cuda, toy_pair, tmp_pa
         assert (LAGS["lag_crval1"][am[0]], LAGS["lag_crval2"][am[1]], LAGS["lag_crota"][am[4]]) == (24.0, 6.0, 0.0)
         res = Alignment(pl, ps, parallelism=True, **LAGS).align_using_carrington(method_carrington_reprojection="sunpy")
         assert res.max_index[:2] == (2, 2)
+
+
+@pytest.mark.gpu
+def test_surface_search_host_entry_equals_the_public_api(torch_cuda, toy_pair, tmp_path):
+    """coreg_surface_search_host (host buffers in, cube out: the non-Python caller's entry at the seam `alignment.py:237`
+    with `_carrington_transform_sunpy`) against `align_using_carrington(method_carrington_reprojection="sunpy")`: the same
+    kernels; the per-lag constants are derived on the device instead of by numpy (last-bit differences of sin / cos)."""
+    from euispice_coreg_b200 import _ext
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    from euispice_coreg_b200.hdrshift import Alignment, engine
+    from euispice_coreg_b200.hdrshift.engine import R_SUN_M
+    pl, ps = _with_observers(toy_pair, tmp_path, tag="host", **CASES["two_observers"])
+    a = Alignment(pl, ps, parallelism=True, **LAGS)
+    gpu = a.align_using_carrington(method="correlation", method_carrington_reprojection="sunpy", return_type="corr")
+    dl, hl, ds, hs = load_pair(pl, ps)
+    from oracle.hpc import check_and_create_pcij
+    check_and_create_pcij(hl)
+    check_and_create_pcij(hs)
+    d = engine.flat_lag_grid(LAGS["lag_crval1"], LAGS["lag_crval2"], [0.0], [0.0], LAGS["lag_crota"])
+    table, dead = engine.tan_wcs_table(a.hdr_small, a, *d)
+    assert not dead.any()
+    g, i = Alignment._surface_frame(hs), Alignment._surface_frame(hl)
+    fr = _ext.CoregSurfaceFrames(g[0], g[1], g[2], i[0], i[1], i[2], (i[3] - g[3]) / 86400.0, 1.004 * R_SUN_M)
+    corr, nvalid = _ext.surface_search_host(dl, TanWcs.from_header(hl), ds, TanWcs.from_header(hs), fr, table)
+    assert np.max(np.abs(corr.reshape(gpu.shape) - gpu)) < 1e-11
+    assert np.array_equal(nvalid.reshape(a.nvalid.shape), a.nvalid)
 
 
 @pytest.mark.gpu
