@@ -1,7 +1,7 @@
 """Carrington search with `method_carrington_reprojection="sunpy"`, CPU restatement (TEST INFRASTRUCTURE).
 
-PARITY UNPINNED. The reference delegates this path to third-party code that is absent from the image (sunpy, reproject,
-astropy; versions left open by the reference's pyproject): `hdrshift/alignment.py:939-985`
+PARITY UNPINNED. The reference delegates this path to third-party code that is absent from the image -- sunpy 6.1.2,
+reproject 0.14.1, astropy 7.2.0 in the reference's poetry.lock (pyproject: sunpy ^6.0.4): `hdrshift/alignment.py:939-985`
 
     with propagate_with_solar_surface():
         map_ref_rep = map_ref.reproject_to(map_to_align.wcs)            # once: large -> grid of the small image
