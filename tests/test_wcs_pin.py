@@ -74,3 +74,52 @@ def test_car_restatements_against_wcslib(hdr):
     xb, yb = w.wcs_world2pix(lon, lat, 0)
     xo, yo = o.world_to_pixel(lon, lat)
     assert np.max(np.abs(xb - xo)) < 1e-8 and np.max(np.abs(yb - yo)) < 1e-8
+
+
+def _sunpy_stack():
+    try:
+        import astropy  # noqa: F401
+        import reproject  # noqa: F401
+        import sunpy.map  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _sunpy_stack(), reason="sunpy / reproject not installed: the solar-surface reprojection stays unpinned")
+def test_surface_reprojection_against_sunpy(tmp_path):
+    """`oracle/surface_reproject.reproject_to` against the real thing -- `Map.reproject_to` under
+    `propagate_with_solar_surface()` (`hdrshift/alignment.py:939-985`) -- on a synthetic pair seen by two observers half an
+    hour apart. Runs wherever sunpy + reproject are importable (never in the build image: sunpy 6.1.2 / reproject 0.14.1
+    are the reference's locked versions)."""
+    import copy
+
+    import astropy.constants
+    from astropy.io import fits
+    from astropy.wcs import WCS
+    from sunpy.coordinates import propagate_with_solar_surface
+    from sunpy.map import Map
+    from euispice_coreg_b200._compat import fits_lite
+    from euispice_coreg_b200._synth.scene import make_pair, small_spec
+    from oracle import surface_reproject as sr
+    from oracle.hpc import check_and_create_pcij
+    pl, ps, _ = make_pair(str(tmp_path), small_spec(96, 160, true_crval=(-12.0, 8.0)), tag="pin")
+    L, S = fits_lite.open(pl)[0], fits_lite.open(ps)[0]
+    hl, hs = dict(L.header.items()), dict(S.header.items())
+    hl.update({"HGLN_OBS": 10.3, "HGLT_OBS": -2.9, "DSUN_OBS": 5.5e10, "DATE-AVG": "2022-03-17T10:20:45.000"})
+    hs.update({"HGLN_OBS": 10.0, "HGLT_OBS": -3.0})
+    for h in (hl, hs):
+        check_and_create_pcij(h)
+        h.pop("CRLN_OBS", None), h.pop("CRLT_OBS", None)       # one observer definition per header
+    rsun = (1.004 * astropy.constants.R_sun).to("m").value
+    assert abs(rsun - 1.004 * sr.R_SUN_M) < 1e-3
+    want_oracle = sr.reproject_to(np.asarray(L.data, dtype=np.float64), hl, hs, rsun)
+    map_ref = Map(np.asarray(L.data, dtype=np.float64), fits.Header(hl))
+    map_ref.meta["rsun_ref"] = rsun
+    hdr_out = copy.deepcopy(hs)
+    hdr_out["RSUN_REF"] = rsun
+    with propagate_with_solar_surface():
+        got = map_ref.reproject_to(WCS(fits.Header(hdr_out))).data
+    both = np.isfinite(got) & np.isfinite(want_oracle)
+    assert both.mean() > 0.9 and (np.isfinite(got) != np.isfinite(want_oracle)).mean() < 0.01
+    assert np.max(np.abs(got[both] - want_oracle[both])) < 1e-6 * np.abs(want_oracle[both]).max()
