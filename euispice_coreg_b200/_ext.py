@@ -99,8 +99,12 @@ _SIGNATURES = {
     "coreg_pixel_shift_corr": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int, _P, _P, C.c_size_t,
                                          _P, _P, _P]),
+    "coreg_spice_wave_sum": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "coreg_synras_build": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
                                      C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "coreg_synras_build_windows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs),
+                                             C.POINTER(C.c_int), C.POINTER(C.c_int), _P, _P, C.c_int, C.c_int, C.c_int,
+                                             _P, _P]),
     "coreg_hpc_search_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int, C.c_int,
                                         C.c_int, C.POINTER(CoregTanWcs), _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
     "coreg_hpc_search_host_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, _P, C.c_int, C.c_int, C.c_int,
@@ -616,8 +620,35 @@ def pixel_shift_corr(large, smalls, x0, y0, lag_dx, lag_dy, pivots, return_nvali
     return (corr, nvalid) if return_nvalid else corr
 
 
-def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):
-    """K6. frames: device [n_frames, fny, fnx]; lng/lat: device [n_rows, n_cols] degrees."""
+def spice_wave_sum(raw, sel, ymin, ymax, device=None):
+    """`coreg_spice_wave_sum`: raw = the [n_lambda, ny, nx] float32 planes of a SPICE L2 cube as a numpy array, big-endian
+    (the FITS payload as stored) or native; sel = boolean [n_lambda]. Returns the float64 [ny, nx] image on the device."""
+    torch = _torch()
+    lib = load()
+    raw = np.asarray(raw)
+    if raw.ndim != 3 or raw.dtype.itemsize != 4 or raw.dtype.kind != "f":
+        raise TypeError("raw must be a [n_lambda, ny, nx] float32 array")
+    big = 0 if raw.dtype.isnative else 1
+    n_lambda, ny, nx = raw.shape
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # "non-writable array": it is only read
+        words = torch.from_numpy(np.ascontiguousarray(raw).view("<i4" if big else "=i4"))
+    d_cube = words.to(dev)
+    out = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+    mask = np.ascontiguousarray(np.asarray(sel, dtype=np.uint8))
+    if mask.shape != (n_lambda,):
+        raise ValueError("sel must hold one flag per wavelength plane")
+    with torch.cuda.device(dev):
+        _check(lib.coreg_spice_wave_sum(_ptr(d_cube), big, n_lambda, ny, nx, mask.ctypes.data_as(_P), int(ymin),
+                                        int(ymax), _ptr(out), _stream()), "coreg_spice_wave_sum")
+    return out
+
+
+def synras_build(frames, wcs_list, frame_of_col, lng, lat, order, origins=None):
+    """K6. frames: device [n_frames, fny, fnx]; lng/lat: device [n_rows, n_cols] degrees. origins: [(x0, y0)] per frame
+    when `frames` holds windows [y0:, x0:] of the images the WCS describe (`coreg_synras_build_windows`)."""
     torch = _torch()
     lib = load()
     _require_cuda(frames, lng, lat)
@@ -626,9 +657,16 @@ def synras_build(frames, wcs_list, frame_of_col, lng, lat, order):
     arr = (CoregTanWcs * n_frames)(*[tan_struct(w) for w in wcs_list])
     cols = (C.c_int * n_cols)(*[int(v) for v in frame_of_col])
     out = torch.empty((n_rows, n_cols), dtype=torch.float64, device=frames.device)
+    org = None
+    if origins is not None:
+        flat = [int(v) for xy in origins for v in xy]
+        if len(flat) != 2 * n_frames:
+            raise ValueError("origins must hold one (x0, y0) per frame")
+        org = (C.c_int * (2 * n_frames))(*flat)
     with torch.cuda.device(frames.device):
-        _check(lib.coreg_synras_build(_ptr(frames), _dt(frames), n_frames, fnx, fny, arr, cols, _ptr(lng), _ptr(lat),
-                                      n_rows, n_cols, int(order), _ptr(out), _stream()), "coreg_synras_build")
+        _check(lib.coreg_synras_build_windows(_ptr(frames), _dt(frames), n_frames, fnx, fny, arr, org, cols, _ptr(lng),
+                                              _ptr(lat), n_rows, n_cols, int(order), _ptr(out), _stream()),
+               "coreg_synras_build")
         torch.cuda.current_stream().synchronize()  # `arr` / `cols` are host temporaries
     return out
 

@@ -414,9 +414,32 @@ struct SynrasWcs {
   TanDev w[kMaxSynrasFrames];
 };
 
+// SPICE L2 cube [n_lambda][ny][nx] (float32 as stored in the FITS file: big-endian) -> 2-D image: `np.nansum` over the
+// selected wavelength planes in float64, planes added in ascending order (numpy reduces the leading axis of a C-ordered
+// array plane by plane: the same additions in the same order, NaN planes skipped, a pixel without any finite plane gives
+// 0.0), rows outside [ymin, ymax) set to NaN (`hdrshift/alignment_spice.py:250-276`).
+__global__ void wave_nansum_kernel(const unsigned* __restrict__ cube, int big_endian, int n_lambda, int ny, int nx,
+                                   const unsigned char* __restrict__ sel, int ymin, int ymax, double* __restrict__ out) {
+  const int64_t n = (int64_t)ny * nx;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / nx);
+    double s = 0.0;
+    for (int k = 0; k < n_lambda; ++k) {
+      if (!sel[k]) continue;
+      unsigned u = cube[(int64_t)k * n + idx];
+      if (big_endian) u = __byte_perm(u, 0, 0x0123);
+      const float v = __uint_as_float(u);
+      if (v == v) s += (double)v;
+    }
+    out[idx] = (row < ymin || row >= ymax) ? CUDART_NAN : s;
+  }
+}
+
 template <int ORDER, typename T>
 __global__ void synras_kernel(const T* __restrict__ frames, int fnx, int fny, const TanDev* __restrict__ wcs,
-                              const int* __restrict__ frame_of_col, const double* __restrict__ lng,
+                              const double* __restrict__ origin, const int* __restrict__ frame_of_col,
+                              const double* __restrict__ lng,
                               const double* __restrict__ lat, int n_rows, int n_cols, double* __restrict__ out) {
   const int64_t n = (int64_t)n_rows * n_cols;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -427,6 +450,10 @@ __global__ void synras_kernel(const T* __restrict__ frames, int fnx, int fny, co
     if (f >= 0) {
       double x, y, s;
       tan_world2pix_dev(wcs[f], lng[idx], lat[idx], x, y);
+      // frames may be windows [y0:, x0:] of the images their WCS describes: coordinates are computed in the full image
+      // and the integer origin comes off exactly -- same taps, same weights, same bits as with the whole frame
+      x -= origin[2 * f];
+      y -= origin[2 * f + 1];
       // interpol2d(dst=None) returns the imager's dtype (utils/Util.py:95-97): float32 frames give float32-rounded
       // samples, which the reference then stores into its float64 raster
       if (spline_sample<ORDER, true, T>(frames + (size_t)f * fnx * fny, fny, fnx, y, x, s))
@@ -580,6 +607,23 @@ int coreg_bswap32(const void* in, int64_t n, void* out, void* stream) {
   return COREG_OK;
 }
 
+int coreg_spice_wave_sum(const void* cube, int big_endian, int n_lambda, int ny, int nx, const unsigned char* sel_host,
+                         int ymin, int ymax, double* out, void* stream) {
+  if (!cube || !sel_host || !out) return fail(COREG_EINVAL, "coreg_spice_wave_sum: null pointer");
+  if (n_lambda <= 0 || ny <= 0 || nx <= 0) return fail(COREG_EINVAL, "coreg_spice_wave_sum: empty cube");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* dsel = nullptr;
+  CK(cudaMallocAsync(&dsel, (size_t)n_lambda, s));
+  CK(cudaMemcpyAsync(dsel, sel_host, (size_t)n_lambda, cudaMemcpyHostToDevice, s));
+  const int64_t n = (int64_t)ny * nx;
+  wave_nansum_kernel<<<grid_for(n), 256, 0, s>>>((const unsigned*)cube, big_endian, n_lambda, ny, nx, dsel, ymin, ymax,
+                                                 out);
+  CK_LAUNCH("wave_nansum_kernel");
+  CK(cudaFreeAsync(dsel, s));
+  CK(cudaStreamSynchronize(s));   // sel_host is the caller's temporary
+  return COREG_OK;
+}
+
 size_t coreg_image_stats_scratch_bytes(void) { return sizeof(StatScratch); }
 
 int coreg_image_stats(const void* img, int dtype, int64_t n, double* widen, double* stats, int stats_stride,
@@ -662,6 +706,13 @@ int coreg_car_world2pix(const CoregLagCar* map, const double* lng, const double*
 int coreg_synras_build(const void* frames, int frame_dtype, int n_frames, int fnx, int fny, const CoregTanWcs* wcs,
                        const int* frame_of_col, const double* lng, const double* lat, int n_rows, int n_cols,
                        int order, double* out, void* stream) {
+  return coreg_synras_build_windows(frames, frame_dtype, n_frames, fnx, fny, wcs, nullptr, frame_of_col, lng, lat,
+                                    n_rows, n_cols, order, out, stream);
+}
+
+int coreg_synras_build_windows(const void* frames, int frame_dtype, int n_frames, int fnx, int fny,
+                               const CoregTanWcs* wcs, const int* origin_xy, const int* frame_of_col, const double* lng,
+                               const double* lat, int n_rows, int n_cols, int order, double* out, void* stream) {
   if (!frames || !wcs || !frame_of_col || !lng || !lat || !out)
     return fail(COREG_EINVAL, "coreg_synras_build: null pointer");
   if (n_frames <= 0 || n_frames > kMaxSynrasFrames) return fail(COREG_EINVAL, "n_frames must be in 1..64 per call");
@@ -675,17 +726,22 @@ int coreg_synras_build(const void* frames, int frame_dtype, int n_frames, int fn
   }
   for (int c = 0; c < n_cols; ++c)
     if (frame_of_col[c] >= n_frames) return fail(COREG_EINVAL, "frame_of_col entry out of range");
+  double horg[2 * kMaxSynrasFrames];
+  for (int f = 0; f < 2 * n_frames; ++f) horg[f] = origin_xy ? (double)origin_xy[f] : 0.0;
   TanDev* dw = nullptr;
+  double* dorg = nullptr;
   int* dcol = nullptr;
   CK(cudaMallocAsync(&dw, sizeof(TanDev) * n_frames, s));
+  CK(cudaMallocAsync(&dorg, sizeof(double) * 2 * n_frames, s));
   CK(cudaMallocAsync(&dcol, sizeof(int) * n_cols, s));
   CK(cudaMemcpyAsync(dw, hw, sizeof(TanDev) * n_frames, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dorg, horg, sizeof(double) * 2 * n_frames, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(dcol, frame_of_col, sizeof(int) * n_cols, cudaMemcpyHostToDevice, s));
   // hw / frame_of_col are pageable: the async copies above have consumed them when the call returns
   const int64_t n = (int64_t)n_rows * n_cols;
   const int g = grid_for(n);
 #define SYN(ORD, T) \
-  synras_kernel<ORD, T><<<g, 256, 0, s>>>((const T*)frames, fnx, fny, dw, dcol, lng, lat, n_rows, n_cols, out)
+  synras_kernel<ORD, T><<<g, 256, 0, s>>>((const T*)frames, fnx, fny, dw, dorg, dcol, lng, lat, n_rows, n_cols, out)
   if (frame_dtype == COREG_F32) {
     switch (order) { case 0: SYN(0, float); break; case 1: SYN(1, float); break; case 2: SYN(2, float); break; default: SYN(3, float); }
   } else if (frame_dtype == COREG_F64) {
@@ -696,6 +752,7 @@ int coreg_synras_build(const void* frames, int frame_dtype, int n_frames, int fn
 #undef SYN
   CK_LAUNCH("synras_kernel");
   CK(cudaFreeAsync(dw, s));
+  CK(cudaFreeAsync(dorg, s));
   CK(cudaFreeAsync(dcol, s));
   return COREG_OK;
 }

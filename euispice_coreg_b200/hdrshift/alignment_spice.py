@@ -120,27 +120,37 @@ class AlignmentSpice(Alignment):
 
     def _prepare_spice_from_l2(self, hdu):
         """`alignment_spice.py:250-323`: 4-D L2 cube -> 2-D image + 2-D header."""
-        data_small = np.array(hdu.data.copy(), dtype=np.float64)
         header_spice = hdu.header
         ymin, ymax = Util.AlignSpiceUtil.vertical_edges_limits(header_spice)
         sw = SpiceWcs(header_spice)
         self.hdr_small = sw.xy_header().copy()
-        data_small[:, :, :ymin, :] = np.nan
-        data_small[:, :, ymax:, :] = np.nan
+        shape4 = tuple(hdu.shape) if getattr(hdu, "shape", None) is not None else np.asarray(hdu.data).shape
         if isinstance(self.wavelength_interval_to_sum, str) and self.wavelength_interval_to_sum == "all":
-            self.data_small = np.nansum(data_small[0, :, :, :], axis=0)
+            sel = np.ones(shape4[1], dtype=bool)
         elif type(self.wavelength_interval_to_sum).__name__ == "list":
             unit = str(header_spice.get("CUNIT%d" % sw.iwave, "nm")).strip()
-            wave = sw.wavelength(np.arange(data_small.shape[1]))
+            wave = sw.wavelength(np.arange(shape4[1]))
             lo = _value_in(self.wavelength_interval_to_sum[0], unit)
             hi = _value_in(self.wavelength_interval_to_sum[1], unit)
             sel = np.logical_and(wave >= lo, wave <= hi)
-            self.data_small = np.nansum(data_small[0, sel, :, :], axis=0)
         else:
             raise ValueError("wavelength_interval_to_sum must be a [wave_min * u.angstrom, wave_max * u.angstrom] "
                              "or 'all' str ")
-        self.data_small[:ymin, :] = np.nan
-        self.data_small[ymax:, :] = np.nan
+        raw = hdu.raw_big_endian() if hasattr(hdu, "raw_big_endian") else None
+        if raw is not None and raw.ndim == 4 and raw.shape[0] == 1 and raw.dtype.itemsize == 4:
+            # The float32 payload goes up as the file stores it; the device adds the selected planes in float64 in
+            # ascending order, skipping NaN samples -- the bits of the host reduction below (numpy reduces the leading
+            # axis of a C-ordered array plane by plane), without two float64 copies of the cube on the host
+            # (25 MB -> 51 MB twice for a 40-plane raster: 45 ms of a 48 ms search).
+            from .. import _ext
+            self.data_small = _ext.spice_wave_sum(raw[0], sel, ymin, ymax).cpu().numpy()
+        else:
+            data_small = np.array(hdu.data.copy(), dtype=np.float64)
+            data_small[:, :, :ymin, :] = np.nan
+            data_small[:, :, ymax:, :] = np.nan
+            self.data_small = np.nansum(data_small[0, sel, :, :], axis=0)
+            self.data_small[:ymin, :] = np.nan
+            self.data_small[ymax:, :] = np.nan
         if self.cut_from_center is not None:
             xlen = self.cut_from_center
             xmid = self.data_small.shape[1] // 2
@@ -150,7 +160,7 @@ class AlignmentSpice(Alignment):
             pass
         elif type(self.sub_fov_window).__name__ == "list":
             w = sw.celestial()
-            x, y = np.meshgrid(np.arange(data_small.shape[3]), np.arange(data_small.shape[2]))
+            x, y = np.meshgrid(np.arange(shape4[3]), np.arange(shape4[2]))
             lon, lat = w.pixel_to_world(x, y)     # degrees, wcslib's longitude range
             lims = [_value_in(v, "arcsec") * units.factor("arcsec", "deg") for v in self.sub_fov_window]
             sel = (lon >= lims[0]) & (lon <= lims[1]) & (lat >= lims[2]) & (lat <= lims[3])

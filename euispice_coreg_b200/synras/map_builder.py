@@ -59,6 +59,7 @@ class ComposedMapBuilder(MapBuilder):
         self.path_output = None
         self.use_sunpy = False
         self.order = 2
+        self.use_windows = True     # read / upload only the part of each imager frame the raster can reach
 
     # ------------------------------------------------------------------------------------------ public
     def process(self, folder_path_output=None, basename_output=None, print_filename=True, level=2,
@@ -128,21 +129,40 @@ class ComposedMapBuilder(MapBuilder):
         used = np.unique(frame_of_col)
         if len(used) > _MAX_FRAMES_PER_CALL:
             raise NotImplementedError("more than 64 distinct imager frames in one raster")
-        frames, wcs_list = [], []
+        # Only the part of each imager frame the raster can reach is read, converted and uploaded (a full-disc FSI frame
+        # is 38 MB, a SPICE raster covers ~200 x 250 of its pixels): every frame contributes a window of one common
+        # shape at its own origin, found from the raster grid's four corners (`LagSearchEngine.large_window`: a
+        # projective map has its extremes there; 4 pixels of margin for the spline support). The kernel computes
+        # coordinates in the full image and subtracts the integer origin exactly: the raster has the bits of the
+        # whole-frame build (tests/test_gpu_spice.py).
+        from ..hdrshift.engine import LagSearchEngine
+        hdus, wcs_list, wins = [], [], []
         for k in used:
             if print_filename:
                 print(f"\nUse imager {os.path.basename(self.list_imager_paths[k])}")
-            with _fits().open(self.list_imager_paths[k]) as hdul:
-                hdu = hdul[self.window_imager]
-                frames.append(np.asarray(hdu.data))
-                wcs_list.append(TanWcs.from_header(hdu.header))
-        if len({f.shape for f in frames}) != 1:
+            hdu = _fits().open(self.list_imager_paths[k])[self.window_imager]
+            hdus.append(hdu)
+            wcs_list.append(TanWcs.from_header(hdu.header))
+            shape = tuple(hdu.shape) if getattr(hdu, "shape", None) is not None else np.asarray(hdu.data).shape
+            wins.append((shape, LagSearchEngine.large_window(wcs_list[-1], self._w_grid, shape)
+                         if self.use_windows and len(shape) == 2 else None))
+        if len({w[0] for w in wins}) != 1:
             raise NotImplementedError("imager frames of different shapes in one raster")
+        origins = None
+        if all(w[1] is not None for w in wins):
+            (ny_f, nx_f) = wins[0][0]
+            wx = min(nx_f, max(w[1][1] - w[1][0] for w in wins))
+            wy = min(ny_f, max(w[1][3] - w[1][2] for w in wins))
+            origins = [(min(w[1][0], nx_f - wx), min(w[1][2], ny_f - wy)) for w in wins]
+            frames = [(h.read_window(y0, y0 + wy, x0, x0 + wx) if hasattr(h, "read_window")
+                       else np.asarray(h.data)[y0:y0 + wy, x0:x0 + wx]) for h, (x0, y0) in zip(hdus, origins)]
+        else:
+            frames = [np.asarray(h.data) for h in hdus]
         dt = np.float32 if all(f.dtype == np.float32 for f in frames) else np.float64
         stack = torch.from_numpy(np.ascontiguousarray(np.stack([f.astype(dt, copy=False) for f in frames]))).cuda()
         remap = {int(k): i for i, k in enumerate(used)}
         cols = [remap[int(k)] for k in frame_of_col]
-        out = _ext.synras_build(stack, wcs_list, cols, lng_dev, lat_dev, self.order)
+        out = _ext.synras_build(stack, wcs_list, cols, lng_dev, lat_dev, self.order, origins=origins)
         self.data_composed = out.cpu().numpy()
         list_hdr_imagers_used = [self.headers[k] for k in frame_of_col]
 
@@ -242,6 +262,7 @@ class SPICEComposedMapBuilder(ComposedMapBuilder):
             y = np.arange(naxis2, dtype=np.float64)
             w_grid = w
         lng, lat = _ext.tan_pix2world(w_grid, len(x), len(y), wrap_pipi=False)
+        self._w_grid = w_grid.replace(naxis1=len(x), naxis2=len(y))     # the raster's grid: bounds the imager windows
         t_ref = timeutil.to_seconds(hdr_spice.get("DATEREF", hdr_spice.get("DATE-BEG", hdr_spice["DATE-OBS"])))
         utc_cols = t_ref + sw.time_seconds(x[None, :], 0.0, y[:, None])      # [len(y), len(x)]
         self.hdr_spice_ = sw.xy_header()

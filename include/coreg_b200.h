@@ -354,6 +354,16 @@ int coreg_pixel_shift_corr(const double* large_dev, int lnx, int lny, const doub
                            const double* pivots_dev, void* work_dev, size_t work_bytes, double* corr_dev,
                            int64_t* nvalid_dev, void* stream);
 
+/* ---- SPICE L2 cube -> 2-D image ---------------------------------------------------------------------------------
+ * Replaces the host arithmetic of AlignmentSpice._prepare_spice_from_l2 (hdrshift/alignment_spice.py:250-276):
+ * `np.array(hdu.data, float64)`, NaN above / below the slit, `np.nansum(data[0, sel], axis=0)`, NaN rows again.
+ *   cube_dev  [n_lambda][ny][nx] float32 as the FITS file stores it (big_endian = 1) or native (0)
+ *   sel_host  [n_lambda] 1 = plane inside the wavelength interval;  rows outside [ymin, ymax) -> NaN
+ *   out_dev   [ny*nx] float64: planes added in ascending order in float64, NaN samples skipped (a pixel without a
+ *             finite sample gives 0.0): the bits of numpy's reduction over the leading axis. Synchronises the stream. */
+int coreg_spice_wave_sum(const void* cube_dev, int big_endian, int n_lambda, int ny, int nx,
+                         const unsigned char* sel_host, int ymin, int ymax, double* out_dev, void* stream);
+
 /* ---- K6: synthetic raster ----------------------------------------------------------------------------------------
  * Replaces the column loop of SPICEComposedMapBuilder._create_map_from_hdu (synras/map_builder.py:95-131):
  * output pixel (row j, column i) = order-k sample of imager frame frame_of_col[i] at the pixel position of the sky
@@ -363,6 +373,15 @@ int coreg_pixel_shift_corr(const double* large_dev, int lnx, int lny, const doub
 int coreg_synras_build(const void* frames_dev, int frame_dtype, int n_frames, int fnx, int fny,
                        const CoregTanWcs* wcs_host, const int* frame_of_col_host, const double* lng_dev,
                        const double* lat_dev, int n_rows, int n_cols, int order, double* out_dev, void* stream);
+/* The same with every frame given as a WINDOW of the image its WCS describes: frames_dev[f] = image_f[y0_f : y0_f + fny,
+ * x0_f : x0_f + fnx], origin_xy_host = {x0_0, y0_0, x0_1, y0_1, ...} (NULL = whole frames). Coordinates are computed in
+ * the full image and the integer origin is subtracted exactly, so the raster has the bits of coreg_synras_build on the
+ * whole frames as long as every sampled position has its spline support inside the window: the host uploads a few
+ * hundred pixels of each full-disc frame instead of 38 MB (SPICEComposedMapBuilder: 0.33 -> 0.03 s per raster). */
+int coreg_synras_build_windows(const void* frames_dev, int frame_dtype, int n_frames, int fnx, int fny,
+                               const CoregTanWcs* wcs_host, const int* origin_xy_host, const int* frame_of_col_host,
+                               const double* lng_dev, const double* lat_dev, int n_rows, int n_cols, int order,
+                               double* out_dev, void* stream);
 
 /* ---- whole helioprojective search from HOST buffers (allocates, copies, runs, copies back, frees) ---------------
  * The call a non-Python host would make: replaces Alignment._find_best_header_parameters for the

@@ -51,6 +51,30 @@ def test_synras_matches_oracle(spice_case):
         SPICEComposedMapBuilder(p_spice, imagers, threshold_time=1.0).process(print_filename=False)
 
 
+def test_synras_from_frame_windows_equals_whole_frames(spice_case, tmp_path):
+    """`SPICEComposedMapBuilder` reads and uploads only the window of each imager frame the raster can reach
+    (`coreg_synras_build_windows`: coordinates in the full image, integer origin subtracted exactly): the raster has the
+    bits of the whole-frame build, and the windows really are small."""
+    from euispice_coreg_b200._compat import fits_lite
+    from euispice_coreg_b200.hdrshift.engine import LagSearchEngine
+    from euispice_coreg_b200.synras import SPICEComposedMapBuilder
+    p_spice, imagers, spec, d = spice_case
+    outs = {}
+    for windows in (True, False):
+        b = SPICEComposedMapBuilder(p_spice, imagers, threshold_time=100.0)
+        b.use_windows = windows
+        name = b.process(folder_path_output=str(tmp_path), basename_output=f"synras_w{int(windows)}.fits",
+                         print_filename=False, return_synras_name=True)
+        outs[windows] = fits_lite.open(name)[0].data
+        grid = b._w_grid
+    assert outs[True].dtype == np.float64 and np.isfinite(outs[True]).mean() > 0.9
+    assert np.array_equal(outs[True].view(np.uint64), outs[False].view(np.uint64))
+    from euispice_coreg_b200._compat.wcs import TanWcs
+    hd = fits_lite.open(imagers[0])[0]
+    win = LagSearchEngine.large_window(TanWcs.from_header(hd.header), grid, hd.data.shape)
+    assert win is not None and (win[1] - win[0]) * (win[3] - win[2]) < 0.5 * hd.data.size
+
+
 def test_synras_keep_original_imager_pixel_size(spice_case):
     """`keep_original_imager_pixel_size=True` (`map_builder.py:259-275, 165-192`): the raster is stepped in units of
     the imager's pixel along both axes (fractional raster pixels), and the composed header is rebuilt around the centre

@@ -124,6 +124,10 @@ def test_c_abi_rejects_bad_arguments_without_a_device():
     assert lib.coreg_hpc_lag_corr_edge(fake, fake, 4, 4, 4, 4, fake, fake, 3, fake, fake, 8, fake, null, 0,
                                        null) == E.ENOMEM and "workspace" in msg()
     assert ctypes.sizeof(_ext.CoregSurfaceFrames) == 64
+    assert lib.coreg_spice_wave_sum(null, 1, 4, 4, 4, fake, 0, 4, fake, null) == E.EINVAL and "null" in msg()
+    assert lib.coreg_spice_wave_sum(fake, 1, 0, 4, 4, fake, 0, 4, fake, null) == E.EINVAL and "empty" in msg()
+    assert lib.coreg_synras_build_windows(null, _ext.F32, 1, 4, 4, ctypes.byref(good), None, None, fake, fake, 2, 2, 2,
+                                          fake, null) == E.EINVAL and "null" in msg()
     assert lib.coreg_surface_search_host(null, _ext.F32, 4, 4, ctypes.byref(good), fake, _ext.F32, 4, 4,
                                          ctypes.byref(good), ctypes.byref(fr), fake, 3, 0, fake,
                                          null) == E.EINVAL and "null" in msg()
