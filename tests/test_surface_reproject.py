@@ -100,6 +100,28 @@ def test_oracle_search_recovers_the_synthetic_shift(toy_pair, tmp_path):
     assert cube.max() > 0.99
 
 
+def test_frames_are_read_from_the_headers_like_sunpy_does():
+    """Host side of the sunpy path: observer = HGLN_OBS / HGLT_OBS / DSUN_OBS, time = DATE-AVG (else DATE-OBS); the product
+    and the oracle read the same frame; a header without the observer keywords is refused."""
+    from euispice_coreg_b200.hdrshift import Alignment
+    from oracle import surface_reproject as sr
+    h = {"HGLN_OBS": 10.25, "HGLT_OBS": -3.5, "DSUN_OBS": 5.7e10, "DATE-OBS": "2022-03-17T09:50:45.000",
+         "DATE-AVG": "2022-03-17T09:50:50.500"}
+    lon, lat, dsun, t = Alignment._surface_frame(h)
+    f = sr.frame_of(h, 1.004 * sr.R_SUN_M)
+    assert (lon, lat, dsun) == (f["lon"], f["lat"], f["dsun"]) == (np.radians(10.25), np.radians(-3.5), 5.7e10)
+    assert t == f["t"]
+    h2 = dict(h)
+    del h2["DATE-AVG"]
+    assert Alignment._surface_frame(h2)[3] == t - 5.5 == sr.frame_of(h2, 1.0)["t"]
+    for k in ("HGLN_OBS", "HGLT_OBS", "DSUN_OBS"):
+        bad = {kk: v for kk, v in h.items() if kk != k}
+        with pytest.raises(ValueError, match=k):
+            Alignment._surface_frame(bad)
+        with pytest.raises(ValueError, match=k):
+            sr.frame_of(bad, 1.0)
+
+
 def test_c_abi_rejects_bad_arguments_without_a_device():
     from euispice_coreg_b200 import _ext
     lib = _ext.load()
